@@ -1,0 +1,70 @@
+"""Builds altro_b200/libaltro_b200.so (sm_100a) in-tree with nvcc.
+
+The solve kernel is instantiated per (model, n, m); each group is its own translation unit
+(csrc/solve_inst.cu with -DALTRO_INST=g) compiled in parallel, then everything is linked into one
+shared library exporting the C ABI of include/altro_b200.h.  Objects are cached under
+altro_b200/build/ and rebuilt only when a source they depend on is newer.
+"""
+import concurrent.futures as cf
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libaltro_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+         "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
+N_INST = 8
+UNITS = [("capi", "capi.cu", []), ("tvlqr", "tvlqr.cu", [])] + \
+        [(f"solve_inst_{g}", "solve_inst.cu", [f"-DALTRO_INST={g}"]) for g in range(N_INST)]
+
+
+def _deps():
+    return glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
+        [os.path.join(HERE, "..", "include", "altro_b200.h")]
+
+
+def _compile(unit, verbose):
+    name, src, defs = unit
+    srcp = os.path.join(CSRC, src)
+    if not os.path.exists(srcp):
+        return name, None, ""
+    obj = os.path.join(OBJ, name + ".o")
+    newest = max(os.path.getmtime(p) for p in [srcp] + _deps())
+    if os.path.exists(obj) and os.path.getmtime(obj) >= newest:
+        return name, obj, "cached"
+    cmd = [NVCC] + FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", srcp, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {name}:\n{r.stderr}")
+    return name, obj, r.stderr
+
+
+def build(verbose=False, jobs=None):
+    os.makedirs(OBJ, exist_ok=True)
+    jobs = jobs or min(len(UNITS), os.cpu_count() or 4)
+    objs, logs = [], {}
+    with cf.ThreadPoolExecutor(max_workers=jobs) as ex:
+        for name, obj, log in ex.map(lambda u: _compile(u, verbose), UNITS):
+            if obj:
+                objs.append(obj)
+                logs[name] = log
+    stale = (not os.path.exists(LIB)) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs)
+    if stale:
+        cmd = [NVCC, "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n" + r.stderr)
+    return LIB, logs
+
+
+if __name__ == "__main__":
+    lib, logs = build(verbose="-v" in sys.argv)
+    for k, v in logs.items():
+        if v and v != "cached":
+            print(f"==== {k}\n{v}")
+    print("built", lib)

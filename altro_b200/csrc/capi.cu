@@ -1,0 +1,888 @@
+// capi.cu -- the extern "C" boundary (include/altro_b200.h, section C) and the host side of the
+// batched solver handle: HBM allocation in the problem-fastest layout, host<->device staging
+// with on-device transposition, model dispatch and kernel launches.
+//
+// Mirrors altro::ALTROSolver (src/altro/altro_solver.cpp) call for call; error codes are the
+// reference's ErrorCodes integers (exceptions.hpp:24-51).  No CPU fallback: without a CUDA device
+// altro_b200_create returns NULL and compute calls return ALTRO_B200_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/altro_b200.h"
+#include "device_problem.h"
+#include "launchers.h"
+#include "models.cuh"
+
+using namespace altro_b200;
+
+#define CUDA_OK(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      fprintf(stderr, "altro_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e__), \
+              __FILE__, __LINE__);                                                      \
+      return ALTRO_B200_ERR_NO_DEVICE;                                                  \
+    }                                                                                   \
+  } while (0)
+
+// ------------------------------------------------------------------ layout kernels
+// dst[j * ld + b] = src[b * W + j]   (problem-major -> problem-fastest), 32x32 smem tiles
+__global__ void k_pm_to_pf(const double* __restrict__ src, int B, long W, double* __restrict__ dst,
+                           long ld) {
+  __shared__ double tile[32][33];
+  const long j0 = (long)blockIdx.x * 32;
+  const int b0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int bb = b0 + r;
+    const long j = j0 + threadIdx.x;
+    if (bb < B && j < W) tile[r][threadIdx.x] = src[(long)bb * W + j];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const long j = j0 + r;
+    const int bb = b0 + threadIdx.x;
+    if (bb < B && j < W) dst[j * ld + bb] = tile[threadIdx.x][r];
+  }
+}
+
+// dst[b * W + j] = src[j * ld + b]   (problem-fastest -> problem-major)
+__global__ void k_pf_to_pm(const double* __restrict__ src, int B, long W, double* __restrict__ dst,
+                           long ld) {
+  __shared__ double tile[32][33];
+  const long j0 = (long)blockIdx.x * 32;
+  const int b0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const long j = j0 + r;
+    const int bb = b0 + threadIdx.x;
+    if (bb < B && j < W) tile[r][threadIdx.x] = src[j * ld + bb];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int bb = b0 + r;
+    const long j = j0 + threadIdx.x;
+    if (bb < B && j < W) dst[(long)bb * W + j] = tile[threadIdx.x][r];
+  }
+}
+
+// dst[j * ld + b] = src[j]  for all b   (broadcast a shared row set to every problem)
+__global__ void k_broadcast(const double* __restrict__ src, int B, long W, double* __restrict__ dst,
+                            long ld) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  for (long j = blockIdx.y; j < W; j += gridDim.y) dst[j * ld + b] = src[j];
+}
+
+__global__ void k_fill(double* dst, long count, double v) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (long)gridDim.x * blockDim.x)
+    dst[i] = v;
+}
+
+// SetLQRCost (altro_solver.cpp:159-169) for knots [k0,k1): q = -(Qd .* xref), r = -(Rd .* uref),
+// c = 1/2 xref' Qd xref (+ 1/2 uref' Rd uref for k < N).
+// ref_mode 0: xref [n], uref [m] shared; 1: per problem, problem-major [B][n]/[B][m];
+// 2: window tables xtab [T][n], utab [T][m] with row = offsets[b] + k.
+__global__ void k_lqr_cost(int n, int m, int N, int B, long ld, int k0, int k1,
+                           const double* __restrict__ Qd, const double* __restrict__ Rd,
+                           const double* __restrict__ xref, const double* __restrict__ uref,
+                           int ref_mode, const int* __restrict__ offsets, double* q, double* r,
+                           double* c) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  for (int k = k0 + blockIdx.y; k < k1; k += gridDim.y) {
+    const double* xr = xref;
+    const double* ur = uref;
+    if (ref_mode == 1) {
+      xr = xref + (long)b * n;
+      ur = uref + (long)b * m;
+    } else if (ref_mode == 2) {
+      const long row = offsets[b] + k;
+      xr = xref + row * n;
+      ur = uref + row * m;
+    }
+    double cc = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double w = Qd[k * n + i];
+      q[((long)k * n + i) * ld + b] = -(w * xr[i]);
+      cc += (0.5 * xr[i]) * w * xr[i];
+    }
+    if (k < N) {
+      double cu = 0.0;
+      for (int i = 0; i < m; ++i) {
+        const double w = Rd[k * m + i];
+        r[((long)k * m + i) * ld + b] = -(w * ur[i]);
+        cu += (0.5 * ur[i]) * w * ur[i];
+      }
+      cc += cu;
+    }
+    c[(long)k * ld + b] = cc;
+  }
+}
+
+__global__ void k_add_int(int* v, int B, int add) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) v[b] += add;
+}
+
+// ShiftTrajectory (altro_solver.cpp:283-293): x_[k] = x_[k+1] for k < N, u_[k] = u_[k+1] for k < N-1
+__global__ void k_shift(int n, int m, int N, int B, long ld, double* x, double* u) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  for (int k = 0; k < N; ++k) {
+    for (int i = 0; i < n; ++i) x[((long)k * n + i) * ld + b] = x[((long)(k + 1) * n + i) * ld + b];
+    if (k < N - 1)
+      for (int i = 0; i < m; ++i) u[((long)k * m + i) * ld + b] = u[((long)(k + 1) * m + i) * ld + b];
+  }
+}
+
+// ------------------------------------------------------------------ handle
+struct altro_b200_solver {
+  int N = 0, B = 0, device = 0;
+  long Bp = 0;
+  int n = 0, m = 0;
+  float h = 0.0f;
+  int model = -1;
+  double params[8] = {0};
+  bool dims_set = false, cost_set = false, initialized = false;
+  cudaStream_t stream = nullptr;
+  long launches = 0;
+  long bytes = 0;
+  altro_b200_options opts;
+
+  // device arrays (problem-fastest)
+  double *Qd = nullptr, *Rd = nullptr, *lin = nullptr;
+  double *q = nullptr, *r = nullptr, *c = nullptr, *x0 = nullptr;
+  double *xbar = nullptr, *ubar = nullptr, *x = nullptr, *u = nullptr, *y = nullptr;
+  double* u_init = nullptr;  // last SetInput guess, restored by altro_b200_reset_trajectory
+  double *A = nullptr, *Bm = nullptr, *lx = nullptr, *lu = nullptr;
+  double *K = nullptr, *d = nullptr, *P = nullptr, *p = nullptr;
+  double *z = nullptr, *zest = nullptr, *rho = nullptr;
+  int *status = nullptr, *iters = nullptr, *merit_evals = nullptr, *ls_fail = nullptr;
+  double *phi = nullptr, *stat = nullptr, *feas = nullptr;
+  // tracking-window cost
+  double *xtab = nullptr, *utab = nullptr;
+  int* offsets = nullptr;
+  int T = 0;
+  // constraints
+  ConTable con_h;
+  ConTable* con_d = nullptr;
+  std::vector<double*> off_b;
+  // host mirrors of the shared weights
+  std::vector<double> Qd_h, Rd_h, lin_h;
+  // staging
+  double* stage = nullptr;
+  long stage_count = 0;
+  std::vector<void*> allocs;
+};
+
+static int dalloc(altro_b200_solver* s, void** p, size_t bytes, bool zero = true) {
+  CUDA_OK(cudaMalloc(p, bytes > 0 ? bytes : 8));
+  if (zero) CUDA_OK(cudaMemsetAsync(*p, 0, bytes > 0 ? bytes : 8, s->stream));
+  s->allocs.push_back(*p);
+  s->bytes += (long)bytes;
+  return 0;
+}
+#define DALLOC(s, ptr, count)                                                      \
+  do {                                                                             \
+    int e__ = dalloc((s), (void**)&(ptr), sizeof(*(ptr)) * (size_t)(count));       \
+    if (e__) return e__;                                                           \
+  } while (0)
+
+static int ensure_stage(altro_b200_solver* s, long count) {
+  if (count <= s->stage_count) return 0;
+  if (s->stage) {
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    CUDA_OK(cudaFree(s->stage));
+    s->bytes -= s->stage_count * 8;
+  }
+  CUDA_OK(cudaMalloc((void**)&s->stage, (size_t)count * 8));
+  s->stage_count = count;
+  s->bytes += count * 8;
+  return 0;
+}
+
+// host problem-major [B][W] -> device problem-fastest rows starting at dst
+static int upload_pm(altro_b200_solver* s, const double* host, long W, double* dst) {
+  int e = ensure_stage(s, (long)s->B * W);
+  if (e) return e;
+  CUDA_OK(cudaMemcpyAsync(s->stage, host, (size_t)s->B * W * 8, cudaMemcpyHostToDevice, s->stream));
+  dim3 grid((unsigned)((W + 31) / 32), (unsigned)((s->B + 31) / 32));
+  k_pm_to_pf<<<grid, dim3(32, 8), 0, s->stream>>>(s->stage, s->B, W, dst, s->Bp);
+  s->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+// host shared [W] -> broadcast to every problem
+static int upload_shared(altro_b200_solver* s, const double* host, long W, double* dst) {
+  int e = ensure_stage(s, W);
+  if (e) return e;
+  CUDA_OK(cudaMemcpyAsync(s->stage, host, (size_t)W * 8, cudaMemcpyHostToDevice, s->stream));
+  dim3 grid((unsigned)((s->B + 127) / 128), (unsigned)(W < 1024 ? W : 1024));
+  k_broadcast<<<grid, 128, 0, s->stream>>>(s->stage, s->B, W, dst, s->Bp);
+  s->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+// device problem-fastest rows -> host problem-major [B][W]
+static int download_pm(altro_b200_solver* s, const double* src, long W, double* host) {
+  int e = ensure_stage(s, (long)s->B * W);
+  if (e) return e;
+  dim3 grid((unsigned)((W + 31) / 32), (unsigned)((s->B + 31) / 32));
+  k_pf_to_pm<<<grid, dim3(32, 8), 0, s->stream>>>(src, s->B, W, s->stage, s->Bp);
+  s->launches++;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(host, s->stage, (size_t)s->B * W * 8, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_OK(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+// Index-range resolution of ALTROSolver::CheckKnotPointIndices (altro_solver.cpp:385-433)
+static int resolve_range(const altro_b200_solver* s, int& k_start, int& k_stop, bool inclusive) {
+  const int terminal_index = inclusive ? s->N : s->N - 1;
+  if (k_start == ALTRO_B200_ALL_INDICES && k_stop == 0) {
+    k_start = 0;
+    k_stop = ALTRO_B200_LAST_INDEX;
+  }
+  if (k_start == 0 && k_stop == ALTRO_B200_LAST_INDEX) {
+    k_start = 0;
+    k_stop = terminal_index + 1;
+  }
+  if (k_stop <= 0) k_stop = k_start + 1;
+  if (k_start < 0 || k_start > terminal_index) return ALTRO_B200_BAD_INDEX;
+  if (k_stop > terminal_index + 1) return ALTRO_B200_BAD_INDEX;
+  return ALTRO_B200_NO_ERROR;
+}
+
+// ------------------------------------------------------------------ model dispatch
+// The per-model kernels are instantiated in solve_inst.cu (one translation unit per group so the
+// build parallelises); launchers.h declares one launcher per compiled-in model.
+static solve_launcher find_launcher(int model, int n, int m, const double* prm) {
+  switch (model) {
+    case MODEL_LINEAR:
+      if (n == 4 && m == 2) return launch_solve_linear_4_2;
+      if (n == 2 && m == 1) return launch_solve_linear_2_1;
+      if (n == 6 && m == 3) return launch_solve_linear_6_3;
+      return nullptr;
+    case MODEL_DOUBLE_INTEGRATOR: {
+      const int dim = (int)prm[0];
+      if (dim == 1 && n == 2 && m == 1) return launch_solve_di_1;
+      if (dim == 2 && n == 4 && m == 2) return launch_solve_di_2;
+      if (dim == 3 && n == 6 && m == 3) return launch_solve_di_3;
+      return nullptr;
+    }
+    case MODEL_PENDULUM:
+      return (n == 2 && m == 1) ? launch_solve_pendulum : nullptr;
+    case MODEL_BICYCLE4:
+      return (n == 4 && m == 2) ? launch_solve_bicycle4 : nullptr;
+    case MODEL_BICYCLE5:
+      return (n == 5 && m == 2) ? launch_solve_bicycle5 : nullptr;
+    case MODEL_CHAIN:
+      if (n == 4 && m == 2) return launch_solve_chain_4_2;
+      if (n == 4 && m == 4) return launch_solve_chain_4_4;
+      if (n == 6 && m == 2) return launch_solve_chain_6_2;
+      if (n == 6 && m == 4) return launch_solve_chain_6_4;
+      if (n == 12 && m == 2) return launch_solve_chain_12_2;
+      if (n == 12 && m == 4) return launch_solve_chain_12_4;
+      return nullptr;
+  }
+  return nullptr;
+}
+
+// ------------------------------------------------------------------ C ABI
+extern "C" {
+
+int altro_b200_device_count(void) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess) return 0;
+  return cnt;
+}
+
+const char* altro_b200_error_string(int code) {
+  switch (code) {  // exceptions.cpp:12-94
+    case ALTRO_B200_NO_ERROR: return "no error";
+    case ALTRO_B200_STATE_DIM_UNKNOWN: return "state dimension unknown";
+    case ALTRO_B200_INPUT_DIM_UNKNOWN: return "input dimension unknown";
+    case ALTRO_B200_NEXT_STATE_DIM_UNKNOWN: return "next state dimension unknown";
+    case ALTRO_B200_DIMENSION_UNKNOWN: return "dimension unknown";
+    case ALTRO_B200_BAD_INDEX: return "bad index";
+    case ALTRO_B200_DIMENSION_MISMATCH: return "dimension mismatch";
+    case ALTRO_B200_SOLVER_NOT_INITIALIZED: return "solver not initialized";
+    case ALTRO_B200_SOLVER_ALREADY_INITIALIZED: return "solver already initialized";
+    case ALTRO_B200_NON_POSITIVE: return "expected a positive value";
+    case ALTRO_B200_TIMESTEP_NOT_POSITIVE: return "timestep not positive";
+    case ALTRO_B200_COST_FUN_NOT_SET: return "cost function not set";
+    case ALTRO_B200_DYNAMICS_FUN_NOT_SET: return "dynamics function not set";
+    case ALTRO_B200_INVALID_OPT_AT_TERMINAL: return "invalid operation at terminal knot point";
+    case ALTRO_B200_MAX_CONSTRAINTS_EXCEEDED: return "max number of constraints exceeded";
+    case ALTRO_B200_INVALID_CONSTRAINT_DIM: return "invalid constraint dimension";
+    case ALTRO_B200_CHOLESKY_FAILED: return "cholesky factorization failed";
+    case ALTRO_B200_OP_ONLY_VALID_AT_TERMINAL: return "operation only valid at terminal knot point";
+    case ALTRO_B200_INVALID_POINTER: return "invalid pointer";
+    case ALTRO_B200_BACKWARD_PASS_FAILED: return "backward pass failed";
+    case ALTRO_B200_LINESEARCH_FAILED: return "line search failed";
+    case ALTRO_B200_MERIT_GRADIENT_TOO_SMALL: return "merit function gradient too small";
+    case ALTRO_B200_INVALID_BOUND_CONSTRAINT: return "invalid bound constraint";
+    case ALTRO_B200_NON_POSITIVE_PENALTY: return "penalty must be positive";
+    case ALTRO_B200_COST_NOT_QUADRATIC: return "cost function not quadratic";
+    case ALTRO_B200_FILE_ERROR: return "file error";
+    case ALTRO_B200_ERR_NO_DEVICE: return "no usable CUDA device (no CPU fallback exists)";
+    case ALTRO_B200_ERR_UNSUPPORTED: return "model/dimension combination not compiled in";
+  }
+  return "unknown error";
+}
+
+void altro_b200_default_options(altro_b200_options* o) {  // solver_options.hpp:18-37
+  o->iterations_max = 200;
+  o->tol_primal_feasibility = 1e-4;
+  o->tol_stationarity = 1e-4;
+  o->tol_meritfun_gradient = 1e-8;
+  o->penalty_initial = 1.0;
+  o->penalty_scaling = 10.0;
+  o->penalty_max = 1e8;
+  o->use_backtracking_linesearch = 0;
+  o->linesearch_c1 = 1e-4;
+  o->linesearch_c2 = 0.9;
+}
+
+altro_b200_solver* altro_b200_create(int horizon_length, int batch, int device) {
+  if (horizon_length <= 0 || batch <= 0) return nullptr;
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt <= 0 || device >= cnt) {
+    fprintf(stderr, "altro_b200: no usable CUDA device; the solve path has no CPU fallback\n");
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+  altro_b200_solver* s = new altro_b200_solver();
+  s->N = horizon_length;
+  s->B = batch;
+  s->Bp = ((long)batch + 31) / 32 * 32;
+  s->device = device;
+  altro_b200_default_options(&s->opts);
+  memset(&s->con_h, 0, sizeof(s->con_h));
+  return s;
+}
+
+void altro_b200_destroy(altro_b200_solver* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaStreamSynchronize(s->stream);
+  for (void* p : s->allocs) cudaFree(p);
+  if (s->stage) cudaFree(s->stage);
+  delete s;
+}
+
+int altro_b200_set_stream(altro_b200_solver* s, void* cuda_stream) {
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  s->stream = (cudaStream_t)cuda_stream;
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_set_dimension(altro_b200_solver* s, int n, int m) {  // altro_solver.cpp:26-47
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  if (s->initialized || s->dims_set) return ALTRO_B200_SOLVER_ALREADY_INITIALIZED;
+  if (n <= 0) return ALTRO_B200_STATE_DIM_UNKNOWN;
+  if (m <= 0) return ALTRO_B200_INPUT_DIM_UNKNOWN;
+  CUDA_OK(cudaSetDevice(s->device));
+  s->n = n;
+  s->m = m;
+  const long N = s->N, S = s->Bp;
+  s->Qd_h.assign((size_t)(N + 1) * n, 0.0);
+  s->Rd_h.assign((size_t)N * m, 0.0);
+  s->lin_h.assign((size_t)N * (n * n + n * m + n), 0.0);
+  DALLOC(s, s->Qd, (N + 1) * n);
+  DALLOC(s, s->Rd, N * m);
+  DALLOC(s, s->q, (N + 1) * n * S);
+  DALLOC(s, s->r, N * m * S);
+  DALLOC(s, s->c, (N + 1) * S);
+  DALLOC(s, s->x0, n * S);
+  DALLOC(s, s->xbar, (N + 1) * n * S);
+  DALLOC(s, s->ubar, N * m * S);
+  DALLOC(s, s->x, (N + 1) * n * S);
+  DALLOC(s, s->u, N * m * S);
+  DALLOC(s, s->u_init, N * m * S);
+  DALLOC(s, s->y, (N + 1) * n * S);
+  DALLOC(s, s->A, N * n * n * S);
+  DALLOC(s, s->Bm, N * n * m * S);
+  DALLOC(s, s->lx, (N + 1) * n * S);
+  DALLOC(s, s->lu, N * m * S);
+  DALLOC(s, s->K, N * m * n * S);
+  DALLOC(s, s->d, N * m * S);
+  DALLOC(s, s->P, (N + 1) * n * n * S);
+  DALLOC(s, s->p, (N + 1) * n * S);
+  DALLOC(s, s->rho, S);
+  DALLOC(s, s->status, S);
+  DALLOC(s, s->iters, S);
+  DALLOC(s, s->merit_evals, S);
+  DALLOC(s, s->ls_fail, S);
+  DALLOC(s, s->phi, S);
+  DALLOC(s, s->stat, S);
+  DALLOC(s, s->feas, S);
+  s->dims_set = true;
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_set_time_step(altro_b200_solver* s, float h) {  // altro_solver.cpp:49-63
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  if (h <= 0.0f) return ALTRO_B200_TIMESTEP_NOT_POSITIVE;
+  s->h = h;
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_set_model(altro_b200_solver* s, int model_id, const double* params, int nparams) {
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  if (!s->dims_set) return ALTRO_B200_DIMENSION_UNKNOWN;
+  double prm[8] = {0};
+  for (int i = 0; i < 8 && i < nparams; ++i) prm[i] = params[i];
+  if (!find_launcher(model_id, s->n, s->m, prm)) return ALTRO_B200_ERR_UNSUPPORTED;
+  s->model = model_id;
+  memcpy(s->params, prm, sizeof(prm));
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_set_linear_dynamics(altro_b200_solver* s, const double* A, const double* B,
+                                   const double* f, int k_start, int k_stop) {
+  if (!s || !A || !B) return ALTRO_B200_INVALID_POINTER;
+  if (!s->dims_set) return ALTRO_B200_DIMENSION_UNKNOWN;
+  int e = resolve_range(s, k_start, k_stop, false);
+  if (e) return e;
+  const int n = s->n, m = s->m;
+  const int W = n * n + n * m + n;
+  for (int k = k_start; k < k_stop; ++k) {
+    double* T = &s->lin_h[(size_t)k * W];
+    memcpy(T, A, sizeof(double) * n * n);
+    memcpy(T + n * n, B, sizeof(double) * n * m);
+    if (f) memcpy(T + n * n + n * m, f, sizeof(double) * n);
+  }
+  if (s->model < 0) s->model = MODEL_LINEAR;
+  return ALTRO_B200_NO_ERROR;
+}
+
+static int store_weights(altro_b200_solver* s, const double* Qd, const double* Rd, int k0, int k1) {
+  const int n = s->n, m = s->m;
+  for (int k = k0; k < k1; ++k) {
+    memcpy(&s->Qd_h[(size_t)k * n], Qd, sizeof(double) * n);
+    if (k < s->N && Rd) memcpy(&s->Rd_h[(size_t)k * m], Rd, sizeof(double) * m);
+  }
+  CUDA_OK(cudaMemcpyAsync(s->Qd, s->Qd_h.data(), s->Qd_h.size() * 8, cudaMemcpyHostToDevice, s->stream));
+  CUDA_OK(cudaMemcpyAsync(s->Rd, s->Rd_h.data(), s->Rd_h.size() * 8, cudaMemcpyHostToDevice, s->stream));
+  CUDA_OK(cudaStreamSynchronize(s->stream));  // the host mirrors may change right after
+  return 0;
+}
+
+int altro_b200_set_lqr_cost(altro_b200_solver* s, const double* Qd, const double* Rd,
+                            const double* xref, const double* uref, int per_problem, int k_start,
+                            int k_stop) {
+  if (!s || !Qd || !Rd || !xref || !uref) return ALTRO_B200_INVALID_POINTER;
+  if (!s->dims_set) return ALTRO_B200_DIMENSION_UNKNOWN;
+  CUDA_OK(cudaSetDevice(s->device));
+  int e = resolve_range(s, k_start, k_stop, true);
+  if (e) return e;
+  e = store_weights(s, Qd, Rd, k_start, k_stop);
+  if (e) return e;
+  const int n = s->n, m = s->m;
+  const long cnt = per_problem ? (long)s->B * (n + m) : (n + m);
+  e = ensure_stage(s, cnt);
+  if (e) return e;
+  double* xr = s->stage;
+  double* ur = s->stage + (per_problem ? (long)s->B * n : n);
+  CUDA_OK(cudaMemcpyAsync(xr, xref, sizeof(double) * (per_problem ? (size_t)s->B * n : n),
+                          cudaMemcpyHostToDevice, s->stream));
+  CUDA_OK(cudaMemcpyAsync(ur, uref, sizeof(double) * (per_problem ? (size_t)s->B * m : m),
+                          cudaMemcpyHostToDevice, s->stream));
+  dim3 grid((s->B + 127) / 128, (unsigned)(k_stop - k_start));
+  k_lqr_cost<<<grid, 128, 0, s->stream>>>(n, m, s->N, s->B, s->Bp, k_start, k_stop, s->Qd, s->Rd,
+                                          xr, ur, per_problem ? 1 : 0, nullptr, s->q, s->r, s->c);
+  s->launches++;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(s->stream));
+  s->cost_set = true;
+  return ALTRO_B200_NO_ERROR;
+}
+
+static int apply_window(altro_b200_solver* s) {
+  dim3 grid((s->B + 127) / 128, (unsigned)(s->N + 1));
+  k_lqr_cost<<<grid, 128, 0, s->stream>>>(s->n, s->m, s->N, s->B, s->Bp, 0, s->N + 1, s->Qd, s->Rd,
+                                          s->xtab, s->utab, 2, s->offsets, s->q, s->r, s->c);
+  s->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int altro_b200_set_lqr_cost_window(altro_b200_solver* s, const double* Qd, const double* Rd,
+                                   const double* xtab, const double* utab, int T,
+                                   const int* offsets) {
+  if (!s || !Qd || !Rd || !xtab || !utab || !offsets) return ALTRO_B200_INVALID_POINTER;
+  if (!s->dims_set) return ALTRO_B200_DIMENSION_UNKNOWN;
+  CUDA_OK(cudaSetDevice(s->device));
+  int e = store_weights(s, Qd, Rd, 0, s->N + 1);
+  if (e) return e;
+  if (!s->xtab || s->T != T) {
+    DALLOC(s, s->xtab, (long)T * s->n);
+    DALLOC(s, s->utab, (long)T * s->m);
+    DALLOC(s, s->offsets, s->Bp);
+    s->T = T;
+  }
+  CUDA_OK(cudaMemcpyAsync(s->xtab, xtab, sizeof(double) * (size_t)T * s->n, cudaMemcpyHostToDevice, s->stream));
+  CUDA_OK(cudaMemcpyAsync(s->utab, utab, sizeof(double) * (size_t)T * s->m, cudaMemcpyHostToDevice, s->stream));
+  CUDA_OK(cudaMemcpyAsync(s->offsets, offsets, sizeof(int) * (size_t)s->B, cudaMemcpyHostToDevice, s->stream));
+  e = apply_window(s);
+  if (e) return e;
+  CUDA_OK(cudaStreamSynchronize(s->stream));
+  s->cost_set = true;
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_advance_window(altro_b200_solver* s, int steps) {
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  if (!s->xtab) return ALTRO_B200_COST_FUN_NOT_SET;
+  CUDA_OK(cudaSetDevice(s->device));
+  k_add_int<<<(s->B + 127) / 128, 128, 0, s->stream>>>(s->offsets, s->B, steps);
+  s->launches++;
+  return apply_window(s);
+}
+
+static int set_linear_terms(altro_b200_solver* s, const double* q, const double* r, const double* c,
+                            int per_problem, int k0, int k1) {
+  const int n = s->n, m = s->m;
+  const int nk = k1 - k0;
+  const int nku = (k1 > s->N ? s->N : k1) - k0;  // knots that carry an input
+  int e = 0;
+  if (per_problem) {
+    if (q) e = upload_pm(s, q, (long)nk * n, s->q + (long)k0 * n * s->Bp);
+    if (!e && r && nku > 0) {
+      if (nku == nk) {
+        e = upload_pm(s, r, (long)nk * m, s->r + (long)k0 * m * s->Bp);
+      } else {  // host rows are [B][nk][m] but only nku of them exist on the device
+        std::vector<double> tmp((size_t)s->B * nku * m);
+        for (int b = 0; b < s->B; ++b)
+          memcpy(&tmp[(size_t)b * nku * m], r + (size_t)b * nk * m, sizeof(double) * nku * m);
+        e = upload_pm(s, tmp.data(), (long)nku * m, s->r + (long)k0 * m * s->Bp);
+        if (!e) CUDA_OK(cudaStreamSynchronize(s->stream));
+      }
+    }
+    if (!e && c) e = upload_pm(s, c, nk, s->c + (long)k0 * s->Bp);
+  } else {
+    std::vector<double> tmp;
+    if (q) {
+      tmp.resize((size_t)nk * n);
+      for (int k = 0; k < nk; ++k) memcpy(&tmp[(size_t)k * n], q, sizeof(double) * n);
+      e = upload_shared(s, tmp.data(), (long)nk * n, s->q + (long)k0 * n * s->Bp);
+      if (!e) CUDA_OK(cudaStreamSynchronize(s->stream));
+    }
+    if (!e && r && nku > 0) {
+      tmp.resize((size_t)nku * m);
+      for (int k = 0; k < nku; ++k) memcpy(&tmp[(size_t)k * m], r, sizeof(double) * m);
+      e = upload_shared(s, tmp.data(), (long)nku * m, s->r + (long)k0 * m * s->Bp);
+      if (!e) CUDA_OK(cudaStreamSynchronize(s->stream));
+    }
+    if (!e && c) {
+      tmp.assign((size_t)nk, c[0]);
+      e = upload_shared(s, tmp.data(), nk, s->c + (long)k0 * s->Bp);
+      if (!e) CUDA_OK(cudaStreamSynchronize(s->stream));
+    }
+  }
+  return e;
+}
+
+int altro_b200_set_diagonal_cost(altro_b200_solver* s, const double* Qd, const double* Rd,
+                                 const double* q, const double* r, const double* c,
+                                 int per_problem, int k_start, int k_stop) {
+  if (!s || !Qd || !q || !c) return ALTRO_B200_INVALID_POINTER;
+  if (!s->dims_set) return ALTRO_B200_DIMENSION_UNKNOWN;
+  CUDA_OK(cudaSetDevice(s->device));
+  int e = resolve_range(s, k_start, k_stop, true);
+  if (e) return e;
+  e = store_weights(s, Qd, Rd, k_start, k_stop);
+  if (e) return e;
+  e = set_linear_terms(s, q, r, c, per_problem, k_start, k_stop);
+  if (e) return e;
+  s->cost_set = true;
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_update_linear_costs(altro_b200_solver* s, const double* q, const double* r,
+                                   const double* c, int per_problem, int k_start, int k_stop) {
+  if (!s || !c) return ALTRO_B200_INVALID_POINTER;
+  if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;  // altro_solver.cpp:268
+  CUDA_OK(cudaSetDevice(s->device));
+  int e = resolve_range(s, k_start, k_stop, true);
+  if (e) return e;
+  if (r && k_stop > s->N && k_stop - k_start == 1) return ALTRO_B200_INVALID_OPT_AT_TERMINAL;
+  return set_linear_terms(s, q, r, c, per_problem, k_start, k_stop);
+}
+
+int altro_b200_set_constraint(altro_b200_solver* s, int cone, int dim, const int* idx,
+                              const double* scale, const double* off, const double* off_b,
+                              int k_start, int k_stop) {  // altro_solver.cpp:192-223
+  if (!s || !idx || !scale || !off) return ALTRO_B200_INVALID_POINTER;
+  if (s->initialized) return ALTRO_B200_SOLVER_ALREADY_INITIALIZED;
+  if (!s->dims_set) return ALTRO_B200_DIMENSION_UNKNOWN;
+  if (dim <= 0 || dim > kMaxConDim) return ALTRO_B200_INVALID_CONSTRAINT_DIM;
+  if (cone == CONE_SOC && dim > kMaxSocDim) return ALTRO_B200_INVALID_CONSTRAINT_DIM;
+  if (s->con_h.ncon >= kMaxCon) return ALTRO_B200_MAX_CONSTRAINTS_EXCEEDED;
+  CUDA_OK(cudaSetDevice(s->device));
+  int e = resolve_range(s, k_start, k_stop, true);
+  if (e) return e;
+  ConSlot& c = s->con_h.slot[s->con_h.ncon];
+  memset(&c, 0, sizeof(c));
+  c.k_start = k_start;
+  c.k_stop = k_stop;
+  c.cone = cone;
+  c.dim = dim;
+  c.row0 = s->con_h.rows;
+  for (int i = 0; i < dim; ++i) {
+    if (idx[i] >= s->n + s->m) return ALTRO_B200_BAD_INDEX;
+    c.idx[i] = idx[i];
+    c.scale[i] = scale[i];
+    c.off[i] = off[i];
+  }
+  if (off_b) {
+    double* dptr = nullptr;
+    DALLOC(s, dptr, (long)dim * s->Bp);
+    e = upload_pm(s, off_b, dim, dptr);
+    if (e) return e;
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    c.off_per_problem = 1;
+    c.off_b = dptr;
+  }
+  s->con_h.rows += dim;
+  s->con_h.ncon += 1;
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_set_initial_state(altro_b200_solver* s, const double* x0, int per_problem) {
+  if (!s || !x0) return ALTRO_B200_INVALID_POINTER;
+  if (!s->dims_set) return ALTRO_B200_DIMENSION_UNKNOWN;
+  CUDA_OK(cudaSetDevice(s->device));
+  int e = per_problem ? upload_pm(s, x0, s->n, s->x0) : upload_shared(s, x0, s->n, s->x0);
+  if (e) return e;
+  CUDA_OK(cudaStreamSynchronize(s->stream));
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_initialize(altro_b200_solver* s) {  // altro_solver.cpp:225-229
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  if (s->initialized) return ALTRO_B200_SOLVER_ALREADY_INITIALIZED;
+  if (!s->dims_set) return ALTRO_B200_STATE_DIM_UNKNOWN;          // knotpoint_data.cpp:242-246
+  if (!(s->h > 0.0f)) return ALTRO_B200_TIMESTEP_NOT_POSITIVE;    // :259-263
+  if (s->model < 0) return ALTRO_B200_DYNAMICS_FUN_NOT_SET;       // :264-269
+  if (!s->cost_set) return ALTRO_B200_COST_FUN_NOT_SET;           // :271-275
+  if (!find_launcher(s->model, s->n, s->m, s->params)) return ALTRO_B200_ERR_UNSUPPORTED;
+  CUDA_OK(cudaSetDevice(s->device));
+  const long rows = s->con_h.rows;
+  if (rows > 0) {
+    DALLOC(s, s->z, (long)(s->N + 1) * rows * s->Bp);
+    DALLOC(s, s->zest, (long)(s->N + 1) * rows * s->Bp);
+    DALLOC(s, s->con_d, 1);
+    CUDA_OK(cudaMemcpyAsync(s->con_d, &s->con_h, sizeof(ConTable), cudaMemcpyHostToDevice, s->stream));
+  }
+  if (s->model == MODEL_LINEAR) {
+    DALLOC(s, s->lin, (long)s->lin_h.size());
+    CUDA_OK(cudaMemcpyAsync(s->lin, s->lin_h.data(), s->lin_h.size() * 8, cudaMemcpyHostToDevice, s->stream));
+  }
+  k_fill<<<64, 256, 0, s->stream>>>(s->rho, s->Bp, 1.0);  // rho_ = 1.0, knotpoint_data.cpp:343
+  s->launches++;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(s->stream));
+  s->initialized = true;
+  return ALTRO_B200_NO_ERROR;
+}
+
+static int set_traj(altro_b200_solver* s, const double* v, int layout, int k0, int k1, int E,
+                    double* dst) {
+  const int nk = k1 - k0;
+  double* base = dst + (long)k0 * E * s->Bp;
+  int e = 0;
+  if (layout == 2) {
+    e = upload_pm(s, v, (long)nk * E, base);
+  } else {
+    std::vector<double> tmp((size_t)nk * E);
+    for (int k = 0; k < nk; ++k)
+      memcpy(&tmp[(size_t)k * E], layout == 1 ? v + (size_t)k * E : v, sizeof(double) * E);
+    e = upload_shared(s, tmp.data(), (long)nk * E, base);
+  }
+  if (e) return e;
+  CUDA_OK(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int altro_b200_set_input(altro_b200_solver* s, const double* u, int layout, int k_start,
+                         int k_stop) {  // altro_solver.cpp:242-251
+  if (!s || !u) return ALTRO_B200_INVALID_POINTER;
+  if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;
+  CUDA_OK(cudaSetDevice(s->device));
+  int e = resolve_range(s, k_start, k_stop, false);
+  if (e) return e;
+  e = set_traj(s, u, layout, k_start, k_stop, s->m, s->u);
+  if (e) return e;
+  const size_t off = (size_t)k_start * s->m * s->Bp, cnt = (size_t)(k_stop - k_start) * s->m * s->Bp;
+  CUDA_OK(cudaMemcpyAsync(s->u_init + off, s->u + off, cnt * 8, cudaMemcpyDeviceToDevice, s->stream));
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_reset_trajectory(altro_b200_solver* s) {
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;
+  CUDA_OK(cudaSetDevice(s->device));
+  CUDA_OK(cudaMemcpyAsync(s->u, s->u_init, (size_t)s->N * s->m * s->Bp * 8, cudaMemcpyDeviceToDevice,
+                          s->stream));
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_set_state(altro_b200_solver* s, const double* x, int layout, int k_start,
+                         int k_stop) {  // altro_solver.cpp:231-240
+  if (!s || !x) return ALTRO_B200_INVALID_POINTER;
+  if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;
+  CUDA_OK(cudaSetDevice(s->device));
+  int e = resolve_range(s, k_start, k_stop, true);
+  if (e) return e;
+  return set_traj(s, x, layout, k_start, k_stop, s->n, s->x);
+}
+
+int altro_b200_set_options(altro_b200_solver* s, const altro_b200_options* o) {
+  if (!s || !o) return ALTRO_B200_INVALID_POINTER;
+  s->opts = *o;
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_reset_duals(altro_b200_solver* s) {
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;
+  CUDA_OK(cudaSetDevice(s->device));
+  if (s->z) CUDA_OK(cudaMemsetAsync(s->z, 0, (size_t)(s->N + 1) * s->con_h.rows * s->Bp * 8, s->stream));
+  k_fill<<<64, 256, 0, s->stream>>>(s->rho, s->Bp, 1.0);
+  s->launches++;
+  CUDA_OK(cudaGetLastError());
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_shift_trajectory(altro_b200_solver* s) {
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;
+  CUDA_OK(cudaSetDevice(s->device));
+  k_shift<<<(s->B + 127) / 128, 128, 0, s->stream>>>(s->n, s->m, s->N, s->B, s->Bp, s->x, s->u);
+  s->launches++;
+  CUDA_OK(cudaGetLastError());
+  return ALTRO_B200_NO_ERROR;
+}
+
+static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
+  memset(&P, 0, sizeof(P));
+  P.N = s->N;
+  P.B = s->B;
+  P.Bp = s->Bp;
+  P.h = s->h;
+  memcpy(P.model_params, s->params, sizeof(P.model_params));
+  P.lin = s->lin;
+  P.Qd = s->Qd;
+  P.Rd = s->Rd;
+  P.q = s->q;
+  P.r = s->r;
+  P.c = s->c;
+  P.x0 = s->x0;
+  P.xbar = s->xbar;
+  P.ubar = s->ubar;
+  P.x = s->x;
+  P.u = s->u;
+  P.y = s->y;
+  P.A = s->A;
+  P.Bm = s->Bm;
+  P.lx = s->lx;
+  P.lu = s->lu;
+  P.K = s->K;
+  P.d = s->d;
+  P.P = s->P;
+  P.p = s->p;
+  P.con = s->con_d;
+  P.z = s->z;
+  P.zest = s->zest;
+  P.rho = s->rho;
+  P.status = s->status;
+  P.iters = s->iters;
+  P.merit_evals = s->merit_evals;
+  P.ls_fail = s->ls_fail;
+  P.phi = s->phi;
+  P.stat = s->stat;
+  P.feas = s->feas;
+  P.opts.iterations_max = s->opts.iterations_max;
+  P.opts.tol_primal_feasibility = s->opts.tol_primal_feasibility;
+  P.opts.tol_stationarity = s->opts.tol_stationarity;
+  P.opts.tol_meritfun_gradient = s->opts.tol_meritfun_gradient;
+  P.opts.penalty_initial = s->opts.penalty_initial;
+  P.opts.penalty_scaling = s->opts.penalty_scaling;
+  P.opts.penalty_max = s->opts.penalty_max;
+  P.opts.use_backtracking_linesearch = s->opts.use_backtracking_linesearch;
+  P.opts.ls_c1 = s->opts.linesearch_c1;
+  P.opts.ls_c2 = s->opts.linesearch_c2;
+}
+
+int altro_b200_solve_async(altro_b200_solver* s) {  // altro_solver.cpp:257-260
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;
+  CUDA_OK(cudaSetDevice(s->device));
+  solve_launcher L = find_launcher(s->model, s->n, s->m, s->params);
+  if (!L) return ALTRO_B200_ERR_UNSUPPORTED;
+  DeviceProblem P;
+  fill_device_problem(s, P);
+  L(P, s->con_h.ncon > 0, s->stream);
+  s->launches++;
+  CUDA_OK(cudaGetLastError());
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_synchronize(altro_b200_solver* s) {
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  CUDA_OK(cudaSetDevice(s->device));
+  CUDA_OK(cudaStreamSynchronize(s->stream));
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_solve(altro_b200_solver* s) {
+  int e = altro_b200_solve_async(s);
+  if (e) return e;
+  return altro_b200_synchronize(s);
+}
+
+long altro_b200_kernel_launches(const altro_b200_solver* s) { return s ? s->launches : 0; }
+
+#define GETTER_PM(name, field, width_expr)                                 \
+  int name(altro_b200_solver* s, double* out) {                            \
+    if (!s || !out) return ALTRO_B200_INVALID_POINTER;                     \
+    if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;         \
+    CUDA_OK(cudaSetDevice(s->device));                                     \
+    return download_pm(s, s->field, (long)(width_expr), out);              \
+  }
+GETTER_PM(altro_b200_get_states, x, (s->N + 1) * s->n)
+GETTER_PM(altro_b200_get_inputs, u, s->N * s->m)
+GETTER_PM(altro_b200_get_dual_dynamics, y, (s->N + 1) * s->n)
+GETTER_PM(altro_b200_get_feedback_gains, K, s->N * s->m * s->n)
+GETTER_PM(altro_b200_get_feedforward_gains, d, s->N * s->m)
+
+#define GETTER_VEC(name, field, type)                                                       \
+  int name(altro_b200_solver* s, type* out) {                                               \
+    if (!s || !out) return ALTRO_B200_INVALID_POINTER;                                      \
+    if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;                          \
+    CUDA_OK(cudaSetDevice(s->device));                                                      \
+    CUDA_OK(cudaMemcpyAsync(out, s->field, sizeof(type) * (size_t)s->B, cudaMemcpyDeviceToHost, \
+                            s->stream));                                                    \
+    CUDA_OK(cudaStreamSynchronize(s->stream));                                              \
+    return ALTRO_B200_NO_ERROR;                                                             \
+  }
+GETTER_VEC(altro_b200_get_status, status, int)
+GETTER_VEC(altro_b200_get_iterations, iters, int)
+GETTER_VEC(altro_b200_get_merit_evals, merit_evals, int)
+GETTER_VEC(altro_b200_get_final_objective, phi, double)
+GETTER_VEC(altro_b200_get_stationarity, stat, double)
+GETTER_VEC(altro_b200_get_primal_feasibility, feas, double)
+GETTER_VEC(altro_b200_get_penalty, rho, double)
+
+int altro_b200_get_horizon_length(const altro_b200_solver* s) { return s ? s->N : 0; }
+int altro_b200_get_batch(const altro_b200_solver* s) { return s ? s->B : 0; }
+int altro_b200_get_state_dim(const altro_b200_solver* s) { return s ? s->n : 0; }
+int altro_b200_get_input_dim(const altro_b200_solver* s) { return s ? s->m : 0; }
+long altro_b200_device_bytes(const altro_b200_solver* s) { return s ? s->bytes : 0; }
+
+}  // extern "C"

@@ -1,0 +1,279 @@
+// models.cuh -- device dynamics models.
+//
+// The reference takes dynamics as host std::function callbacks (typedefs.hpp:31-35), which
+// cannot run on the device; the batched solver selects one of these compiled-in models by id
+// instead (the one API extension, DESIGN.md "boundary").  Each model mirrors what the
+// reference's tests plug in:
+//   DoubleIntegrator<DIM>   test/test_utils.cpp:18-41  (closed-form discrete, `b = h*h/2` in float)
+//   PendulumC               test/test_utils.cpp:43-82
+//   Bicycle4C               test/test_utils.cpp:134-238 (centre-of-gravity frame)
+//   Midpoint<Continuous>    test/test_utils.cpp:84-132  (explicit midpoint; `h/2` is a float op)
+// plus the two models BASELINE.json needs that the reference does not have:
+//   Bicycle5C     [x,y,theta,delta,v], u=[a,delta_dot]
+//   ChainC<n,m>   coupled pendulum chain
+// Model ids must match altro_b200/problems.py and include/altro_b200.h.
+#pragma once
+#include "linalg.cuh"
+
+namespace altro_b200 {
+
+enum ModelId {
+  MODEL_LINEAR = 0,
+  MODEL_DOUBLE_INTEGRATOR = 1,
+  MODEL_PENDULUM = 2,
+  MODEL_BICYCLE4 = 3,
+  MODEL_BICYCLE5 = 4,
+  MODEL_CHAIN = 5,
+};
+
+// ------------------------------------------------------------------ double integrator
+template <int DIM>
+struct DoubleIntegrator {
+  static constexpr int n = 2 * DIM;
+  static constexpr int m = DIM;
+  ALTRO_DEV static void dynamics(const double* prm, const double* x, const double* u, float h,
+                                 double* xn) {
+    (void)prm;
+    const double b = h * h / 2;  // float arithmetic, then widened (test_utils.cpp:20)
+    const double hd = h;
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+      xn[i] = x[i] + x[i + DIM] * hd + u[i] * b;
+      xn[i + DIM] = x[i + DIM] + u[i] * hd;
+    }
+  }
+  ALTRO_DEV static void jacobian(const double* prm, const double* x, const double* u, float h,
+                                 double* A, double* B) {
+    (void)prm;
+    (void)x;
+    (void)u;
+    const double b = h * h / 2;
+    const double hd = h;
+#pragma unroll
+    for (int i = 0; i < n * n; ++i) A[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < n * m; ++i) B[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+      A[i + n * i] = 1.0;
+      A[(i + DIM) + n * (i + DIM)] = 1.0;
+      A[i + n * (i + DIM)] = hd;
+      B[i + n * i] = b;
+      B[(i + DIM) + n * i] = hd;
+    }
+  }
+};
+
+// ------------------------------------------------------------------ continuous models
+struct PendulumC {
+  static constexpr int n = 2;
+  static constexpr int m = 1;
+  ALTRO_DEV static void xdot(const double* prm, const double* x, const double* u, double* f) {
+    (void)prm;
+    const double l = 0.5, g = 9.81, b = 0.1;
+    const double mm_ = 1.0 * l * l;
+    f[0] = x[1];
+    f[1] = u[0] / mm_ - g * sin(x[0]) / l - b * x[1] / mm_;
+  }
+  // J = [A B], column-major n x (n+m)
+  ALTRO_DEV static void jac(const double* prm, const double* x, const double* u, double* A,
+                            double* B) {
+    (void)prm;
+    (void)u;
+    const double l = 0.5, g = 9.81, b = 0.1;
+    const double mm_ = 1.0 * l * l;
+    A[0] = 0.0;
+    A[1] = -g * cos(x[0]) / l;
+    A[2] = 1.0;
+    A[3] = -b / mm_;
+    B[0] = 0.0;
+    B[1] = 1 / mm_;
+  }
+};
+
+struct Bicycle4C {  // prm[0]=L, prm[1]=lr
+  static constexpr int n = 4;
+  static constexpr int m = 2;
+  ALTRO_DEV static void xdot(const double* prm, const double* x, const double* u, double* f) {
+    const double L = prm[0], lr = prm[1];
+    const double v = u[0], theta = x[2], delta = x[3];
+    const double beta = atan2(lr * delta, L);
+    const double omega = v * cos(beta) * tan(delta) / L;
+    double s, c;
+    sincos(theta + beta, &s, &c);
+    f[0] = v * c;
+    f[1] = v * s;
+    f[2] = omega;
+    f[3] = u[1];
+  }
+  ALTRO_DEV static void jac(const double* prm, const double* x, const double* u, double* A,
+                            double* B) {
+    const double L = prm[0], lr = prm[1];
+    const double v = u[0], theta = x[2], delta = x[3];
+    const double by = lr * delta, bx = L;
+    const double beta = atan2(by, bx);
+    const double dbeta_ddelta = bx / (bx * bx + by * by) * lr;
+    double sb, cb, sd, cd, st, ct;
+    sincos(beta, &sb, &cb);
+    sincos(delta, &sd, &cd);
+    sincos(theta + beta, &st, &ct);
+    const double tand = tan(delta);
+    const double domega_ddelta = v / L * (-sb * tand * dbeta_ddelta + cb / (cd * cd));
+    const double domega_dv = cb * tand / L;
+#pragma unroll
+    for (int i = 0; i < n * n; ++i) A[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < n * m; ++i) B[i] = 0.0;
+    A[0 + n * 2] = v * -st;
+    A[0 + n * 3] = v * (-st * dbeta_ddelta);
+    B[0 + n * 0] = ct;
+    A[1 + n * 2] = v * ct;
+    A[1 + n * 3] = v * (ct * dbeta_ddelta);
+    B[1 + n * 0] = st;
+    A[2 + n * 3] = domega_ddelta;
+    B[2 + n * 0] = domega_dv;
+    B[3 + n * 1] = 1.0;
+  }
+};
+
+struct Bicycle5C {  // state [x,y,theta,delta,v], input [a, delta_dot]
+  static constexpr int n = 5;
+  static constexpr int m = 2;
+  ALTRO_DEV static void xdot(const double* prm, const double* x, const double* u, double* f) {
+    const double L = prm[0], lr = prm[1];
+    const double theta = x[2], delta = x[3], v = x[4];
+    const double beta = atan2(lr * delta, L);
+    const double omega = v * cos(beta) * tan(delta) / L;
+    double s, c;
+    sincos(theta + beta, &s, &c);
+    f[0] = v * c;
+    f[1] = v * s;
+    f[2] = omega;
+    f[3] = u[1];
+    f[4] = u[0];
+  }
+  ALTRO_DEV static void jac(const double* prm, const double* x, const double* u, double* A,
+                            double* B) {
+    (void)u;
+    const double L = prm[0], lr = prm[1];
+    const double theta = x[2], delta = x[3], v = x[4];
+    const double by = lr * delta, bx = L;
+    const double beta = atan2(by, bx);
+    const double dbeta_ddelta = bx / (bx * bx + by * by) * lr;
+    double sb, cb, sd, cd, st, ct;
+    sincos(beta, &sb, &cb);
+    sincos(delta, &sd, &cd);
+    sincos(theta + beta, &st, &ct);
+    const double tand = tan(delta);
+    const double domega_ddelta = v / L * (-sb * tand * dbeta_ddelta + cb / (cd * cd));
+    const double domega_dv = cb * tand / L;
+#pragma unroll
+    for (int i = 0; i < n * n; ++i) A[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < n * m; ++i) B[i] = 0.0;
+    A[0 + n * 2] = -v * st;
+    A[0 + n * 3] = -v * st * dbeta_ddelta;
+    A[0 + n * 4] = ct;
+    A[1 + n * 2] = v * ct;
+    A[1 + n * 3] = v * ct * dbeta_ddelta;
+    A[1 + n * 4] = st;
+    A[2 + n * 3] = domega_ddelta;
+    A[2 + n * 4] = domega_dv;
+    B[3 + n * 1] = 1.0;
+    B[4 + n * 0] = 1.0;
+  }
+};
+
+template <int NS, int NI>
+struct ChainC {  // q_i'' = -g sin q_i - b q_i' + kc (q_{i-1} - 2 q_i + q_{i+1}) + u_i [i < m]
+  static constexpr int n = NS;
+  static constexpr int m = NI;
+  static constexpr int nq = NS / 2;
+  ALTRO_DEV static void xdot(const double* prm, const double* x, const double* u, double* f) {
+    (void)prm;
+    const double g = 9.81, b = 0.1, kc = 1.0;
+#pragma unroll
+    for (int i = 0; i < nq; ++i) {
+      const double ql = (i > 0) ? x[i - 1] : 0.0;
+      const double qr = (i < nq - 1) ? x[i + 1] : 0.0;
+      double acc = -g * sin(x[i]) - b * x[nq + i] + kc * (ql - 2.0 * x[i] + qr);
+      if (i < m) acc += u[i];
+      f[i] = x[nq + i];
+      f[nq + i] = acc;
+    }
+  }
+  ALTRO_DEV static void jac(const double* prm, const double* x, const double* u, double* A,
+                            double* B) {
+    (void)prm;
+    (void)u;
+    const double g = 9.81, b = 0.1, kc = 1.0;
+    for (int i = 0; i < n * n; ++i) A[i] = 0.0;
+    for (int i = 0; i < n * m; ++i) B[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < nq; ++i) {
+      A[i + n * (nq + i)] = 1.0;
+      A[(nq + i) + n * i] = -g * cos(x[i]) - 2.0 * kc;
+      if (i > 0) A[(nq + i) + n * (i - 1)] = kc;
+      if (i < nq - 1) A[(nq + i) + n * (i + 1)] = kc;
+      A[(nq + i) + n * (nq + i)] = -b;
+      if (i < m) B[(nq + i) + n * i] = 1.0;
+    }
+  }
+};
+
+// ------------------------------------------------------------------ explicit midpoint
+template <class CM>
+struct Midpoint {
+  static constexpr int n = CM::n;
+  static constexpr int m = CM::m;
+  // test_utils.cpp:84-97
+  ALTRO_DEV static void dynamics(const double* prm, const double* x, const double* u, float h,
+                                 double* xn) {
+    const double hh = h / 2;  // float division, then widened
+    const double hd = h;
+    double xm[n];
+    CM::xdot(prm, x, u, xm);
+#pragma unroll
+    for (int i = 0; i < n; ++i) xm[i] = fma(xm[i], hh, x[i]);
+    double f[n];
+    CM::xdot(prm, xm, u, f);
+#pragma unroll
+    for (int i = 0; i < n; ++i) xn[i] = fma(hd, f[i], x[i]);
+  }
+  // test_utils.cpp:99-132:  A_d = I + h Am (I + h/2 A),  B_d = h (Am h/2 B + Bm)
+  ALTRO_DEV static void jacobian(const double* prm, const double* x, const double* u, float h,
+                                 double* Ad, double* Bd) {
+    const double hh = h / 2;
+    const double hd = h;
+    double xm[n];
+    CM::xdot(prm, x, u, xm);
+#pragma unroll
+    for (int i = 0; i < n; ++i) xm[i] = fma(hh, xm[i], x[i]);
+    double T[n * n], Bc[n * m], Am[n * n], Bm[n * m];
+    CM::jac(prm, x, u, T, Bc);
+    CM::jac(prm, xm, u, Am, Bm);
+    // T = I + h/2 A ; Bc = h/2 B
+#pragma unroll
+    for (int j = 0; j < n; ++j)
+#pragma unroll
+      for (int i = 0; i < n; ++i) T[i + n * j] = (i == j ? 1.0 : 0.0) + hh * T[i + n * j];
+#pragma unroll
+    for (int i = 0; i < n * m; ++i) Bc[i] *= hh;
+    mm<n, n, n, false, false, 0>(Am, T, Ad);
+#pragma unroll
+    for (int j = 0; j < n; ++j)
+#pragma unroll
+      for (int i = 0; i < n; ++i) Ad[i + n * j] = (i == j ? 1.0 : 0.0) + hd * Ad[i + n * j];
+    mm<n, m, n, false, false, 0>(Am, Bc, Bd);
+#pragma unroll
+    for (int i = 0; i < n * m; ++i) Bd[i] = hd * (Bd[i] + Bm[i]);
+  }
+};
+
+using Pendulum = Midpoint<PendulumC>;
+using Bicycle4 = Midpoint<Bicycle4C>;
+using Bicycle5 = Midpoint<Bicycle5C>;
+template <int NS, int NI>
+using Chain = Midpoint<ChainC<NS, NI>>;
+
+}  // namespace altro_b200

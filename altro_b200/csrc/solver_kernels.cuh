@@ -1,0 +1,765 @@
+// solver_kernels.cuh -- the batched AL-iLQR hot path, one thread per trajectory.
+//
+// What the reference runs per problem on one CPU thread (SolverImpl::Solve,
+// src/altro/solver/solver.cpp:414-511, with tvlqr_BackwardPass src/tvlqr/tvlqr.cpp:65-195,
+// MeritFunction solver.cpp:273-355, the AL terms of knotpoint_data.cpp:473-613 and the cones of
+// cones.cpp) runs here as ONE persistent kernel: lane = trajectory, warp = 32 consecutive problems
+// of the problem-fastest HBM layout (device_problem.h).  All n x n / n x m / m x m blocks of the
+// current knot live in the registers of the owning thread; HBM is touched once per block per
+// sweep with fully coalesced 256-byte rows.  Control flow (line-search branches, the
+// `stat < sqrt(tol)` dual-update trigger, the `feas > tol` penalty trigger, quirks Q1-Q4 of
+// SURVEY.md Appendix C) follows the reference decision for decision so iteration counts match.
+#pragma once
+#include <math.h>
+
+#include "device_problem.h"
+#include "linalg.cuh"
+#include "linesearch.cuh"
+#include "models.cuh"
+
+namespace altro_b200 {
+
+// ErrorCodes subset (exceptions.hpp:24-51)
+enum DevErr { ERR_NONE = 0, ERR_LINESEARCH_FAILED = 20, ERR_MERIT_GRAD_TOO_SMALL = 21 };
+
+
+
+// ---------------------------------------------------------------- linear model (shared A,B,f)
+template <int NS, int NI>
+struct LinearModel {
+  static constexpr int n = NS;
+  static constexpr int m = NI;
+};
+
+template <class Model>
+struct ModelTraits {
+  static constexpr bool is_linear = false;
+};
+template <int NS, int NI>
+struct ModelTraits<LinearModel<NS, NI>> {
+  static constexpr bool is_linear = true;
+};
+
+// ---------------------------------------------------------------- second-order cone pieces
+// cones.cpp:13-39
+ALTRO_DEV void soc_projection(int dim, const double* x, double* px) {
+  const int nn = dim - 1;
+  const double s = x[nn];
+  double a = 0.0;
+  for (int i = 0; i < nn; ++i) a += x[i] * x[i];
+  a = sqrt(a);
+  if (a <= -s) {
+    for (int i = 0; i < dim; ++i) px[i] = 0.0;
+  } else if (a <= s) {
+    for (int i = 0; i < dim; ++i) px[i] = x[i];
+  } else {
+    const double c = 0.5 * (1 + s / a);
+    for (int i = 0; i < nn; ++i) px[i] = c * x[i];
+    px[nn] = c * a;
+  }
+}
+
+// cones.cpp:41-77, column-major dim x dim
+ALTRO_DEV void soc_jacobian(int dim, const double* x, double* J) {
+  const int nn = dim - 1;
+  const double s = x[nn];
+  double a = 0.0;
+  for (int i = 0; i < nn; ++i) a += x[i] * x[i];
+  a = sqrt(a);
+  for (int i = 0; i < dim * dim; ++i) J[i] = 0.0;
+  if (a <= -s) {
+    return;
+  } else if (a <= s) {
+    for (int i = 0; i < dim; ++i) J[i + dim * i] = 1.0;
+  } else {
+    const double c = 0.5 * (1 + s / a);
+    for (int j = 0; j < nn; ++j)
+      for (int i = 0; i < nn; ++i) {
+        double v = -0.5 * s / (a * a * a) * x[i] * x[j];
+        v += (i == j) ? c : 0;
+        J[i + dim * j] = v;
+      }
+    for (int i = 0; i < nn; ++i) J[i + dim * nn] = 0.5 * x[i] / a;
+    for (int j = 0; j < nn; ++j) J[nn + dim * j] = ((-0.5 * s / (a * a)) + c / a) * x[j];
+    J[nn + dim * nn] = 0.5;
+  }
+}
+
+// cones.cpp:79-123
+ALTRO_DEV void soc_hessian(int dim, const double* x, const double* b, double* H) {
+  const int nn = dim - 1;
+  const double s = x[nn], bs = b[nn];
+  double vbv = 0, a = 0;
+  for (int i = 0; i < nn; ++i) {
+    a += x[i] * x[i];
+    vbv += x[i] * b[i];
+  }
+  a = sqrt(a);
+  for (int i = 0; i < dim * dim; ++i) H[i] = 0.0;
+  if (a <= -s || a <= s) return;
+  for (int i = 0; i < nn; ++i) {
+    double hi = 0;
+    for (int j = 0; j < nn; ++j) {
+      double Hij = -x[i] * x[j] / (a * a);
+      Hij += (i == j) ? 1 : 0;
+      hi += Hij * b[j];
+    }
+    H[i + dim * nn] = hi / (2 * a);
+    H[nn + dim * i] = hi / (2 * a);
+    for (int j = 0; j <= i; ++j) {
+      const double vij = x[i] * x[j];
+      const double H1 = hi * x[j] * (-s / (a * a * a));
+      double H2 = vij * (2 * vbv) / (a * a * a * a) - x[i] * b[j] / (a * a);
+      double H3 = -vij / (a * a);
+      if (i == j) {
+        H2 -= vbv / (a * a);
+        H3 += 1;
+      }
+      H2 *= s / a;
+      H3 *= bs / a;
+      H[i + dim * j] = (H1 + H2 + H3) / 2.0;
+      H[j + dim * i] = (H1 + H2 + H3) / 2.0;
+    }
+  }
+  H[nn + dim * nn] = 0.0;
+}
+
+// ---------------------------------------------------------------- the per-trajectory solver
+template <class Model, bool CON>
+struct TrajSolver {
+  static constexpr int n = Model::n;
+  static constexpr int m = Model::m;
+  static constexpr bool kLinear = ModelTraits<Model>::is_linear;
+
+  const DeviceProblem& P;
+  const long S;  // stride between elements = padded batch
+  const int b;   // this thread's problem
+  const int N;
+  double rho;    // penalty (uniform over this trajectory's constraints)
+  int merit_evals;
+
+  ALTRO_DEV TrajSolver(const DeviceProblem& p, int b_)
+      : P(p), S(p.Bp), b(b_), N(p.N), rho(1.0), merit_evals(0) {}
+
+  // ---- selector helpers (static indices only, so x/u stay in registers)
+  ALTRO_DEV static double pick(int id, const double* x, const double* u) {
+    double v = 0.0;
+#pragma unroll
+    for (int e = 0; e < n; ++e) v = (id == e) ? x[e] : v;
+#pragma unroll
+    for (int e = 0; e < m; ++e) v = (id == n + e) ? u[e] : v;
+    return v;
+  }
+  ALTRO_DEV static void scatter_sub(int id, double val, double* lx, double* lu, bool terminal) {
+#pragma unroll
+    for (int e = 0; e < n; ++e) lx[e] -= (id == e) ? val : 0.0;
+    if (!terminal) {
+#pragma unroll
+      for (int e = 0; e < m; ++e) lu[e] -= (id == n + e) ? val : 0.0;
+    }
+  }
+  ALTRO_DEV double row_offset(const ConSlot& s, int i) const {
+    return s.off_per_problem ? s.off_b[(long)i * S + b] : s.off[i];
+  }
+  ALTRO_DEV double row_value(const ConSlot& s, int i, const double* x, const double* u) const {
+    const int id = s.idx[i];
+    const double off = row_offset(s, i);
+    return (id < 0) ? off : fma(s.scale[i], pick(id, x, u), off);
+  }
+
+  // ---- dynamics through the model (or the shared linear table)
+  ALTRO_DEV void dynamics(int k, const double* x, const double* u, double* xn) const {
+    if constexpr (kLinear) {
+      const double* T = P.lin + (long)k * (n * n + n * m + n);
+      // xnext = A x + B u + affine_term   (knotpoint_data.cpp:712-714)
+      double t[n];
+      mm<n, 1, n, false, false, 0>(T, x, t);
+      mm<n, 1, m, false, false, 1>(T + n * n, u, t);
+#pragma unroll
+      for (int i = 0; i < n; ++i) xn[i] = t[i] + T[n * n + n * m + i];
+    } else {
+      Model::dynamics(P.model_params, x, u, P.h, xn);
+    }
+  }
+  ALTRO_DEV void jacobian(int k, const double* x, const double* u, double* A, double* B) const {
+    if constexpr (kLinear) {
+      const double* T = P.lin + (long)k * (n * n + n * m + n);
+#pragma unroll
+      for (int i = 0; i < n * n; ++i) A[i] = T[i];
+#pragma unroll
+      for (int i = 0; i < n * m; ++i) B[i] = T[n * n + i];
+    } else {
+      Model::jacobian(P.model_params, x, u, P.h, A, B);
+    }
+  }
+
+  // ---- original (diagonal LQR) cost, knotpoint_data.cpp:636-645, :670-678
+  ALTRO_DEV double stage_cost(int k, const double* x, const double* u, const double* q,
+                              const double* r, bool terminal) const {
+    double J = 0.0;
+    double a = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) a += (0.5 * x[i]) * P.Qd[k * n + i] * x[i];
+    J = a;
+    J += dot<n>(q, x);
+    if (!terminal) {
+      double bb = 0.0;
+#pragma unroll
+      for (int i = 0; i < m; ++i) bb += (0.5 * u[i]) * P.Rd[k * m + i] * u[i];
+      J += bb;
+      J += dot<m>(r, u);
+    }
+    J += P.c[(long)k * S + b];
+    return J;
+  }
+  ALTRO_DEV void stage_gradient(int k, const double* x, const double* u, const double* q,
+                                const double* r, bool terminal, double* lx, double* lu) const {
+#pragma unroll
+    for (int i = 0; i < n; ++i) lx[i] = P.Qd[k * n + i] * x[i] + q[i];
+    if (!terminal) {
+#pragma unroll
+      for (int i = 0; i < m; ++i) lu[i] = P.Rd[k * m + i] * u[i] + r[i];
+    }
+  }
+
+  // ---- augmented-Lagrangian terms of knot k (knotpoint_data.cpp:473-595).
+  // Evaluates c, z_est = z - rho c (stored), returns sum ||Pi(z_est)||^2 / (2 rho) and, if
+  // want_grad, subtracts J^T dPi^T Pi(z_est) from lx, lu.
+  ALTRO_DEV double al_terms(int k, const double* x, const double* u, bool terminal,
+                            bool want_grad, double* lx, double* lu) {
+    if constexpr (!CON) {
+      return 0.0;
+    } else {
+      const ConTable& T = *P.con;
+      double cost = 0.0;
+      for (int j = 0; j < T.ncon; ++j) {
+        const ConSlot& s = T.slot[j];
+        if (k < s.k_start || k >= s.k_stop) continue;
+        const long zrow = ((long)k * T.rows + s.row0) * S + b;
+        if (s.cone == CONE_SOC) {
+          double zt[kMaxSocDim], zp[kMaxSocDim];
+          for (int i = 0; i < s.dim; ++i) {
+            const double c = row_value(s, i, x, u);
+            zt[i] = P.z[zrow + (long)i * S] - rho * c;
+            P.zest[zrow + (long)i * S] = zt[i];
+          }
+          soc_projection(s.dim, zt, zp);
+          double nrm = 0.0;
+          for (int i = 0; i < s.dim; ++i) nrm += zp[i] * zp[i];
+          cost += nrm / (2 * rho);
+          if (want_grad) {
+            double J[kMaxSocDim * kMaxSocDim];
+            soc_jacobian(s.dim, zt, J);
+            for (int i = 0; i < s.dim; ++i) {
+              double v = 0.0;  // (dPi^T zp)_i
+              for (int l = 0; l < s.dim; ++l) v += J[l + s.dim * i] * zp[l];
+              scatter_sub(s.idx[i], s.scale[i] * v, lx, lu, terminal);
+            }
+          }
+        } else {
+          double nrm = 0.0;
+          for (int i = 0; i < s.dim; ++i) {
+            const double c = row_value(s, i, x, u);
+            const double zt = P.z[zrow + (long)i * S] - rho * c;
+            P.zest[zrow + (long)i * S] = zt;
+            // dual cones (cones.hpp:13-30): EQUALITY -> IDENTITY, INEQUALITY -> INEQUALITY,
+            // IDENTITY -> EQUALITY (projection onto {0})
+            double zp = 0.0;
+            if (s.cone == CONE_EQUALITY) zp = zt;
+            if (s.cone == CONE_INEQUALITY) zp = fmin(0.0, zt);
+            nrm += zp * zp;
+            // dPi is diagonal with entries {1 | zt<=0 | 0}; dPi^T zp == zp in all three cases
+            if (want_grad) scatter_sub(s.idx[i], s.scale[i] * zp, lx, lu, terminal);
+          }
+          cost += nrm / (2 * rho);
+        }
+      }
+      return cost;
+    }
+  }
+
+  // ---- Gauss-Newton AL Hessian of knot k from the STORED z_est and the CURRENT rho
+  // (knotpoint_data.cpp:549-570, :597-613).  Adds into lxx (n x n), luu (m x m), lux (m x n).
+  ALTRO_DEV void al_hessian(int k, bool terminal, double* lxx, double* luu, double* lux) const {
+    if constexpr (CON) {
+      const ConTable& T = *P.con;
+      for (int j = 0; j < T.ncon; ++j) {
+        const ConSlot& s = T.slot[j];
+        if (k < s.k_start || k >= s.k_stop) continue;
+        const long zrow = ((long)k * T.rows + s.row0) * S + b;
+        if (s.cone == CONE_SOC) {
+          const int p = s.dim;
+          double zt[kMaxSocDim], zp[kMaxSocDim];
+          double J[kMaxSocDim * kMaxSocDim], H[kMaxSocDim * kMaxSocDim];
+          for (int i = 0; i < p; ++i) zt[i] = P.zest[zrow + (long)i * S];
+          soc_projection(p, zt, zp);
+          soc_jacobian(p, zt, J);
+          soc_hessian(p, zt, zp, H);
+          // W = dPi^T dPi + H ; G[idx_i, idx_j] += rho s_i s_j W_ij
+          double G[(n + m) * (n + m)];
+          for (int i = 0; i < (n + m) * (n + m); ++i) G[i] = 0.0;
+          for (int i = 0; i < p; ++i) {
+            if (s.idx[i] < 0) continue;
+            for (int jj = 0; jj < p; ++jj) {
+              if (s.idx[jj] < 0) continue;
+              double w = H[i + p * jj];
+              for (int l = 0; l < p; ++l) w += J[l + p * i] * J[l + p * jj];
+              G[s.idx[i] + (n + m) * s.idx[jj]] += rho * s.scale[i] * s.scale[jj] * w;
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < n; ++c)
+#pragma unroll
+            for (int r = 0; r < n; ++r) lxx[r + n * c] += G[r + (n + m) * c];
+          if (!terminal) {
+#pragma unroll
+            for (int c = 0; c < m; ++c)
+#pragma unroll
+              for (int r = 0; r < m; ++r) luu[r + m * c] += G[(n + r) + (n + m) * (n + c)];
+#pragma unroll
+            for (int c = 0; c < n; ++c)
+#pragma unroll
+              for (int r = 0; r < m; ++r) lux[r + m * c] += G[(n + r) + (n + m) * c];
+          }
+        } else {
+          for (int i = 0; i < s.dim; ++i) {
+            const int id = s.idx[i];
+            if (id < 0) continue;
+            const double zt = P.zest[zrow + (long)i * S];
+            double act = 0.0;  // diagonal of the dual-cone projection Jacobian (cones.cpp:160-171)
+            if (s.cone == CONE_EQUALITY) act = 1.0;
+            if (s.cone == CONE_INEQUALITY) act = (zt <= 0) ? 1.0 : 0.0;
+            const double g = rho * ((act * s.scale[i]) * (act * s.scale[i]));
+#pragma unroll
+            for (int e = 0; e < n; ++e) lxx[e + n * e] += (id == e) ? g : 0.0;
+            if (!terminal) {
+#pragma unroll
+              for (int e = 0; e < m; ++e) luu[e + m * e] += (id == n + e) ? g : 0.0;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- max_j || Pi_K(c_j) - c_j ||_inf at knot k (knotpoint_data.cpp:489-501)
+  ALTRO_DEV double al_violation(int k, const double* x, const double* u) const {
+    double viol = 0.0;
+    if constexpr (CON) {
+      const ConTable& T = *P.con;
+      for (int j = 0; j < T.ncon; ++j) {
+        const ConSlot& s = T.slot[j];
+        if (k < s.k_start || k >= s.k_stop) continue;
+        if (s.cone == CONE_SOC) {
+          double c[kMaxSocDim], pc[kMaxSocDim];
+          for (int i = 0; i < s.dim; ++i) c[i] = row_value(s, i, x, u);
+          soc_projection(s.dim, c, pc);
+          for (int i = 0; i < s.dim; ++i) viol = fmax(viol, fabs(pc[i] - c[i]));
+        } else {
+          for (int i = 0; i < s.dim; ++i) {
+            const double c = row_value(s, i, x, u);
+            double pc = 0.0;  // EQUALITY: projection onto {0}
+            if (s.cone == CONE_IDENTITY) pc = c;
+            if (s.cone == CONE_INEQUALITY) pc = fmin(0.0, c);
+            viol = fmax(viol, fabs(pc - c));
+          }
+        }
+      }
+    }
+    return viol;
+  }
+
+  // ---- DualUpdate (z <- Pi(z_est), knotpoint_data.cpp:503-510) over the whole trajectory
+  ALTRO_DEV void dual_update() {
+    if constexpr (CON) {
+      const ConTable& T = *P.con;
+      for (int j = 0; j < T.ncon; ++j) {
+        const ConSlot& s = T.slot[j];
+        for (int k = s.k_start; k < s.k_stop; ++k) {
+          const long zrow = ((long)k * T.rows + s.row0) * S + b;
+          if (s.cone == CONE_SOC) {
+            double zt[kMaxSocDim], zp[kMaxSocDim];
+            for (int i = 0; i < s.dim; ++i) zt[i] = P.zest[zrow + (long)i * S];
+            soc_projection(s.dim, zt, zp);
+            for (int i = 0; i < s.dim; ++i) P.z[zrow + (long)i * S] = zp[i];
+          } else {
+            for (int i = 0; i < s.dim; ++i) {
+              const double zt = P.zest[zrow + (long)i * S];
+              double zp = 0.0;
+              if (s.cone == CONE_EQUALITY) zp = zt;
+              if (s.cone == CONE_INEQUALITY) zp = fmin(0.0, zt);
+              P.z[zrow + (long)i * S] = zp;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // =================================================================== sweeps
+  // Initial sweep of Solve (solver.cpp:422-430): open-loop rollout, copy to the reference
+  // trajectory, constraint values + projected duals with the OLD penalty, expansions and
+  // gradients, then the penalty reset (quirk Q3: gradient before SetPenalty).
+  ALTRO_DEV void initial_sweep() {
+    double x[n], u[m], xn[n], q[n], r[m], lx[n], lu[m], A[n * n], Bm[n * m];
+    load_block<n>(P.x0 + b, S, 0, x);
+    for (int k = 0; k < N; ++k) {
+      load_block<m>(P.u + b, S, k, u);
+      dynamics(k, x, u, xn);
+      store_block<n>(P.x + b, S, k, x);
+      store_block<n>(P.xbar + b, S, k, x);
+      store_block<m>(P.ubar + b, S, k, u);
+      load_block<n>(P.q + b, S, k, q);
+      load_block<m>(P.r + b, S, k, r);
+      jacobian(k, x, u, A, Bm);
+      store_block<n * n>(P.A + b, S, k, A);
+      store_block<n * m>(P.Bm + b, S, k, Bm);
+      stage_gradient(k, x, u, q, r, false, lx, lu);
+      al_terms(k, x, u, false, true, lx, lu);
+      store_block<n>(P.lx + b, S, k, lx);
+      store_block<m>(P.lu + b, S, k, lu);
+#pragma unroll
+      for (int i = 0; i < n; ++i) x[i] = xn[i];
+    }
+    store_block<n>(P.x + b, S, N, x);
+    store_block<n>(P.xbar + b, S, N, x);
+    load_block<n>(P.q + b, S, N, q);
+#pragma unroll
+    for (int i = 0; i < m; ++i) u[i] = 0.0;  // terminal u_ is a zero m-vector (quirk Q8)
+    stage_gradient(N, x, u, q, r, true, lx, lu);
+    al_terms(N, x, u, true, true, lx, lu);
+    store_block<n>(P.lx + b, S, N, lx);
+    rho = P.opts.penalty_initial;
+  }
+
+  // Backward Riccati sweep = CalcExpansions + tvlqr_BackwardPass (solver.cpp:448-449,
+  // tvlqr.cpp:65-195) with reg = 0, f = 0.  The cost Hessian is rebuilt per knot from the
+  // diagonal weights and the AL Gauss-Newton terms instead of being stored.
+  ALTRO_DEV void backward_sweep() {
+    double Pn[n * n], pn[n];
+    {
+#pragma unroll
+      for (int i = 0; i < n * n; ++i) Pn[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < n; ++i) Pn[i + n * i] = P.Qd[N * n + i];
+      al_hessian(N, true, Pn, nullptr, nullptr);
+      load_block<n>(P.lx + b, S, N, pn);
+      store_block<n * n>(P.P + b, S, N, Pn);
+      store_block<n>(P.p + b, S, N, pn);
+    }
+    for (int k = N - 1; k >= 0; --k) {
+      double A[n * n], Bm[n * m];
+      load_block<n * n>(P.A + b, S, k, A);
+      load_block<n * m>(P.Bm + b, S, k, Bm);
+      double Qxx[n * n], Quu[m * m], Qux[m * n], Qx[n], Qu[m];
+#pragma unroll
+      for (int i = 0; i < n * n; ++i) Qxx[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < n; ++i) Qxx[i + n * i] = P.Qd[k * n + i];
+#pragma unroll
+      for (int i = 0; i < m * m; ++i) Quu[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < m; ++i) Quu[i + m * i] = P.Rd[k * m + i];
+#pragma unroll
+      for (int i = 0; i < m * n; ++i) Qux[i] = 0.0;
+      al_hessian(k, false, Qxx, Quu, Qux);
+      {
+        double T1[n * n];
+        mm<n, n, n, true, false, 0>(A, Pn, T1);    // A' P+            tvlqr.cpp:135
+        mm<n, n, n, false, false, 1>(T1, A, Qxx);  // Qxx += (A'P+) A  :136
+      }
+      {
+        double T2[m * n];
+        mm<m, n, n, true, false, 0>(Bm, Pn, T2);    // B' P+            :139
+        mm<m, m, n, false, false, 1>(T2, Bm, Quu);  // Quu += (B'P+) B  :140
+        mm<m, n, n, false, false, 1>(T2, A, Qux);   // Qux += (B'P+) A  :143
+      }
+      load_block<n>(P.lx + b, S, k, Qx);
+      load_block<m>(P.lu + b, S, k, Qu);
+      mm<n, 1, n, true, false, 1>(A, pn, Qx);   // Qx = q + A' p+     :147-150 (f = 0)
+      mm<m, 1, n, true, false, 1>(Bm, pn, Qu);  // Qu = r + B' p+     :151-152
+      double K[m * n], d[m], L[m * m];
+#pragma unroll
+      for (int i = 0; i < m * n; ++i) K[i] = Qux[i];
+#pragma unroll
+      for (int i = 0; i < m; ++i) d[i] = -Qu[i];
+#pragma unroll
+      for (int i = 0; i < m * m; ++i) L[i] = Quu[i];
+      const bool ok = cholesky<m>(L);  // :161
+      if (!ok) {
+        // tvlqr returns here (:162-164) and Solve ignores it (quirk Q2): this knot keeps the
+        // unsolved K = Qux, d = -Qu; P_k, p_k and everything below stay stale.
+        store_block<m * n>(P.K + b, S, k, K);
+        store_block<m>(P.d + b, S, k, d);
+        return;
+      }
+      cholesky_solve<m, n>(L, K);
+      cholesky_solve<m, 1>(L, d);
+      store_block<m * n>(P.K + b, S, k, K);
+      store_block<m>(P.d + b, S, k, d);
+      // cost-to-go, :173-186
+      double QuuK[m * n], KtQux[n * n];
+      mm<m, n, m, false, false, 0>(Quu, K, QuuK);
+      mm<n, n, m, true, false, 0>(K, Qux, KtQux);
+#pragma unroll
+      for (int i = 0; i < n * n; ++i) Pn[i] = Qxx[i];
+      mm<n, n, m, true, false, 1>(QuuK, K, Pn);
+#pragma unroll
+      for (int c = 0; c < n; ++c)
+#pragma unroll
+        for (int rr = 0; rr < n; ++rr) Pn[rr + n * c] -= KtQux[rr + n * c];
+#pragma unroll
+      for (int c = 0; c < n; ++c)
+#pragma unroll
+        for (int rr = 0; rr < n; ++rr) Pn[rr + n * c] -= KtQux[c + n * rr];
+#pragma unroll
+      for (int i = 0; i < n; ++i) pn[i] = Qx[i];
+      mm<n, 1, m, true, false, -1>(QuuK, d, pn);
+      mm<n, 1, m, true, false, -1>(K, Qu, pn);
+      mm<n, 1, m, true, false, 1>(Qux, d, pn);
+      store_block<n * n>(P.P + b, S, k, Pn);
+      store_block<n>(P.p + b, S, k, pn);
+    }
+  }
+
+  // MeritFunction (solver.cpp:273-355): nonlinear closed-loop rollout at step `alpha`.
+  ALTRO_DEV void merit(double alpha, bool want, double* phi_out, double* dphi_out) {
+    merit_evals += 1;
+    double phi = 0.0, dphi = 0.0;
+    double x[n], dxda[n];
+    load_block<n>(P.x0 + b, S, 0, x);
+#pragma unroll
+    for (int i = 0; i < n; ++i) dxda[i] = 0.0;
+    for (int k = 0; k < N; ++k) {
+      double xb[n], ub[m], K[m * n], d[m], dx[n], u[m], y[n], xn[n], q[n], r[m];
+      load_block<n>(P.xbar + b, S, k, xb);
+      load_block<m>(P.ubar + b, S, k, ub);
+      load_block<m * n>(P.K + b, S, k, K);
+      load_block<m>(P.d + b, S, k, d);
+#pragma unroll
+      for (int i = 0; i < n; ++i) dx[i] = x[i] - xb[i];  // :290
+      {
+        double Kdx[m];
+        mm<m, 1, n, false, false, 0>(K, dx, Kdx);
+#pragma unroll
+        for (int i = 0; i < m; ++i) u[i] = ub[i] + (-Kdx[i] + alpha * d[i]);  // :291-292
+      }
+      {
+        double Pk[n * n];
+        load_block<n * n>(P.P + b, S, k, Pk);
+        load_block<n>(P.p + b, S, k, y);
+        mm<n, 1, n, false, false, 1>(Pk, dx, y);  // y = P dx + p, :293
+      }
+      store_block<n>(P.x + b, S, k, x);
+      store_block<m>(P.u + b, S, k, u);
+      store_block<n>(P.y + b, S, k, y);
+      dynamics(k, x, u, xn);  // :296
+      load_block<n>(P.q + b, S, k, q);
+      load_block<m>(P.r + b, S, k, r);
+      double lx[n], lu[m];
+      if (want) stage_gradient(k, x, u, q, r, false, lx, lu);
+      phi += stage_cost(k, x, u, q, r, false) + al_terms(k, x, u, false, want, lx, lu);  // :299-301
+      if (want) {
+        double A[n * n], Bm[n * m], duda[m], dxn[n];
+        jacobian(k, x, u, A, Bm);  // :305
+        store_block<n * n>(P.A + b, S, k, A);
+        store_block<n * m>(P.Bm + b, S, k, Bm);
+        {
+          double Kd[m];
+          mm<m, 1, n, false, false, 0>(K, dxda, Kd);
+#pragma unroll
+          for (int i = 0; i < m; ++i) duda[i] = -Kd[i] + d[i];  // :306
+        }
+        mm<n, 1, n, false, false, 0>(A, dxda, dxn);  // :307-308
+        mm<n, 1, m, false, false, 1>(Bm, duda, dxn);
+        store_block<n>(P.lx + b, S, k, lx);
+        store_block<m>(P.lu + b, S, k, lu);
+        dphi += dot<n>(lx, dxda);  // :313-314
+        dphi += dot<m>(lu, duda);
+#pragma unroll
+        for (int i = 0; i < n; ++i) dxda[i] = dxn[i];
+      }
+#pragma unroll
+      for (int i = 0; i < n; ++i) x[i] = xn[i];
+    }
+    {  // terminal knot, :319-332
+      double xb[n], dx[n], y[n], q[n], u0[m], lx[n];
+      load_block<n>(P.xbar + b, S, N, xb);
+      load_block<n>(P.q + b, S, N, q);
+#pragma unroll
+      for (int i = 0; i < m; ++i) u0[i] = 0.0;
+      if (want) stage_gradient(N, x, u0, q, nullptr, true, lx, nullptr);
+      phi += stage_cost(N, x, u0, q, nullptr, true) + al_terms(N, x, u0, true, want, lx, nullptr);
+#pragma unroll
+      for (int i = 0; i < n; ++i) dx[i] = x[i] - xb[i];
+      double Pk[n * n];
+      load_block<n * n>(P.P + b, S, N, Pk);
+      load_block<n>(P.p + b, S, N, y);
+      mm<n, 1, n, false, false, 1>(Pk, dx, y);
+      store_block<n>(P.x + b, S, N, x);
+      store_block<n>(P.y + b, S, N, y);
+      if (want) {
+        store_block<n>(P.lx + b, S, N, lx);
+        dphi += dot<n>(lx, dxda);
+      }
+    }
+    *phi_out = phi;
+    if (want) *dphi_out = dphi;
+  }
+
+  // Refresh A, B, lx, lu at the working trajectory.  with_dynamics: the post-line-search fix of
+  // ForwardPass for backtracking (solver.cpp:256-262).  !with_dynamics: CalcProjectedDuals +
+  // CalcCostGradient after a dual/penalty update (solver.cpp:483-486).
+  ALTRO_DEV void refresh_sweep(bool with_dynamics) {
+    for (int k = 0; k <= N; ++k) {
+      const bool terminal = (k == N);
+      double x[n], u[m], q[n], r[m], lx[n], lu[m];
+      load_block<n>(P.x + b, S, k, x);
+      load_block<n>(P.q + b, S, k, q);
+      if (!terminal) {
+        load_block<m>(P.u + b, S, k, u);
+        load_block<m>(P.r + b, S, k, r);
+        if (with_dynamics) {
+          double A[n * n], Bm[n * m];
+          jacobian(k, x, u, A, Bm);
+          store_block<n * n>(P.A + b, S, k, A);
+          store_block<n * m>(P.Bm + b, S, k, Bm);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < m; ++i) u[i] = 0.0;
+      }
+      stage_gradient(k, x, u, q, r, terminal, lx, lu);
+      al_terms(k, x, u, terminal, true, lx, lu);
+      store_block<n>(P.lx + b, S, k, lx);
+      if (!terminal) store_block<m>(P.lu + b, S, k, lu);
+    }
+  }
+
+  // Stationarity (solver.cpp:207-222) + Feasibility (:224-231) + CopyTrajectory (:148-157)
+  ALTRO_DEV void criteria_sweep(double* stat_out, double* feas_out) {
+    double res_x = 0.0, res_u = 0.0, viol = 0.0;
+    double y[n];
+    load_block<n>(P.y + b, S, 0, y);
+    for (int k = 0; k < N; ++k) {
+      double yn[n], A[n * n], Bm[n * m], lx[n], lu[m], x[n], u[m];
+      load_block<n>(P.y + b, S, k + 1, yn);
+      load_block<n * n>(P.A + b, S, k, A);
+      load_block<n * m>(P.Bm + b, S, k, Bm);
+      load_block<n>(P.lx + b, S, k, lx);
+      load_block<m>(P.lu + b, S, k, lu);
+      mm<n, 1, n, true, false, 1>(A, yn, lx);  // lx + A' y+
+      mm<m, 1, n, true, false, 1>(Bm, yn, lu);
+#pragma unroll
+      for (int i = 0; i < n; ++i) res_x = fmax(res_x, fabs(lx[i] - y[i]));
+#pragma unroll
+      for (int i = 0; i < m; ++i) res_u = fmax(res_u, fabs(lu[i]));
+      load_block<n>(P.x + b, S, k, x);
+      load_block<m>(P.u + b, S, k, u);
+      viol = fmax(viol, al_violation(k, x, u));
+      store_block<n>(P.xbar + b, S, k, x);
+      store_block<m>(P.ubar + b, S, k, u);
+#pragma unroll
+      for (int i = 0; i < n; ++i) y[i] = yn[i];
+    }
+    {
+      double lx[n], x[n], u0[m];
+      load_block<n>(P.lx + b, S, N, lx);
+#pragma unroll
+      for (int i = 0; i < n; ++i) res_x = fmax(res_x, fabs(lx[i] - y[i]));
+      load_block<n>(P.x + b, S, N, x);
+#pragma unroll
+      for (int i = 0; i < m; ++i) u0[i] = 0.0;
+      viol = fmax(viol, al_violation(N, x, u0));
+      store_block<n>(P.xbar + b, S, N, x);
+    }
+    *stat_out = fmax(res_x, res_u);
+    *feas_out = viol;
+  }
+
+  // ForwardPass (solver.cpp:237-271)
+  ALTRO_DEV int forward_pass(double* alpha_out, double* phi_final) {
+    double phi0, dphi0;
+    merit(0.0, true, &phi0, &dphi0);
+    *phi_final = phi0;
+    if (fabs(dphi0) < P.opts.tol_meritfun_gradient) {
+      *alpha_out = 0.0;
+      return ERR_MERIT_GRAD_TOO_SMALL;
+    }
+    LsOptions lo;
+    lo.try_cubic_first = true;  // solver.cpp:248
+    lo.use_backtracking = P.opts.use_backtracking_linesearch != 0;
+    lo.c1 = P.opts.ls_c1;
+    lo.c2 = P.opts.ls_c2;
+    LsMachine ls;
+    ls.start(lo, 1.0, phi0, dphi0);
+    while (!ls.done()) {
+      double ph = 0.0, dph = 0.0;
+      merit(ls.alpha, ls.want_derivative(), &ph, &dph);
+      ls.update(lo, ph, dph);
+    }
+    const double alpha = ls.alpha;
+    *alpha_out = alpha;
+    *phi_final = ls.phi;
+    if (lo.use_backtracking && fabs(alpha - 1.0) > 0) refresh_sweep(true);
+    if (isnan(alpha) || !(ls.status == LS_MINIMUM_FOUND || ls.status == LS_HIT_MAX_STEPSIZE)) {
+      return ERR_LINESEARCH_FAILED;
+    }
+    return ERR_NONE;
+  }
+
+  // SolverImpl::Solve (solver.cpp:414-511)
+  ALTRO_DEV void solve() {
+    const DevOptions& o = P.opts;
+    rho = CON ? P.rho[b] : 1.0;  // penalties persist between solves (MPC warm start)
+    initial_sweep();
+    bool is_converged = false, stop_iterating = false;
+    int status = SOLVE_UNSOLVED;
+    double stationarity = 0.0, feasibility = 0.0, phi = 0.0;
+    int ls_fail = 0;
+    int iter;
+    for (iter = 0; iter < o.iterations_max; ++iter) {
+      backward_sweep();
+      double alpha;
+      const int err = forward_pass(&alpha, &phi);
+      if (!(err == ERR_NONE || err == ERR_MERIT_GRAD_TOO_SMALL)) {
+        stop_iterating = true;
+        ls_fail = 1;
+      }
+      criteria_sweep(&stationarity, &feasibility);
+      if (fabs(stationarity) < o.tol_stationarity && feasibility < o.tol_primal_feasibility) {
+        is_converged = true;
+        stop_iterating = true;
+        status = SOLVE_SUCCESS;
+      }
+      if (stationarity < sqrt(o.tol_stationarity)) {  // :474-489
+        if constexpr (CON) {
+          dual_update();
+          if (feasibility > o.tol_primal_feasibility)
+            rho = fmin(rho * o.penalty_scaling, o.penalty_max);
+        }
+        refresh_sweep(false);
+      }
+      if (stop_iterating) break;
+    }
+    if (!is_converged && iter == o.iterations_max) status = SOLVE_MAX_ITERATIONS;
+    P.status[b] = status;
+    P.iters[b] = iter + 1;  // quirk Q4
+    P.merit_evals[b] = merit_evals;
+    P.ls_fail[b] = ls_fail;
+    P.phi[b] = phi;
+    P.stat[b] = stationarity;
+    P.feas[b] = feasibility;
+    if constexpr (CON) P.rho[b] = rho;
+  }
+};
+
+template <class Model, bool CON>
+__global__ void __launch_bounds__(32) solve_kernel(const DeviceProblem P) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.B) return;
+  TrajSolver<Model, CON> s(P, b);
+  s.solve();
+}
+
+}  // namespace altro_b200

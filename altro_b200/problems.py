@@ -156,8 +156,10 @@ def bicycle_turn90():
                    options={"iterations_max": 30, "use_backtracking_linesearch": 1})
 
 
-def bicycle(B=16384, N=100, tf=3.0, seed=1, n=5, iterations_max=100):
-    """BASELINE C2: random goals; n=5 model [x,y,theta,delta,v], u=[a,delta_dot]."""
+def bicycle(B=16384, N=100, tf=3.0, seed=1, n=5, iterations_max=30):
+    """BASELINE C2: random goals; n=5 model [x,y,theta,delta,v], u=[a,delta_dot].
+    Options are those of the reference's own bicycle solve (bicycle_test.cpp:124-129):
+    iterations_max = 30, backtracking line search."""
     m = 2
     h = _f32(tf / N)
     Qd = np.full((N + 1, n), 1e-2)

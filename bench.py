@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched AL-iLQR solve path.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, 1 rank/GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W     (CPU arm: oracle, all cores)
+
+Metric (BASELINE.json): trajectory solves/sec, full AL-iLQR solve to the reference's convergence
+criteria.  Workload at every N: BASELINE config "bicycle (n=5, m=2, N=100), batch 16384 random
+goals" PER GPU (weak scaling; the batch shards embarrassingly, no collective on the data path).
+A step = one batched Solve() of the whole per-GPU batch.
+
+Prints ONE JSON line (rank 0).  `value` = solves/s with inputs resident in HBM; `e2e` = the same
+through the public C ABI with host buffers (H2D of problem data and D2H of the solution inside
+the timed region); `roofline` = algorithmic HBM bytes of the solve kernel / its CUDA-event time
+against the measured copy bandwidth; `cpu_baseline` = the CPU oracle (restatement of the
+reference, oracle/) timed on this box's host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from altro_b200 import problems as PR  # noqa: E402
+
+METRIC = "trajectory_solves_per_sec"
+UNIT = "solves/s"
+
+
+def workload(name, per_gpu_batch, rank, world):
+    """The per-rank slice of the global synthetic batch (rank r owns problems [r*B, (r+1)*B))."""
+    B = per_gpu_batch
+    gen = {
+        "bicycle": lambda total: PR.bicycle(B=total, N=100, n=5),
+        "pendulum": lambda total: PR.pendulum(B=total, N=100),
+        "scotty": lambda total: PR.scotty(B=total, N=50, n=5),
+        "chain12": lambda total: PR.chain(B=total, n=12, m=4, N=200),
+        "chain6": lambda total: PR.chain(B=total, n=6, m=2, N=200),
+    }[name]
+    P = gen(B * world)
+    return P.subset(rank * B, (rank + 1) * B)
+
+
+def workload_desc(name, P, world):
+    return {"workload": f"{name}: {P.name}, n={P.n} m={P.m} N={P.N}, batch {P.B}/GPU x {world} GPU, "
+                        f"synthetic random problems (SURVEY 8d seeds), iterations_max="
+                        f"{P.options.get('iterations_max', 200)}, "
+                        f"{'backtracking' if P.options.get('use_backtracking_linesearch') else 'cubic'} "
+                        f"line search",
+            "batch_per_gpu": P.B, "n": P.n, "m": P.m, "horizon": P.N,
+            "l2_policy": "working set (>= 1.4 GB of per-trajectory state) is far larger than the "
+                         "126 MB L2; no flush needed"}
+
+
+def algorithmic_bytes(P, iters, evals):
+    """SURVEY.md 8(d) 'Algorithmic bytes per unit of work', summed over the batch.
+    Unit = knot-point-iteration: 8*(4n^2+4nm+8n+7m) bytes; every merit evaluation beyond one per
+    iteration adds (mn+3n+4m+(n+m)) doubles per knot; problem I/O (N+1)n+Nm doubles in and out.
+    Constraint duals add 2 doubles per row per knot-iteration."""
+    n, m, N = P.n, P.m, P.N
+    D = 4 * n * n + 4 * n * m + 8 * n + 7 * m
+    E = m * n + 3 * n + 4 * m + (n + m)
+    rows = P.n_constraint_rows()
+    it = iters.astype(np.float64)
+    extra = np.maximum(evals.astype(np.float64) - it, 0.0)
+    per = 8.0 * (N * it * (D + 2 * rows) + N * extra * E + 2 * ((N + 1) * n + N * m))
+    return float(per.sum())
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active," \
+        "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6),
+                                  ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload_name):
+    """dram bytes per launch of the solve kernel from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload_name, {}).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def cpu_oracle_rate(P, target_seconds, threads=None):
+    """Times the CPU oracle on a bounded prefix of the workload.  Returns dict for the JSON."""
+    from oracle import oracle as O
+    threads = threads or O.lib().oracle_max_threads()
+    probe = min(P.B, 4 * threads)
+    r = O.solve_batch(P, 0, probe, nthreads=threads)
+    rate = probe / max(r["seconds"], 1e-9)
+    nb = int(min(P.B, max(probe, rate * target_seconds)))
+    r = O.solve_batch(P, 0, nb, nthreads=threads)
+    return {"value": nb / r["seconds"], "unit": UNIT, "cores": int(threads), "kind": "port",
+            "sample": f"first {nb} problems of the per-GPU batch, Solve() only, {r['seconds']:.2f} s "
+                      f"wall, mean {r['iters'].mean():.1f} iterations / {r['merit_evals'].mean():.1f} "
+                      f"merit evaluations per solve, oracle = C restatement of the reference "
+                      f"(Eigen reference not buildable here: DESIGN.md)"}, r, nb
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's algorithm on the host cores (oracle port)."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    P = workload(args.workload, args.batch, 0, 1)
+    threads = O.lib().oracle_max_threads()
+    probe = min(P.B, 4 * threads)
+    r = O.solve_batch(P, 0, probe, nthreads=threads)
+    rate = probe / max(r["seconds"], 1e-9)
+    per_step = int(min(P.B, max(probe, rate * args.ref_step_seconds)))
+    for _ in range(args.warmup):
+        O.solve_batch(P, 0, min(per_step, 2 * threads), nthreads=threads)
+    tot_s, tot_n, its = 0.0, 0, []
+    for s in range(args.steps):
+        b0 = (s * per_step) % max(P.B - per_step, 1)
+        r = O.solve_batch(P, b0, b0 + per_step, nthreads=threads)
+        tot_s += r["seconds"]
+        tot_n += per_step
+        its.append(r["iters"].mean())
+    val = tot_n / tot_s
+    sample = f"{per_step} problems of the per-GPU batch per step, {args.steps} steps, Solve() only, " \
+             f"mean {np.mean(its):.1f} iterations per solve"
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "config": workload_desc(args.workload, P, 1),
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": int(threads), "kind": "port",
+                            "sample": sample},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="bicycle")
+    ap.add_argument("--batch", type=int, default=None, help="problems per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-step-seconds", type=float, default=6.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
+    args = ap.parse_args()
+    if args.batch is None:
+        args.batch = {"bicycle": 16384, "pendulum": 4096, "scotty": 8192, "chain12": 4096,
+                      "chain6": 32768}[args.workload]
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import altro_b200
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the solve path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    P = workload(args.workload, args.batch, rank, world)
+    solver = altro_b200.make_solver(P, device=local_rank)
+    solver.SetStream(torch.cuda.current_stream().cuda_stream)
+    B, N, n, m = P.B, P.N, P.n, P.m
+
+    # ------------------------------------------------------------ (1) resident-in-HBM steps
+    def resident_step(ev=None):
+        solver.ResetTrajectory()
+        solver.ResetDuals()
+        if ev:
+            ev[0].record()
+        solver.SolveAsync()
+        if ev:
+            ev[1].record()
+
+    for _ in range(args.warmup):
+        resident_step()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    kernel_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                 for _ in range(args.steps)]
+    l0 = solver.KernelLaunches()
+    barrier()
+    clocks.start()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for s in range(args.steps):
+        resident_step(kernel_ev[s])
+    t_end.record()
+    barrier()
+    clk = clocks.stop()
+    launches = solver.KernelLaunches() - l0
+    elapsed_ms = t_start.elapsed_time(t_end)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_ev]))
+    iters, evals, status = solver.GetIterations(), solver.GetMeritEvals(), solver.GetStatus()
+
+    # ------------------------------------------------------------ (2) end to end through the C ABI
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    x0_h, xref_h, uref_h = pin(P.x0), pin(P.xref) if P.ref_mode == PR.REF_GOAL else None, \
+        pin(P.uref) if P.ref_mode == PR.REF_GOAL else None
+    U0_h = pin(P.U0)
+    X_h = torch.empty((B, N + 1, n), dtype=torch.float64).pin_memory().numpy()
+    U_h = torch.empty((B, N, m), dtype=torch.float64).pin_memory().numpy()
+    st_h = torch.empty((B,), dtype=torch.int32).pin_memory().numpy()
+    phi_h = torch.empty((B,), dtype=torch.float64).pin_memory().numpy()
+
+    def e2e_step():
+        solver.SetInitialState(x0_h)
+        if P.ref_mode == PR.REF_GOAL:
+            solver.SetLQRCost(P.Qd[0], P.Rd[0], xref_h, uref_h, 0, N)
+            solver.SetLQRCost(P.Qd[N], P.Rd[N - 1], xref_h, uref_h, N, N + 1)
+        else:
+            altro_b200.solver.set_cost(solver, P)
+        solver.SetInput(U0_h)
+        solver.ResetDuals()
+        solver.Solve()
+        solver.GetStates(out=X_h)
+        solver.GetInputs(out=U_h)
+        solver.GetStatus(out=st_h)
+        solver.GetFinalObjective(out=phi_h)
+
+    h2d = x0_h.nbytes + U0_h.nbytes
+    if P.ref_mode == PR.REF_GOAL:
+        h2d += 2 * (xref_h.nbytes + uref_h.nbytes)
+    elif P.ref_mode == PR.REF_WINDOW:
+        h2d += P.xref.nbytes + P.uref.nbytes + P.offsets.nbytes
+    d2h = X_h.nbytes + U_h.nbytes + st_h.nbytes + phi_h.nbytes
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    for s in range(args.steps):
+        e2e_step()
+    e_end.record()
+    barrier()
+    e2e_ms = e_start.elapsed_time(e_end)
+
+    # ------------------------------------------------------------ max over ranks
+    times = torch.tensor([elapsed_ms, e2e_ms, kernel_ms], dtype=torch.float64, device="cuda")
+    counts = torch.tensor([float(B)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    elapsed_ms, e2e_ms, kernel_ms_max = [float(v) for v in times.cpu()]
+    total_solves = float(counts.cpu()[0])
+
+    out = None
+    if rank == 0:
+        value = total_solves * args.steps / (elapsed_ms * 1e-3)
+        e2e_value = total_solves * args.steps / (e2e_ms * 1e-3)
+        peak, peak_src = peak_hbm()
+        alg_bytes = algorithmic_bytes(P, iters, evals)
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic", "config": workload_desc(args.workload, P, world),
+               "clocks": clk,
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                       "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
+               "gpu_launches": int(launches),
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
+                            "kernel": "altro_b200::solve_kernel<Model,CON> (one launch per step)",
+                            "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                            "peak_source": peak_src,
+                            "note": "latency/FP64-issue bound, not HBM bound: see DESIGN.md"},
+               "solve_stats": {"mean_iterations": float(iters.mean()),
+                               "mean_merit_evals": float(evals.mean()),
+                               "success_frac": float((status == 0).mean()),
+                               "max_iterations_frac": float((status == 2).mean()),
+                               "hbm_bytes_resident": int(solver.DeviceBytes())}}
+        if not args.no_cpu_baseline and world == 1:
+            cb, ref, nb = cpu_oracle_rate(P, args.cpu_seconds)
+            out["cpu_baseline"] = cb
+            if not args.no_check:
+                from parity_util import compare
+                gpu = {"X": X_h, "U": U_h, "status": st_h, "iters": iters, "cost": phi_h}
+                try:
+                    rep = compare(gpu, ref)
+                    out["parity_check"] = {"ok": True, **rep}
+                except AssertionError as e:
+                    out["parity_check"] = {"ok": False, "error": str(e)[:300]}
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    solver.close()
+
+
+if __name__ == "__main__":
+    main()

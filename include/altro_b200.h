@@ -1,0 +1,242 @@
+/*
+ * altro_b200.h -- C ABI of the B200-native batched AL-iLQR solve path.
+ *
+ * This is the drop-in boundary for the hot path of bjack205/altro (reference paths relative to
+ * /root/reference).  Plain pointers and sizes only; every call returns the reference's
+ * ErrorCodes integer (src/altro/solver/exceptions.hpp:24-51) unless stated otherwise.
+ *
+ *   section A  tvlqr_*            : the reference's inner C-style API (src/tvlqr/tvlqr.h:15-33),
+ *                                   same argument lists, now `extern "C"`, executed on the GPU.
+ *   section B  altro_b200_tvlqr_* : batched variants over device-resident problem-fastest arrays.
+ *   section C  altro_b200_*       : batched solver handle mirroring altro::ALTROSolver
+ *                                   (src/altro/altro_solver.hpp:21-442); one handle = B problems.
+ *
+ * Host arrays are problem-major ("B separate solvers laid end to end"): [B][...]; matrices inside
+ * a problem are column-major (altro_solver.hpp:185).  Device arrays are problem-fastest
+ * (altro_b200/csrc/device_problem.h).  No CPU fallback exists: every compute entry point fails
+ * with ALTRO_B200_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef ALTRO_B200_H
+#define ALTRO_B200_H
+
+#include <stdbool.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- enums shared with the reference (same integer values) -------------------------------- */
+/* ErrorCodes, exceptions.hpp:24-51 */
+enum {
+  ALTRO_B200_NO_ERROR = 0,
+  ALTRO_B200_STATE_DIM_UNKNOWN = 1,
+  ALTRO_B200_INPUT_DIM_UNKNOWN = 2,
+  ALTRO_B200_NEXT_STATE_DIM_UNKNOWN = 3,
+  ALTRO_B200_DIMENSION_UNKNOWN = 4,
+  ALTRO_B200_BAD_INDEX = 5,
+  ALTRO_B200_DIMENSION_MISMATCH = 6,
+  ALTRO_B200_SOLVER_NOT_INITIALIZED = 7,
+  ALTRO_B200_SOLVER_ALREADY_INITIALIZED = 8,
+  ALTRO_B200_NON_POSITIVE = 9,
+  ALTRO_B200_TIMESTEP_NOT_POSITIVE = 10,
+  ALTRO_B200_COST_FUN_NOT_SET = 11,
+  ALTRO_B200_DYNAMICS_FUN_NOT_SET = 12,
+  ALTRO_B200_INVALID_OPT_AT_TERMINAL = 13,
+  ALTRO_B200_MAX_CONSTRAINTS_EXCEEDED = 14,
+  ALTRO_B200_INVALID_CONSTRAINT_DIM = 15,
+  ALTRO_B200_CHOLESKY_FAILED = 16,
+  ALTRO_B200_OP_ONLY_VALID_AT_TERMINAL = 17,
+  ALTRO_B200_INVALID_POINTER = 18,
+  ALTRO_B200_BACKWARD_PASS_FAILED = 19,
+  ALTRO_B200_LINESEARCH_FAILED = 20,
+  ALTRO_B200_MERIT_GRADIENT_TOO_SMALL = 21,
+  ALTRO_B200_INVALID_BOUND_CONSTRAINT = 22,
+  ALTRO_B200_NON_POSITIVE_PENALTY = 23,
+  ALTRO_B200_COST_NOT_QUADRATIC = 24,
+  ALTRO_B200_FILE_ERROR = 25,
+  /* extensions (not in the reference) */
+  ALTRO_B200_ERR_NO_DEVICE = 100,   /* no CUDA device / CUDA runtime error                    */
+  ALTRO_B200_ERR_UNSUPPORTED = 101, /* model/dimension combination not compiled in            */
+};
+/* SolveStatus, typedefs.hpp:19-27 */
+enum { ALTRO_B200_SUCCESS = 0, ALTRO_B200_UNSOLVED = 1, ALTRO_B200_MAX_ITERATIONS = 2 };
+/* ConstraintType, typedefs.hpp:53 */
+enum {
+  ALTRO_B200_EQUALITY = 0,
+  ALTRO_B200_IDENTITY = 1,
+  ALTRO_B200_INEQUALITY = 2,
+  ALTRO_B200_SECOND_ORDER_CONE = 3,
+};
+/* index sentinels, typedefs.hpp:16-17 */
+enum { ALTRO_B200_LAST_INDEX = -1, ALTRO_B200_ALL_INDICES = -2 };
+/* device dynamics models replacing the std::function callbacks (typedefs.hpp:31-35) */
+enum {
+  ALTRO_B200_MODEL_LINEAR = 0,            /* KnotPointData::SetLinearDynamics                 */
+  ALTRO_B200_MODEL_DOUBLE_INTEGRATOR = 1, /* test/test_utils.cpp:18-41, params[0] = dim       */
+  ALTRO_B200_MODEL_PENDULUM = 2,          /* test/test_utils.cpp:43-82 + midpoint :84-132     */
+  ALTRO_B200_MODEL_BICYCLE4 = 3,          /* test/test_utils.cpp:134-238, params = {L, lr}    */
+  ALTRO_B200_MODEL_BICYCLE5 = 4,          /* [x,y,theta,delta,v], u=[a,delta_dot], {L, lr}    */
+  ALTRO_B200_MODEL_CHAIN = 5,             /* coupled pendulum chain, params = {n, m}          */
+};
+
+/* ================================================================================ section A
+ * Drop-in for src/tvlqr/tvlqr.h:15-33 (declared there without extern "C"; same arguments,
+ * same return convention: TVLQR_SUCCESS = -1, or the knot index whose Cholesky failed,
+ * tvlqr.cpp:162-164).  Host pointer tables, one pointer per knot; the caller owns all memory.
+ * Dimensions must be uniform over the horizon (every reference call site is); otherwise -2.
+ * The Q*_tmp scratch tables may be NULL (the GPU path keeps scratch in registers).          */
+#ifndef TVLQR_SUCCESS
+#define TVLQR_SUCCESS -1
+#endif
+typedef double lqr_float;
+
+int tvlqr_TotalMemSize(const int *nx, const int *nu, int num_horizon, bool is_diag);
+
+int tvlqr_BackwardPass(const int *nx, const int *nu, int num_horizon,
+                       const lqr_float *const *A, const lqr_float *const *B, const lqr_float *const *f,
+                       const lqr_float *const *Q, const lqr_float *const *R, const lqr_float *const *H,
+                       const lqr_float *const *q, const lqr_float *const *r, lqr_float reg,
+                       lqr_float **K, lqr_float **d,
+                       lqr_float **P, lqr_float **p, lqr_float *delta_V,
+                       lqr_float **Qxx, lqr_float **Quu, lqr_float **Qux,
+                       lqr_float **Qx, lqr_float **Qu,
+                       lqr_float **Qxx_tmp, lqr_float **Quu_tmp, lqr_float **Qux_tmp,
+                       lqr_float **Qx_tmp, lqr_float **Qu_tmp,
+                       bool linear_only_update, bool is_diag);
+
+int tvlqr_ForwardPass(const int *nx, const int *nu, int num_horizon,
+                      const lqr_float *const *A, const lqr_float *const *B, const lqr_float *const *f,
+                      const lqr_float *const *K, const lqr_float *const *d,
+                      const lqr_float *const *P, const lqr_float *const *p,
+                      const lqr_float *x0, lqr_float **x, lqr_float **u, lqr_float **y);
+
+/* ================================================================================ section B
+ * Batched TVLQR over B independent LQ problems.  HOST arrays, problem-major:
+ *   A [B][N][n*n]  B [B][N][n*m]  f [B][N][n]  Q [B][N+1][n*n or n]  R [B][N][m*m or m]
+ *   H [B][N][m*n] (ignored when is_diag)  q [B][N+1][n]  r [B][N][m]
+ * outputs K [B][N][m*n]  d [B][N][m]  P [B][N+1][n*n]  p [B][N+1][n]  delta_V [B][2]
+ * status[B]: -1 or failing knot (same convention as section A).  Any output may be NULL.       */
+int altro_b200_tvlqr_backward_batch(int batch, int n, int m, int num_horizon, const double *A,
+                                    const double *B, const double *f, const double *Q,
+                                    const double *R, const double *H, const double *q,
+                                    const double *r, double reg, bool is_diag, double *K,
+                                    double *d, double *P, double *p, double *delta_V,
+                                    int *status);
+/* x0 [B][n]; outputs x [B][N+1][n], u [B][N][m], y [B][N+1][n] (y may be NULL) */
+int altro_b200_tvlqr_forward_batch(int batch, int n, int m, int num_horizon, const double *A,
+                                   const double *B, const double *f, const double *K,
+                                   const double *d, const double *P, const double *p,
+                                   const double *x0, double *x, double *u, double *y);
+
+/* ================================================================================ section C */
+typedef struct altro_b200_solver altro_b200_solver;
+
+/* AltroOptions fields read by the solve path (solver_options.hpp:16-39) */
+typedef struct {
+  int iterations_max;
+  double tol_primal_feasibility;
+  double tol_stationarity;
+  double tol_meritfun_gradient;
+  double penalty_initial;
+  double penalty_scaling;
+  double penalty_max;
+  int use_backtracking_linesearch;
+  double linesearch_c1, linesearch_c2; /* CubicLineSearch::SetOptimalityTolerances */
+} altro_b200_options;
+
+int altro_b200_device_count(void);
+const char *altro_b200_error_string(int code);          /* ErrorCodeToString, exceptions.cpp   */
+void altro_b200_default_options(altro_b200_options *o); /* AltroOptions defaults               */
+
+/* ALTROSolver(horizon_length) for `batch` independent problems on CUDA device `device`.
+ * Returns NULL if no device is available (no CPU fallback). */
+altro_b200_solver *altro_b200_create(int horizon_length, int batch, int device);
+void altro_b200_destroy(altro_b200_solver *s);
+int altro_b200_set_stream(altro_b200_solver *s, void *cuda_stream);
+
+int altro_b200_set_dimension(altro_b200_solver *s, int num_states, int num_inputs); /* SetDimension */
+int altro_b200_set_time_step(altro_b200_solver *s, float h);                        /* SetTimeStep  */
+/* SetExplicitDynamics with a device model id instead of callbacks */
+int altro_b200_set_model(altro_b200_solver *s, int model_id, const double *params, int nparams);
+/* KnotPointData::SetLinearDynamics for knots [k_start,k_stop): A n*n, B n*m, f n (f may be NULL);
+ * shared by the whole batch; requires ALTRO_B200_MODEL_LINEAR */
+int altro_b200_set_linear_dynamics(altro_b200_solver *s, const double *A, const double *B,
+                                   const double *f, int k_start, int k_stop);
+
+/* SetLQRCost (altro_solver.cpp:138-172) on knots [k_start,k_stop) (inclusive-terminal index
+ * semantics of altro_solver.cpp:385-433).  Qd[n], Rd[m] shared; xref/uref are [n]/[m] when
+ * per_problem == 0, else [B][n] / [B][m]. */
+int altro_b200_set_lqr_cost(altro_b200_solver *s, const double *Qd, const double *Rd,
+                            const double *xref, const double *uref, int per_problem, int k_start,
+                            int k_stop);
+/* Tracking form of SetLQRCost (test/bicycle_test.cpp:183-186): knot k of problem b tracks row
+ * offsets[b] + k of the shared reference tables xtab [T][n], utab [T][m]; all knots 0..N. */
+int altro_b200_set_lqr_cost_window(altro_b200_solver *s, const double *Qd, const double *Rd,
+                                   const double *xtab, const double *utab, int T,
+                                   const int *offsets);
+/* SetDiagonalCost: q [n], r [m], c scalar per knot (per_problem == 0: one knot's worth applied to
+ * every knot in range; per_problem == 1: [B][k_stop-k_start][n], [B][..][m], [B][..]) */
+int altro_b200_set_diagonal_cost(altro_b200_solver *s, const double *Qd, const double *Rd,
+                                 const double *q, const double *r, const double *c,
+                                 int per_problem, int k_start, int k_stop);
+/* UpdateLinearCosts (altro_solver.cpp:266-281): q and/or r may be NULL */
+int altro_b200_update_linear_costs(altro_b200_solver *s, const double *q, const double *r,
+                                   const double *c, int per_problem, int k_start, int k_stop);
+/* advance every problem's tracking window by `steps` rows (on-device UpdateLinearCosts for the
+ * receding-horizon loop of test/bicycle_test.cpp:320-331) */
+int altro_b200_advance_window(altro_b200_solver *s, int steps);
+
+/* SetConstraint with a built-in row family instead of callbacks:
+ *   c_i = scale_i * [x;u][idx_i] + off_i   (idx_i = -1: c_i = off_i),   i < dim
+ * off_b: optional per-problem offsets [B][dim] (NULL: shared `off`). */
+int altro_b200_set_constraint(altro_b200_solver *s, int cone, int dim, const int *idx,
+                              const double *scale, const double *off, const double *off_b,
+                              int k_start, int k_stop);
+
+int altro_b200_set_initial_state(altro_b200_solver *s, const double *x0, int per_problem);
+int altro_b200_initialize(altro_b200_solver *s);
+/* SetInput: layout 0: u[m] for every knot in range and every problem; 1: [k_stop-k_start][m]
+ * shared by the batch; 2: [B][k_stop-k_start][m] */
+int altro_b200_set_input(altro_b200_solver *s, const double *u, int layout, int k_start,
+                         int k_stop);
+int altro_b200_set_state(altro_b200_solver *s, const double *x, int layout, int k_start,
+                         int k_stop);
+int altro_b200_set_options(altro_b200_solver *s, const altro_b200_options *o);
+/* reset duals (z = 0) and penalties (rho = 1) to their post-Initialize values */
+int altro_b200_reset_duals(altro_b200_solver *s);
+int altro_b200_shift_trajectory(altro_b200_solver *s); /* ShiftTrajectory, altro_solver.cpp:283 */
+/* restore the working inputs u_ to the last SetInput guess (device-to-device; lets a resident
+ * batch be re-solved from the same starting point without a host round trip) */
+int altro_b200_reset_trajectory(altro_b200_solver *s);
+
+/* Solve() for all B problems: launches the kernel sequence on the handle's stream and waits. */
+int altro_b200_solve(altro_b200_solver *s);
+int altro_b200_solve_async(altro_b200_solver *s); /* no wait; use altro_b200_synchronize */
+int altro_b200_synchronize(altro_b200_solver *s);
+/* number of kernels this handle has launched since creation */
+long altro_b200_kernel_launches(const altro_b200_solver *s);
+
+/* getters: caller-owned host buffers, problem-major */
+int altro_b200_get_states(altro_b200_solver *s, double *X);  /* [B][N+1][n]  GetState          */
+int altro_b200_get_inputs(altro_b200_solver *s, double *U);  /* [B][N][m]    GetInput          */
+int altro_b200_get_dual_dynamics(altro_b200_solver *s, double *Y); /* [B][N+1][n]             */
+int altro_b200_get_feedback_gains(altro_b200_solver *s, double *K); /* [B][N][m*n]            */
+int altro_b200_get_feedforward_gains(altro_b200_solver *s, double *d); /* [B][N][m]           */
+int altro_b200_get_status(altro_b200_solver *s, int *status);       /* [B] SolveStatus        */
+int altro_b200_get_iterations(altro_b200_solver *s, int *iters);    /* [B] GetIterations      */
+int altro_b200_get_merit_evals(altro_b200_solver *s, int *evals);   /* [B]                    */
+int altro_b200_get_final_objective(altro_b200_solver *s, double *phi);   /* [B]               */
+int altro_b200_get_stationarity(altro_b200_solver *s, double *stat);     /* [B]               */
+int altro_b200_get_primal_feasibility(altro_b200_solver *s, double *feas); /* [B]             */
+int altro_b200_get_penalty(altro_b200_solver *s, double *rho);      /* [B]                    */
+int altro_b200_get_horizon_length(const altro_b200_solver *s);
+int altro_b200_get_batch(const altro_b200_solver *s);
+int altro_b200_get_state_dim(const altro_b200_solver *s);
+int altro_b200_get_input_dim(const altro_b200_solver *s);
+/* bytes of HBM held by the handle */
+long altro_b200_device_bytes(const altro_b200_solver *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -86,16 +86,27 @@ def build(force=False):
             ("altro_oracle.c", "linesearch_port.c", "models.c", "batch.c", "altro_oracle.h")]
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if force or stale:
-        subprocess.run(["make", "-C", _HERE, "liboracle.so"], check=True, capture_output=True)
+        subprocess.run(["make", "-C", _HERE, "liboracle.so", "liboracle_fma.so"], check=True,
+                       capture_output=True)
     if os.path.isdir("/root/reference/src/linesearch"):
         subprocess.run(["make", "-C", _HERE, "ref"], check=True, capture_output=True)
     return so
 
 
+def use_variant(name="liboracle.so"):
+    """Switch the loaded oracle build (liboracle.so | liboracle_fma.so); test use only."""
+    global _LIB, _SO_NAME
+    _LIB = None
+    _SO_NAME = name
+
+
+_SO_NAME = "liboracle.so"
+
+
 def lib():
     global _LIB
     if _LIB is None:
-        so = os.path.join(_HERE, "liboracle.so")
+        so = os.path.join(_HERE, _SO_NAME)
         if not os.path.exists(so):
             build()
         L = C.CDLL(so)

@@ -1,0 +1,57 @@
+"""GPU-vs-oracle comparison shared by the parity tests, smoke() and bench.py's checker.
+
+Acceptance (SURVEY.md 8d / BASELINE.md), per problem the ORACLE solves to Success:
+  same SolveStatus, same iteration count, states/controls max-abs diff <= 1e-6 * max(1,|.|_inf),
+  final cost relative diff <= 1e-5 (the north-star tolerance).
+
+Documented exception -- the chaotic tail.  AL-iLQR without regularisation (reg is hard-wired to 0,
+solver.cpp:363) is a chaotic iteration on hard instances: a last-bit difference in one sin() or
+one fused multiply-add can flip a single Armijo decision 20 iterations later and shift the
+iteration count or push the solve past iterations_max.  The CPU oracle disagrees WITH ITSELF at
+the same rate when it is merely recompiled with -ffp-contract=fast (FMA contraction)
+(tests/test_oracle_selfconsistency.py), so this is a property of the algorithm, not of the port.
+`tail_frac` of the converged problems may therefore fall outside the strict criteria; they are
+counted and reported, never silently dropped.
+
+Problems the oracle itself does NOT solve (MaxIterations / line-search failure) have no
+well-defined answer; for those only the status is compared, on >= 97 % of them.
+"""
+import numpy as np
+
+STATE_TOL = 1e-6
+COST_RTOL = 1e-5
+
+
+def errors(a, ref):
+    nb = ref["X"].shape[0]
+    xs = np.maximum(1.0, np.abs(ref["X"]).reshape(nb, -1).max(axis=1))
+    us = np.maximum(1.0, np.abs(ref["U"]).reshape(nb, -1).max(axis=1))
+    ex = np.abs(a["X"][:nb] - ref["X"]).reshape(nb, -1).max(axis=1) / xs
+    eu = np.abs(a["U"][:nb] - ref["U"]).reshape(nb, -1).max(axis=1) / us
+    ec = np.abs(a["cost"][:nb] - ref["cost"]) / np.maximum(np.abs(ref["cost"]), 1e-300)
+    return ex, eu, ec
+
+
+def compare(gpu, ref, tail_frac=0.01):
+    nb = ref["X"].shape[0]
+    gi, gs = gpu["iters"][:nb], gpu["status"][:nb]
+    conv = ref["status"] == 0
+    same = (gi == ref["iters"]) & (gs == ref["status"])
+    ex, eu, ec = errors(gpu, ref)
+    within = (ex <= STATE_TOL) & (eu <= STATE_TOL) & (ec <= COST_RTOL)
+    strict = conv & same & within
+    tail = conv & ~strict
+    n_conv = int(conv.sum())
+    allowed = int(np.ceil(tail_frac * n_conv)) if tail_frac > 0 else 0
+    assert int(tail.sum()) <= allowed, \
+        f"{int(tail.sum())}/{n_conv} converged problems outside the strict criteria " \
+        f"(allowed {allowed}): iteration/status mismatches {int((conv & ~same).sum())}, " \
+        f"max state err {ex[conv & same].max(initial=0):.3e}, max cost err {ec[conv & same].max(initial=0):.3e}"
+    if (~conv).any():
+        st_same = (gs[~conv] == ref["status"][~conv]).mean()
+        assert st_same >= 0.97, f"status differs on {1 - st_same:.3f} of the unsolved problems"
+    return dict(n=int(nb), converged=n_conv, strict=int(strict.sum()), tail=int(tail.sum()),
+                max_state_err=float(ex[strict].max(initial=0)),
+                max_input_err=float(eu[strict].max(initial=0)),
+                max_cost_rel=float(ec[strict].max(initial=0)),
+                mean_iters=float(ref["iters"].mean()), mean_evals=float(ref["merit_evals"].mean()))

@@ -1,0 +1,126 @@
+"""Parity tests proper: the CUDA solve path (through the C ABI) against the CPU oracle on the
+same seeded inputs.  Run on the B200 box: python -m pytest tests -m gpu"""
+import math
+
+import numpy as np
+import pytest
+
+import altro_b200
+from altro_b200 import problems as PR
+from parity_util import compare
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(oracle, P, nref=None):
+    gpu = altro_b200.solve_problem(P)
+    ref = oracle.solve_batch(P, 0, nref or P.B)
+    return gpu, ref
+
+
+@pytest.mark.parametrize("variant,iters", [("unconstrained", 1), ("goal", 3), ("ubox", 5), ("usoc", 9)])
+def test_double_integrator_variants(oracle, variant, iters):
+    """double_integrator_test.cpp: pinned iteration counts 3 / 5 / 9 (and 1 unconstrained)."""
+    P = PR.double_integrator(N=10, variant=variant, B=3)
+    gpu, ref = run_both(oracle, P)
+    rep = compare(gpu, ref, tail_frac=0.0)
+    assert np.all(gpu["iters"] == iters) and np.all(gpu["status"] == 0)
+    assert np.linalg.norm(gpu["X"][0, -1]) < (1e-1 if variant == "unconstrained" else 1e-4)
+
+
+def test_double_integrator_n50(oracle):
+    """BASELINE config C0 shape (N=50, h=0.1f), all four variants."""
+    for variant in ("unconstrained", "goal", "ubox", "usoc"):
+        P = PR.double_integrator(N=50, variant=variant, B=2)
+        P.options.pop("iterations_max", None)
+        compare(*run_both(oracle, P))
+
+
+def test_pendulum_reference_cases(oracle):
+    """pendulum_test.cpp: unconstrained N=50 golden x_N, goal-constrained N=20."""
+    P = PR.pendulum(B=1, N=50, tf=3.0, perturb=False, iterations_max=20)
+    gpu, ref = run_both(oracle, P)
+    compare(gpu, ref)
+    assert gpu["status"][0] == 0 and gpu["iters"][0] == 10
+    assert np.linalg.norm(gpu["X"][0, -1] - [3.12099917161669, 0.0011966258762942175]) < 1e-5
+    P = PR.pendulum(B=1, N=20, tf=2.0, perturb=False, goal_constraint=True, iterations_max=100)
+    gpu, ref = run_both(oracle, P)
+    compare(gpu, ref)
+    assert gpu["status"][0] == 0 and gpu["iters"][0] == 9
+    assert np.linalg.norm(gpu["X"][0, -1] - [math.pi, 0]) < 1e-4
+
+
+@pytest.mark.parametrize("goal", [False, True])
+def test_pendulum_batch(oracle, goal):
+    """BASELINE C1 shape (N=100), perturbed initial states, ragged batch size."""
+    P = PR.pendulum(B=200, N=100, goal_constraint=goal)
+    rep = compare(*run_both(oracle, P))
+    assert rep["n"] == 200
+
+
+def test_bicycle_turn90(oracle):
+    """bicycle_test.cpp:53-138 (n=4, N=30, backtracking)."""
+    P = PR.bicycle_turn90()
+    gpu, ref = run_both(oracle, P)
+    compare(gpu, ref)
+    assert gpu["iters"][0] == 17 and gpu["merit_evals"][0] == 40
+    assert np.linalg.norm(gpu["X"][0, -1] - P.xref[0]) < 1e-2
+
+
+@pytest.mark.parametrize("n", [4, 5])
+def test_bicycle_batch(oracle, n):
+    """BASELINE C2 shape: random goals, N=100."""
+    P = PR.bicycle(B=160, N=100, n=n)
+    rep = compare(*run_both(oracle, P))
+    assert rep["strict"] >= 40
+
+
+@pytest.mark.parametrize("n,N", [(4, 30), (5, 50)])
+def test_scotty_batch(oracle, n, N):
+    """BASELINE C3 shape: tracking windows with the steering-angle inequality at every knot."""
+    P = PR.scotty(B=96, N=N, n=n)
+    gpu, ref = run_both(oracle, P)
+    rep = compare(gpu, ref)
+    assert rep["converged"] > 0.7 * P.B
+
+
+@pytest.mark.parametrize("n,m,N,box", [(4, 2, 50, False), (4, 4, 50, True), (6, 2, 50, True),
+                                        (6, 4, 200, False), (12, 2, 50, False), (12, 4, 50, True)])
+def test_chain_sweep(oracle, n, m, N, box):
+    """BASELINE C4 dimension sweep family."""
+    P = PR.chain(B=40, n=n, m=m, N=N, control_box=box)
+    compare(*run_both(oracle, P))
+
+
+def test_mpc_warm_start_sequence(oracle):
+    """Receding-horizon use of one handle: Solve -> advance window -> new x0 -> ShiftTrajectory,
+    duals and penalties carried over (bicycle_test.cpp:302-337, quirk Q14)."""
+    xref, uref, h = PR.load_scotty()
+    n, m, N, B = 4, 2, 30, 1
+    P = PR.scotty(B=B, N=N, n=4)
+    P.x0 = xref[:1].copy()
+    P.offsets = np.zeros(1, dtype=np.int32)
+    P.U0 = np.tile([uref[0][0], 0.0], (1, N, 1))
+    s = altro_b200.make_solver(P)
+    import json, os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "scotty_mpc.json")))
+    x = xref[0].copy()
+    for it in range(40):
+        status = s.Solve()
+        assert status[0] == 0
+        assert s.GetIterations()[0] == gold["solve_iters"][it]
+        u0 = s.GetInputs()[0, 0]
+        x = oracle.model_dynamics(oracle.MODEL_BICYCLE4, [2.7, 1.5], x, u0, h)
+        assert np.abs(x - np.array(gold["state_trajectory"][it + 1])).max() < 1e-9
+        s.AdvanceWindow(1)
+        s.SetInitialState(x)
+        s.ShiftTrajectory()
+    s.close()
+
+
+def test_results_do_not_depend_on_batch_neighbours(oracle):
+    """A problem's solution is independent of where it sits in the batch (no cross-lane state)."""
+    P = PR.bicycle(B=70, N=60, n=5)
+    full = altro_b200.solve_problem(P)
+    part = altro_b200.solve_problem(P.subset(33, 70))
+    assert np.array_equal(full["X"][33:], part["X"]) and np.array_equal(full["iters"][33:], part["iters"])
