@@ -16,7 +16,10 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libaltro_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+# -fmad=false: no implicit multiply-add contraction, so every kernel that evaluates the same
+# expression (persistent kernel, phase kernels) produces the same bits; the matrix helpers use
+# explicit fma().
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
 N_INST = 8
 UNITS = [("capi", "capi.cu", []), ("tvlqr", "tvlqr.cu", [])] + \
@@ -45,7 +48,16 @@ def _compile(unit, verbose):
 
 
 def build(verbose=False, jobs=None):
+    """ALTRO_ONLY=2,1 (env) recompiles only those solve_inst groups (+capi/tvlqr) and links the rest
+    from stale objects -- for quick kernel experiments; never commit a library built that way."""
     os.makedirs(OBJ, exist_ok=True)
+    only = os.environ.get("ALTRO_ONLY")
+    units = UNITS
+    if only:
+        keep = {f"solve_inst_{g}" for g in only.split(",")} | {"capi", "tvlqr"}
+        for name, src, defs in UNITS:
+            if name not in keep and os.path.exists(os.path.join(OBJ, name + ".o")):
+                os.utime(os.path.join(OBJ, name + ".o"))
     jobs = jobs or min(len(UNITS), os.cpu_count() or 4)
     objs, logs = [], {}
     with cf.ThreadPoolExecutor(max_workers=jobs) as ex:

@@ -162,6 +162,17 @@ struct altro_b200_solver {
   double *z = nullptr, *zest = nullptr, *rho = nullptr;
   int *status = nullptr, *iters = nullptr, *merit_evals = nullptr, *ls_fail = nullptr;
   double *phi = nullptr, *stat = nullptr, *feas = nullptr;
+  // phase pipeline state
+  LsMachine* ls = nullptr;
+  double *alpha_eval = nullptr, *alpha_bt = nullptr, *phi_eval = nullptr, *phi0 = nullptr, *dphi0 = nullptr;
+  double *xs = nullptr, *us = nullptr, *phi_s = nullptr;
+  int* sel = nullptr;
+  unsigned long long *stat_acc = nullptr, *feas_acc = nullptr;
+  int nslots = 10;  // candidates per speculative line-search round
+  int *flags = nullptr, *iter_count = nullptr, *list_iter = nullptr, *list_ls = nullptr,
+      *list_tmp = nullptr, *list_aux = nullptr, *counters = nullptr;
+  PhaseHost ph;
+  int solve_mode = 0;  // 0: phase pipeline (default), 1: single persistent kernel
   // tracking-window cost
   double *xtab = nullptr, *utab = nullptr;
   int* offsets = nullptr;
@@ -371,6 +382,11 @@ void altro_b200_destroy(altro_b200_solver* s) {
   cudaStreamSynchronize(s->stream);
   for (void* p : s->allocs) cudaFree(p);
   if (s->stage) cudaFree(s->stage);
+  if (s->ph.h_counters) {
+    cudaFreeHost(s->ph.h_counters);
+    cudaEventDestroy(s->ph.ev0);
+    cudaEventDestroy(s->ph.ev1);
+  }
   delete s;
 }
 
@@ -420,6 +436,27 @@ int altro_b200_set_dimension(altro_b200_solver* s, int n, int m) {  // altro_sol
   DALLOC(s, s->phi, S);
   DALLOC(s, s->stat, S);
   DALLOC(s, s->feas, S);
+  DALLOC(s, s->ls, S);
+  DALLOC(s, s->alpha_eval, S);
+  DALLOC(s, s->alpha_bt, S);
+  DALLOC(s, s->sel, S);
+  DALLOC(s, s->stat_acc, S);
+  DALLOC(s, s->feas_acc, S);
+  DALLOC(s, s->phi_eval, S);
+  DALLOC(s, s->phi0, S);
+  DALLOC(s, s->dphi0, S);
+  DALLOC(s, s->flags, S);
+  DALLOC(s, s->iter_count, S);
+  DALLOC(s, s->list_iter, S);
+  DALLOC(s, s->list_ls, S);
+  DALLOC(s, s->list_tmp, S);
+  DALLOC(s, s->list_aux, S);
+  DALLOC(s, s->counters, 8);
+  memset(&s->ph, 0, sizeof(s->ph));
+  CUDA_OK(cudaMallocHost((void**)&s->ph.h_counters, 8 * sizeof(int)));
+  CUDA_OK(cudaEventCreate(&s->ph.ev0));
+  CUDA_OK(cudaEventCreate(&s->ph.ev1));
+  s->ph.list_aux = s->list_aux;
   s->dims_set = true;
   return ALTRO_B200_NO_ERROR;
 }
@@ -686,6 +723,10 @@ int altro_b200_initialize(altro_b200_solver* s) {  // altro_solver.cpp:225-229
   k_fill<<<64, 256, 0, s->stream>>>(s->rho, s->Bp, 1.0);  // rho_ = 1.0, knotpoint_data.cpp:343
   s->launches++;
   CUDA_OK(cudaGetLastError());
+  // candidate slots of the speculative line search
+  DALLOC(s, s->xs, (long)s->nslots * (s->N + 1) * s->n * s->Bp);
+  DALLOC(s, s->us, (long)s->nslots * s->N * s->m * s->Bp);
+  DALLOC(s, s->phi_s, (long)s->nslots * s->Bp);
   CUDA_OK(cudaStreamSynchronize(s->stream));
   s->initialized = true;
   return ALTRO_B200_NO_ERROR;
@@ -807,6 +848,25 @@ static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   P.phi = s->phi;
   P.stat = s->stat;
   P.feas = s->feas;
+  P.ls = s->ls;
+  P.alpha_eval = s->alpha_eval;
+  P.alpha_bt = s->alpha_bt;
+  P.nslots = s->nslots;
+  P.xs = s->xs;
+  P.us = s->us;
+  P.phi_s = s->phi_s;
+  P.sel = s->sel;
+  P.stat_acc = s->stat_acc;
+  P.feas_acc = s->feas_acc;
+  P.phi_eval = s->phi_eval;
+  P.phi0 = s->phi0;
+  P.dphi0 = s->dphi0;
+  P.flags = s->flags;
+  P.iter_count = s->iter_count;
+  P.list_iter = s->list_iter;
+  P.list_ls = s->list_ls;
+  P.list_tmp = s->list_tmp;
+  P.counters = s->counters;
   P.opts.iterations_max = s->opts.iterations_max;
   P.opts.tol_primal_feasibility = s->opts.tol_primal_feasibility;
   P.opts.tol_stationarity = s->opts.tol_stationarity;
@@ -827,9 +887,61 @@ int altro_b200_solve_async(altro_b200_solver* s) {  // altro_solver.cpp:257-260
   if (!L) return ALTRO_B200_ERR_UNSUPPORTED;
   DeviceProblem P;
   fill_device_problem(s, P);
-  L(P, s->con_h.ncon > 0, s->stream);
-  s->launches++;
-  CUDA_OK(cudaGetLastError());
+  if (s->solve_mode == 1) {
+    int e = L(P, s->con_h.ncon > 0, s->stream, nullptr);
+    s->launches++;
+    if (e) return ALTRO_B200_ERR_NO_DEVICE;
+  } else {
+    long before = 0;
+    for (int i = 0; i < PH_COUNT; ++i) before += s->ph.launches[i];
+    int e = L(P, s->con_h.ncon > 0, s->stream, &s->ph);
+    long after = 0;
+    for (int i = 0; i < PH_COUNT; ++i) after += s->ph.launches[i];
+    s->launches += after - before;
+    if (e) {
+      fprintf(stderr, "altro_b200: CUDA error %d in the phase pipeline\n", e);
+      return ALTRO_B200_ERR_NO_DEVICE;
+    }
+  }
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_set_solve_mode(altro_b200_solver* s, int mode) {
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  if (mode != 0 && mode != 1) return ALTRO_B200_BAD_INDEX;
+  s->solve_mode = mode;
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_set_speculation(altro_b200_solver* s, int nslots) {
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  if (s->initialized) return ALTRO_B200_SOLVER_ALREADY_INITIALIZED;
+  if (nslots < 1 || nslots > 24) return ALTRO_B200_BAD_INDEX;
+  s->nslots = nslots;
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_set_profiling(altro_b200_solver* s, int on) {
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  s->ph.profile = on != 0;
+  for (int i = 0; i < PH_COUNT; ++i) {
+    s->ph.ms[i] = 0.0;
+    s->ph.launches[i] = 0;
+    s->ph.units[i] = 0.0;
+  }
+  s->ph.syncs = 0;
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_get_phase_stats(altro_b200_solver* s, double* ms, long* launches, double* units,
+                               long* syncs) {
+  if (!s || !ms || !launches || !units) return ALTRO_B200_INVALID_POINTER;
+  for (int i = 0; i < PH_COUNT; ++i) {
+    ms[i] = s->ph.ms[i];
+    launches[i] = s->ph.launches[i];
+    units[i] = s->ph.units[i];
+  }
+  if (syncs) *syncs = s->ph.syncs;
   return ALTRO_B200_NO_ERROR;
 }
 

@@ -7,6 +7,7 @@
 // (knotpoint_data.hpp:160-233) transposed so that the 32 lanes of a warp -- 32 consecutive
 // problems -- read one contiguous 256-byte row per matrix element.
 #pragma once
+#include "linesearch.cuh"
 
 namespace altro_b200 {
 
@@ -83,7 +84,38 @@ struct DeviceProblem {
   int *status, *iters, *merit_evals, *ls_fail;
   double *phi, *stat, *feas;
 
+  // ---- phase-kernel pipeline (solver_phases.cuh): per-trajectory scalar state + work lists
+  LsMachine* ls;        // [B] line-search state machines
+  double *alpha_eval;   // [Bp] step length of the pending merit evaluation
+  double *alpha_bt;     // [Bp] first backtracking step after alpha_eval (speculative rounds)
+  double *phi_eval;     // [Bp] merit value produced by the last rollout
+  double *phi0, *dphi0; // [Bp]
+  int* flags;           // [Bp] bit mask, see TrajFlags
+  int* iter_count;      // [Bp] iLQR iterations done so far
+  int *list_iter, *list_ls, *list_tmp;  // compacted problem indices
+  int* counters;        // [8] device-side counts (see PhaseCounter)
+  // speculative line-search slots: candidate step lengths of one trajectory are rolled out
+  // concurrently, each into its own copy of the working trajectory
+  int nslots;           // candidates per speculative round (>= 1)
+  double *xs, *us;      // [nslots][(N+1)*n][Bp], [nslots][N*m][Bp]
+  double* phi_s;        // [nslots][Bp] merit value per candidate
+  int* sel;             // [Bp] slot holding the working trajectory (-1: the main x, u arrays)
+  unsigned long long *stat_acc, *feas_acc;  // [Bp] max-reductions over knots (bit patterns of doubles >= 0)
+
   DevOptions opts;
 };
+
+enum TrajFlags {
+  TF_NEED_EVAL = 1,         // the line search asked for a merit evaluation at alpha_eval
+  TF_WANT_DERIV = 2,        // ... with derivative
+  TF_REFRESH_DYN = 4,       // backtracking accepted alpha != 1: recompute A,B,lx,lu (solver.cpp:256-262)
+  TF_REFRESH_GRAD = 8,      // duals/penalty changed: recompute projected duals and lx,lu (:483-486)
+  TF_ACTIVE = 16,           // still iterating
+  TF_LS_FAILED = 32,
+  TF_CONVERGED = 64,
+  TF_SPECULATE = 128,       // the pending evaluations are a speculative batch (slots)
+};
+
+enum PhaseCounter { PC_LS = 0, PC_DERIV = 1, PC_REFRESH_DYN = 2, PC_REFRESH_GRAD = 3, PC_ITER = 4 };
 
 }  // namespace altro_b200

@@ -6,10 +6,26 @@
 
 namespace altro_b200 {
 
-typedef void (*solve_launcher)(const DeviceProblem&, int has_constraints, cudaStream_t);
+// Host-side state of the phase-kernel pipeline (solver_phases.cuh)
+enum Phase { PH_INIT = 0, PH_EXPAND, PH_BACKWARD, PH_ROLLOUT, PH_LSUPDATE, PH_CRITERIA, PH_COMPACT, PH_COUNT };
+
+struct PhaseHost {
+  int* h_counters;     // pinned, 8 ints
+  int* list_aux;       // second buffer for list_iter
+  bool profile;        // record CUDA events around every launch
+  double ms[PH_COUNT];         // accumulated kernel time per phase (profile mode)
+  long launches[PH_COUNT];     // launches per phase
+  double units[PH_COUNT];      // trajectories (or trajectory-knots for PH_EXPAND) processed
+  long syncs;                  // host<->device count readbacks
+  cudaEvent_t ev0, ev1;
+};
+
+// has_constraints selects the AL-enabled instantiation.  host == nullptr: the single persistent
+// kernel (solver_kernels.cuh); otherwise the phase pipeline.  Returns 0 or a cudaError_t.
+typedef int (*solve_launcher)(const DeviceProblem&, int has_constraints, cudaStream_t, PhaseHost* host);
 
 #define ALTRO_DECLARE_LAUNCHER(name) \
-  void name(const DeviceProblem& P, int has_constraints, cudaStream_t stream)
+  int name(const DeviceProblem& P, int has_constraints, cudaStream_t stream, PhaseHost* host)
 
 ALTRO_DECLARE_LAUNCHER(launch_solve_linear_4_2);
 ALTRO_DECLARE_LAUNCHER(launch_solve_linear_2_1);

@@ -139,44 +139,59 @@ struct Bicycle4C {  // prm[0]=L, prm[1]=lr
 struct Bicycle5C {  // state [x,y,theta,delta,v], input [a, delta_dot]
   static constexpr int n = 5;
   static constexpr int m = 2;
-  ALTRO_DEV static void xdot(const double* prm, const double* x, const double* u, double* f) {
+  // Defined (here and in oracle/models.c, identically) in the algebraic form that avoids atan2:
+  // with beta = atan(lr*delta/L): cos(beta) = L/hyp, sin(beta) = lr*delta/hyp,
+  // hyp = sqrt(L^2 + (lr*delta)^2); sin/cos(theta+beta) by angle addition.  Two independent
+  // sincos per evaluation instead of a chain of five transcendental calls.
+  struct Trig {
+    double sb, cb, tand, s_tb, c_tb, cd, dbeta;
+  };
+  ALTRO_DEV static Trig trig(const double* prm, const double* x) {
     const double L = prm[0], lr = prm[1];
-    const double theta = x[2], delta = x[3], v = x[4];
-    const double beta = atan2(lr * delta, L);
-    const double omega = v * cos(beta) * tan(delta) / L;
-    double s, c;
-    sincos(theta + beta, &s, &c);
-    f[0] = v * c;
-    f[1] = v * s;
-    f[2] = omega;
+    double sd, cd, st, ct;
+    sincos(x[3], &sd, &cd);
+    sincos(x[2], &st, &ct);
+    const double by = lr * x[3];
+    const double h2 = L * L + by * by;
+    const double hyp = sqrt(h2);
+    Trig t;
+    t.cb = L / hyp;
+    t.sb = by / hyp;
+    t.tand = sd / cd;
+    t.s_tb = st * t.cb + ct * t.sb;
+    t.c_tb = ct * t.cb - st * t.sb;
+    t.cd = cd;
+    t.dbeta = L / h2 * lr;
+    return t;
+  }
+  ALTRO_DEV static void xdot(const double* prm, const double* x, const double* u, double* f) {
+    const double L = prm[0];
+    const double v = x[4];
+    const Trig t = trig(prm, x);
+    f[0] = v * t.c_tb;
+    f[1] = v * t.s_tb;
+    f[2] = v * t.cb * t.tand / L;
     f[3] = u[1];
     f[4] = u[0];
   }
   ALTRO_DEV static void jac(const double* prm, const double* x, const double* u, double* A,
                             double* B) {
     (void)u;
-    const double L = prm[0], lr = prm[1];
-    const double theta = x[2], delta = x[3], v = x[4];
-    const double by = lr * delta, bx = L;
-    const double beta = atan2(by, bx);
-    const double dbeta_ddelta = bx / (bx * bx + by * by) * lr;
-    double sb, cb, sd, cd, st, ct;
-    sincos(beta, &sb, &cb);
-    sincos(delta, &sd, &cd);
-    sincos(theta + beta, &st, &ct);
-    const double tand = tan(delta);
-    const double domega_ddelta = v / L * (-sb * tand * dbeta_ddelta + cb / (cd * cd));
-    const double domega_dv = cb * tand / L;
+    const double L = prm[0];
+    const double v = x[4];
+    const Trig t = trig(prm, x);
+    const double domega_ddelta = v / L * (-t.sb * t.tand * t.dbeta + t.cb / (t.cd * t.cd));
+    const double domega_dv = t.cb * t.tand / L;
 #pragma unroll
     for (int i = 0; i < n * n; ++i) A[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < n * m; ++i) B[i] = 0.0;
-    A[0 + n * 2] = -v * st;
-    A[0 + n * 3] = -v * st * dbeta_ddelta;
-    A[0 + n * 4] = ct;
-    A[1 + n * 2] = v * ct;
-    A[1 + n * 3] = v * ct * dbeta_ddelta;
-    A[1 + n * 4] = st;
+    A[0 + n * 2] = -v * t.s_tb;
+    A[0 + n * 3] = -v * t.s_tb * t.dbeta;
+    A[0 + n * 4] = t.c_tb;
+    A[1 + n * 2] = v * t.c_tb;
+    A[1 + n * 3] = v * t.c_tb * t.dbeta;
+    A[1 + n * 4] = t.s_tb;
     A[2 + n * 3] = domega_ddelta;
     A[2 + n * 4] = domega_dv;
     B[3 + n * 1] = 1.0;

@@ -1,23 +1,138 @@
 // solve_inst.cu -- explicit instantiations of the solve kernel, one group per translation unit
 // (compiled with -DALTRO_INST=<group>) so altro_b200/build.py can compile them in parallel.
 #include "launchers.h"
-#include "solver_kernels.cuh"
+#include "solver_phases.cuh"
 
 namespace altro_b200 {
 
+template <class Model, bool CON>
+static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
+  const int B = P.B, N = P.N;
+  auto g32 = [](int count) { return (count + 31) / 32; };
+  auto g128 = [](int count) { return (count + 127) / 128; };
+  cudaError_t err = cudaSuccess;
+  // launch wrapper: counts launches/units and, in profile mode, times the kernel with events
+  auto timed = [&](int phase, double units, auto&& launch) {
+    if (H->profile) cudaEventRecord(H->ev0, st);
+    launch();
+    if (H->profile) {
+      cudaEventRecord(H->ev1, st);
+      cudaEventSynchronize(H->ev1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, H->ev0, H->ev1);
+      H->ms[phase] += ms;
+    }
+    H->launches[phase] += 1;
+    H->units[phase] += units;
+  };
+  auto readback = [&]() {
+    cudaMemcpyAsync(H->h_counters, P.counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, st);
+    err = cudaStreamSynchronize(st);
+    H->syncs += 1;
+  };
+  auto expand = [&](const int* list, int count, const int* dcount, int mask, bool with_dyn,
+                    int slot_mode, bool dual_first) {
+    timed(PH_EXPAND, (double)count * (N + 1), [&] {
+      k_phase_expand<Model, CON><<<dim3(g128(count), N + 1), 128, 0, st>>>(
+          P, list, count, dcount, mask, with_dyn, slot_mode, dual_first);
+    });
+  };
+  auto compact = [&](const int* in, int count, const int* dcount, int mask, int* out, int slot,
+                     int mask2, int slot2) {
+    timed(PH_COMPACT, count, [&] {
+      k_compact<<<1, 1024, 0, st>>>(in, count, dcount, P.flags, mask, out, P.counters, slot, mask2, slot2);
+    });
+  };
+  auto rollout = [&](const int* list, int count, const int* dcount, bool spec) {
+    const int slots = spec ? P.nslots : 1;
+    timed(PH_ROLLOUT, (double)count * slots, [&] {
+      k_phase_rollout<Model, CON><<<dim3(g32(count), slots), 32, 0, st>>>(P, list, count, dcount, spec);
+    });
+  };
+  auto lsupdate = [&](const int* list, int count, const int* dcount, bool spec) {
+    timed(PH_LSUPDATE, count, [&] {
+      k_phase_lsupdate<Model, CON><<<g32(count), 32, 0, st>>>(P, list, count, dcount, spec);
+    });
+  };
+
+  // ---- prologue (solver.cpp:417-430)
+  timed(PH_INIT, B, [&] { k_phase_init<Model, CON><<<g32(B), 32, 0, st>>>(P); });
+  expand(nullptr, B, nullptr, 0, true, -1, false);  // with the OLD penalty (quirk Q3) ...
+  if (CON) k_phase_set_rho<<<g128(B), 128, 0, st>>>(P.rho, B, P.opts.penalty_initial);  // ... then reset
+  int* list_iter = P.list_iter;
+  int* list_iter_next = H->list_aux;
+  compact(nullptr, B, nullptr, TF_ACTIVE, list_iter, PC_ITER, 0, 0);
+  int count_iter = B;
+  const bool backtracking = P.opts.use_backtracking_linesearch != 0;
+
+  for (int iter = 0; iter < P.opts.iterations_max && count_iter > 0; ++iter) {
+    timed(PH_BACKWARD, count_iter,
+          [&] { k_phase_backward<Model, CON><<<g32(count_iter), 32, 0, st>>>(P, list_iter, count_iter); });
+    int* cur = P.list_ls;
+    int* nxt = P.list_tmp;
+    compact(list_iter, count_iter, nullptr, TF_NEED_EVAL, cur, PC_LS, TF_WANT_DERIV, PC_DERIV);
+    // round 1: alpha = 1 with derivative for everybody still searching; the exact list length
+    // stays on the device (no host round trip), count_iter bounds the grid
+    const int* dcount = P.counters + PC_LS;
+    rollout(cur, count_iter, dcount, false);
+    expand(cur, count_iter, dcount, TF_WANT_DERIV, true, -1, false);
+    lsupdate(cur, count_iter, dcount, false);
+    compact(cur, count_iter, dcount, TF_NEED_EVAL, nxt, PC_LS, TF_WANT_DERIV, PC_DERIV);
+    readback();
+    if (err != cudaSuccess) return (int)err;
+    int count_ls = H->h_counters[PC_LS], count_deriv = H->h_counters[PC_DERIV];
+    {
+      int* t = cur;
+      cur = nxt;
+      nxt = t;
+    }
+    while (count_ls > 0) {  // further rounds: speculative batches (backtracking) or single steps
+      rollout(cur, count_ls, nullptr, backtracking);
+      if (count_deriv > 0) expand(cur, count_ls, nullptr, TF_WANT_DERIV, true, backtracking ? 0 : -1, false);
+      lsupdate(cur, count_ls, nullptr, backtracking);
+      compact(cur, count_ls, nullptr, TF_NEED_EVAL, nxt, PC_LS, TF_WANT_DERIV, PC_DERIV);
+      readback();
+      if (err != cudaSuccess) return (int)err;
+      count_ls = H->h_counters[PC_LS];
+      count_deriv = H->h_counters[PC_DERIV];
+      int* t = cur;
+      cur = nxt;
+      nxt = t;
+    }
+    if (backtracking) expand(list_iter, count_iter, nullptr, TF_REFRESH_DYN, true, -2, false);  // solver.cpp:256-262
+    timed(PH_CRITERIA, (double)count_iter * (N + 1), [&] {
+      k_phase_costate<Model, CON><<<dim3(g128(count_iter), N + 1), 128, 0, st>>>(P, list_iter, count_iter);
+      k_phase_residual<Model, CON><<<dim3(g128(count_iter), N + 1), 128, 0, st>>>(P, list_iter, count_iter);
+      k_phase_decide<CON><<<g128(count_iter), 128, 0, st>>>(P, list_iter, count_iter);
+    });
+    H->launches[PH_CRITERIA] += 2;
+    if (CON) expand(list_iter, count_iter, nullptr, TF_REFRESH_GRAD, false, -1, true);  // solver.cpp:475-486
+    compact(list_iter, count_iter, nullptr, TF_ACTIVE, list_iter_next, PC_ITER, 0, 0);
+    readback();
+    if (err != cudaSuccess) return (int)err;
+    count_iter = H->h_counters[PC_ITER];
+    int* t = list_iter;
+    list_iter = list_iter_next;
+    list_iter_next = t;
+  }
+  return (int)cudaGetLastError();
+}
+
 template <class Model>
-static void launch_solve(const DeviceProblem& P, int has_con, cudaStream_t st) {
+static int launch_solve(const DeviceProblem& P, int has_con, cudaStream_t st, PhaseHost* host) {
+  if (host) return has_con ? run_phased<Model, true>(P, st, host) : run_phased<Model, false>(P, st, host);
   const int threads = 32;  // one warp per CTA: 32 consecutive problems
   const int blocks = (P.B + threads - 1) / threads;
   if (has_con)
     solve_kernel<Model, true><<<blocks, threads, 0, st>>>(P);
   else
     solve_kernel<Model, false><<<blocks, threads, 0, st>>>(P);
+  return (int)cudaGetLastError();
 }
 
-#define ALTRO_DEFINE_LAUNCHER(name, ...)                                          \
-  void name(const DeviceProblem& P, int has_constraints, cudaStream_t stream) {   \
-    launch_solve<__VA_ARGS__>(P, has_constraints, stream);                        \
+#define ALTRO_DEFINE_LAUNCHER(name, ...)                                                        \
+  int name(const DeviceProblem& P, int has_constraints, cudaStream_t stream, PhaseHost* host) { \
+    return launch_solve<__VA_ARGS__>(P, has_constraints, stream, host);                         \
   }
 
 #if ALTRO_INST == 0

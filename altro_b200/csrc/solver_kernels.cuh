@@ -226,7 +226,7 @@ struct TrajSolver {
   // Evaluates c, z_est = z - rho c (stored), returns sum ||Pi(z_est)||^2 / (2 rho) and, if
   // want_grad, subtracts J^T dPi^T Pi(z_est) from lx, lu.
   ALTRO_DEV double al_terms(int k, const double* x, const double* u, bool terminal,
-                            bool want_grad, double* lx, double* lu) {
+                            bool want_grad, double* lx, double* lu, bool store_zest = true) {
     if constexpr (!CON) {
       return 0.0;
     } else {
@@ -241,7 +241,7 @@ struct TrajSolver {
           for (int i = 0; i < s.dim; ++i) {
             const double c = row_value(s, i, x, u);
             zt[i] = P.z[zrow + (long)i * S] - rho * c;
-            P.zest[zrow + (long)i * S] = zt[i];
+            if (store_zest) P.zest[zrow + (long)i * S] = zt[i];
           }
           soc_projection(s.dim, zt, zp);
           double nrm = 0.0;
@@ -261,7 +261,7 @@ struct TrajSolver {
           for (int i = 0; i < s.dim; ++i) {
             const double c = row_value(s, i, x, u);
             const double zt = P.z[zrow + (long)i * S] - rho * c;
-            P.zest[zrow + (long)i * S] = zt;
+            if (store_zest) P.zest[zrow + (long)i * S] = zt;
             // dual cones (cones.hpp:13-30): EQUALITY -> IDENTITY, INEQUALITY -> INEQUALITY,
             // IDENTITY -> EQUALITY (projection onto {0})
             double zp = 0.0;
@@ -448,6 +448,12 @@ struct TrajSolver {
       store_block<n>(P.p + b, S, N, pn);
     }
     for (int k = N - 1; k >= 0; --k) {
+      if (k > 0) {
+        prefetch_block<n * n>(P.A + b, S, k - 1);
+        prefetch_block<n * m>(P.Bm + b, S, k - 1);
+        prefetch_block<n>(P.lx + b, S, k - 1);
+        prefetch_block<m>(P.lu + b, S, k - 1);
+      }
       double A[n * n], Bm[n * m];
       load_block<n * n>(P.A + b, S, k, A);
       load_block<n * m>(P.Bm + b, S, k, Bm);
@@ -700,12 +706,320 @@ struct TrajSolver {
     }
     const double alpha = ls.alpha;
     *alpha_out = alpha;
-    *phi_final = ls.phi;
+    if (ls.n_iters > 0) *phi_final = ls.phi;
     if (lo.use_backtracking && fabs(alpha - 1.0) > 0) refresh_sweep(true);
     if (isnan(alpha) || !(ls.status == LS_MINIMUM_FOUND || ls.status == LS_HIT_MAX_STEPSIZE)) {
       return ERR_LINESEARCH_FAILED;
     }
     return ERR_NONE;
+  }
+
+  // =================================================================== phase pieces
+  // The same mathematics split so that (i) work that is independent per knot (dynamics
+  // Jacobians, projected duals, cost gradients, costates, residuals) runs one thread per
+  // (trajectory, knot), and (ii) the sequential sweeps carry as little as possible and prefetch
+  // the next knot while they work on the current one.  Used by solver_phases.cuh.
+
+  // working trajectory of candidate `slot` (-1: the main x_, u_ arrays)
+  ALTRO_DEV double* xw(int slot) const {
+    return slot < 0 ? P.x : P.xs + (long)slot * (N + 1) * n * S;
+  }
+  ALTRO_DEV double* uw(int slot) const { return slot < 0 ? P.u : P.us + (long)slot * N * m * S; }
+
+  // OpenLoopRollout + CopyTrajectory (solver.cpp:422-423): x_, x, u from the working inputs.
+  ALTRO_DEV void phase_init_rollout() {
+    double x[n], u[m], xn[n];
+    load_block<n>(P.x0 + b, S, 0, x);
+    for (int k = 0; k < N; ++k) {
+      if (k + 1 < N) prefetch_block<m>(P.u + b, S, k + 1);
+      load_block<m>(P.u + b, S, k, u);
+      dynamics(k, x, u, xn);
+      store_block<n>(P.x + b, S, k, x);
+      store_block<n>(P.xbar + b, S, k, x);
+      store_block<m>(P.ubar + b, S, k, u);
+#pragma unroll
+      for (int i = 0; i < n; ++i) x[i] = xn[i];
+    }
+    store_block<n>(P.x + b, S, N, x);
+    store_block<n>(P.xbar + b, S, N, x);
+  }
+
+  // z <- Pi(z_est) for the rows of knot k (KnotPointData::DualUpdate, knotpoint_data.cpp:503-510)
+  ALTRO_DEV void dual_update_knot(int k) {
+    if constexpr (CON) {
+      const ConTable& T = *P.con;
+      for (int j = 0; j < T.ncon; ++j) {
+        const ConSlot& s = T.slot[j];
+        if (k < s.k_start || k >= s.k_stop) continue;
+        const long zrow = ((long)k * T.rows + s.row0) * S + b;
+        if (s.cone == CONE_SOC) {
+          double zt[kMaxSocDim], zp[kMaxSocDim];
+          for (int i = 0; i < s.dim; ++i) zt[i] = P.zest[zrow + (long)i * S];
+          soc_projection(s.dim, zt, zp);
+          for (int i = 0; i < s.dim; ++i) P.z[zrow + (long)i * S] = zp[i];
+        } else {
+          for (int i = 0; i < s.dim; ++i) {
+            const double zt = P.zest[zrow + (long)i * S];
+            double zp = 0.0;
+            if (s.cone == CONE_EQUALITY) zp = zt;
+            if (s.cone == CONE_INEQUALITY) zp = fmin(0.0, zt);
+            P.z[zrow + (long)i * S] = zp;
+          }
+        }
+      }
+    }
+  }
+
+  // Expansion of ONE knot: [A B] (if with_dyn), projected duals, cost gradient with AL terms
+  // (CalcDynamicsExpansion, CalcConstraintJacobians, CalcProjectedDuals, CalcCostGradient;
+  // knotpoint_data.cpp:406-437).  The trajectory is read from candidate `slot`; when that is not
+  // the main copy it is also written there (the accepted candidate becomes x_, u_).
+  ALTRO_DEV void phase_expand_knot(int k, bool with_dyn, int slot, bool dual_first) {
+    const bool terminal = (k == N);
+    double x[n], u[m], q[n], r[m], lx[n], lu[m];
+    load_block<n>(xw(slot) + b, S, k, x);
+    load_block<n>(P.q + b, S, k, q);
+    if (slot >= 0) store_block<n>(P.x + b, S, k, x);
+    if (!terminal) {
+      load_block<m>(uw(slot) + b, S, k, u);
+      load_block<m>(P.r + b, S, k, r);
+      if (slot >= 0) store_block<m>(P.u + b, S, k, u);
+      if (with_dyn) {
+        double A[n * n], Bm[n * m];
+        jacobian(k, x, u, A, Bm);
+        store_block<n * n>(P.A + b, S, k, A);
+        store_block<n * m>(P.Bm + b, S, k, Bm);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < m; ++i) u[i] = 0.0;
+    }
+    if (dual_first) dual_update_knot(k);
+    stage_gradient(k, x, u, q, r, terminal, lx, lu);
+    al_terms(k, x, u, terminal, true, lx, lu);
+    store_block<n>(P.lx + b, S, k, lx);
+    if (!terminal) store_block<m>(P.lu + b, S, k, lu);
+  }
+
+  // merit(0, derivative) of ForwardPass (solver.cpp:241) WITHOUT re-simulating: at alpha = 0 the
+  // closed-loop rollout reproduces the accepted trajectory bit for bit (dx = 0), so x_, u_, A, B
+  // are already in HBM; what changes with the new gains / duals / penalty is the cost, the
+  // projected duals, the gradients and the directional derivative, recomputed here in one
+  // linear scan.
+  ALTRO_DEV void phase_phi0_scan(double* phi_out, double* dphi_out) {
+    double phi = 0.0, dphi = 0.0;
+    double dxda[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) dxda[i] = 0.0;
+    for (int k = 0; k < N; ++k) {
+      {
+        const int kn = k + 1;
+        prefetch_block<n>(P.x + b, S, kn);
+        prefetch_block<n>(P.q + b, S, kn);
+        if (kn < N) {
+          prefetch_block<m>(P.u + b, S, kn);
+          prefetch_block<m>(P.r + b, S, kn);
+          prefetch_block<m * n>(P.K + b, S, kn);
+          prefetch_block<m>(P.d + b, S, kn);
+          prefetch_block<n * n>(P.A + b, S, kn);
+          prefetch_block<n * m>(P.Bm + b, S, kn);
+        }
+      }
+      double x[n], u[m], q[n], r[m], lx[n], lu[m];
+      load_block<n>(P.x + b, S, k, x);
+      load_block<m>(P.u + b, S, k, u);
+      load_block<n>(P.q + b, S, k, q);
+      load_block<m>(P.r + b, S, k, r);
+      stage_gradient(k, x, u, q, r, false, lx, lu);
+      phi += stage_cost(k, x, u, q, r, false) + al_terms(k, x, u, false, true, lx, lu);
+      store_block<n>(P.lx + b, S, k, lx);
+      store_block<m>(P.lu + b, S, k, lu);
+      double K[m * n], d[m], A[n * n], Bm[n * m], duda[m], dxn[n];
+      load_block<m * n>(P.K + b, S, k, K);
+      load_block<m>(P.d + b, S, k, d);
+      load_block<n * n>(P.A + b, S, k, A);
+      load_block<n * m>(P.Bm + b, S, k, Bm);
+      {
+        double Kd[m];
+        mm<m, 1, n, false, false, 0>(K, dxda, Kd);
+#pragma unroll
+        for (int i = 0; i < m; ++i) duda[i] = -Kd[i] + d[i];
+      }
+      mm<n, 1, n, false, false, 0>(A, dxda, dxn);
+      mm<n, 1, m, false, false, 1>(Bm, duda, dxn);
+      dphi += dot<n>(lx, dxda);
+      dphi += dot<m>(lu, duda);
+#pragma unroll
+      for (int i = 0; i < n; ++i) dxda[i] = dxn[i];
+    }
+    {
+      double x[n], q[n], u0[m], lx[n];
+      load_block<n>(P.x + b, S, N, x);
+      load_block<n>(P.q + b, S, N, q);
+#pragma unroll
+      for (int i = 0; i < m; ++i) u0[i] = 0.0;
+      stage_gradient(N, x, u0, q, nullptr, true, lx, nullptr);
+      phi += stage_cost(N, x, u0, q, nullptr, true) + al_terms(N, x, u0, true, true, lx, nullptr);
+      store_block<n>(P.lx + b, S, N, lx);
+      dphi += dot<n>(lx, dxda);
+    }
+    *phi_out = phi;
+    *dphi_out = dphi;
+  }
+
+  // The simulation half of MeritFunction (solver.cpp:285-301, :319-322): closed-loop rollout at
+  // step alpha into candidate `slot`, returning the merit value.  Derivative work is left to
+  // phase_expand_knot (parallel over knots) + phase_dphi_scan; y_ is produced for the accepted
+  // point only (phase_costate_knot).  z_est is not stored here: every candidate that can be
+  // accepted is expanded afterwards, which stores it.
+  ALTRO_DEV double phase_rollout(double alpha, int slot) {
+    double phi = 0.0;
+    double x[n];
+    double* xo = xw(slot) + b;
+    double* uo = uw(slot) + b;
+    load_block<n>(P.x0 + b, S, 0, x);
+    for (int k = 0; k < N; ++k) {
+      {
+        const int kn = k + 1;
+        prefetch_block<n>(P.xbar + b, S, kn);
+        prefetch_block<n>(P.q + b, S, kn);
+        if (kn < N) {
+          prefetch_block<m>(P.ubar + b, S, kn);
+          prefetch_block<m * n>(P.K + b, S, kn);
+          prefetch_block<m>(P.d + b, S, kn);
+          prefetch_block<m>(P.r + b, S, kn);
+        }
+      }
+      double xb[n], ub[m], K[m * n], d[m], dx[n], u[m], xn[n], q[n], r[m];
+      load_block<n>(P.xbar + b, S, k, xb);
+      load_block<m>(P.ubar + b, S, k, ub);
+      load_block<m * n>(P.K + b, S, k, K);
+      load_block<m>(P.d + b, S, k, d);
+      load_block<n>(P.q + b, S, k, q);
+      load_block<m>(P.r + b, S, k, r);
+#pragma unroll
+      for (int i = 0; i < n; ++i) dx[i] = x[i] - xb[i];
+      {
+        double Kdx[m];
+        mm<m, 1, n, false, false, 0>(K, dx, Kdx);
+#pragma unroll
+        for (int i = 0; i < m; ++i) u[i] = ub[i] + (-Kdx[i] + alpha * d[i]);
+      }
+      store_block<n>(xo, S, k, x);
+      store_block<m>(uo, S, k, u);
+      dynamics(k, x, u, xn);
+      phi += stage_cost(k, x, u, q, r, false) +
+             al_terms(k, x, u, false, false, nullptr, nullptr, false);
+#pragma unroll
+      for (int i = 0; i < n; ++i) x[i] = xn[i];
+    }
+    {
+      double q[n], u0[m];
+      load_block<n>(P.q + b, S, N, q);
+#pragma unroll
+      for (int i = 0; i < m; ++i) u0[i] = 0.0;
+      phi += stage_cost(N, x, u0, q, nullptr, true) +
+             al_terms(N, x, u0, true, false, nullptr, nullptr, false);
+      store_block<n>(xo, S, N, x);
+    }
+    return phi;
+  }
+
+  // The derivative half of MeritFunction (solver.cpp:303-315, :327-331) once A, B, lx, lu of the
+  // trial trajectory are in HBM.
+  ALTRO_DEV double phase_dphi_scan() {
+    double dphi = 0.0;
+    double dxda[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) dxda[i] = 0.0;
+    for (int k = 0; k < N; ++k) {
+      {
+        const int kn = k + 1;
+        prefetch_block<n>(P.lx + b, S, kn);
+        if (kn < N) {
+          prefetch_block<m * n>(P.K + b, S, kn);
+          prefetch_block<m>(P.d + b, S, kn);
+          prefetch_block<n * n>(P.A + b, S, kn);
+          prefetch_block<n * m>(P.Bm + b, S, kn);
+          prefetch_block<m>(P.lu + b, S, kn);
+        }
+      }
+      double K[m * n], d[m], A[n * n], Bm[n * m], lx[n], lu[m], duda[m], dxn[n];
+      load_block<m * n>(P.K + b, S, k, K);
+      load_block<m>(P.d + b, S, k, d);
+      load_block<n * n>(P.A + b, S, k, A);
+      load_block<n * m>(P.Bm + b, S, k, Bm);
+      load_block<n>(P.lx + b, S, k, lx);
+      load_block<m>(P.lu + b, S, k, lu);
+      {
+        double Kd[m];
+        mm<m, 1, n, false, false, 0>(K, dxda, Kd);
+#pragma unroll
+        for (int i = 0; i < m; ++i) duda[i] = -Kd[i] + d[i];
+      }
+      mm<n, 1, n, false, false, 0>(A, dxda, dxn);
+      mm<n, 1, m, false, false, 1>(Bm, duda, dxn);
+      dphi += dot<n>(lx, dxda);
+      dphi += dot<m>(lu, duda);
+#pragma unroll
+      for (int i = 0; i < n; ++i) dxda[i] = dxn[i];
+    }
+    double lx[n];
+    load_block<n>(P.lx + b, S, N, lx);
+    dphi += dot<n>(lx, dxda);
+    return dphi;
+  }
+
+  // y_k = P_k (x_k - xbar_k) + p_k for the accepted point (solver.cpp:293, :324)
+  ALTRO_DEV void phase_costate_knot(int k) {
+    double x[n], xb[n], dx[n], Pk[n * n], y[n];
+    load_block<n>(P.x + b, S, k, x);
+    load_block<n>(P.xbar + b, S, k, xb);
+#pragma unroll
+    for (int i = 0; i < n; ++i) dx[i] = x[i] - xb[i];
+    load_block<n * n>(P.P + b, S, k, Pk);
+    load_block<n>(P.p + b, S, k, y);
+    mm<n, 1, n, false, false, 1>(Pk, dx, y);
+    store_block<n>(P.y + b, S, k, y);
+  }
+
+  // knot k's contribution to Stationarity (solver.cpp:207-222) and Feasibility (:224-231), and its
+  // share of CopyTrajectory (:148-157).  Max-reduced over knots with atomics on the bit patterns
+  // (all values are >= 0; NaNs are skipped exactly as std::max skips them).
+  ALTRO_DEV void phase_residual_knot(int k) {
+    double res = 0.0, viol = 0.0;
+    double x[n], u[m];
+    load_block<n>(P.x + b, S, k, x);
+    if (k < N) {
+      double y[n], yn[n], A[n * n], Bm[n * m], lx[n], lu[m];
+      load_block<n>(P.y + b, S, k, y);
+      load_block<n>(P.y + b, S, k + 1, yn);
+      load_block<n * n>(P.A + b, S, k, A);
+      load_block<n * m>(P.Bm + b, S, k, Bm);
+      load_block<n>(P.lx + b, S, k, lx);
+      load_block<m>(P.lu + b, S, k, lu);
+      load_block<m>(P.u + b, S, k, u);
+      mm<n, 1, n, true, false, 1>(A, yn, lx);
+      mm<m, 1, n, true, false, 1>(Bm, yn, lu);
+#pragma unroll
+      for (int i = 0; i < n; ++i) res = fmax(res, fabs(lx[i] - y[i]));
+#pragma unroll
+      for (int i = 0; i < m; ++i) res = fmax(res, fabs(lu[i]));
+      viol = al_violation(k, x, u);
+      store_block<m>(P.ubar + b, S, k, u);
+    } else {
+      double y[n], lx[n];
+      load_block<n>(P.y + b, S, N, y);
+      load_block<n>(P.lx + b, S, N, lx);
+#pragma unroll
+      for (int i = 0; i < n; ++i) res = fmax(res, fabs(lx[i] - y[i]));
+#pragma unroll
+      for (int i = 0; i < m; ++i) u[i] = 0.0;
+      viol = al_violation(N, x, u);
+    }
+    store_block<n>(P.xbar + b, S, k, x);
+    if (res > 0.0) atomicMax(P.stat_acc + b, (unsigned long long)__double_as_longlong(res));
+    if (CON && viol > 0.0) atomicMax(P.feas_acc + b, (unsigned long long)__double_as_longlong(viol));
   }
 
   // SolverImpl::Solve (solver.cpp:414-511)

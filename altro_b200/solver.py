@@ -95,6 +95,10 @@ def load_library():
             getattr(L, "altro_b200_" + f).argtypes = [vp, dptr]
         for f in ("get_status", "get_iterations", "get_merit_evals"):
             getattr(L, "altro_b200_" + f).argtypes = [vp, iptr]
+        L.altro_b200_set_solve_mode.argtypes = [vp, C.c_int]
+        L.altro_b200_set_profiling.argtypes = [vp, C.c_int]
+        L.altro_b200_set_speculation.argtypes = [vp, C.c_int]
+        L.altro_b200_get_phase_stats.argtypes = [vp, dptr, C.POINTER(C.c_long), dptr, C.POINTER(C.c_long)]
         L.altro_b200_tvlqr_backward_batch.argtypes = [C.c_int] * 4 + [dptr] * 8 + [C.c_double, C.c_bool] + \
             [dptr] * 5 + [iptr]
         L.altro_b200_tvlqr_forward_batch.argtypes = [C.c_int] * 4 + [dptr] * 11
@@ -246,6 +250,28 @@ class BatchSolver:
     def SetStream(self, cuda_stream_ptr):
         self._ck(self.L.altro_b200_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "SetStream")
 
+    def SetSolveMode(self, mode):
+        """0: phase-kernel pipeline (default); 1: single persistent kernel."""
+        self._ck(self.L.altro_b200_set_solve_mode(self.h, mode), "SetSolveMode")
+
+    def SetSpeculation(self, nslots):
+        self._ck(self.L.altro_b200_set_speculation(self.h, nslots), "SetSpeculation")
+
+    def SetProfiling(self, on):
+        self._ck(self.L.altro_b200_set_profiling(self.h, int(on)), "SetProfiling")
+
+    PHASES = ("init_rollout", "expand", "backward", "rollout", "lsupdate", "criteria", "compact")
+
+    def GetPhaseStats(self):
+        ms = np.zeros(7)
+        units = np.zeros(7)
+        launches = (C.c_long * 7)()
+        syncs = C.c_long()
+        self._ck(self.L.altro_b200_get_phase_stats(self.h, ms.ctypes.data_as(dptr), launches,
+                                                   units.ctypes.data_as(dptr), C.byref(syncs)), "GetPhaseStats")
+        return {p: dict(ms=float(ms[i]), launches=int(launches[i]), units=float(units[i]))
+                for i, p in enumerate(self.PHASES)}, int(syncs.value)
+
     def ResetDuals(self):
         self._ck(self.L.altro_b200_reset_duals(self.h), "ResetDuals")
 
@@ -319,7 +345,7 @@ class BatchSolver:
         return self._get("get_penalty", (self.B,))
 
 
-def make_solver(P, device=0):
+def make_solver(P, device=0, nslots=None):
     """Builds and initialises a BatchSolver from a problems.Problem (the same sequence of calls
     the reference tests make: SetDimension, SetTimeStep, SetExplicitDynamics, SetLQRCost,
     SetConstraint, SetInitialState, Initialize, SetInput)."""
@@ -332,6 +358,8 @@ def make_solver(P, device=0):
     for cs in P.constraints:
         s.SetConstraint(cs.cone, cs.idx, cs.scale, cs.off, cs.k_start, cs.k_stop, off_b=cs.off_b)
     s.SetInitialState(P.x0)
+    if nslots is not None:
+        s.SetSpeculation(nslots)
     s.Initialize()
     s.SetInput(P.U0)
     s.SetOptions(default_options(**P.options))
@@ -363,9 +391,10 @@ def set_cost(s, P):
                               P.r[:, min(k, N - 1):min(k, N - 1) + 1, :], P.c[:, k:k + 1], k, k + 1)
 
 
-def solve_problem(P, device=0):
+def solve_problem(P, device=0, mode=0):
     """Convenience: build, solve, gather.  Returns the same dict as oracle.solve_batch."""
     s = make_solver(P, device)
+    s.SetSolveMode(mode)
     status = s.Solve()
     out = dict(X=s.GetStates(), U=s.GetInputs(), Y=s.GetDualDynamics(), status=status,
                iters=s.GetIterations(), merit_evals=s.GetMeritEvals(), cost=s.GetFinalObjective(),

@@ -213,6 +213,20 @@ int altro_b200_reset_trajectory(altro_b200_solver *s);
 int altro_b200_solve(altro_b200_solver *s);
 int altro_b200_solve_async(altro_b200_solver *s); /* no wait; use altro_b200_synchronize */
 int altro_b200_synchronize(altro_b200_solver *s);
+/* 0 (default): pipeline of phase kernels over compacted work lists (needs a few host round
+ * trips per iteration, so solve_async returns when the last kernel is queued);
+ * 1: one persistent kernel for the whole solve (thread per trajectory, no host interaction) */
+int altro_b200_set_solve_mode(altro_b200_solver *s, int mode);
+/* number of candidate step lengths rolled out concurrently per backtracking round (1..24,
+ * default 10; before altro_b200_initialize).  1 reproduces the strictly sequential search. */
+int altro_b200_set_speculation(altro_b200_solver *s, int nslots);
+/* per-phase instrumentation of the pipeline.  Phases: 0 init rollout, 1 expansion (knot-parallel),
+ * 2 backward Riccati + alpha=0 scan, 3 rollout, 4 d(phi) scan + line-search step, 5 criteria +
+ * AL update, 6 list compaction.  on=1 additionally times every launch with CUDA events
+ * (serialises the pipeline; not for throughput runs).  Arrays of 7 entries. */
+int altro_b200_set_profiling(altro_b200_solver *s, int on);
+int altro_b200_get_phase_stats(altro_b200_solver *s, double *ms, long *launches, double *units,
+                               long *syncs);
 /* number of kernels this handle has launched since creation */
 long altro_b200_kernel_launches(const altro_b200_solver *s);
 

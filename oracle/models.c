@@ -123,39 +123,57 @@ static void bicycle4_cjac(const double *prm, double *jac, const double *x, const
 #undef J
 }
 
-/* bicycle5: bicycle-4 equations with the speed as fifth state */
-static void bicycle5_xdot(const double *prm, double *xdot, const double *x, const double *u) {
+/* bicycle5: bicycle-4 equations with the speed as fifth state.  This model does
+ * not exist in the reference; it is DEFINED here (and identically in altro_b200/csrc/models.cuh)
+ * in the algebraic form that avoids atan2: with beta = atan(lr*delta/L),
+ *   cos(beta) = L / hypot,  sin(beta) = lr*delta / hypot,  hypot = sqrt(L^2 + (lr*delta)^2),
+ * and sin/cos(theta+beta) by the angle-addition formulas. */
+static void bicycle5_trig(const double *prm, const double *x, double *sb, double *cb, double *tand,
+                          double *s_tb, double *c_tb, double *cd_out, double *dbeta) {
   double L = prm[0], lr = prm[1];
-  double theta = x[2], delta = x[3], v = x[4];
-  double beta = atan2(lr * delta, L);
-  double omega = v * cos(beta) * tan(delta) / L;
-  xdot[0] = v * cos(theta + beta);
-  xdot[1] = v * sin(theta + beta);
-  xdot[2] = omega;
+  double theta = x[2], delta = x[3];
+  double sd = sin(delta), cd = cos(delta), st = sin(theta), ct = cos(theta);
+  double by = lr * delta;
+  double h2 = L * L + by * by;
+  double hyp = sqrt(h2);
+  *cb = L / hyp;
+  *sb = by / hyp;
+  *tand = sd / cd;
+  *s_tb = st * (*cb) + ct * (*sb);
+  *c_tb = ct * (*cb) - st * (*sb);
+  *cd_out = cd;
+  *dbeta = L / h2 * lr;
+}
+
+static void bicycle5_xdot(const double *prm, double *xdot, const double *x, const double *u) {
+  double L = prm[0];
+  double v = x[4];
+  double sb, cb, tand, s_tb, c_tb, cd, dbeta;
+  bicycle5_trig(prm, x, &sb, &cb, &tand, &s_tb, &c_tb, &cd, &dbeta);
+  xdot[0] = v * c_tb;
+  xdot[1] = v * s_tb;
+  xdot[2] = v * cb * tand / L;
   xdot[3] = u[1];
   xdot[4] = u[0];
 }
 
 static void bicycle5_cjac(const double *prm, double *jac, const double *x, const double *u) {
   (void)u;
-  double L = prm[0], lr = prm[1];
-  double theta = x[2], delta = x[3], v = x[4];
-  double by = lr * delta, bx = L;
-  double beta = atan2(by, bx);
-  double dbeta_ddelta = bx / (bx * bx + by * by) * lr;
-  double domega_ddelta =
-      v / L * (-sin(beta) * tan(delta) * dbeta_ddelta + cos(beta) / (cos(delta) * cos(delta)));
-  double domega_dv = cos(beta) * tan(delta) / L;
-  double stheta = sin(theta + beta), ctheta = cos(theta + beta);
+  double L = prm[0];
+  double v = x[4];
+  double sb, cb, tand, s_tb, c_tb, cd, dbeta;
+  bicycle5_trig(prm, x, &sb, &cb, &tand, &s_tb, &c_tb, &cd, &dbeta);
+  double domega_ddelta = v / L * (-sb * tand * dbeta + cb / (cd * cd));
+  double domega_dv = cb * tand / L;
   const int n = 5;
   memset(jac, 0, sizeof(double) * 5 * 7);
 #define J(i, j) jac[(i) + n * (j)]
-  J(0, 2) = -v * stheta;
-  J(0, 3) = -v * stheta * dbeta_ddelta;
-  J(0, 4) = ctheta;
-  J(1, 2) = v * ctheta;
-  J(1, 3) = v * ctheta * dbeta_ddelta;
-  J(1, 4) = stheta;
+  J(0, 2) = -v * s_tb;
+  J(0, 3) = -v * s_tb * dbeta;
+  J(0, 4) = c_tb;
+  J(1, 2) = v * c_tb;
+  J(1, 3) = v * c_tb * dbeta;
+  J(1, 4) = s_tb;
   J(2, 3) = domega_ddelta;
   J(2, 4) = domega_dv;
   J(3, 6) = 1.0; /* d delta' / d u1 */
