@@ -22,13 +22,14 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
 N_INST = 8
-UNITS = [("capi", "capi.cu", []), ("tvlqr", "tvlqr.cu", [])] + \
+UNITS = [("capi", "capi.cu", []), ("tvlqr", "tvlqr.cu", []), ("facade", "altro_solver.cpp", [])] + \
         [(f"solve_inst_{g}", "solve_inst.cu", [f"-DALTRO_INST={g}"]) for g in range(N_INST)]
 
 
 def _deps():
     return glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
-        [os.path.join(HERE, "..", "include", "altro_b200.h")]
+        [os.path.join(HERE, "..", "include", "altro_b200.h"),
+         os.path.join(HERE, "..", "include", "altro", "altro_solver.hpp")]
 
 
 def _compile(unit, verbose):
@@ -54,7 +55,7 @@ def build(verbose=False, jobs=None):
     only = os.environ.get("ALTRO_ONLY")
     units = UNITS
     if only:
-        keep = {f"solve_inst_{g}" for g in only.split(",")} | {"capi", "tvlqr"}
+        keep = {f"solve_inst_{g}" for g in only.split(",")} | {"capi", "tvlqr", "facade"}
         for name, src, defs in UNITS:
             if name not in keep and os.path.exists(os.path.join(OBJ, name + ".o")):
                 os.utime(os.path.join(OBJ, name + ".o"))

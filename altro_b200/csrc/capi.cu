@@ -906,6 +906,36 @@ int altro_b200_solve_async(altro_b200_solver* s) {  // altro_solver.cpp:257-260
   return ALTRO_B200_NO_ERROR;
 }
 
+static int run_host_op(altro_b200_solver* s, int op, double* cost_out) {
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;
+  CUDA_OK(cudaSetDevice(s->device));
+  solve_launcher L = find_launcher(s->model, s->n, s->m, s->params);
+  if (!L) return ALTRO_B200_ERR_UNSUPPORTED;
+  DeviceProblem P;
+  fill_device_problem(s, P);
+  s->ph.op = op;
+  s->ph.cost_out = cost_out;
+  int e = L(P, s->con_h.ncon > 0, s->stream, &s->ph);
+  s->ph.op = OP_SOLVE;
+  s->launches++;
+  if (e) return ALTRO_B200_ERR_NO_DEVICE;
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_open_loop_rollout(altro_b200_solver* s) {  // altro_solver.cpp:253
+  return run_host_op(s, OP_OPEN_LOOP_ROLLOUT, nullptr);
+}
+
+int altro_b200_calc_cost(altro_b200_solver* s, double* cost) {  // altro_solver.cpp:313
+  if (!cost) return ALTRO_B200_INVALID_POINTER;
+  int e = run_host_op(s, OP_CALC_COST, s ? s->phi_eval : nullptr);
+  if (e) return e;
+  CUDA_OK(cudaMemcpyAsync(cost, s->phi_eval, sizeof(double) * (size_t)s->B, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_OK(cudaStreamSynchronize(s->stream));
+  return ALTRO_B200_NO_ERROR;
+}
+
 int altro_b200_set_solve_mode(altro_b200_solver* s, int mode) {
   if (!s) return ALTRO_B200_INVALID_POINTER;
   if (mode != 0 && mode != 1) return ALTRO_B200_BAD_INDEX;

@@ -120,6 +120,20 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
 
 template <class Model>
 static int launch_solve(const DeviceProblem& P, int has_con, cudaStream_t st, PhaseHost* host) {
+  if (host && host->op == OP_OPEN_LOOP_ROLLOUT) {
+    if (has_con)
+      k_open_loop_rollout<Model, true><<<(P.B + 31) / 32, 32, 0, st>>>(P);
+    else
+      k_open_loop_rollout<Model, false><<<(P.B + 31) / 32, 32, 0, st>>>(P);
+    return (int)cudaGetLastError();
+  }
+  if (host && host->op == OP_CALC_COST) {
+    if (has_con)
+      k_calc_cost<Model, true><<<(P.B + 31) / 32, 32, 0, st>>>(P, host->cost_out);
+    else
+      k_calc_cost<Model, false><<<(P.B + 31) / 32, 32, 0, st>>>(P, host->cost_out);
+    return (int)cudaGetLastError();
+  }
   if (host) return has_con ? run_phased<Model, true>(P, st, host) : run_phased<Model, false>(P, st, host);
   const int threads = 32;  // one warp per CTA: 32 consecutive problems
   const int blocks = (P.B + threads - 1) / threads;

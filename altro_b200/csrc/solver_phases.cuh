@@ -334,4 +334,50 @@ __global__ void __launch_bounds__(128) k_phase_decide(const DeviceProblem P, con
   P.flags[b] = f;
 }
 
+// ALTROSolver::OpenLoopRollout (solver.cpp:116-131): x_[k+1] = f(x_[k], u_[k]) from the initial state
+template <class Model, bool CON>
+__global__ void __launch_bounds__(32) k_open_loop_rollout(const DeviceProblem P) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.B) return;
+  TrajSolver<Model, CON> s(P, b);
+  constexpr int n = Model::n, m = Model::m;
+  double x[n], u[m], xn[n];
+  load_block<n>(P.x0 + b, P.Bp, 0, x);
+  for (int k = 0; k < P.N; ++k) {
+    load_block<m>(P.u + b, P.Bp, k, u);
+    s.dynamics(k, x, u, xn);
+    store_block<n>(P.x + b, P.Bp, k, x);
+#pragma unroll
+    for (int i = 0; i < n; ++i) x[i] = xn[i];
+  }
+  store_block<n>(P.x + b, P.Bp, P.N, x);
+}
+
+// ALTROSolver::CalcCost (solver.cpp:163-174): sum_k cost(k) incl. the AL terms at the working
+// trajectory; refreshes the projected duals like the reference does.
+template <class Model, bool CON>
+__global__ void __launch_bounds__(32) k_calc_cost(const DeviceProblem P, double* out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.B) return;
+  TrajSolver<Model, CON> s(P, b);
+  s.rho = CON ? P.rho[b] : 1.0;
+  constexpr int n = Model::n, m = Model::m;
+  double cost = 0.0;
+  for (int k = 0; k <= P.N; ++k) {
+    const bool terminal = (k == P.N);
+    double x[n], u[m], q[n], r[m];
+    load_block<n>(P.x + b, P.Bp, k, x);
+    load_block<n>(P.q + b, P.Bp, k, q);
+    if (!terminal) {
+      load_block<m>(P.u + b, P.Bp, k, u);
+      load_block<m>(P.r + b, P.Bp, k, r);
+    } else {
+#pragma unroll
+      for (int i = 0; i < m; ++i) u[i] = 0.0;
+    }
+    cost += s.stage_cost(k, x, u, q, r, terminal) + s.al_terms(k, x, u, terminal, false, nullptr, nullptr);
+  }
+  out[b] = cost;
+}
+
 }  // namespace altro_b200

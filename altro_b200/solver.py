@@ -87,7 +87,9 @@ def load_library():
         L.altro_b200_set_input.argtypes = [vp, dptr, C.c_int, C.c_int, C.c_int]
         L.altro_b200_set_state.argtypes = [vp, dptr, C.c_int, C.c_int, C.c_int]
         L.altro_b200_set_options.argtypes = [vp, C.POINTER(Options)]
-        for f in ("reset_duals", "reset_trajectory", "shift_trajectory", "solve", "solve_async", "synchronize"):
+        L.altro_b200_calc_cost.argtypes = [vp, dptr]
+        for f in ("reset_duals", "reset_trajectory", "shift_trajectory", "solve", "solve_async", "synchronize",
+                  "open_loop_rollout"):
             getattr(L, "altro_b200_" + f).argtypes = [vp]
         for f in ("get_states", "get_inputs", "get_dual_dynamics", "get_feedback_gains",
                   "get_feedforward_gains", "get_final_objective", "get_stationarity",
@@ -280,6 +282,12 @@ class BatchSolver:
 
     def ShiftTrajectory(self):
         self._ck(self.L.altro_b200_shift_trajectory(self.h), "ShiftTrajectory")
+
+    def OpenLoopRollout(self):
+        self._ck(self.L.altro_b200_open_loop_rollout(self.h), "OpenLoopRollout")
+
+    def CalcCost(self):
+        return self._get("calc_cost", (self.B,))
 
     # ---- solve
     def Solve(self):

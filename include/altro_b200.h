@@ -209,6 +209,11 @@ int altro_b200_shift_trajectory(altro_b200_solver *s); /* ShiftTrajectory, altro
  * batch be re-solved from the same starting point without a host round trip) */
 int altro_b200_reset_trajectory(altro_b200_solver *s);
 
+/* OpenLoopRollout (altro_solver.cpp:253): x_[k+1] = f(x_[k], u_[k]) from the initial state */
+int altro_b200_open_loop_rollout(altro_b200_solver *s);
+/* CalcCost (altro_solver.cpp:313): total cost incl. AL terms of the working trajectory, [B] */
+int altro_b200_calc_cost(altro_b200_solver *s, double *cost);
+
 /* Solve() for all B problems: launches the kernel sequence on the handle's stream and waits. */
 int altro_b200_solve(altro_b200_solver *s);
 int altro_b200_solve_async(altro_b200_solver *s); /* no wait; use altro_b200_synchronize */
