@@ -29,9 +29,22 @@ using namespace altro_b200;
   } while (0)
 
 // ------------------------------------------------------------------ layout kernels
-// dst[j * ld + b] = src[b * W + j]   (problem-major -> problem-fastest), 32x32 smem tiles
-__global__ void k_pm_to_pf(const double* __restrict__ src, int B, long W, double* __restrict__ dst,
-                           long ld) {
+// One field of a record stream (device_problem.h) as the layout kernels see it: element (k, e) of
+// problem b lives at p[(b / 32) * GS + k * R + e * 32 + b % 32]; a flat per-problem index
+// j = k * E + e enumerates the elements the way the host's problem-major arrays do.
+struct FieldView {
+  double* p;
+  int E;
+  long R, GS;
+};
+__device__ __forceinline__ long fv_index(const FieldView& f, long j, int b) {
+  const long k = j / f.E;
+  const int e = (int)(j - k * f.E);
+  return (long)(b >> 5) * f.GS + k * f.R + (long)e * 32 + (b & 31);
+}
+
+// dst(j, b) = src[b * W + j]   (host problem-major -> knot records), 32x32 smem tiles
+__global__ void k_pm_to_pf(const double* __restrict__ src, int B, long W, FieldView dst) {
   __shared__ double tile[32][33];
   const long j0 = (long)blockIdx.x * 32;
   const int b0 = blockIdx.y * 32;
@@ -44,20 +57,19 @@ __global__ void k_pm_to_pf(const double* __restrict__ src, int B, long W, double
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const long j = j0 + r;
     const int bb = b0 + threadIdx.x;
-    if (bb < B && j < W) dst[j * ld + bb] = tile[threadIdx.x][r];
+    if (bb < B && j < W) dst.p[fv_index(dst, j, bb)] = tile[threadIdx.x][r];
   }
 }
 
-// dst[b * W + j] = src[j * ld + b]   (problem-fastest -> problem-major)
-__global__ void k_pf_to_pm(const double* __restrict__ src, int B, long W, double* __restrict__ dst,
-                           long ld) {
+// dst[b * W + j] = src(j, b)   (knot records -> host problem-major)
+__global__ void k_pf_to_pm(FieldView src, int B, long W, double* __restrict__ dst) {
   __shared__ double tile[32][33];
   const long j0 = (long)blockIdx.x * 32;
   const int b0 = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const long j = j0 + r;
     const int bb = b0 + threadIdx.x;
-    if (bb < B && j < W) tile[r][threadIdx.x] = src[j * ld + bb];
+    if (bb < B && j < W) tile[r][threadIdx.x] = src.p[fv_index(src, j, bb)];
   }
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -67,12 +79,24 @@ __global__ void k_pf_to_pm(const double* __restrict__ src, int B, long W, double
   }
 }
 
-// dst[j * ld + b] = src[j]  for all b   (broadcast a shared row set to every problem)
-__global__ void k_broadcast(const double* __restrict__ src, int B, long W, double* __restrict__ dst,
-                            long ld) {
+// dst(j, b) = src[j]  for all b   (broadcast a shared row set to every problem)
+__global__ void k_broadcast(const double* __restrict__ src, int B, long W, FieldView dst) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  for (long j = blockIdx.y; j < W; j += gridDim.y) dst[j * ld + b] = src[j];
+  for (long j = blockIdx.y; j < W; j += gridDim.y) dst.p[fv_index(dst, j, b)] = src[j];
+}
+
+// dst(j, b) = src(j, b)  (device-to-device copy between two fields of the same width)
+__global__ void k_copy_field(FieldView src, FieldView dst, int B, long W) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  for (long j = blockIdx.y; j < W; j += gridDim.y) dst.p[fv_index(dst, j, b)] = src.p[fv_index(src, j, b)];
+}
+
+__global__ void k_fill_field(FieldView dst, int B, long W, double v) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  for (long j = blockIdx.y; j < W; j += gridDim.y) dst.p[fv_index(dst, j, b)] = v;
 }
 
 __global__ void k_fill(double* dst, long count, double v) {
@@ -85,11 +109,11 @@ __global__ void k_fill(double* dst, long count, double v) {
 // c = 1/2 xref' Qd xref (+ 1/2 uref' Rd uref for k < N).
 // ref_mode 0: xref [n], uref [m] shared; 1: per problem, problem-major [B][n]/[B][m];
 // 2: window tables xtab [T][n], utab [T][m] with row = offsets[b] + k.
-__global__ void k_lqr_cost(int n, int m, int N, int B, long ld, int k0, int k1,
+__global__ void k_lqr_cost(int n, int m, int N, int B, int k0, int k1,
                            const double* __restrict__ Qd, const double* __restrict__ Rd,
                            const double* __restrict__ xref, const double* __restrict__ uref,
-                           int ref_mode, const int* __restrict__ offsets, double* q, double* r,
-                           double* c) {
+                           int ref_mode, const int* __restrict__ offsets, FieldView q, FieldView r,
+                           FieldView c) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   for (int k = k0 + blockIdx.y; k < k1; k += gridDim.y) {
@@ -106,19 +130,19 @@ __global__ void k_lqr_cost(int n, int m, int N, int B, long ld, int k0, int k1,
     double cc = 0.0;
     for (int i = 0; i < n; ++i) {
       const double w = Qd[k * n + i];
-      q[((long)k * n + i) * ld + b] = -(w * xr[i]);
+      q.p[fv_index(q, (long)k * n + i, b)] = -(w * xr[i]);
       cc += (0.5 * xr[i]) * w * xr[i];
     }
     if (k < N) {
       double cu = 0.0;
       for (int i = 0; i < m; ++i) {
         const double w = Rd[k * m + i];
-        r[((long)k * m + i) * ld + b] = -(w * ur[i]);
+        r.p[fv_index(r, (long)k * m + i, b)] = -(w * ur[i]);
         cu += (0.5 * ur[i]) * w * ur[i];
       }
       cc += cu;
     }
-    c[(long)k * ld + b] = cc;
+    c.p[fv_index(c, k, b)] = cc;
   }
 }
 
@@ -128,13 +152,15 @@ __global__ void k_add_int(int* v, int B, int add) {
 }
 
 // ShiftTrajectory (altro_solver.cpp:283-293): x_[k] = x_[k+1] for k < N, u_[k] = u_[k+1] for k < N-1
-__global__ void k_shift(int n, int m, int N, int B, long ld, double* x, double* u) {
+__global__ void k_shift(int n, int m, int N, int B, FieldView x, FieldView u) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   for (int k = 0; k < N; ++k) {
-    for (int i = 0; i < n; ++i) x[((long)k * n + i) * ld + b] = x[((long)(k + 1) * n + i) * ld + b];
+    for (int i = 0; i < n; ++i)
+      x.p[fv_index(x, (long)k * n + i, b)] = x.p[fv_index(x, (long)(k + 1) * n + i, b)];
     if (k < N - 1)
-      for (int i = 0; i < m; ++i) u[((long)k * m + i) * ld + b] = u[((long)(k + 1) * m + i) * ld + b];
+      for (int i = 0; i < m; ++i)
+        u.p[fv_index(u, (long)k * m + i, b)] = u.p[fv_index(u, (long)(k + 1) * m + i, b)];
   }
 }
 
@@ -152,7 +178,13 @@ struct altro_b200_solver {
   long bytes = 0;
   altro_b200_options opts;
 
-  // device arrays (problem-fastest)
+  // device arrays: knot records (device_problem.h); every per-knot field below points into `rec`
+  double* rec = nullptr;
+  long R = 0, GS = 0;    // knot / group stride of the main record stream (doubles)
+  double* zrec = nullptr;
+  long Rz = 0, GSz = 0;  // dual record stream
+  long Rs = 0;           // candidate-slot record stream
+  int G = 0;             // groups of 32 problems
   double *Qd = nullptr, *Rd = nullptr, *lin = nullptr;
   double *q = nullptr, *r = nullptr, *c = nullptr, *x0 = nullptr;
   double *xbar = nullptr, *ubar = nullptr, *x = nullptr, *u = nullptr, *y = nullptr;
@@ -215,34 +247,41 @@ static int ensure_stage(altro_b200_solver* s, long count) {
   return 0;
 }
 
-// host problem-major [B][W] -> device problem-fastest rows starting at dst
-static int upload_pm(altro_b200_solver* s, const double* host, long W, double* dst) {
+// view of knots [k0, ...) of a per-knot field with E rows
+static FieldView fview(const altro_b200_solver* s, double* field, int E, int k0 = 0) {
+  return FieldView{field + (long)k0 * s->R, E, s->R, s->GS};
+}
+// view of a per-group block that is not per knot: [G][E][32]
+static FieldView gview(double* base, int E) { return FieldView{base, E, 0, (long)E * 32}; }
+
+// host problem-major [B][W] -> device field
+static int upload_pm(altro_b200_solver* s, const double* host, long W, FieldView dst) {
   int e = ensure_stage(s, (long)s->B * W);
   if (e) return e;
   CUDA_OK(cudaMemcpyAsync(s->stage, host, (size_t)s->B * W * 8, cudaMemcpyHostToDevice, s->stream));
   dim3 grid((unsigned)((W + 31) / 32), (unsigned)((s->B + 31) / 32));
-  k_pm_to_pf<<<grid, dim3(32, 8), 0, s->stream>>>(s->stage, s->B, W, dst, s->Bp);
+  k_pm_to_pf<<<grid, dim3(32, 8), 0, s->stream>>>(s->stage, s->B, W, dst);
   s->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
 }
 // host shared [W] -> broadcast to every problem
-static int upload_shared(altro_b200_solver* s, const double* host, long W, double* dst) {
+static int upload_shared(altro_b200_solver* s, const double* host, long W, FieldView dst) {
   int e = ensure_stage(s, W);
   if (e) return e;
   CUDA_OK(cudaMemcpyAsync(s->stage, host, (size_t)W * 8, cudaMemcpyHostToDevice, s->stream));
   dim3 grid((unsigned)((s->B + 127) / 128), (unsigned)(W < 1024 ? W : 1024));
-  k_broadcast<<<grid, 128, 0, s->stream>>>(s->stage, s->B, W, dst, s->Bp);
+  k_broadcast<<<grid, 128, 0, s->stream>>>(s->stage, s->B, W, dst);
   s->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
 }
-// device problem-fastest rows -> host problem-major [B][W]
-static int download_pm(altro_b200_solver* s, const double* src, long W, double* host) {
+// device field -> host problem-major [B][W]
+static int download_pm(altro_b200_solver* s, FieldView src, long W, double* host) {
   int e = ensure_stage(s, (long)s->B * W);
   if (e) return e;
   dim3 grid((unsigned)((W + 31) / 32), (unsigned)((s->B + 31) / 32));
-  k_pf_to_pm<<<grid, dim3(32, 8), 0, s->stream>>>(src, s->B, W, s->stage, s->Bp);
+  k_pf_to_pm<<<grid, dim3(32, 8), 0, s->stream>>>(src, s->B, W, s->stage);
   s->launches++;
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaMemcpyAsync(host, s->stage, (size_t)s->B * W * 8, cudaMemcpyDeviceToHost, s->stream));
@@ -410,24 +449,39 @@ int altro_b200_set_dimension(altro_b200_solver* s, int n, int m) {  // altro_sol
   s->lin_h.assign((size_t)N * (n * n + n * m + n), 0.0);
   DALLOC(s, s->Qd, (N + 1) * n);
   DALLOC(s, s->Rd, N * m);
-  DALLOC(s, s->q, (N + 1) * n * S);
-  DALLOC(s, s->r, N * m * S);
-  DALLOC(s, s->c, (N + 1) * S);
-  DALLOC(s, s->x0, n * S);
-  DALLOC(s, s->xbar, (N + 1) * n * S);
-  DALLOC(s, s->ubar, N * m * S);
-  DALLOC(s, s->x, (N + 1) * n * S);
-  DALLOC(s, s->u, N * m * S);
-  DALLOC(s, s->u_init, N * m * S);
-  DALLOC(s, s->y, (N + 1) * n * S);
-  DALLOC(s, s->A, N * n * n * S);
-  DALLOC(s, s->Bm, N * n * m * S);
-  DALLOC(s, s->lx, (N + 1) * n * S);
-  DALLOC(s, s->lu, N * m * S);
-  DALLOC(s, s->K, N * m * n * S);
-  DALLOC(s, s->d, N * m * S);
-  DALLOC(s, s->P, (N + 1) * n * n * S);
-  DALLOC(s, s->p, (N + 1) * n * S);
+  {
+    // main record stream; row order documented in device_problem.h
+    s->G = (int)(S / 32);
+    const long rows = 2L * (n + m) + (n + m + 1) + (m * n + m) + (n * n + n * m + n + m) + n +
+                      (n * n + n) + m;
+    s->R = rows * 32;
+    s->GS = (N + 1) * s->R;
+    DALLOC(s, s->rec, (long)s->G * s->GS);
+    long row = 0;
+    auto take = [&](int nrows) {
+      double* ptr = s->rec + row * 32;
+      row += nrows;
+      return ptr;
+    };
+    s->xbar = take(n);
+    s->ubar = take(m);
+    s->q = take(n);
+    s->r = take(m);
+    s->c = take(1);
+    s->K = take(m * n);
+    s->d = take(m);
+    s->x = take(n);
+    s->u = take(m);
+    s->A = take(n * n);
+    s->Bm = take(n * m);
+    s->lx = take(n);
+    s->lu = take(m);
+    s->y = take(n);
+    s->P = take(n * n);
+    s->p = take(n);
+    s->u_init = take(m);
+    DALLOC(s, s->x0, (long)s->G * n * 32);
+  }
   DALLOC(s, s->rho, S);
   DALLOC(s, s->status, S);
   DALLOC(s, s->iters, S);
@@ -453,6 +507,15 @@ int altro_b200_set_dimension(altro_b200_solver* s, int n, int m) {  // altro_sol
   DALLOC(s, s->list_aux, S);
   DALLOC(s, s->counters, 8);
   memset(&s->ph, 0, sizeof(s->ph));
+  {  // device limits that size the staging rings of the sequential sweeps (solve_inst.cu)
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, s->device);
+    s->ph.num_sms = v > 0 ? v : 148;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, s->device);
+    s->ph.smem_per_sm = v > 0 ? (size_t)v : (size_t)228 * 1024;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device);
+    s->ph.smem_per_cta = v > 0 ? (size_t)v : (size_t)227 * 1024;
+  }
   CUDA_OK(cudaMallocHost((void**)&s->ph.h_counters, 8 * sizeof(int)));
   CUDA_OK(cudaEventCreate(&s->ph.ev0));
   CUDA_OK(cudaEventCreate(&s->ph.ev1));
@@ -530,8 +593,9 @@ int altro_b200_set_lqr_cost(altro_b200_solver* s, const double* Qd, const double
   CUDA_OK(cudaMemcpyAsync(ur, uref, sizeof(double) * (per_problem ? (size_t)s->B * m : m),
                           cudaMemcpyHostToDevice, s->stream));
   dim3 grid((s->B + 127) / 128, (unsigned)(k_stop - k_start));
-  k_lqr_cost<<<grid, 128, 0, s->stream>>>(n, m, s->N, s->B, s->Bp, k_start, k_stop, s->Qd, s->Rd,
-                                          xr, ur, per_problem ? 1 : 0, nullptr, s->q, s->r, s->c);
+  k_lqr_cost<<<grid, 128, 0, s->stream>>>(n, m, s->N, s->B, k_start, k_stop, s->Qd, s->Rd, xr, ur,
+                                          per_problem ? 1 : 0, nullptr, fview(s, s->q, n),
+                                          fview(s, s->r, m), fview(s, s->c, 1));
   s->launches++;
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(s->stream));
@@ -541,8 +605,9 @@ int altro_b200_set_lqr_cost(altro_b200_solver* s, const double* Qd, const double
 
 static int apply_window(altro_b200_solver* s) {
   dim3 grid((s->B + 127) / 128, (unsigned)(s->N + 1));
-  k_lqr_cost<<<grid, 128, 0, s->stream>>>(s->n, s->m, s->N, s->B, s->Bp, 0, s->N + 1, s->Qd, s->Rd,
-                                          s->xtab, s->utab, 2, s->offsets, s->q, s->r, s->c);
+  k_lqr_cost<<<grid, 128, 0, s->stream>>>(s->n, s->m, s->N, s->B, 0, s->N + 1, s->Qd, s->Rd, s->xtab,
+                                          s->utab, 2, s->offsets, fview(s, s->q, s->n),
+                                          fview(s, s->r, s->m), fview(s, s->c, 1));
   s->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -588,36 +653,36 @@ static int set_linear_terms(altro_b200_solver* s, const double* q, const double*
   const int nku = (k1 > s->N ? s->N : k1) - k0;  // knots that carry an input
   int e = 0;
   if (per_problem) {
-    if (q) e = upload_pm(s, q, (long)nk * n, s->q + (long)k0 * n * s->Bp);
+    if (q) e = upload_pm(s, q, (long)nk * n, fview(s, s->q, n, k0));
     if (!e && r && nku > 0) {
       if (nku == nk) {
-        e = upload_pm(s, r, (long)nk * m, s->r + (long)k0 * m * s->Bp);
+        e = upload_pm(s, r, (long)nk * m, fview(s, s->r, m, k0));
       } else {  // host rows are [B][nk][m] but only nku of them exist on the device
         std::vector<double> tmp((size_t)s->B * nku * m);
         for (int b = 0; b < s->B; ++b)
           memcpy(&tmp[(size_t)b * nku * m], r + (size_t)b * nk * m, sizeof(double) * nku * m);
-        e = upload_pm(s, tmp.data(), (long)nku * m, s->r + (long)k0 * m * s->Bp);
+        e = upload_pm(s, tmp.data(), (long)nku * m, fview(s, s->r, m, k0));
         if (!e) CUDA_OK(cudaStreamSynchronize(s->stream));
       }
     }
-    if (!e && c) e = upload_pm(s, c, nk, s->c + (long)k0 * s->Bp);
+    if (!e && c) e = upload_pm(s, c, nk, fview(s, s->c, 1, k0));
   } else {
     std::vector<double> tmp;
     if (q) {
       tmp.resize((size_t)nk * n);
       for (int k = 0; k < nk; ++k) memcpy(&tmp[(size_t)k * n], q, sizeof(double) * n);
-      e = upload_shared(s, tmp.data(), (long)nk * n, s->q + (long)k0 * n * s->Bp);
+      e = upload_shared(s, tmp.data(), (long)nk * n, fview(s, s->q, n, k0));
       if (!e) CUDA_OK(cudaStreamSynchronize(s->stream));
     }
     if (!e && r && nku > 0) {
       tmp.resize((size_t)nku * m);
       for (int k = 0; k < nku; ++k) memcpy(&tmp[(size_t)k * m], r, sizeof(double) * m);
-      e = upload_shared(s, tmp.data(), (long)nku * m, s->r + (long)k0 * m * s->Bp);
+      e = upload_shared(s, tmp.data(), (long)nku * m, fview(s, s->r, m, k0));
       if (!e) CUDA_OK(cudaStreamSynchronize(s->stream));
     }
     if (!e && c) {
       tmp.assign((size_t)nk, c[0]);
-      e = upload_shared(s, tmp.data(), nk, s->c + (long)k0 * s->Bp);
+      e = upload_shared(s, tmp.data(), nk, fview(s, s->c, 1, k0));
       if (!e) CUDA_OK(cudaStreamSynchronize(s->stream));
     }
   }
@@ -679,7 +744,7 @@ int altro_b200_set_constraint(altro_b200_solver* s, int cone, int dim, const int
   if (off_b) {
     double* dptr = nullptr;
     DALLOC(s, dptr, (long)dim * s->Bp);
-    e = upload_pm(s, off_b, dim, dptr);
+    e = upload_pm(s, off_b, dim, gview(dptr, dim));
     if (e) return e;
     CUDA_OK(cudaStreamSynchronize(s->stream));
     c.off_per_problem = 1;
@@ -694,7 +759,7 @@ int altro_b200_set_initial_state(altro_b200_solver* s, const double* x0, int per
   if (!s || !x0) return ALTRO_B200_INVALID_POINTER;
   if (!s->dims_set) return ALTRO_B200_DIMENSION_UNKNOWN;
   CUDA_OK(cudaSetDevice(s->device));
-  int e = per_problem ? upload_pm(s, x0, s->n, s->x0) : upload_shared(s, x0, s->n, s->x0);
+  int e = per_problem ? upload_pm(s, x0, s->n, gview(s->x0, s->n)) : upload_shared(s, x0, s->n, gview(s->x0, s->n));
   if (e) return e;
   CUDA_OK(cudaStreamSynchronize(s->stream));
   return ALTRO_B200_NO_ERROR;
@@ -711,8 +776,11 @@ int altro_b200_initialize(altro_b200_solver* s) {  // altro_solver.cpp:225-229
   CUDA_OK(cudaSetDevice(s->device));
   const long rows = s->con_h.rows;
   if (rows > 0) {
-    DALLOC(s, s->z, (long)(s->N + 1) * rows * s->Bp);
-    DALLOC(s, s->zest, (long)(s->N + 1) * rows * s->Bp);
+    s->Rz = 2 * rows * 32;
+    s->GSz = (long)(s->N + 1) * s->Rz;
+    DALLOC(s, s->zrec, (long)s->G * s->GSz);
+    s->z = s->zrec;
+    s->zest = s->zrec + rows * 32;
     DALLOC(s, s->con_d, 1);
     CUDA_OK(cudaMemcpyAsync(s->con_d, &s->con_h, sizeof(ConTable), cudaMemcpyHostToDevice, s->stream));
   }
@@ -724,8 +792,9 @@ int altro_b200_initialize(altro_b200_solver* s) {  // altro_solver.cpp:225-229
   s->launches++;
   CUDA_OK(cudaGetLastError());
   // candidate slots of the speculative line search
-  DALLOC(s, s->xs, (long)s->nslots * (s->N + 1) * s->n * s->Bp);
-  DALLOC(s, s->us, (long)s->nslots * s->N * s->m * s->Bp);
+  s->Rs = (long)(s->n + s->m) * 32;
+  DALLOC(s, s->xs, (long)s->nslots * s->G * (s->N + 1) * s->Rs);
+  s->us = s->xs + (long)s->n * 32;
   DALLOC(s, s->phi_s, (long)s->nslots * s->Bp);
   CUDA_OK(cudaStreamSynchronize(s->stream));
   s->initialized = true;
@@ -735,7 +804,7 @@ int altro_b200_initialize(altro_b200_solver* s) {  // altro_solver.cpp:225-229
 static int set_traj(altro_b200_solver* s, const double* v, int layout, int k0, int k1, int E,
                     double* dst) {
   const int nk = k1 - k0;
-  double* base = dst + (long)k0 * E * s->Bp;
+  const FieldView base = fview(s, dst, E, k0);
   int e = 0;
   if (layout == 2) {
     e = upload_pm(s, v, (long)nk * E, base);
@@ -759,8 +828,12 @@ int altro_b200_set_input(altro_b200_solver* s, const double* u, int layout, int 
   if (e) return e;
   e = set_traj(s, u, layout, k_start, k_stop, s->m, s->u);
   if (e) return e;
-  const size_t off = (size_t)k_start * s->m * s->Bp, cnt = (size_t)(k_stop - k_start) * s->m * s->Bp;
-  CUDA_OK(cudaMemcpyAsync(s->u_init + off, s->u + off, cnt * 8, cudaMemcpyDeviceToDevice, s->stream));
+  const long W = (long)(k_stop - k_start) * s->m;
+  dim3 grid((unsigned)((s->B + 127) / 128), (unsigned)(W < 1024 ? W : 1024));
+  k_copy_field<<<grid, 128, 0, s->stream>>>(fview(s, s->u, s->m, k_start), fview(s, s->u_init, s->m, k_start),
+                                            s->B, W);
+  s->launches++;
+  CUDA_OK(cudaGetLastError());
   return ALTRO_B200_NO_ERROR;
 }
 
@@ -768,8 +841,11 @@ int altro_b200_reset_trajectory(altro_b200_solver* s) {
   if (!s) return ALTRO_B200_INVALID_POINTER;
   if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;
   CUDA_OK(cudaSetDevice(s->device));
-  CUDA_OK(cudaMemcpyAsync(s->u, s->u_init, (size_t)s->N * s->m * s->Bp * 8, cudaMemcpyDeviceToDevice,
-                          s->stream));
+  const long W = (long)s->N * s->m;
+  dim3 grid((unsigned)((s->B + 127) / 128), (unsigned)(W < 1024 ? W : 1024));
+  k_copy_field<<<grid, 128, 0, s->stream>>>(fview(s, s->u_init, s->m), fview(s, s->u, s->m), s->B, W);
+  s->launches++;
+  CUDA_OK(cudaGetLastError());
   return ALTRO_B200_NO_ERROR;
 }
 
@@ -793,7 +869,7 @@ int altro_b200_reset_duals(altro_b200_solver* s) {
   if (!s) return ALTRO_B200_INVALID_POINTER;
   if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;
   CUDA_OK(cudaSetDevice(s->device));
-  if (s->z) CUDA_OK(cudaMemsetAsync(s->z, 0, (size_t)(s->N + 1) * s->con_h.rows * s->Bp * 8, s->stream));
+  if (s->zrec) CUDA_OK(cudaMemsetAsync(s->zrec, 0, (size_t)s->G * s->GSz * 8, s->stream));
   k_fill<<<64, 256, 0, s->stream>>>(s->rho, s->Bp, 1.0);
   s->launches++;
   CUDA_OK(cudaGetLastError());
@@ -804,7 +880,8 @@ int altro_b200_shift_trajectory(altro_b200_solver* s) {
   if (!s) return ALTRO_B200_INVALID_POINTER;
   if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;
   CUDA_OK(cudaSetDevice(s->device));
-  k_shift<<<(s->B + 127) / 128, 128, 0, s->stream>>>(s->n, s->m, s->N, s->B, s->Bp, s->x, s->u);
+  k_shift<<<(s->B + 127) / 128, 128, 0, s->stream>>>(s->n, s->m, s->N, s->B, fview(s, s->x, s->n),
+                                                     fview(s, s->u, s->m));
   s->launches++;
   CUDA_OK(cudaGetLastError());
   return ALTRO_B200_NO_ERROR;
@@ -815,6 +892,12 @@ static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   P.N = s->N;
   P.B = s->B;
   P.Bp = s->Bp;
+  P.G = s->G;
+  P.R = s->R;
+  P.GS = s->GS;
+  P.Rz = s->Rz;
+  P.GSz = s->GSz;
+  P.Rs = s->Rs;
   P.h = s->h;
   memcpy(P.model_params, s->params, sizeof(P.model_params));
   P.lin = s->lin;
@@ -990,18 +1073,18 @@ int altro_b200_solve(altro_b200_solver* s) {
 
 long altro_b200_kernel_launches(const altro_b200_solver* s) { return s ? s->launches : 0; }
 
-#define GETTER_PM(name, field, width_expr)                                 \
+#define GETTER_PM(name, field, rows_expr, width_expr)                                 \
   int name(altro_b200_solver* s, double* out) {                            \
     if (!s || !out) return ALTRO_B200_INVALID_POINTER;                     \
     if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;         \
     CUDA_OK(cudaSetDevice(s->device));                                     \
-    return download_pm(s, s->field, (long)(width_expr), out);              \
+    return download_pm(s, fview(s, s->field, (rows_expr)), (long)(width_expr), out); \
   }
-GETTER_PM(altro_b200_get_states, x, (s->N + 1) * s->n)
-GETTER_PM(altro_b200_get_inputs, u, s->N * s->m)
-GETTER_PM(altro_b200_get_dual_dynamics, y, (s->N + 1) * s->n)
-GETTER_PM(altro_b200_get_feedback_gains, K, s->N * s->m * s->n)
-GETTER_PM(altro_b200_get_feedforward_gains, d, s->N * s->m)
+GETTER_PM(altro_b200_get_states, x, s->n, (s->N + 1) * s->n)
+GETTER_PM(altro_b200_get_inputs, u, s->m, s->N * s->m)
+GETTER_PM(altro_b200_get_dual_dynamics, y, s->n, (s->N + 1) * s->n)
+GETTER_PM(altro_b200_get_feedback_gains, K, s->m * s->n, s->N * s->m * s->n)
+GETTER_PM(altro_b200_get_feedforward_gains, d, s->m, s->N * s->m)
 
 #define GETTER_VEC(name, field, type)                                                       \
   int name(altro_b200_solver* s, type* out) {                                               \

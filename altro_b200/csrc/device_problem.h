@@ -1,11 +1,19 @@
 // device_problem.h -- the batched problem as the kernels see it (plain pointers into HBM).
 //
-// HBM layout (DESIGN.md "Data layout"): structure-of-arrays, PROBLEM INDEX FASTEST.  A field with
-// E doubles per knot point stores element e of knot k of problem b at
-//     field[(k*E + e) * Bp + b]            (Bp = batch padded to a multiple of 32)
-// with blocks column-major inside a knot, i.e. the reference's KnotPointData members
-// (knotpoint_data.hpp:160-233) transposed so that the 32 lanes of a warp -- 32 consecutive
-// problems -- read one contiguous 256-byte row per matrix element.
+// HBM layout (DESIGN.md "Data layout"): KNOT RECORDS.  The batch is cut into groups of 32
+// consecutive problems (one warp); everything a group owns at knot k -- the reference's
+// KnotPointData members (knotpoint_data.hpp:160-233), each block column-major -- is ONE contiguous
+// record of `rows` 256-byte lines, line = one block element for the 32 problems of the group:
+//     element e of field F at knot k of problem b:
+//         F[(b / 32) * GS + k * R + e * 32 + (b % 32)],   R = rows * 32,  GS = (N + 1) * R
+// (F = record buffer + 32 * the field's first row, so all fields share R and GS).  Row order:
+//     xbar ubar | q r c | K d | x u | A B lx lu | y | P p | u_init
+// chosen so that what each sequential sweep reads per knot is one contiguous multi-KB range: the
+// rollout [xbar..d], the phi0 scan [q..B], the d(phi) scan [K..lu] minus [x u], the Riccati sweep
+// [A..lu], the residual kernel [x..y].  A warp therefore streams whole records with one TMA bulk
+// copy (cp.async.bulk) per knot into a shared-memory ring instead of E separate 256-byte pieces
+// Bp*8 bytes apart: measured 6.8 TB/s vs 3.2 TB/s at the 3.5 warps/SM of B = 16384
+// (profiles/r01_microbench_layout.txt).
 #pragma once
 #include "linesearch.cuh"
 
@@ -33,7 +41,7 @@ struct ConSlot {
   int idx[kMaxConDim];
   double scale[kMaxConDim];
   double off[kMaxConDim];
-  const double* off_b;  // [dim][Bp]
+  const double* off_b;  // [G][dim][32]
 };
 
 struct ConTable {
@@ -57,7 +65,11 @@ struct DevOptions {
 
 struct DeviceProblem {
   int N, B;
-  long Bp;  // padded batch = stride between consecutive elements
+  long Bp;  // batch padded to a multiple of 32 (per-problem scalar arrays)
+  int G;    // groups = Bp / 32
+  long R, GS;    // main record stream: knot stride, group stride (doubles)
+  long Rz, GSz;  // dual record stream [group][knot][z rows | z_est rows][32]
+  long Rs;       // candidate-slot record stream [slot][group][knot][x rows | u rows][32]
   float h;
   double model_params[8];
   const double* lin;  // MODEL_LINEAR: per knot [A (n*n) | B (n*m) | f (n)], shared by the batch
@@ -65,11 +77,11 @@ struct DeviceProblem {
   // cost (KnotPointData Q_, R_, q_, r_, c_): diagonal weights shared per knot, linear terms per problem
   const double* Qd;  // [(N+1)*n]
   const double* Rd;  // [N*m]
-  const double* q;   // [(N+1)*n][Bp]
-  const double* r;   // [N*m][Bp]
-  const double* c;   // [(N+1)][Bp]
+  const double* q;   // record field, n rows
+  const double* r;   // record field, m rows
+  const double* c;   // record field, 1 row
 
-  const double* x0;  // [n][Bp]            (SolverImpl::initial_state_)
+  const double* x0;  // [G][n][32]         (SolverImpl::initial_state_)
   double *xbar, *ubar;      // accepted trajectory  (KnotPointData x, u)
   double *x, *u, *y;        // working trajectory   (x_, u_, y_)
   double *A, *Bm;           // dynamics expansion   (A_, B_)
@@ -77,7 +89,7 @@ struct DeviceProblem {
   double *K, *d, *P, *p;    // gains / cost-to-go   (K_, d_, P_, p_)
 
   const ConTable* con;      // device pointer; ncon == 0 when unconstrained
-  double *z, *zest;         // duals z_ and estimates z_est_: [(N+1)*rows][Bp]
+  double *z, *zest;         // duals z_ and estimates z_est_ (dual record stream)
   double* rho;              // penalty rho_ (uniform over knots and constraints): [Bp]
 
   // per-problem results
@@ -97,7 +109,7 @@ struct DeviceProblem {
   // speculative line-search slots: candidate step lengths of one trajectory are rolled out
   // concurrently, each into its own copy of the working trajectory
   int nslots;           // candidates per speculative round (>= 1)
-  double *xs, *us;      // [nslots][(N+1)*n][Bp], [nslots][N*m][Bp]
+  double *xs, *us;      // slot record stream; us = xs + n * 32
   double* phi_s;        // [nslots][Bp] merit value per candidate
   int* sel;             // [Bp] slot holding the working trajectory (-1: the main x, u arrays)
   unsigned long long *stat_acc, *feas_acc;  // [Bp] max-reductions over knots (bit patterns of doubles >= 0)

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstddef>
+
 #include "device_problem.h"
 
 namespace altro_b200 {
@@ -22,6 +24,9 @@ struct PhaseHost {
   double units[PH_COUNT];      // trajectories (or trajectory-knots for PH_EXPAND) processed
   long syncs;                  // host<->device count readbacks
   cudaEvent_t ev0, ev1;
+  // device limits that size the shared-memory staging rings of the sequential sweeps
+  int num_sms;
+  size_t smem_per_sm, smem_per_cta;
 };
 
 // has_constraints selects the AL-enabled instantiation.  host == nullptr: the single persistent

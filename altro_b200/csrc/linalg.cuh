@@ -1,8 +1,8 @@
 // linalg.cuh -- fixed-size dense helpers for the thread-per-trajectory kernels.
 //
 // Every block the Riccati recursion touches is tiny (n <= 12, m <= 4), so each
-// trajectory keeps its blocks in registers of ONE thread and a warp works on 32 consecutive
-// problems of the problem-fastest HBM layout (one coalesced 256-byte row per matrix element).
+// trajectory keeps its blocks in registers of ONE thread and a warp works on the 32 problems of
+// one group of the knot-record HBM layout (one coalesced 256-byte row per matrix element).
 // All matrices are column-major (Eigen's default, which the reference's raw-pointer API exposes:
 // altro_solver.hpp:185) and sizes are template parameters so loops unroll into straight-line
 // DFMA code with no indexing.
@@ -137,44 +137,82 @@ ALTRO_DEV void cholesky_solve(const double* L, double* X) {
   }
 }
 
-// Problem-fastest field access: element e of knot k of problem b lives at
-// base[(k*E + e) * stride + b]; consecutive lanes (problems) touch consecutive doubles.
+// Knot-record field access (device_problem.h): `base` already points at this problem's lane of
+// the field's first row in knot 0 of its group; knot k is `rec` doubles further, rows of a block
+// are 32 doubles (one 256-byte line holding the 32 problems of the group) apart.
+constexpr int kLanes = 32;
 template <int E>
-ALTRO_DEV void load_block(const double* __restrict__ base, long stride, int k, double* out) {
-  const double* p = base + (long)k * E * stride;
+ALTRO_DEV void load_block(const double* __restrict__ base, long rec, int k, double* out) {
+  const double* p = base + (long)k * rec;
   if constexpr (E <= 4 * kUnrollDim * kUnrollDim) {
 #pragma unroll
-    for (int e = 0; e < E; ++e) out[e] = p[(long)e * stride];
+    for (int e = 0; e < E; ++e) out[e] = p[e * kLanes];
   } else {
 #pragma unroll 8
-    for (int e = 0; e < E; ++e) out[e] = p[(long)e * stride];
+    for (int e = 0; e < E; ++e) out[e] = p[e * kLanes];
   }
 }
 
-// Software prefetch of the E rows of knot k into L1/L2: the sequential sweeps issue it one knot
-// ahead so the dependent chain of a knot never waits on HBM (ncu r01: the un-prefetched sweeps
-// spend 45-95 % of their issue slots in long-scoreboard stalls).  No register cost.
+// Software prefetch of the E rows of knot k into L2 (no register cost): used by the sweeps that
+// do not stage through shared memory.
 template <int E>
-ALTRO_DEV void prefetch_block(const double* __restrict__ base, long stride, int k) {
-  const double* p = base + (long)k * E * stride;
+ALTRO_DEV void prefetch_block(const double* __restrict__ base, long rec, int k) {
+  const double* p = base + (long)k * rec;
   if constexpr (E <= 4 * kUnrollDim * kUnrollDim) {
 #pragma unroll
-    for (int e = 0; e < E; ++e) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + (long)e * stride));
+    for (int e = 0; e < E; ++e) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + e * kLanes));
   } else {
 #pragma unroll 8
-    for (int e = 0; e < E; ++e) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + (long)e * stride));
+    for (int e = 0; e < E; ++e) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + e * kLanes));
   }
 }
 
+// ---- asynchronous staging of the NEXT knots' rows into shared memory (cp.async / LDGSTS).
+// The sequential sweeps are bound by the latency of their per-knot loads (ncu r01 v2: 60-70 % of
+// all stall cycles are long-scoreboard even with an L2 prefetch one knot ahead).  Each lane copies
+// the elements of ITS OWN problem into ITS OWN column of a per-warp ring in shared memory,
+//     ring[stage][element][lane]      (256-byte rows: conflict-free 8-byte accesses)
+// one to three knots ahead, and reads them back with LDS (~30 cycles) when the knot's turn comes.
+// A lane only ever reads what it copied itself, so cp.async.wait_group is the only
+// synchronisation needed -- no barrier -- and compacted (non-contiguous) problem lists work.
+ALTRO_DEV void cp_async_f64(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+ALTRO_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most `pending` (0..2) of the most recent groups are still in flight
+ALTRO_DEV void cp_async_wait(int pending) {
+  if (pending <= 0)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  else if (pending == 1)
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+  else
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+}
+constexpr int kMaxStageDepth = 3;
+
+// stage: st points at this lane's column of one ring stage; `off` = first element row
 template <int E>
-ALTRO_DEV void store_block(double* __restrict__ base, long stride, int k, const double* in) {
-  double* p = base + (long)k * E * stride;
+ALTRO_DEV void stage_block(double* st, int off, const double* __restrict__ base, long rec, int k) {
+  const double* p = base + (long)k * rec;
+#pragma unroll
+  for (int e = 0; e < E; ++e) cp_async_f64(st + (off + e) * 32, p + e * 32);
+}
+template <int E>
+ALTRO_DEV void unstage_block(const double* st, int off, double* out) {
+#pragma unroll
+  for (int e = 0; e < E; ++e) out[e] = st[(off + e) * 32];
+}
+
+template <int E>
+ALTRO_DEV void store_block(double* __restrict__ base, long rec, int k, const double* in) {
+  double* p = base + (long)k * rec;
   if constexpr (E <= 4 * kUnrollDim * kUnrollDim) {
 #pragma unroll
-    for (int e = 0; e < E; ++e) p[(long)e * stride] = in[e];
+    for (int e = 0; e < E; ++e) p[e * kLanes] = in[e];
   } else {
 #pragma unroll 8
-    for (int e = 0; e < E; ++e) p[(long)e * stride] = in[e];
+    for (int e = 0; e < E; ++e) p[e * kLanes] = in[e];
   }
 }
 

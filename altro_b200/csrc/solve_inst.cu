@@ -1,5 +1,7 @@
 // solve_inst.cu -- explicit instantiations of the solve kernel, one group per translation unit
 // (compiled with -DALTRO_INST=<group>) so altro_b200/build.py can compile them in parallel.
+#include <algorithm>
+
 #include "launchers.h"
 #include "solver_phases.cuh"
 
@@ -43,15 +45,39 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
       k_compact<<<1, 1024, 0, st>>>(in, count, dcount, P.flags, mask, out, P.counters, slot, mask2, slot2);
     });
   };
+  // Staging ring of the sequential sweeps (linalg.cuh): depth = knots in flight per warp, as deep
+  // as shared memory allows with every CTA of the launch resident (<= kMaxStageDepth, >= 1).
+  using TS = TrajSolver<Model, CON>;
+  auto ring = [&](int ctas, int stage_elems, int* depth) -> size_t {
+    if (!TS::kStaged) {
+      *depth = 0;
+      return 0;
+    }
+    const size_t stage_bytes = (size_t)stage_elems * 32 * sizeof(double);
+    const int per_sm = (ctas + H->num_sms - 1) / H->num_sms;
+    const size_t budget = std::min<size_t>(H->smem_per_sm / std::max(per_sm, 1), H->smem_per_cta) - 1024;
+    *depth = (int)std::max<size_t>(1, std::min<size_t>(kMaxStageDepth, budget / stage_bytes));
+    return stage_bytes * *depth;
+  };
+  if (TS::kStaged) {
+    const int mx = (int)H->smem_per_cta;
+    cudaFuncSetAttribute(k_phase_backward<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_phase_rollout<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_phase_lsupdate<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  }
   auto rollout = [&](const int* list, int count, const int* dcount, bool spec) {
     const int slots = spec ? P.nslots : 1;
+    int depth;
+    const size_t sm = ring(g32(count) * slots, TS::kStageRollout, &depth);
     timed(PH_ROLLOUT, (double)count * slots, [&] {
-      k_phase_rollout<Model, CON><<<dim3(g32(count), slots), 32, 0, st>>>(P, list, count, dcount, spec);
+      k_phase_rollout<Model, CON><<<dim3(g32(count), slots), 32, sm, st>>>(P, list, count, dcount, spec, depth);
     });
   };
   auto lsupdate = [&](const int* list, int count, const int* dcount, bool spec) {
+    int depth;
+    const size_t sm = ring(g32(count), TS::kStageDphi, &depth);
     timed(PH_LSUPDATE, count, [&] {
-      k_phase_lsupdate<Model, CON><<<g32(count), 32, 0, st>>>(P, list, count, dcount, spec);
+      k_phase_lsupdate<Model, CON><<<g32(count), 32, sm, st>>>(P, list, count, dcount, spec, depth);
     });
   };
 
@@ -66,8 +92,13 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
   const bool backtracking = P.opts.use_backtracking_linesearch != 0;
 
   for (int iter = 0; iter < P.opts.iterations_max && count_iter > 0; ++iter) {
-    timed(PH_BACKWARD, count_iter,
-          [&] { k_phase_backward<Model, CON><<<g32(count_iter), 32, 0, st>>>(P, list_iter, count_iter); });
+    {
+      int depth;
+      const size_t sm = ring(g32(count_iter), TS::kStageMax, &depth);
+      timed(PH_BACKWARD, count_iter, [&] {
+        k_phase_backward<Model, CON><<<g32(count_iter), 32, sm, st>>>(P, list_iter, count_iter, depth);
+      });
+    }
     int* cur = P.list_ls;
     int* nxt = P.list_tmp;
     compact(list_iter, count_iter, nullptr, TF_NEED_EVAL, cur, PC_LS, TF_WANT_DERIV, PC_DERIV);

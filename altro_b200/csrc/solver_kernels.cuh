@@ -129,17 +129,37 @@ template <class Model, bool CON>
 struct TrajSolver {
   static constexpr int n = Model::n;
   static constexpr int m = Model::m;
+  static constexpr int NS_ = Model::n, NI_ = Model::m;
   static constexpr bool kLinear = ModelTraits<Model>::is_linear;
+  // the sequential sweeps of the phase pipeline stage their per-knot loads through shared
+  // memory when the blocks are small enough to live in registers (larger n keeps rolled loops
+  // over local-memory arrays and is bound by arithmetic, not by load latency)
+  static constexpr bool kStaged = (NS_ <= kUnrollDim);
+  static constexpr int kStageMax =
+      (2 * (NS_ + NI_) + NI_ * NS_ + NI_ + NS_ * NS_ + NS_ * NI_);  // = kStagePhi0, the largest
 
   const DeviceProblem& P;
-  const long S;  // stride between elements = padded batch
+  const long S;   // knot-record stride (doubles) of the main record stream
+  const long go;  // this problem's offset inside a field: group * group_stride + lane
   const int b;   // this thread's problem
   const int N;
   double rho;    // penalty (uniform over this trajectory's constraints)
   int merit_evals;
 
   ALTRO_DEV TrajSolver(const DeviceProblem& p, int b_)
-      : P(p), S(p.Bp), b(b_), N(p.N), rho(1.0), merit_evals(0) {}
+      : P(p), S(p.R), go((long)(b_ >> 5) * p.GS + (b_ & 31)), b(b_), N(p.N), rho(1.0), merit_evals(0) {}
+
+  // field pointer of this problem (knot 0); knot k is k * S further, rows are 32 doubles apart
+  ALTRO_DEV double* F(double* field) const { return field + go; }
+  ALTRO_DEV const double* F(const double* field) const { return field + go; }
+  // per-group blocks that are not per knot: [group][rows][32]
+  ALTRO_DEV const double* G(const double* base, int rows) const {
+    return base + (long)(b >> 5) * rows * 32 + (b & 31);
+  }
+  // constraint duals live in their own record stream [group][knot][z rows | z_est rows][32]
+  ALTRO_DEV long zoff(int k, int row0) const {
+    return (long)(b >> 5) * P.GSz + (long)k * P.Rz + (long)row0 * 32 + (b & 31);
+  }
 
   // ---- selector helpers (static indices only, so x/u stay in registers)
   ALTRO_DEV static double pick(int id, const double* x, const double* u) {
@@ -159,7 +179,7 @@ struct TrajSolver {
     }
   }
   ALTRO_DEV double row_offset(const ConSlot& s, int i) const {
-    return s.off_per_problem ? s.off_b[(long)i * S + b] : s.off[i];
+    return s.off_per_problem ? G(s.off_b, s.dim)[i * 32] : s.off[i];
   }
   ALTRO_DEV double row_value(const ConSlot& s, int i, const double* x, const double* u) const {
     const int id = s.idx[i];
@@ -209,7 +229,7 @@ struct TrajSolver {
       J += bb;
       J += dot<m>(r, u);
     }
-    J += P.c[(long)k * S + b];
+    J += F(P.c)[(long)k * S];
     return J;
   }
   ALTRO_DEV void stage_gradient(int k, const double* x, const double* u, const double* q,
@@ -235,13 +255,13 @@ struct TrajSolver {
       for (int j = 0; j < T.ncon; ++j) {
         const ConSlot& s = T.slot[j];
         if (k < s.k_start || k >= s.k_stop) continue;
-        const long zrow = ((long)k * T.rows + s.row0) * S + b;
+        const long zrow = zoff(k, s.row0);
         if (s.cone == CONE_SOC) {
           double zt[kMaxSocDim], zp[kMaxSocDim];
           for (int i = 0; i < s.dim; ++i) {
             const double c = row_value(s, i, x, u);
-            zt[i] = P.z[zrow + (long)i * S] - rho * c;
-            if (store_zest) P.zest[zrow + (long)i * S] = zt[i];
+            zt[i] = P.z[zrow + i * 32] - rho * c;
+            if (store_zest) P.zest[zrow + i * 32] = zt[i];
           }
           soc_projection(s.dim, zt, zp);
           double nrm = 0.0;
@@ -260,8 +280,8 @@ struct TrajSolver {
           double nrm = 0.0;
           for (int i = 0; i < s.dim; ++i) {
             const double c = row_value(s, i, x, u);
-            const double zt = P.z[zrow + (long)i * S] - rho * c;
-            if (store_zest) P.zest[zrow + (long)i * S] = zt;
+            const double zt = P.z[zrow + i * 32] - rho * c;
+            if (store_zest) P.zest[zrow + i * 32] = zt;
             // dual cones (cones.hpp:13-30): EQUALITY -> IDENTITY, INEQUALITY -> INEQUALITY,
             // IDENTITY -> EQUALITY (projection onto {0})
             double zp = 0.0;
@@ -286,12 +306,12 @@ struct TrajSolver {
       for (int j = 0; j < T.ncon; ++j) {
         const ConSlot& s = T.slot[j];
         if (k < s.k_start || k >= s.k_stop) continue;
-        const long zrow = ((long)k * T.rows + s.row0) * S + b;
+        const long zrow = zoff(k, s.row0);
         if (s.cone == CONE_SOC) {
           const int p = s.dim;
           double zt[kMaxSocDim], zp[kMaxSocDim];
           double J[kMaxSocDim * kMaxSocDim], H[kMaxSocDim * kMaxSocDim];
-          for (int i = 0; i < p; ++i) zt[i] = P.zest[zrow + (long)i * S];
+          for (int i = 0; i < p; ++i) zt[i] = P.zest[zrow + i * 32];
           soc_projection(p, zt, zp);
           soc_jacobian(p, zt, J);
           soc_hessian(p, zt, zp, H);
@@ -325,7 +345,7 @@ struct TrajSolver {
           for (int i = 0; i < s.dim; ++i) {
             const int id = s.idx[i];
             if (id < 0) continue;
-            const double zt = P.zest[zrow + (long)i * S];
+            const double zt = P.zest[zrow + i * 32];
             double act = 0.0;  // diagonal of the dual-cone projection Jacobian (cones.cpp:160-171)
             if (s.cone == CONE_EQUALITY) act = 1.0;
             if (s.cone == CONE_INEQUALITY) act = (zt <= 0) ? 1.0 : 0.0;
@@ -376,19 +396,19 @@ struct TrajSolver {
       for (int j = 0; j < T.ncon; ++j) {
         const ConSlot& s = T.slot[j];
         for (int k = s.k_start; k < s.k_stop; ++k) {
-          const long zrow = ((long)k * T.rows + s.row0) * S + b;
+          const long zrow = zoff(k, s.row0);
           if (s.cone == CONE_SOC) {
             double zt[kMaxSocDim], zp[kMaxSocDim];
-            for (int i = 0; i < s.dim; ++i) zt[i] = P.zest[zrow + (long)i * S];
+            for (int i = 0; i < s.dim; ++i) zt[i] = P.zest[zrow + i * 32];
             soc_projection(s.dim, zt, zp);
-            for (int i = 0; i < s.dim; ++i) P.z[zrow + (long)i * S] = zp[i];
+            for (int i = 0; i < s.dim; ++i) P.z[zrow + i * 32] = zp[i];
           } else {
             for (int i = 0; i < s.dim; ++i) {
-              const double zt = P.zest[zrow + (long)i * S];
+              const double zt = P.zest[zrow + i * 32];
               double zp = 0.0;
               if (s.cone == CONE_EQUALITY) zp = zt;
               if (s.cone == CONE_INEQUALITY) zp = fmin(0.0, zt);
-              P.z[zrow + (long)i * S] = zp;
+              P.z[zrow + i * 32] = zp;
             }
           }
         }
@@ -402,62 +422,92 @@ struct TrajSolver {
   // gradients, then the penalty reset (quirk Q3: gradient before SetPenalty).
   ALTRO_DEV void initial_sweep() {
     double x[n], u[m], xn[n], q[n], r[m], lx[n], lu[m], A[n * n], Bm[n * m];
-    load_block<n>(P.x0 + b, S, 0, x);
+    load_block<n>(G(P.x0, n), 0, 0, x);
     for (int k = 0; k < N; ++k) {
-      load_block<m>(P.u + b, S, k, u);
+      load_block<m>(F(P.u), S, k, u);
       dynamics(k, x, u, xn);
-      store_block<n>(P.x + b, S, k, x);
-      store_block<n>(P.xbar + b, S, k, x);
-      store_block<m>(P.ubar + b, S, k, u);
-      load_block<n>(P.q + b, S, k, q);
-      load_block<m>(P.r + b, S, k, r);
+      store_block<n>(F(P.x), S, k, x);
+      store_block<n>(F(P.xbar), S, k, x);
+      store_block<m>(F(P.ubar), S, k, u);
+      load_block<n>(F(P.q), S, k, q);
+      load_block<m>(F(P.r), S, k, r);
       jacobian(k, x, u, A, Bm);
-      store_block<n * n>(P.A + b, S, k, A);
-      store_block<n * m>(P.Bm + b, S, k, Bm);
+      store_block<n * n>(F(P.A), S, k, A);
+      store_block<n * m>(F(P.Bm), S, k, Bm);
       stage_gradient(k, x, u, q, r, false, lx, lu);
       al_terms(k, x, u, false, true, lx, lu);
-      store_block<n>(P.lx + b, S, k, lx);
-      store_block<m>(P.lu + b, S, k, lu);
+      store_block<n>(F(P.lx), S, k, lx);
+      store_block<m>(F(P.lu), S, k, lu);
 #pragma unroll
       for (int i = 0; i < n; ++i) x[i] = xn[i];
     }
-    store_block<n>(P.x + b, S, N, x);
-    store_block<n>(P.xbar + b, S, N, x);
-    load_block<n>(P.q + b, S, N, q);
+    store_block<n>(F(P.x), S, N, x);
+    store_block<n>(F(P.xbar), S, N, x);
+    load_block<n>(F(P.q), S, N, q);
 #pragma unroll
     for (int i = 0; i < m; ++i) u[i] = 0.0;  // terminal u_ is a zero m-vector (quirk Q8)
     stage_gradient(N, x, u, q, r, true, lx, lu);
     al_terms(N, x, u, true, true, lx, lu);
-    store_block<n>(P.lx + b, S, N, lx);
+    store_block<n>(F(P.lx), S, N, lx);
     rho = P.opts.penalty_initial;
   }
 
   // Backward Riccati sweep = CalcExpansions + tvlqr_BackwardPass (solver.cpp:448-449,
   // tvlqr.cpp:65-195) with reg = 0, f = 0.  The cost Hessian is rebuilt per knot from the
   // diagonal weights and the AL Gauss-Newton terms instead of being stored.
-  ALTRO_DEV void backward_sweep() {
+  // STAGED: A, B, lx, lu of the next `depth` knots are in flight into this lane's column of the
+  // shared-memory ring (linalg.cuh) while the current knot is being worked on.
+  static constexpr int kStageBackward = n * n + n * m + n + m;
+  template <bool STAGED = false>
+  ALTRO_DEV void backward_sweep(double* ring = nullptr, int depth = 0) {
     double Pn[n * n], pn[n];
+    auto fetch = [&](int k, int stage) {
+      double* st = ring + stage * (kStageBackward * 32);
+      stage_block<n * n>(st, 0, F(P.A), S, k);
+      stage_block<n * m>(st, n * n, F(P.Bm), S, k);
+      stage_block<n>(st, n * n + n * m, F(P.lx), S, k);
+      stage_block<m>(st, n * n + n * m + n, F(P.lu), S, k);
+    };
+    if constexpr (STAGED) {
+      for (int j = 0; j < depth; ++j) {
+        if (N - 1 - j >= 0) fetch(N - 1 - j, j);
+        cp_async_commit();
+      }
+    }
+    int stage = 0;
     {
 #pragma unroll
       for (int i = 0; i < n * n; ++i) Pn[i] = 0.0;
 #pragma unroll
       for (int i = 0; i < n; ++i) Pn[i + n * i] = P.Qd[N * n + i];
       al_hessian(N, true, Pn, nullptr, nullptr);
-      load_block<n>(P.lx + b, S, N, pn);
-      store_block<n * n>(P.P + b, S, N, Pn);
-      store_block<n>(P.p + b, S, N, pn);
+      load_block<n>(F(P.lx), S, N, pn);
+      store_block<n * n>(F(P.P), S, N, Pn);
+      store_block<n>(F(P.p), S, N, pn);
     }
     for (int k = N - 1; k >= 0; --k) {
-      if (k > 0) {
-        prefetch_block<n * n>(P.A + b, S, k - 1);
-        prefetch_block<n * m>(P.Bm + b, S, k - 1);
-        prefetch_block<n>(P.lx + b, S, k - 1);
-        prefetch_block<m>(P.lu + b, S, k - 1);
-      }
       double A[n * n], Bm[n * m];
-      load_block<n * n>(P.A + b, S, k, A);
-      load_block<n * m>(P.Bm + b, S, k, Bm);
       double Qxx[n * n], Quu[m * m], Qux[m * n], Qx[n], Qu[m];
+      if constexpr (STAGED) {
+        cp_async_wait(depth - 1);
+        const double* st = ring + stage * (kStageBackward * 32);
+        unstage_block<n * n>(st, 0, A);
+        unstage_block<n * m>(st, n * n, Bm);
+        unstage_block<n>(st, n * n + n * m, Qx);
+        unstage_block<m>(st, n * n + n * m + n, Qu);
+        if (k - depth >= 0) fetch(k - depth, stage);  // refill the stage just consumed
+        cp_async_commit();
+        stage = (stage + 1 == depth) ? 0 : stage + 1;
+      } else {
+        if (k > 0) {
+          prefetch_block<n * n>(F(P.A), S, k - 1);
+          prefetch_block<n * m>(F(P.Bm), S, k - 1);
+          prefetch_block<n>(F(P.lx), S, k - 1);
+          prefetch_block<m>(F(P.lu), S, k - 1);
+        }
+        load_block<n * n>(F(P.A), S, k, A);
+        load_block<n * m>(F(P.Bm), S, k, Bm);
+      }
 #pragma unroll
       for (int i = 0; i < n * n; ++i) Qxx[i] = 0.0;
 #pragma unroll
@@ -480,8 +530,10 @@ struct TrajSolver {
         mm<m, m, n, false, false, 1>(T2, Bm, Quu);  // Quu += (B'P+) B  :140
         mm<m, n, n, false, false, 1>(T2, A, Qux);   // Qux += (B'P+) A  :143
       }
-      load_block<n>(P.lx + b, S, k, Qx);
-      load_block<m>(P.lu + b, S, k, Qu);
+      if constexpr (!STAGED) {
+        load_block<n>(F(P.lx), S, k, Qx);
+        load_block<m>(F(P.lu), S, k, Qu);
+      }
       mm<n, 1, n, true, false, 1>(A, pn, Qx);   // Qx = q + A' p+     :147-150 (f = 0)
       mm<m, 1, n, true, false, 1>(Bm, pn, Qu);  // Qu = r + B' p+     :151-152
       double K[m * n], d[m], L[m * m];
@@ -495,14 +547,14 @@ struct TrajSolver {
       if (!ok) {
         // tvlqr returns here (:162-164) and Solve ignores it (quirk Q2): this knot keeps the
         // unsolved K = Qux, d = -Qu; P_k, p_k and everything below stay stale.
-        store_block<m * n>(P.K + b, S, k, K);
-        store_block<m>(P.d + b, S, k, d);
+        store_block<m * n>(F(P.K), S, k, K);
+        store_block<m>(F(P.d), S, k, d);
         return;
       }
       cholesky_solve<m, n>(L, K);
       cholesky_solve<m, 1>(L, d);
-      store_block<m * n>(P.K + b, S, k, K);
-      store_block<m>(P.d + b, S, k, d);
+      store_block<m * n>(F(P.K), S, k, K);
+      store_block<m>(F(P.d), S, k, d);
       // cost-to-go, :173-186
       double QuuK[m * n], KtQux[n * n];
       mm<m, n, m, false, false, 0>(Quu, K, QuuK);
@@ -523,8 +575,8 @@ struct TrajSolver {
       mm<n, 1, m, true, false, -1>(QuuK, d, pn);
       mm<n, 1, m, true, false, -1>(K, Qu, pn);
       mm<n, 1, m, true, false, 1>(Qux, d, pn);
-      store_block<n * n>(P.P + b, S, k, Pn);
-      store_block<n>(P.p + b, S, k, pn);
+      store_block<n * n>(F(P.P), S, k, Pn);
+      store_block<n>(F(P.p), S, k, pn);
     }
   }
 
@@ -533,15 +585,15 @@ struct TrajSolver {
     merit_evals += 1;
     double phi = 0.0, dphi = 0.0;
     double x[n], dxda[n];
-    load_block<n>(P.x0 + b, S, 0, x);
+    load_block<n>(G(P.x0, n), 0, 0, x);
 #pragma unroll
     for (int i = 0; i < n; ++i) dxda[i] = 0.0;
     for (int k = 0; k < N; ++k) {
       double xb[n], ub[m], K[m * n], d[m], dx[n], u[m], y[n], xn[n], q[n], r[m];
-      load_block<n>(P.xbar + b, S, k, xb);
-      load_block<m>(P.ubar + b, S, k, ub);
-      load_block<m * n>(P.K + b, S, k, K);
-      load_block<m>(P.d + b, S, k, d);
+      load_block<n>(F(P.xbar), S, k, xb);
+      load_block<m>(F(P.ubar), S, k, ub);
+      load_block<m * n>(F(P.K), S, k, K);
+      load_block<m>(F(P.d), S, k, d);
 #pragma unroll
       for (int i = 0; i < n; ++i) dx[i] = x[i] - xb[i];  // :290
       {
@@ -552,24 +604,24 @@ struct TrajSolver {
       }
       {
         double Pk[n * n];
-        load_block<n * n>(P.P + b, S, k, Pk);
-        load_block<n>(P.p + b, S, k, y);
+        load_block<n * n>(F(P.P), S, k, Pk);
+        load_block<n>(F(P.p), S, k, y);
         mm<n, 1, n, false, false, 1>(Pk, dx, y);  // y = P dx + p, :293
       }
-      store_block<n>(P.x + b, S, k, x);
-      store_block<m>(P.u + b, S, k, u);
-      store_block<n>(P.y + b, S, k, y);
+      store_block<n>(F(P.x), S, k, x);
+      store_block<m>(F(P.u), S, k, u);
+      store_block<n>(F(P.y), S, k, y);
       dynamics(k, x, u, xn);  // :296
-      load_block<n>(P.q + b, S, k, q);
-      load_block<m>(P.r + b, S, k, r);
+      load_block<n>(F(P.q), S, k, q);
+      load_block<m>(F(P.r), S, k, r);
       double lx[n], lu[m];
       if (want) stage_gradient(k, x, u, q, r, false, lx, lu);
       phi += stage_cost(k, x, u, q, r, false) + al_terms(k, x, u, false, want, lx, lu);  // :299-301
       if (want) {
         double A[n * n], Bm[n * m], duda[m], dxn[n];
         jacobian(k, x, u, A, Bm);  // :305
-        store_block<n * n>(P.A + b, S, k, A);
-        store_block<n * m>(P.Bm + b, S, k, Bm);
+        store_block<n * n>(F(P.A), S, k, A);
+        store_block<n * m>(F(P.Bm), S, k, Bm);
         {
           double Kd[m];
           mm<m, 1, n, false, false, 0>(K, dxda, Kd);
@@ -578,8 +630,8 @@ struct TrajSolver {
         }
         mm<n, 1, n, false, false, 0>(A, dxda, dxn);  // :307-308
         mm<n, 1, m, false, false, 1>(Bm, duda, dxn);
-        store_block<n>(P.lx + b, S, k, lx);
-        store_block<m>(P.lu + b, S, k, lu);
+        store_block<n>(F(P.lx), S, k, lx);
+        store_block<m>(F(P.lu), S, k, lu);
         dphi += dot<n>(lx, dxda);  // :313-314
         dphi += dot<m>(lu, duda);
 #pragma unroll
@@ -590,8 +642,8 @@ struct TrajSolver {
     }
     {  // terminal knot, :319-332
       double xb[n], dx[n], y[n], q[n], u0[m], lx[n];
-      load_block<n>(P.xbar + b, S, N, xb);
-      load_block<n>(P.q + b, S, N, q);
+      load_block<n>(F(P.xbar), S, N, xb);
+      load_block<n>(F(P.q), S, N, q);
 #pragma unroll
       for (int i = 0; i < m; ++i) u0[i] = 0.0;
       if (want) stage_gradient(N, x, u0, q, nullptr, true, lx, nullptr);
@@ -599,13 +651,13 @@ struct TrajSolver {
 #pragma unroll
       for (int i = 0; i < n; ++i) dx[i] = x[i] - xb[i];
       double Pk[n * n];
-      load_block<n * n>(P.P + b, S, N, Pk);
-      load_block<n>(P.p + b, S, N, y);
+      load_block<n * n>(F(P.P), S, N, Pk);
+      load_block<n>(F(P.p), S, N, y);
       mm<n, 1, n, false, false, 1>(Pk, dx, y);
-      store_block<n>(P.x + b, S, N, x);
-      store_block<n>(P.y + b, S, N, y);
+      store_block<n>(F(P.x), S, N, x);
+      store_block<n>(F(P.y), S, N, y);
       if (want) {
-        store_block<n>(P.lx + b, S, N, lx);
+        store_block<n>(F(P.lx), S, N, lx);
         dphi += dot<n>(lx, dxda);
       }
     }
@@ -620,16 +672,16 @@ struct TrajSolver {
     for (int k = 0; k <= N; ++k) {
       const bool terminal = (k == N);
       double x[n], u[m], q[n], r[m], lx[n], lu[m];
-      load_block<n>(P.x + b, S, k, x);
-      load_block<n>(P.q + b, S, k, q);
+      load_block<n>(F(P.x), S, k, x);
+      load_block<n>(F(P.q), S, k, q);
       if (!terminal) {
-        load_block<m>(P.u + b, S, k, u);
-        load_block<m>(P.r + b, S, k, r);
+        load_block<m>(F(P.u), S, k, u);
+        load_block<m>(F(P.r), S, k, r);
         if (with_dynamics) {
           double A[n * n], Bm[n * m];
           jacobian(k, x, u, A, Bm);
-          store_block<n * n>(P.A + b, S, k, A);
-          store_block<n * m>(P.Bm + b, S, k, Bm);
+          store_block<n * n>(F(P.A), S, k, A);
+          store_block<n * m>(F(P.Bm), S, k, Bm);
         }
       } else {
 #pragma unroll
@@ -637,8 +689,8 @@ struct TrajSolver {
       }
       stage_gradient(k, x, u, q, r, terminal, lx, lu);
       al_terms(k, x, u, terminal, true, lx, lu);
-      store_block<n>(P.lx + b, S, k, lx);
-      if (!terminal) store_block<m>(P.lu + b, S, k, lu);
+      store_block<n>(F(P.lx), S, k, lx);
+      if (!terminal) store_block<m>(F(P.lu), S, k, lu);
     }
   }
 
@@ -646,38 +698,38 @@ struct TrajSolver {
   ALTRO_DEV void criteria_sweep(double* stat_out, double* feas_out) {
     double res_x = 0.0, res_u = 0.0, viol = 0.0;
     double y[n];
-    load_block<n>(P.y + b, S, 0, y);
+    load_block<n>(F(P.y), S, 0, y);
     for (int k = 0; k < N; ++k) {
       double yn[n], A[n * n], Bm[n * m], lx[n], lu[m], x[n], u[m];
-      load_block<n>(P.y + b, S, k + 1, yn);
-      load_block<n * n>(P.A + b, S, k, A);
-      load_block<n * m>(P.Bm + b, S, k, Bm);
-      load_block<n>(P.lx + b, S, k, lx);
-      load_block<m>(P.lu + b, S, k, lu);
+      load_block<n>(F(P.y), S, k + 1, yn);
+      load_block<n * n>(F(P.A), S, k, A);
+      load_block<n * m>(F(P.Bm), S, k, Bm);
+      load_block<n>(F(P.lx), S, k, lx);
+      load_block<m>(F(P.lu), S, k, lu);
       mm<n, 1, n, true, false, 1>(A, yn, lx);  // lx + A' y+
       mm<m, 1, n, true, false, 1>(Bm, yn, lu);
 #pragma unroll
       for (int i = 0; i < n; ++i) res_x = fmax(res_x, fabs(lx[i] - y[i]));
 #pragma unroll
       for (int i = 0; i < m; ++i) res_u = fmax(res_u, fabs(lu[i]));
-      load_block<n>(P.x + b, S, k, x);
-      load_block<m>(P.u + b, S, k, u);
+      load_block<n>(F(P.x), S, k, x);
+      load_block<m>(F(P.u), S, k, u);
       viol = fmax(viol, al_violation(k, x, u));
-      store_block<n>(P.xbar + b, S, k, x);
-      store_block<m>(P.ubar + b, S, k, u);
+      store_block<n>(F(P.xbar), S, k, x);
+      store_block<m>(F(P.ubar), S, k, u);
 #pragma unroll
       for (int i = 0; i < n; ++i) y[i] = yn[i];
     }
     {
       double lx[n], x[n], u0[m];
-      load_block<n>(P.lx + b, S, N, lx);
+      load_block<n>(F(P.lx), S, N, lx);
 #pragma unroll
       for (int i = 0; i < n; ++i) res_x = fmax(res_x, fabs(lx[i] - y[i]));
-      load_block<n>(P.x + b, S, N, x);
+      load_block<n>(F(P.x), S, N, x);
 #pragma unroll
       for (int i = 0; i < m; ++i) u0[i] = 0.0;
       viol = fmax(viol, al_violation(N, x, u0));
-      store_block<n>(P.xbar + b, S, N, x);
+      store_block<n>(F(P.xbar), S, N, x);
     }
     *stat_out = fmax(res_x, res_u);
     *feas_out = viol;
@@ -722,26 +774,31 @@ struct TrajSolver {
 
   // working trajectory of candidate `slot` (-1: the main x_, u_ arrays)
   ALTRO_DEV double* xw(int slot) const {
-    return slot < 0 ? P.x : P.xs + (long)slot * (N + 1) * n * S;
+    return slot < 0 ? F(P.x) : P.xs + slot_off(slot);
   }
-  ALTRO_DEV double* uw(int slot) const { return slot < 0 ? P.u : P.us + (long)slot * N * m * S; }
+  ALTRO_DEV double* uw(int slot) const { return slot < 0 ? F(P.u) : P.us + slot_off(slot); }
+  // candidate slots: [slot][group][knot][x rows | u rows][32]
+  ALTRO_DEV long slot_off(int slot) const {
+    return ((long)slot * P.G + (b >> 5)) * (long)(N + 1) * P.Rs + (b & 31);
+  }
+  ALTRO_DEV long sw(int slot) const { return slot < 0 ? S : P.Rs; }
 
   // OpenLoopRollout + CopyTrajectory (solver.cpp:422-423): x_, x, u from the working inputs.
   ALTRO_DEV void phase_init_rollout() {
     double x[n], u[m], xn[n];
-    load_block<n>(P.x0 + b, S, 0, x);
+    load_block<n>(G(P.x0, n), 0, 0, x);
     for (int k = 0; k < N; ++k) {
-      if (k + 1 < N) prefetch_block<m>(P.u + b, S, k + 1);
-      load_block<m>(P.u + b, S, k, u);
+      if (k + 1 < N) prefetch_block<m>(F(P.u), S, k + 1);
+      load_block<m>(F(P.u), S, k, u);
       dynamics(k, x, u, xn);
-      store_block<n>(P.x + b, S, k, x);
-      store_block<n>(P.xbar + b, S, k, x);
-      store_block<m>(P.ubar + b, S, k, u);
+      store_block<n>(F(P.x), S, k, x);
+      store_block<n>(F(P.xbar), S, k, x);
+      store_block<m>(F(P.ubar), S, k, u);
 #pragma unroll
       for (int i = 0; i < n; ++i) x[i] = xn[i];
     }
-    store_block<n>(P.x + b, S, N, x);
-    store_block<n>(P.xbar + b, S, N, x);
+    store_block<n>(F(P.x), S, N, x);
+    store_block<n>(F(P.xbar), S, N, x);
   }
 
   // z <- Pi(z_est) for the rows of knot k (KnotPointData::DualUpdate, knotpoint_data.cpp:503-510)
@@ -751,19 +808,19 @@ struct TrajSolver {
       for (int j = 0; j < T.ncon; ++j) {
         const ConSlot& s = T.slot[j];
         if (k < s.k_start || k >= s.k_stop) continue;
-        const long zrow = ((long)k * T.rows + s.row0) * S + b;
+        const long zrow = zoff(k, s.row0);
         if (s.cone == CONE_SOC) {
           double zt[kMaxSocDim], zp[kMaxSocDim];
-          for (int i = 0; i < s.dim; ++i) zt[i] = P.zest[zrow + (long)i * S];
+          for (int i = 0; i < s.dim; ++i) zt[i] = P.zest[zrow + i * 32];
           soc_projection(s.dim, zt, zp);
-          for (int i = 0; i < s.dim; ++i) P.z[zrow + (long)i * S] = zp[i];
+          for (int i = 0; i < s.dim; ++i) P.z[zrow + i * 32] = zp[i];
         } else {
           for (int i = 0; i < s.dim; ++i) {
-            const double zt = P.zest[zrow + (long)i * S];
+            const double zt = P.zest[zrow + i * 32];
             double zp = 0.0;
             if (s.cone == CONE_EQUALITY) zp = zt;
             if (s.cone == CONE_INEQUALITY) zp = fmin(0.0, zt);
-            P.z[zrow + (long)i * S] = zp;
+            P.z[zrow + i * 32] = zp;
           }
         }
       }
@@ -777,18 +834,18 @@ struct TrajSolver {
   ALTRO_DEV void phase_expand_knot(int k, bool with_dyn, int slot, bool dual_first) {
     const bool terminal = (k == N);
     double x[n], u[m], q[n], r[m], lx[n], lu[m];
-    load_block<n>(xw(slot) + b, S, k, x);
-    load_block<n>(P.q + b, S, k, q);
-    if (slot >= 0) store_block<n>(P.x + b, S, k, x);
+    load_block<n>(xw(slot), sw(slot), k, x);
+    load_block<n>(F(P.q), S, k, q);
+    if (slot >= 0) store_block<n>(F(P.x), S, k, x);
     if (!terminal) {
-      load_block<m>(uw(slot) + b, S, k, u);
-      load_block<m>(P.r + b, S, k, r);
-      if (slot >= 0) store_block<m>(P.u + b, S, k, u);
+      load_block<m>(uw(slot), sw(slot), k, u);
+      load_block<m>(F(P.r), S, k, r);
+      if (slot >= 0) store_block<m>(F(P.u), S, k, u);
       if (with_dyn) {
         double A[n * n], Bm[n * m];
         jacobian(k, x, u, A, Bm);
-        store_block<n * n>(P.A + b, S, k, A);
-        store_block<n * m>(P.Bm + b, S, k, Bm);
+        store_block<n * n>(F(P.A), S, k, A);
+        store_block<n * m>(F(P.Bm), S, k, Bm);
       }
     } else {
 #pragma unroll
@@ -797,8 +854,8 @@ struct TrajSolver {
     if (dual_first) dual_update_knot(k);
     stage_gradient(k, x, u, q, r, terminal, lx, lu);
     al_terms(k, x, u, terminal, true, lx, lu);
-    store_block<n>(P.lx + b, S, k, lx);
-    if (!terminal) store_block<m>(P.lu + b, S, k, lu);
+    store_block<n>(F(P.lx), S, k, lx);
+    if (!terminal) store_block<m>(F(P.lu), S, k, lu);
   }
 
   // merit(0, derivative) of ForwardPass (solver.cpp:241) WITHOUT re-simulating: at alpha = 0 the
@@ -806,39 +863,78 @@ struct TrajSolver {
   // are already in HBM; what changes with the new gains / duals / penalty is the cost, the
   // projected duals, the gradients and the directional derivative, recomputed here in one
   // linear scan.
-  ALTRO_DEV void phase_phi0_scan(double* phi_out, double* dphi_out) {
+  static constexpr int kStagePhi0 = 2 * (n + m) + m * n + m + n * n + n * m;
+  template <bool STAGED = false>
+  ALTRO_DEV void phase_phi0_scan(double* phi_out, double* dphi_out, double* ring = nullptr,
+                                 int depth = 0) {
     double phi = 0.0, dphi = 0.0;
     double dxda[n];
 #pragma unroll
     for (int i = 0; i < n; ++i) dxda[i] = 0.0;
-    for (int k = 0; k < N; ++k) {
-      {
-        const int kn = k + 1;
-        prefetch_block<n>(P.x + b, S, kn);
-        prefetch_block<n>(P.q + b, S, kn);
-        if (kn < N) {
-          prefetch_block<m>(P.u + b, S, kn);
-          prefetch_block<m>(P.r + b, S, kn);
-          prefetch_block<m * n>(P.K + b, S, kn);
-          prefetch_block<m>(P.d + b, S, kn);
-          prefetch_block<n * n>(P.A + b, S, kn);
-          prefetch_block<n * m>(P.Bm + b, S, kn);
-        }
+    constexpr int oU = n, oQ = n + m, oR = 2 * n + m, oK = 2 * (n + m), oD = oK + m * n,
+                  oA = oD + m, oB = oA + n * n;
+    auto fetch = [&](int k, int stage) {  // knots 0..N-1 (the terminal knot is read directly)
+      double* st = ring + stage * (kStagePhi0 * 32);
+      stage_block<n>(st, 0, F(P.x), S, k);
+      stage_block<m>(st, oU, F(P.u), S, k);
+      stage_block<n>(st, oQ, F(P.q), S, k);
+      stage_block<m>(st, oR, F(P.r), S, k);
+      stage_block<m * n>(st, oK, F(P.K), S, k);
+      stage_block<m>(st, oD, F(P.d), S, k);
+      stage_block<n * n>(st, oA, F(P.A), S, k);
+      stage_block<n * m>(st, oB, F(P.Bm), S, k);
+    };
+    if constexpr (STAGED) {
+      for (int j = 0; j < depth; ++j) {
+        if (j < N) fetch(j, j);
+        cp_async_commit();
       }
+    }
+    int stage = 0;
+    for (int k = 0; k < N; ++k) {
       double x[n], u[m], q[n], r[m], lx[n], lu[m];
-      load_block<n>(P.x + b, S, k, x);
-      load_block<m>(P.u + b, S, k, u);
-      load_block<n>(P.q + b, S, k, q);
-      load_block<m>(P.r + b, S, k, r);
+      double K[m * n], d[m], A[n * n], Bm[n * m], duda[m], dxn[n];
+      if constexpr (STAGED) {
+        cp_async_wait(depth - 1);
+        const double* st = ring + stage * (kStagePhi0 * 32);
+        unstage_block<n>(st, 0, x);
+        unstage_block<m>(st, oU, u);
+        unstage_block<n>(st, oQ, q);
+        unstage_block<m>(st, oR, r);
+        unstage_block<m * n>(st, oK, K);
+        unstage_block<m>(st, oD, d);
+        unstage_block<n * n>(st, oA, A);
+        unstage_block<n * m>(st, oB, Bm);
+        if (k + depth < N) fetch(k + depth, stage);
+        cp_async_commit();
+        stage = (stage + 1 == depth) ? 0 : stage + 1;
+      } else {
+        const int kn = k + 1;
+        prefetch_block<n>(F(P.x), S, kn);
+        prefetch_block<n>(F(P.q), S, kn);
+        if (kn < N) {
+          prefetch_block<m>(F(P.u), S, kn);
+          prefetch_block<m>(F(P.r), S, kn);
+          prefetch_block<m * n>(F(P.K), S, kn);
+          prefetch_block<m>(F(P.d), S, kn);
+          prefetch_block<n * n>(F(P.A), S, kn);
+          prefetch_block<n * m>(F(P.Bm), S, kn);
+        }
+        load_block<n>(F(P.x), S, k, x);
+        load_block<m>(F(P.u), S, k, u);
+        load_block<n>(F(P.q), S, k, q);
+        load_block<m>(F(P.r), S, k, r);
+      }
       stage_gradient(k, x, u, q, r, false, lx, lu);
       phi += stage_cost(k, x, u, q, r, false) + al_terms(k, x, u, false, true, lx, lu);
-      store_block<n>(P.lx + b, S, k, lx);
-      store_block<m>(P.lu + b, S, k, lu);
-      double K[m * n], d[m], A[n * n], Bm[n * m], duda[m], dxn[n];
-      load_block<m * n>(P.K + b, S, k, K);
-      load_block<m>(P.d + b, S, k, d);
-      load_block<n * n>(P.A + b, S, k, A);
-      load_block<n * m>(P.Bm + b, S, k, Bm);
+      store_block<n>(F(P.lx), S, k, lx);
+      store_block<m>(F(P.lu), S, k, lu);
+      if constexpr (!STAGED) {
+        load_block<m * n>(F(P.K), S, k, K);
+        load_block<m>(F(P.d), S, k, d);
+        load_block<n * n>(F(P.A), S, k, A);
+        load_block<n * m>(F(P.Bm), S, k, Bm);
+      }
       {
         double Kd[m];
         mm<m, 1, n, false, false, 0>(K, dxda, Kd);
@@ -854,13 +950,13 @@ struct TrajSolver {
     }
     {
       double x[n], q[n], u0[m], lx[n];
-      load_block<n>(P.x + b, S, N, x);
-      load_block<n>(P.q + b, S, N, q);
+      load_block<n>(F(P.x), S, N, x);
+      load_block<n>(F(P.q), S, N, q);
 #pragma unroll
       for (int i = 0; i < m; ++i) u0[i] = 0.0;
       stage_gradient(N, x, u0, q, nullptr, true, lx, nullptr);
       phi += stage_cost(N, x, u0, q, nullptr, true) + al_terms(N, x, u0, true, true, lx, nullptr);
-      store_block<n>(P.lx + b, S, N, lx);
+      store_block<n>(F(P.lx), S, N, lx);
       dphi += dot<n>(lx, dxda);
     }
     *phi_out = phi;
@@ -872,31 +968,63 @@ struct TrajSolver {
   // phase_expand_knot (parallel over knots) + phase_dphi_scan; y_ is produced for the accepted
   // point only (phase_costate_knot).  z_est is not stored here: every candidate that can be
   // accepted is expanded afterwards, which stores it.
-  ALTRO_DEV double phase_rollout(double alpha, int slot) {
+  static constexpr int kStageRollout = 2 * (n + m) + m * n + m;
+  template <bool STAGED = false>
+  ALTRO_DEV double phase_rollout(double alpha, int slot, double* ring = nullptr, int depth = 0) {
     double phi = 0.0;
     double x[n];
-    double* xo = xw(slot) + b;
-    double* uo = uw(slot) + b;
-    load_block<n>(P.x0 + b, S, 0, x);
-    for (int k = 0; k < N; ++k) {
-      {
-        const int kn = k + 1;
-        prefetch_block<n>(P.xbar + b, S, kn);
-        prefetch_block<n>(P.q + b, S, kn);
-        if (kn < N) {
-          prefetch_block<m>(P.ubar + b, S, kn);
-          prefetch_block<m * n>(P.K + b, S, kn);
-          prefetch_block<m>(P.d + b, S, kn);
-          prefetch_block<m>(P.r + b, S, kn);
-        }
+    double* xo = xw(slot);
+    double* uo = uw(slot);
+    const long so = sw(slot);
+    constexpr int oU = n, oK = n + m, oD = oK + m * n, oQ = oD + m, oR = oQ + n;
+    auto fetch = [&](int k, int stage) {
+      double* st = ring + stage * (kStageRollout * 32);
+      stage_block<n>(st, 0, F(P.xbar), S, k);
+      stage_block<m>(st, oU, F(P.ubar), S, k);
+      stage_block<m * n>(st, oK, F(P.K), S, k);
+      stage_block<m>(st, oD, F(P.d), S, k);
+      stage_block<n>(st, oQ, F(P.q), S, k);
+      stage_block<m>(st, oR, F(P.r), S, k);
+    };
+    if constexpr (STAGED) {
+      for (int j = 0; j < depth; ++j) {
+        if (j < N) fetch(j, j);
+        cp_async_commit();
       }
+    }
+    int stage = 0;
+    load_block<n>(G(P.x0, n), 0, 0, x);
+    for (int k = 0; k < N; ++k) {
       double xb[n], ub[m], K[m * n], d[m], dx[n], u[m], xn[n], q[n], r[m];
-      load_block<n>(P.xbar + b, S, k, xb);
-      load_block<m>(P.ubar + b, S, k, ub);
-      load_block<m * n>(P.K + b, S, k, K);
-      load_block<m>(P.d + b, S, k, d);
-      load_block<n>(P.q + b, S, k, q);
-      load_block<m>(P.r + b, S, k, r);
+      if constexpr (STAGED) {
+        cp_async_wait(depth - 1);
+        const double* st = ring + stage * (kStageRollout * 32);
+        unstage_block<n>(st, 0, xb);
+        unstage_block<m>(st, oU, ub);
+        unstage_block<m * n>(st, oK, K);
+        unstage_block<m>(st, oD, d);
+        unstage_block<n>(st, oQ, q);
+        unstage_block<m>(st, oR, r);
+        if (k + depth < N) fetch(k + depth, stage);
+        cp_async_commit();
+        stage = (stage + 1 == depth) ? 0 : stage + 1;
+      } else {
+        const int kn = k + 1;
+        prefetch_block<n>(F(P.xbar), S, kn);
+        prefetch_block<n>(F(P.q), S, kn);
+        if (kn < N) {
+          prefetch_block<m>(F(P.ubar), S, kn);
+          prefetch_block<m * n>(F(P.K), S, kn);
+          prefetch_block<m>(F(P.d), S, kn);
+          prefetch_block<m>(F(P.r), S, kn);
+        }
+        load_block<n>(F(P.xbar), S, k, xb);
+        load_block<m>(F(P.ubar), S, k, ub);
+        load_block<m * n>(F(P.K), S, k, K);
+        load_block<m>(F(P.d), S, k, d);
+        load_block<n>(F(P.q), S, k, q);
+        load_block<m>(F(P.r), S, k, r);
+      }
 #pragma unroll
       for (int i = 0; i < n; ++i) dx[i] = x[i] - xb[i];
       {
@@ -905,8 +1033,8 @@ struct TrajSolver {
 #pragma unroll
         for (int i = 0; i < m; ++i) u[i] = ub[i] + (-Kdx[i] + alpha * d[i]);
       }
-      store_block<n>(xo, S, k, x);
-      store_block<m>(uo, S, k, u);
+      store_block<n>(xo, so, k, x);
+      store_block<m>(uo, so, k, u);
       dynamics(k, x, u, xn);
       phi += stage_cost(k, x, u, q, r, false) +
              al_terms(k, x, u, false, false, nullptr, nullptr, false);
@@ -915,42 +1043,73 @@ struct TrajSolver {
     }
     {
       double q[n], u0[m];
-      load_block<n>(P.q + b, S, N, q);
+      load_block<n>(F(P.q), S, N, q);
 #pragma unroll
       for (int i = 0; i < m; ++i) u0[i] = 0.0;
       phi += stage_cost(N, x, u0, q, nullptr, true) +
              al_terms(N, x, u0, true, false, nullptr, nullptr, false);
-      store_block<n>(xo, S, N, x);
+      store_block<n>(xo, so, N, x);
     }
     return phi;
   }
 
   // The derivative half of MeritFunction (solver.cpp:303-315, :327-331) once A, B, lx, lu of the
   // trial trajectory are in HBM.
-  ALTRO_DEV double phase_dphi_scan() {
+  static constexpr int kStageDphi = m * n + m + n * n + n * m + n + m;
+  template <bool STAGED = false>
+  ALTRO_DEV double phase_dphi_scan(double* ring = nullptr, int depth = 0) {
     double dphi = 0.0;
     double dxda[n];
 #pragma unroll
     for (int i = 0; i < n; ++i) dxda[i] = 0.0;
-    for (int k = 0; k < N; ++k) {
-      {
-        const int kn = k + 1;
-        prefetch_block<n>(P.lx + b, S, kn);
-        if (kn < N) {
-          prefetch_block<m * n>(P.K + b, S, kn);
-          prefetch_block<m>(P.d + b, S, kn);
-          prefetch_block<n * n>(P.A + b, S, kn);
-          prefetch_block<n * m>(P.Bm + b, S, kn);
-          prefetch_block<m>(P.lu + b, S, kn);
-        }
+    constexpr int oD = m * n, oA = oD + m, oB = oA + n * n, oLx = oB + n * m, oLu = oLx + n;
+    auto fetch = [&](int k, int stage) {
+      double* st = ring + stage * (kStageDphi * 32);
+      stage_block<m * n>(st, 0, F(P.K), S, k);
+      stage_block<m>(st, oD, F(P.d), S, k);
+      stage_block<n * n>(st, oA, F(P.A), S, k);
+      stage_block<n * m>(st, oB, F(P.Bm), S, k);
+      stage_block<n>(st, oLx, F(P.lx), S, k);
+      stage_block<m>(st, oLu, F(P.lu), S, k);
+    };
+    if constexpr (STAGED) {
+      for (int j = 0; j < depth; ++j) {
+        if (j < N) fetch(j, j);
+        cp_async_commit();
       }
+    }
+    int stage = 0;
+    for (int k = 0; k < N; ++k) {
       double K[m * n], d[m], A[n * n], Bm[n * m], lx[n], lu[m], duda[m], dxn[n];
-      load_block<m * n>(P.K + b, S, k, K);
-      load_block<m>(P.d + b, S, k, d);
-      load_block<n * n>(P.A + b, S, k, A);
-      load_block<n * m>(P.Bm + b, S, k, Bm);
-      load_block<n>(P.lx + b, S, k, lx);
-      load_block<m>(P.lu + b, S, k, lu);
+      if constexpr (STAGED) {
+        cp_async_wait(depth - 1);
+        const double* st = ring + stage * (kStageDphi * 32);
+        unstage_block<m * n>(st, 0, K);
+        unstage_block<m>(st, oD, d);
+        unstage_block<n * n>(st, oA, A);
+        unstage_block<n * m>(st, oB, Bm);
+        unstage_block<n>(st, oLx, lx);
+        unstage_block<m>(st, oLu, lu);
+        if (k + depth < N) fetch(k + depth, stage);
+        cp_async_commit();
+        stage = (stage + 1 == depth) ? 0 : stage + 1;
+      } else {
+        const int kn = k + 1;
+        prefetch_block<n>(F(P.lx), S, kn);
+        if (kn < N) {
+          prefetch_block<m * n>(F(P.K), S, kn);
+          prefetch_block<m>(F(P.d), S, kn);
+          prefetch_block<n * n>(F(P.A), S, kn);
+          prefetch_block<n * m>(F(P.Bm), S, kn);
+          prefetch_block<m>(F(P.lu), S, kn);
+        }
+        load_block<m * n>(F(P.K), S, k, K);
+        load_block<m>(F(P.d), S, k, d);
+        load_block<n * n>(F(P.A), S, k, A);
+        load_block<n * m>(F(P.Bm), S, k, Bm);
+        load_block<n>(F(P.lx), S, k, lx);
+        load_block<m>(F(P.lu), S, k, lu);
+      }
       {
         double Kd[m];
         mm<m, 1, n, false, false, 0>(K, dxda, Kd);
@@ -965,7 +1124,7 @@ struct TrajSolver {
       for (int i = 0; i < n; ++i) dxda[i] = dxn[i];
     }
     double lx[n];
-    load_block<n>(P.lx + b, S, N, lx);
+    load_block<n>(F(P.lx), S, N, lx);
     dphi += dot<n>(lx, dxda);
     return dphi;
   }
@@ -973,14 +1132,14 @@ struct TrajSolver {
   // y_k = P_k (x_k - xbar_k) + p_k for the accepted point (solver.cpp:293, :324)
   ALTRO_DEV void phase_costate_knot(int k) {
     double x[n], xb[n], dx[n], Pk[n * n], y[n];
-    load_block<n>(P.x + b, S, k, x);
-    load_block<n>(P.xbar + b, S, k, xb);
+    load_block<n>(F(P.x), S, k, x);
+    load_block<n>(F(P.xbar), S, k, xb);
 #pragma unroll
     for (int i = 0; i < n; ++i) dx[i] = x[i] - xb[i];
-    load_block<n * n>(P.P + b, S, k, Pk);
-    load_block<n>(P.p + b, S, k, y);
+    load_block<n * n>(F(P.P), S, k, Pk);
+    load_block<n>(F(P.p), S, k, y);
     mm<n, 1, n, false, false, 1>(Pk, dx, y);
-    store_block<n>(P.y + b, S, k, y);
+    store_block<n>(F(P.y), S, k, y);
   }
 
   // knot k's contribution to Stationarity (solver.cpp:207-222) and Feasibility (:224-231), and its
@@ -989,16 +1148,16 @@ struct TrajSolver {
   ALTRO_DEV void phase_residual_knot(int k) {
     double res = 0.0, viol = 0.0;
     double x[n], u[m];
-    load_block<n>(P.x + b, S, k, x);
+    load_block<n>(F(P.x), S, k, x);
     if (k < N) {
       double y[n], yn[n], A[n * n], Bm[n * m], lx[n], lu[m];
-      load_block<n>(P.y + b, S, k, y);
-      load_block<n>(P.y + b, S, k + 1, yn);
-      load_block<n * n>(P.A + b, S, k, A);
-      load_block<n * m>(P.Bm + b, S, k, Bm);
-      load_block<n>(P.lx + b, S, k, lx);
-      load_block<m>(P.lu + b, S, k, lu);
-      load_block<m>(P.u + b, S, k, u);
+      load_block<n>(F(P.y), S, k, y);
+      load_block<n>(F(P.y), S, k + 1, yn);
+      load_block<n * n>(F(P.A), S, k, A);
+      load_block<n * m>(F(P.Bm), S, k, Bm);
+      load_block<n>(F(P.lx), S, k, lx);
+      load_block<m>(F(P.lu), S, k, lu);
+      load_block<m>(F(P.u), S, k, u);
       mm<n, 1, n, true, false, 1>(A, yn, lx);
       mm<m, 1, n, true, false, 1>(Bm, yn, lu);
 #pragma unroll
@@ -1006,18 +1165,18 @@ struct TrajSolver {
 #pragma unroll
       for (int i = 0; i < m; ++i) res = fmax(res, fabs(lu[i]));
       viol = al_violation(k, x, u);
-      store_block<m>(P.ubar + b, S, k, u);
+      store_block<m>(F(P.ubar), S, k, u);
     } else {
       double y[n], lx[n];
-      load_block<n>(P.y + b, S, N, y);
-      load_block<n>(P.lx + b, S, N, lx);
+      load_block<n>(F(P.y), S, N, y);
+      load_block<n>(F(P.lx), S, N, lx);
 #pragma unroll
       for (int i = 0; i < n; ++i) res = fmax(res, fabs(lx[i] - y[i]));
 #pragma unroll
       for (int i = 0; i < m; ++i) u[i] = 0.0;
       viol = al_violation(N, x, u);
     }
-    store_block<n>(P.xbar + b, S, k, x);
+    store_block<n>(F(P.xbar), S, k, x);
     if (res > 0.0) atomicMax(P.stat_acc + b, (unsigned long long)__double_as_longlong(res));
     if (CON && viol > 0.0) atomicMax(P.feas_acc + b, (unsigned long long)__double_as_longlong(viol));
   }

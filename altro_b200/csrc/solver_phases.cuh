@@ -95,6 +95,10 @@ __device__ __forceinline__ LsOptions ls_options(const DevOptions& o) {
   return lo;
 }
 
+// this lane's column of the per-warp staging ring (dynamic shared memory; CTA = one warp)
+extern __shared__ double altro_stage_ring[];
+__device__ __forceinline__ double* lane_ring() { return altro_stage_ring + (threadIdx.x & 31); }
+
 // K0: Solve() prologue, sequential part (solver.cpp:417-423)
 template <class Model, bool CON>
 __global__ void __launch_bounds__(32) k_phase_init(const DeviceProblem P) {
@@ -142,15 +146,16 @@ static __global__ void k_phase_set_rho(double* rho, int B, double value) {
 // :241-245) and the start of the line search.
 template <class Model, bool CON>
 __global__ void __launch_bounds__(32) k_phase_backward(const DeviceProblem P, const int* list,
-                                                       int count) {
+                                                       int count, int depth) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= count) return;
   const int b = list[t];
   TrajSolver<Model, CON> s(P, b);
   s.rho = CON ? P.rho[b] : 1.0;
-  s.backward_sweep();
+  constexpr bool ST = TrajSolver<Model, CON>::kStaged;
+  s.template backward_sweep<ST>(lane_ring(), depth);
   double phi0, dphi0;
-  s.phase_phi0_scan(&phi0, &dphi0);
+  s.template phase_phi0_scan<ST>(&phi0, &dphi0, lane_ring(), depth);
   P.phi0[b] = phi0;
   P.dphi0[b] = dphi0;
   P.phi[b] = phi0;
@@ -186,18 +191,19 @@ __global__ void __launch_bounds__(32) k_phase_backward(const DeviceProblem P, co
 template <class Model, bool CON>
 __global__ void __launch_bounds__(32) k_phase_rollout(const DeviceProblem P, const int* list,
                                                       int count, const int* dcount,
-                                                      bool speculative) {
+                                                      bool speculative, int depth) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= list_count(count, dcount)) return;
   const int b = list[t];
   TrajSolver<Model, CON> s(P, b);
   s.rho = CON ? P.rho[b] : 1.0;
+  constexpr bool ST = TrajSolver<Model, CON>::kStaged;
   if (!speculative) {
-    P.phi_eval[b] = s.phase_rollout(P.alpha_eval[b], -1);
+    P.phi_eval[b] = s.template phase_rollout<ST>(P.alpha_eval[b], -1, lane_ring(), depth);
   } else {
     const int slot = blockIdx.y;
     const double alpha = (slot == 0) ? P.alpha_eval[b] : ldexp(P.alpha_bt[b], -(slot - 1));
-    P.phi_s[(long)slot * P.Bp + b] = s.phase_rollout(alpha, slot);
+    P.phi_s[(long)slot * P.Bp + b] = s.template phase_rollout<ST>(alpha, slot, lane_ring(), depth);
   }
 }
 
@@ -208,7 +214,7 @@ __global__ void __launch_bounds__(32) k_phase_rollout(const DeviceProblem P, con
 template <class Model, bool CON>
 __global__ void __launch_bounds__(32) k_phase_lsupdate(const DeviceProblem P, const int* list,
                                                        int count, const int* dcount,
-                                                       bool speculative) {
+                                                       bool speculative, int depth) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= list_count(count, dcount)) return;
   const int b = list[t];
@@ -217,7 +223,7 @@ __global__ void __launch_bounds__(32) k_phase_lsupdate(const DeviceProblem P, co
   double dphi = 0.0;
   if (had_deriv) {
     TrajSolver<Model, CON> s(P, b);
-    dphi = s.phase_dphi_scan();
+    dphi = s.template phase_dphi_scan<TrajSolver<Model, CON>::kStaged>(lane_ring(), depth);
   }
   const LsOptions lo = ls_options(P.opts);
   LsMachine ls = P.ls[b];
@@ -342,15 +348,15 @@ __global__ void __launch_bounds__(32) k_open_loop_rollout(const DeviceProblem P)
   TrajSolver<Model, CON> s(P, b);
   constexpr int n = Model::n, m = Model::m;
   double x[n], u[m], xn[n];
-  load_block<n>(P.x0 + b, P.Bp, 0, x);
+  load_block<n>(s.G(P.x0, n), 0, 0, x);
   for (int k = 0; k < P.N; ++k) {
-    load_block<m>(P.u + b, P.Bp, k, u);
+    load_block<m>(s.F(P.u), s.S, k, u);
     s.dynamics(k, x, u, xn);
-    store_block<n>(P.x + b, P.Bp, k, x);
+    store_block<n>(s.F(P.x), s.S, k, x);
 #pragma unroll
     for (int i = 0; i < n; ++i) x[i] = xn[i];
   }
-  store_block<n>(P.x + b, P.Bp, P.N, x);
+  store_block<n>(s.F(P.x), s.S, P.N, x);
 }
 
 // ALTROSolver::CalcCost (solver.cpp:163-174): sum_k cost(k) incl. the AL terms at the working
@@ -366,11 +372,11 @@ __global__ void __launch_bounds__(32) k_calc_cost(const DeviceProblem P, double*
   for (int k = 0; k <= P.N; ++k) {
     const bool terminal = (k == P.N);
     double x[n], u[m], q[n], r[m];
-    load_block<n>(P.x + b, P.Bp, k, x);
-    load_block<n>(P.q + b, P.Bp, k, q);
+    load_block<n>(s.F(P.x), s.S, k, x);
+    load_block<n>(s.F(P.q), s.S, k, q);
     if (!terminal) {
-      load_block<m>(P.u + b, P.Bp, k, u);
-      load_block<m>(P.r + b, P.Bp, k, r);
+      load_block<m>(s.F(P.u), s.S, k, u);
+      load_block<m>(s.F(P.r), s.S, k, r);
     } else {
 #pragma unroll
       for (int i = 0; i < m; ++i) u[i] = 0.0;
