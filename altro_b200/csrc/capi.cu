@@ -200,9 +200,11 @@ struct altro_b200_solver {
   double *xs = nullptr, *us = nullptr, *phi_s = nullptr;
   int* sel = nullptr;
   unsigned long long *stat_acc = nullptr, *feas_acc = nullptr;
-  int nslots = 10;  // candidates per speculative line-search round
+  int nslots = 10;  // candidate steps per speculative line-search round (slot 0 = requested step)
+  int nstore = 1;   // halvings 1..nstore also keep their trajectory (candidate slot buffers)
   int *flags = nullptr, *iter_count = nullptr, *list_iter = nullptr, *list_ls = nullptr,
       *list_tmp = nullptr, *list_aux = nullptr, *counters = nullptr;
+  unsigned long long* ls_hist = nullptr;
   PhaseHost ph;
   int solve_mode = 0;  // 0: phase pipeline (default), 1: single persistent kernel
   // tracking-window cost
@@ -506,6 +508,7 @@ int altro_b200_set_dimension(altro_b200_solver* s, int n, int m) {  // altro_sol
   DALLOC(s, s->list_tmp, S);
   DALLOC(s, s->list_aux, S);
   DALLOC(s, s->counters, 8);
+  DALLOC(s, s->ls_hist, 32);
   memset(&s->ph, 0, sizeof(s->ph));
   {  // device limits that size the staging rings of the sequential sweeps (solve_inst.cu)
     int v = 0;
@@ -793,7 +796,7 @@ int altro_b200_initialize(altro_b200_solver* s) {  // altro_solver.cpp:225-229
   CUDA_OK(cudaGetLastError());
   // candidate slots of the speculative line search
   s->Rs = (long)(s->n + s->m) * 32;
-  DALLOC(s, s->xs, (long)s->nslots * s->G * (s->N + 1) * s->Rs);
+  DALLOC(s, s->xs, (long)(s->nstore > 0 ? s->nstore : 1) * s->G * (s->N + 1) * s->Rs);
   s->us = s->xs + (long)s->n * 32;
   DALLOC(s, s->phi_s, (long)s->nslots * s->Bp);
   CUDA_OK(cudaStreamSynchronize(s->stream));
@@ -935,6 +938,7 @@ static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   P.alpha_eval = s->alpha_eval;
   P.alpha_bt = s->alpha_bt;
   P.nslots = s->nslots;
+  P.nstore = s->nstore < s->nslots - 1 ? s->nstore : s->nslots - 1;
   P.xs = s->xs;
   P.us = s->us;
   P.phi_s = s->phi_s;
@@ -950,6 +954,7 @@ static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   P.list_ls = s->list_ls;
   P.list_tmp = s->list_tmp;
   P.counters = s->counters;
+  P.ls_hist = s->ls_hist;
   P.opts.iterations_max = s->opts.iterations_max;
   P.opts.tol_primal_feasibility = s->opts.tol_primal_feasibility;
   P.opts.tol_stationarity = s->opts.tol_stationarity;
@@ -1029,7 +1034,7 @@ int altro_b200_set_solve_mode(altro_b200_solver* s, int mode) {
 int altro_b200_set_speculation(altro_b200_solver* s, int nslots) {
   if (!s) return ALTRO_B200_INVALID_POINTER;
   if (s->initialized) return ALTRO_B200_SOLVER_ALREADY_INITIALIZED;
-  if (nslots < 1 || nslots > 24) return ALTRO_B200_BAD_INDEX;
+  if (nslots < 1 || nslots > 16) return ALTRO_B200_BAD_INDEX;
   s->nslots = nslots;
   return ALTRO_B200_NO_ERROR;
 }
@@ -1073,6 +1078,18 @@ int altro_b200_solve(altro_b200_solver* s) {
 
 long altro_b200_kernel_launches(const altro_b200_solver* s) { return s ? s->launches : 0; }
 
+int altro_b200_get_linesearch_histogram(altro_b200_solver* s, long* hist32, int reset) {
+  if (!s || !hist32) return ALTRO_B200_INVALID_POINTER;
+  if (!s->dims_set) return ALTRO_B200_DIMENSION_UNKNOWN;
+  CUDA_OK(cudaSetDevice(s->device));
+  unsigned long long h[32];
+  CUDA_OK(cudaMemcpyAsync(h, s->ls_hist, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_OK(cudaStreamSynchronize(s->stream));
+  for (int i = 0; i < 32; ++i) hist32[i] = (long)h[i];
+  if (reset) CUDA_OK(cudaMemsetAsync(s->ls_hist, 0, sizeof(h), s->stream));
+  return ALTRO_B200_NO_ERROR;
+}
+
 #define GETTER_PM(name, field, rows_expr, width_expr)                                 \
   int name(altro_b200_solver* s, double* out) {                            \
     if (!s || !out) return ALTRO_B200_INVALID_POINTER;                     \
@@ -1085,6 +1102,29 @@ GETTER_PM(altro_b200_get_inputs, u, s->m, s->N * s->m)
 GETTER_PM(altro_b200_get_dual_dynamics, y, s->n, (s->N + 1) * s->n)
 GETTER_PM(altro_b200_get_feedback_gains, K, s->m * s->n, s->N * s->m * s->n)
 GETTER_PM(altro_b200_get_feedforward_gains, d, s->m, s->N * s->m)
+
+// KnotPointData member of every problem by name (knotpoint_data.hpp:160-233): x u y (accepted
+// point = working copy after Solve), xbar ubar, A B, lx lu, K d, P p, q r c.  out: [B][knots][rows]
+// with knots = N + 1 (fields that do not exist at the terminal knot hold zeros / stale data there).
+int altro_b200_get_field(altro_b200_solver* s, const char* name, double* out, int* rows_out) {
+  if (!s || !name) return ALTRO_B200_INVALID_POINTER;
+  if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;
+  const int n = s->n, m = s->m;
+  struct { const char* nm; double* p; int rows; } tab[] = {
+      {"x", s->x, n}, {"u", s->u, m}, {"y", s->y, n}, {"xbar", s->xbar, n}, {"ubar", s->ubar, m},
+      {"A", s->A, n * n}, {"B", s->Bm, n * m}, {"lx", s->lx, n}, {"lu", s->lu, m},
+      {"K", s->K, m * n}, {"d", s->d, m}, {"P", s->P, n * n}, {"p", s->p, n},
+      {"q", s->q, n}, {"r", s->r, m}, {"c", s->c, 1}};
+  for (auto& t : tab) {
+    if (strcmp(t.nm, name) == 0) {
+      if (rows_out) *rows_out = t.rows;
+      if (!out) return ALTRO_B200_NO_ERROR;
+      CUDA_OK(cudaSetDevice(s->device));
+      return download_pm(s, fview(s, t.p, t.rows), (long)(s->N + 1) * t.rows, out);
+    }
+  }
+  return ALTRO_B200_BAD_INDEX;
+}
 
 #define GETTER_VEC(name, field, type)                                                       \
   int name(altro_b200_solver* s, type* out) {                                               \

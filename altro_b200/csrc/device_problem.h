@@ -104,11 +104,15 @@ struct DeviceProblem {
   double *phi0, *dphi0; // [Bp]
   int* flags;           // [Bp] bit mask, see TrajFlags
   int* iter_count;      // [Bp] iLQR iterations done so far
-  int *list_iter, *list_ls, *list_tmp;  // compacted problem indices
+  int *list_iter, *list_ls, *list_tmp;  // compacted GROUP indices (a group = 32 problems = 1 warp)
   int* counters;        // [8] device-side counts (see PhaseCounter)
+  // [32] accepted-step histogram of the line search: 0 alpha0 accepted, 1..15 halving j accepted,
+  // 16 cubic-first probe accepted, 17 zoom/other, 18 failed, 19 merit gradient too small
+  unsigned long long* ls_hist;
   // speculative line-search slots: candidate step lengths of one trajectory are rolled out
   // concurrently, each into its own copy of the working trajectory
-  int nslots;           // candidates per speculative round (>= 1)
+  int nslots;           // candidates per speculative round (>= 1): slot 0 = the requested step
+  int nstore;           // speculative slots 1..nstore also keep their trajectory (slot buffers)
   double *xs, *us;      // slot record stream; us = xs + n * 32
   double* phi_s;        // [nslots][Bp] merit value per candidate
   int* sel;             // [Bp] slot holding the working trajectory (-1: the main x, u arrays)
@@ -125,9 +129,11 @@ enum TrajFlags {
   TF_ACTIVE = 16,           // still iterating
   TF_LS_FAILED = 32,
   TF_CONVERGED = 64,
-  TF_SPECULATE = 128,       // the pending evaluations are a speculative batch (slots)
+  TF_SPECULATE = 128,       // the pending round also rolls out the halvings alpha_bt * 2^-j (merit only)
+  TF_REROLL = 256,          // accepted step came from a merit-only candidate: roll it out again, storing
+  TF_SPEC_VALID = 512,      // phi_s holds merit values of alpha_bt * 2^-j for this iteration's gains
 };
 
-enum PhaseCounter { PC_LS = 0, PC_DERIV = 1, PC_REFRESH_DYN = 2, PC_REFRESH_GRAD = 3, PC_ITER = 4 };
+enum PhaseCounter { PC_LS = 0, PC_DERIV = 1, PC_SPEC = 2, PC_REFRESH_GRAD = 3, PC_ITER = 4 };
 
 }  // namespace altro_b200

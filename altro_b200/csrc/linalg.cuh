@@ -167,41 +167,81 @@ ALTRO_DEV void prefetch_block(const double* __restrict__ base, long rec, int k) 
   }
 }
 
-// ---- asynchronous staging of the NEXT knots' rows into shared memory (cp.async / LDGSTS).
-// The sequential sweeps are bound by the latency of their per-knot loads (ncu r01 v2: 60-70 % of
-// all stall cycles are long-scoreboard even with an L2 prefetch one knot ahead).  Each lane copies
-// the elements of ITS OWN problem into ITS OWN column of a per-warp ring in shared memory,
-//     ring[stage][element][lane]      (256-byte rows: conflict-free 8-byte accesses)
-// one to three knots ahead, and reads them back with LDS (~30 cycles) when the knot's turn comes.
-// A lane only ever reads what it copied itself, so cp.async.wait_group is the only
-// synchronisation needed -- no barrier -- and compacted (non-contiguous) problem lists work.
-ALTRO_DEV void cp_async_f64(double* smem_dst, const double* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-}
-ALTRO_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-// wait until at most `pending` (0..2) of the most recent groups are still in flight
-ALTRO_DEV void cp_async_wait(int pending) {
-  if (pending <= 0)
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-  else if (pending == 1)
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-  else
-    asm volatile("cp.async.wait_group 2;" ::: "memory");
-}
-constexpr int kMaxStageDepth = 3;
+// ---- TMA staging of whole knot records into shared memory (cp.async.bulk, SASS UBLKCP).
+// The sequential sweeps read, per knot, one contiguous multi-KB range of the group's knot record
+// (device_problem.h).  A BulkRing keeps the next `depth` knots in flight: the leader thread arms
+// the stage's mbarrier with the byte count and issues one bulk copy per contiguous piece; every
+// thread waits on the mbarrier parity, reads ITS lane's column of the stage
+//     stage[row][lane]      (256-byte rows: conflict-free 8-byte accesses)
+// into registers, and after a warp/CTA barrier the leader refills the stage.  Measured at the
+// 3.5 warps/SM of B = 16384: 6.8 TB/s vs 3.2 TB/s for per-element LDG from the old
+// problem-fastest layout and 5.0 TB/s for per-lane cp.async (profiles/r01_microbench_layout.txt).
+constexpr int kMaxStageDepth = 4;
 
-// stage: st points at this lane's column of one ring stage; `off` = first element row
+struct BulkRing {
+  double* data;             // [depth][stage_doubles], 128-byte aligned
+  unsigned long long* bar;  // [depth] "stage full" mbarriers
+  int depth, stage_doubles;
+  int s;                    // stage the consumer reads next
+  unsigned parity;
+
+  // smem: dynamic shared memory of the CTA (>= 128 + depth * stage_doubles * 8 bytes).  All threads
+  // call init; the caller synchronises the CTA (or warp) afterwards.
+  ALTRO_DEV void init(unsigned char* smem, int depth_, int stage_doubles_, bool leader) {
+    bar = reinterpret_cast<unsigned long long*>(smem);
+    data = reinterpret_cast<double*>(smem + 128);
+    depth = depth_;
+    stage_doubles = stage_doubles_;
+    s = 0;
+    parity = 0;
+    if (leader) {
+      for (int j = 0; j < depth; ++j) {
+        const unsigned a = (unsigned)__cvta_generic_to_shared(bar + j);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a));
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  // leader only: announce `bytes` for `stage`, then issue the copies that add up to it
+  ALTRO_DEV void expect(int stage, unsigned bytes) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar + stage);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+  }
+  ALTRO_DEV void copy(int stage, int row, const double* src, unsigned bytes) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar + stage);
+    const unsigned d = (unsigned)__cvta_generic_to_shared(data + (long)stage * stage_doubles + row * 32);
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+        "l"(src), "r"(bytes), "r"(a)
+        : "memory");
+  }
+  // all threads: block until the current stage has landed; returns its first row
+  ALTRO_DEV const double* wait() const {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar + s);
+    unsigned ok = 0;
+    while (!ok) {
+      asm volatile(
+          "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+          : "=r"(ok)
+          : "r"(a), "r"(parity)
+          : "memory");
+    }
+    return data + (long)s * stage_doubles;
+  }
+  ALTRO_DEV void advance() {
+    if (++s == depth) {
+      s = 0;
+      parity ^= 1u;
+    }
+  }
+  static size_t bytes(int depth, int stage_doubles) { return 128 + (size_t)depth * stage_doubles * 8; }
+};
+
+// this lane's element e of a block that starts at `row` of a landed stage
 template <int E>
-ALTRO_DEV void stage_block(double* st, int off, const double* __restrict__ base, long rec, int k) {
-  const double* p = base + (long)k * rec;
+ALTRO_DEV void unstage_block(const double* stage, int row, int lane, double* out) {
 #pragma unroll
-  for (int e = 0; e < E; ++e) cp_async_f64(st + (off + e) * 32, p + e * 32);
-}
-template <int E>
-ALTRO_DEV void unstage_block(const double* st, int off, double* out) {
-#pragma unroll
-  for (int e = 0; e < E; ++e) out[e] = st[(off + e) * 32];
+  for (int e = 0; e < E; ++e) out[e] = stage[(row + e) * 32 + lane];
 }
 
 template <int E>

@@ -9,7 +9,9 @@ namespace altro_b200 {
 
 template <class Model, bool CON>
 static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
-  const int B = P.B, N = P.N;
+  using TS = TrajSolver<Model, CON>;
+  constexpr int n = Model::n, m = Model::m;
+  const int B = P.B, N = P.N, G = P.G;
   auto g32 = [](int count) { return (count + 31) / 32; };
   auto g128 = [](int count) { return (count + 127) / 128; };
   cudaError_t err = cudaSuccess;
@@ -32,32 +34,34 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
     err = cudaStreamSynchronize(st);
     H->syncs += 1;
   };
+  // lists hold GROUP ids; `count` = groups
   auto expand = [&](const int* list, int count, const int* dcount, int mask, bool with_dyn,
                     int slot_mode, bool dual_first) {
-    timed(PH_EXPAND, (double)count * (N + 1), [&] {
-      k_phase_expand<Model, CON><<<dim3(g128(count), N + 1), 128, 0, st>>>(
+    timed(PH_EXPAND, (double)count * 32 * (N + 1), [&] {
+      k_phase_expand<Model, CON><<<dim3(g128(count * 32), N + 1), 128, 0, st>>>(
           P, list, count, dcount, mask, with_dyn, slot_mode, dual_first);
     });
   };
   auto compact = [&](const int* in, int count, const int* dcount, int mask, int* out, int slot,
-                     int mask2, int slot2) {
+                     int mask2, int slot2, int mask3, int slot3) {
     timed(PH_COMPACT, count, [&] {
-      k_compact<<<1, 1024, 0, st>>>(in, count, dcount, P.flags, mask, out, P.counters, slot, mask2, slot2);
+      k_compact<<<1, 1024, 0, st>>>(in, count, dcount, P.flags, mask, out, P.counters, slot, mask2,
+                                    slot2, mask3, slot3);
     });
   };
-  // Staging ring of the sequential sweeps (linalg.cuh): depth = knots in flight per warp, as deep
-  // as shared memory allows with every CTA of the launch resident (<= kMaxStageDepth, >= 1).
-  using TS = TrajSolver<Model, CON>;
-  auto ring = [&](int ctas, int stage_elems, int* depth) -> size_t {
+  // TMA staging ring of the sequential sweeps (linalg.cuh): depth = knots in flight per CTA, as
+  // deep as shared memory allows with every CTA of the launch resident (<= kMaxStageDepth).
+  auto ring = [&](int ctas, int stage_rows, int* depth) -> size_t {
     if (!TS::kStaged) {
       *depth = 0;
       return 0;
     }
-    const size_t stage_bytes = (size_t)stage_elems * 32 * sizeof(double);
+    const size_t stage_bytes = (size_t)stage_rows * 256;
     const int per_sm = (ctas + H->num_sms - 1) / H->num_sms;
-    const size_t budget = std::min<size_t>(H->smem_per_sm / std::max(per_sm, 1), H->smem_per_cta) - 1024;
-    *depth = (int)std::max<size_t>(1, std::min<size_t>(kMaxStageDepth, budget / stage_bytes));
-    return stage_bytes * *depth;
+    const size_t budget =
+        std::min<size_t>(H->smem_per_sm / std::max(per_sm, 1) - 1024, H->smem_per_cta) - 128;
+    *depth = (int)std::max<size_t>(2, std::min<size_t>(kMaxStageDepth, budget / stage_bytes));
+    return BulkRing::bytes(*depth, stage_rows * 32);
   };
   if (TS::kStaged) {
     const int mx = (int)H->smem_per_cta;
@@ -65,86 +69,86 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
     cudaFuncSetAttribute(k_phase_rollout<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_phase_lsupdate<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   }
-  auto rollout = [&](const int* list, int count, const int* dcount, bool spec) {
-    const int slots = spec ? P.nslots : 1;
+  constexpr int kRowsBackward = std::max(n * n + n * m + n + m, TS::rB + n * m - TS::rQ);
+  constexpr int kRowsRollout = TS::rD + m;
+  constexpr int kRowsDphi = m * n + m + n * n + n * m + n + m;
+  // warps = candidate steps rolled out per group (1 = only the requested step)
+  auto rollout = [&](const int* list, int count, const int* dcount, int warps) {
     int depth;
-    const size_t sm = ring(g32(count) * slots, TS::kStageRollout, &depth);
-    timed(PH_ROLLOUT, (double)count * slots, [&] {
-      k_phase_rollout<Model, CON><<<dim3(g32(count), slots), 32, sm, st>>>(P, list, count, dcount, spec, depth);
+    const size_t sm = ring(count, kRowsRollout, &depth);
+    timed(PH_ROLLOUT, (double)count * 32 * warps, [&] {
+      k_phase_rollout<Model, CON><<<count, 32 * warps, sm, st>>>(P, list, count, dcount, depth);
     });
   };
-  auto lsupdate = [&](const int* list, int count, const int* dcount, bool spec) {
+  auto lsupdate = [&](const int* list, int count, const int* dcount) {
     int depth;
-    const size_t sm = ring(g32(count), TS::kStageDphi, &depth);
-    timed(PH_LSUPDATE, count, [&] {
-      k_phase_lsupdate<Model, CON><<<g32(count), 32, sm, st>>>(P, list, count, dcount, spec, depth);
+    const size_t sm = ring(count, kRowsDphi, &depth);
+    timed(PH_LSUPDATE, (double)count * 32, [&] {
+      k_phase_lsupdate<Model, CON><<<count, 32, sm, st>>>(P, list, count, dcount, depth);
     });
   };
 
   // ---- prologue (solver.cpp:417-430)
   timed(PH_INIT, B, [&] { k_phase_init<Model, CON><<<g32(B), 32, 0, st>>>(P); });
-  expand(nullptr, B, nullptr, 0, true, -1, false);  // with the OLD penalty (quirk Q3) ...
+  expand(nullptr, G, nullptr, 0, true, -1, false);  // with the OLD penalty (quirk Q3) ...
   if (CON) k_phase_set_rho<<<g128(B), 128, 0, st>>>(P.rho, B, P.opts.penalty_initial);  // ... then reset
   int* list_iter = P.list_iter;
   int* list_iter_next = H->list_aux;
-  compact(nullptr, B, nullptr, TF_ACTIVE, list_iter, PC_ITER, 0, 0);
-  int count_iter = B;
+  compact(nullptr, G, nullptr, TF_ACTIVE, list_iter, PC_ITER, 0, 0, 0, 0);
+  int count_iter = G;
   const bool backtracking = P.opts.use_backtracking_linesearch != 0;
+  const int spec_warps = (backtracking && P.nslots > 1) ? std::min(P.nslots, 16) : 1;
+  const int LS_MASK = TF_NEED_EVAL | TF_REROLL;
 
   for (int iter = 0; iter < P.opts.iterations_max && count_iter > 0; ++iter) {
     {
       int depth;
-      const size_t sm = ring(g32(count_iter), TS::kStageMax, &depth);
-      timed(PH_BACKWARD, count_iter, [&] {
-        k_phase_backward<Model, CON><<<g32(count_iter), 32, sm, st>>>(P, list_iter, count_iter, depth);
+      const size_t sm = ring(count_iter, kRowsBackward, &depth);
+      timed(PH_BACKWARD, (double)count_iter * 32, [&] {
+        k_phase_backward<Model, CON><<<count_iter, 32, sm, st>>>(P, list_iter, count_iter, depth);
       });
     }
     int* cur = P.list_ls;
     int* nxt = P.list_tmp;
-    compact(list_iter, count_iter, nullptr, TF_NEED_EVAL, cur, PC_LS, TF_WANT_DERIV, PC_DERIV);
-    // round 1: alpha = 1 with derivative for everybody still searching; the exact list length
-    // stays on the device (no host round trip), count_iter bounds the grid
+    compact(list_iter, count_iter, nullptr, LS_MASK, cur, PC_LS, TF_WANT_DERIV, PC_DERIV, TF_SPECULATE, PC_SPEC);
+    // round 1: the requested step (alpha0 = 1, with derivative) for every problem still searching,
+    // plus, for the backtracking search, the halvings it would try next.  The exact list length
+    // stays on the device (no host round trip); count_iter bounds the grid.
     const int* dcount = P.counters + PC_LS;
-    rollout(cur, count_iter, dcount, false);
+    rollout(cur, count_iter, dcount, spec_warps);
     expand(cur, count_iter, dcount, TF_WANT_DERIV, true, -1, false);
-    lsupdate(cur, count_iter, dcount, false);
-    compact(cur, count_iter, dcount, TF_NEED_EVAL, nxt, PC_LS, TF_WANT_DERIV, PC_DERIV);
+    lsupdate(cur, count_iter, dcount);
+    compact(cur, count_iter, dcount, LS_MASK, nxt, PC_LS, TF_WANT_DERIV, PC_DERIV, TF_SPECULATE, PC_SPEC);
     readback();
     if (err != cudaSuccess) return (int)err;
-    int count_ls = H->h_counters[PC_LS], count_deriv = H->h_counters[PC_DERIV];
-    {
-      int* t = cur;
-      cur = nxt;
-      nxt = t;
-    }
-    while (count_ls > 0) {  // further rounds: speculative batches (backtracking) or single steps
-      rollout(cur, count_ls, nullptr, backtracking);
-      if (count_deriv > 0) expand(cur, count_ls, nullptr, TF_WANT_DERIV, true, backtracking ? 0 : -1, false);
-      lsupdate(cur, count_ls, nullptr, backtracking);
-      compact(cur, count_ls, nullptr, TF_NEED_EVAL, nxt, PC_LS, TF_WANT_DERIV, PC_DERIV);
+    int count_ls = H->h_counters[PC_LS], count_deriv = H->h_counters[PC_DERIV],
+        count_spec = H->h_counters[PC_SPEC];
+    std::swap(cur, nxt);
+    while (count_ls > 0) {  // further rounds: cubic-first probe, zoom steps, re-rollouts, deeper halvings
+      rollout(cur, count_ls, nullptr, count_spec > 0 ? spec_warps : 1);
+      if (count_deriv > 0) expand(cur, count_ls, nullptr, TF_WANT_DERIV, true, -1, false);
+      lsupdate(cur, count_ls, nullptr);
+      compact(cur, count_ls, nullptr, LS_MASK, nxt, PC_LS, TF_WANT_DERIV, PC_DERIV, TF_SPECULATE, PC_SPEC);
       readback();
       if (err != cudaSuccess) return (int)err;
       count_ls = H->h_counters[PC_LS];
       count_deriv = H->h_counters[PC_DERIV];
-      int* t = cur;
-      cur = nxt;
-      nxt = t;
+      count_spec = H->h_counters[PC_SPEC];
+      std::swap(cur, nxt);
     }
     if (backtracking) expand(list_iter, count_iter, nullptr, TF_REFRESH_DYN, true, -2, false);  // solver.cpp:256-262
-    timed(PH_CRITERIA, (double)count_iter * (N + 1), [&] {
-      k_phase_costate<Model, CON><<<dim3(g128(count_iter), N + 1), 128, 0, st>>>(P, list_iter, count_iter);
-      k_phase_residual<Model, CON><<<dim3(g128(count_iter), N + 1), 128, 0, st>>>(P, list_iter, count_iter);
-      k_phase_decide<CON><<<g128(count_iter), 128, 0, st>>>(P, list_iter, count_iter);
+    timed(PH_CRITERIA, (double)count_iter * 32 * (N + 1), [&] {
+      k_phase_costate<Model, CON><<<dim3(g128(count_iter * 32), N + 1), 128, 0, st>>>(P, list_iter, count_iter);
+      k_phase_residual<Model, CON><<<dim3(g128(count_iter * 32), N + 1), 128, 0, st>>>(P, list_iter, count_iter);
+      k_phase_decide<CON><<<g128(count_iter * 32), 128, 0, st>>>(P, list_iter, count_iter);
     });
     H->launches[PH_CRITERIA] += 2;
     if (CON) expand(list_iter, count_iter, nullptr, TF_REFRESH_GRAD, false, -1, true);  // solver.cpp:475-486
-    compact(list_iter, count_iter, nullptr, TF_ACTIVE, list_iter_next, PC_ITER, 0, 0);
+    compact(list_iter, count_iter, nullptr, TF_ACTIVE, list_iter_next, PC_ITER, 0, 0, 0, 0);
     readback();
     if (err != cudaSuccess) return (int)err;
     count_iter = H->h_counters[PC_ITER];
-    int* t = list_iter;
-    list_iter = list_iter_next;
-    list_iter_next = t;
+    std::swap(list_iter, list_iter_next);
   }
   return (int)cudaGetLastError();
 }

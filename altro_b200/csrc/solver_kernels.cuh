@@ -131,12 +131,15 @@ struct TrajSolver {
   static constexpr int m = Model::m;
   static constexpr int NS_ = Model::n, NI_ = Model::m;
   static constexpr bool kLinear = ModelTraits<Model>::is_linear;
-  // the sequential sweeps of the phase pipeline stage their per-knot loads through shared
-  // memory when the blocks are small enough to live in registers (larger n keeps rolled loops
-  // over local-memory arrays and is bound by arithmetic, not by load latency)
+  // TMA staging of the sequential sweeps (solver_phases.cuh) when the blocks are small enough to
+  // live in registers (larger n keeps rolled loops over local-memory arrays, is bound by
+  // arithmetic rather than by load latency, and a stage would not fit shared memory).
   static constexpr bool kStaged = (NS_ <= kUnrollDim);
-  static constexpr int kStageMax =
-      (2 * (NS_ + NI_) + NI_ * NS_ + NI_ + NS_ * NS_ + NS_ * NI_);  // = kStagePhi0, the largest
+  // first row of each field inside a knot record; order = device_problem.h / capi.cu
+  static constexpr int rXbar = 0, rUbar = rXbar + NS_, rQ = rUbar + NI_, rR = rQ + NS_, rC = rR + NI_,
+                       rK = rC + 1, rD = rK + NI_ * NS_, rX = rD + NI_, rU = rX + NS_, rA = rU + NI_,
+                       rB = rA + NS_ * NS_, rLx = rB + NS_ * NI_, rLu = rLx + NS_, rY = rLu + NI_,
+                       rP = rY + NS_, rPv = rP + NS_ * NS_, rUinit = rPv + NS_, kRecordRows = rUinit + NI_;
 
   const DeviceProblem& P;
   const long S;   // knot-record stride (doubles) of the main record stream
@@ -216,6 +219,11 @@ struct TrajSolver {
   // ---- original (diagonal LQR) cost, knotpoint_data.cpp:636-645, :670-678
   ALTRO_DEV double stage_cost(int k, const double* x, const double* u, const double* q,
                               const double* r, bool terminal) const {
+    return stage_cost(k, x, u, q, r, terminal, F(P.c)[(long)k * S]);
+  }
+  // cval: the constant term c_k of this problem (already loaded / staged)
+  ALTRO_DEV double stage_cost(int k, const double* x, const double* u, const double* q,
+                              const double* r, bool terminal, double cval) const {
     double J = 0.0;
     double a = 0.0;
 #pragma unroll
@@ -229,7 +237,7 @@ struct TrajSolver {
       J += bb;
       J += dot<m>(r, u);
     }
-    J += F(P.c)[(long)k * S];
+    J += cval;
     return J;
   }
   ALTRO_DEV void stage_gradient(int k, const double* x, const double* u, const double* q,
@@ -454,129 +462,122 @@ struct TrajSolver {
 
   // Backward Riccati sweep = CalcExpansions + tvlqr_BackwardPass (solver.cpp:448-449,
   // tvlqr.cpp:65-195) with reg = 0, f = 0.  The cost Hessian is rebuilt per knot from the
-  // diagonal weights and the AL Gauss-Newton terms instead of being stored.
-  // STAGED: A, B, lx, lu of the next `depth` knots are in flight into this lane's column of the
-  // shared-memory ring (linalg.cuh) while the current knot is being worked on.
-  static constexpr int kStageBackward = n * n + n * m + n + m;
-  template <bool STAGED = false>
-  ALTRO_DEV void backward_sweep(double* ring = nullptr, int depth = 0) {
-    double Pn[n * n], pn[n];
-    auto fetch = [&](int k, int stage) {
-      double* st = ring + stage * (kStageBackward * 32);
-      stage_block<n * n>(st, 0, F(P.A), S, k);
-      stage_block<n * m>(st, n * n, F(P.Bm), S, k);
-      stage_block<n>(st, n * n + n * m, F(P.lx), S, k);
-      stage_block<m>(st, n * n + n * m + n, F(P.lu), S, k);
-    };
-    if constexpr (STAGED) {
-      for (int j = 0; j < depth; ++j) {
-        if (N - 1 - j >= 0) fetch(N - 1 - j, j);
-        cp_async_commit();
-      }
-    }
-    int stage = 0;
+  // diagonal weights and the AL Gauss-Newton terms instead of being stored.  Split into a
+  // terminal part and a per-knot step so that the plain sweep below (direct loads) and the
+  // TMA-staged group kernel (solver_phases.cuh) run the identical arithmetic.
+  ALTRO_DEV void riccati_terminal(double* Pn, double* pn) {  // tvlqr.cpp:85-90
+#pragma unroll
+    for (int i = 0; i < n * n; ++i) Pn[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) Pn[i + n * i] = P.Qd[N * n + i];
+    al_hessian(N, true, Pn, nullptr, nullptr);
+    load_block<n>(F(P.lx), S, N, pn);
+    store_block<n * n>(F(P.P), S, N, Pn);
+    store_block<n>(F(P.p), S, N, pn);
+  }
+
+  // One knot (tvlqr.cpp:92-192).  A, Bm: dynamics expansion; Qx, Qu hold lx, lu on entry; Pn, pn
+  // carry the cost-to-go.  Returns false when the Cholesky of Quu fails: tvlqr returns there
+  // (:162-164) and Solve ignores it (quirk Q2), so this knot keeps the unsolved K = Qux,
+  // d = -Qu and P_k, p_k and everything below stay stale -- the caller must stop the sweep.
+  ALTRO_DEV bool riccati_step(int k, const double* A, const double* Bm, double* Qx, double* Qu,
+                              double* Pn, double* pn) {
+    double Qxx[n * n], Quu[m * m], Qux[m * n];
+#pragma unroll
+    for (int i = 0; i < n * n; ++i) Qxx[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) Qxx[i + n * i] = P.Qd[k * n + i];
+#pragma unroll
+    for (int i = 0; i < m * m; ++i) Quu[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < m; ++i) Quu[i + m * i] = P.Rd[k * m + i];
+#pragma unroll
+    for (int i = 0; i < m * n; ++i) Qux[i] = 0.0;
+    al_hessian(k, false, Qxx, Quu, Qux);
     {
-#pragma unroll
-      for (int i = 0; i < n * n; ++i) Pn[i] = 0.0;
-#pragma unroll
-      for (int i = 0; i < n; ++i) Pn[i + n * i] = P.Qd[N * n + i];
-      al_hessian(N, true, Pn, nullptr, nullptr);
-      load_block<n>(F(P.lx), S, N, pn);
-      store_block<n * n>(F(P.P), S, N, Pn);
-      store_block<n>(F(P.p), S, N, pn);
+      double T1[n * n];
+      mm<n, n, n, true, false, 0>(A, Pn, T1);    // A' P+            tvlqr.cpp:135
+      mm<n, n, n, false, false, 1>(T1, A, Qxx);  // Qxx += (A'P+) A  :136
     }
-    for (int k = N - 1; k >= 0; --k) {
-      double A[n * n], Bm[n * m];
-      double Qxx[n * n], Quu[m * m], Qux[m * n], Qx[n], Qu[m];
-      if constexpr (STAGED) {
-        cp_async_wait(depth - 1);
-        const double* st = ring + stage * (kStageBackward * 32);
-        unstage_block<n * n>(st, 0, A);
-        unstage_block<n * m>(st, n * n, Bm);
-        unstage_block<n>(st, n * n + n * m, Qx);
-        unstage_block<m>(st, n * n + n * m + n, Qu);
-        if (k - depth >= 0) fetch(k - depth, stage);  // refill the stage just consumed
-        cp_async_commit();
-        stage = (stage + 1 == depth) ? 0 : stage + 1;
-      } else {
-        if (k > 0) {
-          prefetch_block<n * n>(F(P.A), S, k - 1);
-          prefetch_block<n * m>(F(P.Bm), S, k - 1);
-          prefetch_block<n>(F(P.lx), S, k - 1);
-          prefetch_block<m>(F(P.lu), S, k - 1);
-        }
-        load_block<n * n>(F(P.A), S, k, A);
-        load_block<n * m>(F(P.Bm), S, k, Bm);
-      }
+    {
+      double T2[m * n];
+      mm<m, n, n, true, false, 0>(Bm, Pn, T2);    // B' P+            :139
+      mm<m, m, n, false, false, 1>(T2, Bm, Quu);  // Quu += (B'P+) B  :140
+      mm<m, n, n, false, false, 1>(T2, A, Qux);   // Qux += (B'P+) A  :143
+    }
+    mm<n, 1, n, true, false, 1>(A, pn, Qx);   // Qx = q + A' p+     :147-150 (f = 0)
+    mm<m, 1, n, true, false, 1>(Bm, pn, Qu);  // Qu = r + B' p+     :151-152
+    double K[m * n], d[m], L[m * m];
 #pragma unroll
-      for (int i = 0; i < n * n; ++i) Qxx[i] = 0.0;
+    for (int i = 0; i < m * n; ++i) K[i] = Qux[i];
 #pragma unroll
-      for (int i = 0; i < n; ++i) Qxx[i + n * i] = P.Qd[k * n + i];
+    for (int i = 0; i < m; ++i) d[i] = -Qu[i];
 #pragma unroll
-      for (int i = 0; i < m * m; ++i) Quu[i] = 0.0;
-#pragma unroll
-      for (int i = 0; i < m; ++i) Quu[i + m * i] = P.Rd[k * m + i];
-#pragma unroll
-      for (int i = 0; i < m * n; ++i) Qux[i] = 0.0;
-      al_hessian(k, false, Qxx, Quu, Qux);
-      {
-        double T1[n * n];
-        mm<n, n, n, true, false, 0>(A, Pn, T1);    // A' P+            tvlqr.cpp:135
-        mm<n, n, n, false, false, 1>(T1, A, Qxx);  // Qxx += (A'P+) A  :136
-      }
-      {
-        double T2[m * n];
-        mm<m, n, n, true, false, 0>(Bm, Pn, T2);    // B' P+            :139
-        mm<m, m, n, false, false, 1>(T2, Bm, Quu);  // Quu += (B'P+) B  :140
-        mm<m, n, n, false, false, 1>(T2, A, Qux);   // Qux += (B'P+) A  :143
-      }
-      if constexpr (!STAGED) {
-        load_block<n>(F(P.lx), S, k, Qx);
-        load_block<m>(F(P.lu), S, k, Qu);
-      }
-      mm<n, 1, n, true, false, 1>(A, pn, Qx);   // Qx = q + A' p+     :147-150 (f = 0)
-      mm<m, 1, n, true, false, 1>(Bm, pn, Qu);  // Qu = r + B' p+     :151-152
-      double K[m * n], d[m], L[m * m];
-#pragma unroll
-      for (int i = 0; i < m * n; ++i) K[i] = Qux[i];
-#pragma unroll
-      for (int i = 0; i < m; ++i) d[i] = -Qu[i];
-#pragma unroll
-      for (int i = 0; i < m * m; ++i) L[i] = Quu[i];
-      const bool ok = cholesky<m>(L);  // :161
-      if (!ok) {
-        // tvlqr returns here (:162-164) and Solve ignores it (quirk Q2): this knot keeps the
-        // unsolved K = Qux, d = -Qu; P_k, p_k and everything below stay stale.
-        store_block<m * n>(F(P.K), S, k, K);
-        store_block<m>(F(P.d), S, k, d);
-        return;
-      }
-      cholesky_solve<m, n>(L, K);
-      cholesky_solve<m, 1>(L, d);
+    for (int i = 0; i < m * m; ++i) L[i] = Quu[i];
+    const bool ok = cholesky<m>(L);  // :161
+    if (!ok) {
       store_block<m * n>(F(P.K), S, k, K);
       store_block<m>(F(P.d), S, k, d);
-      // cost-to-go, :173-186
-      double QuuK[m * n], KtQux[n * n];
-      mm<m, n, m, false, false, 0>(Quu, K, QuuK);
-      mm<n, n, m, true, false, 0>(K, Qux, KtQux);
+      return false;
+    }
+    cholesky_solve<m, n>(L, K);
+    cholesky_solve<m, 1>(L, d);
+    store_block<m * n>(F(P.K), S, k, K);
+    store_block<m>(F(P.d), S, k, d);
+    // cost-to-go, :173-186
+    double QuuK[m * n], KtQux[n * n];
+    mm<m, n, m, false, false, 0>(Quu, K, QuuK);
+    mm<n, n, m, true, false, 0>(K, Qux, KtQux);
 #pragma unroll
-      for (int i = 0; i < n * n; ++i) Pn[i] = Qxx[i];
-      mm<n, n, m, true, false, 1>(QuuK, K, Pn);
+    for (int i = 0; i < n * n; ++i) Pn[i] = Qxx[i];
+    mm<n, n, m, true, false, 1>(QuuK, K, Pn);
 #pragma unroll
-      for (int c = 0; c < n; ++c)
+    for (int c = 0; c < n; ++c)
 #pragma unroll
-        for (int rr = 0; rr < n; ++rr) Pn[rr + n * c] -= KtQux[rr + n * c];
+      for (int rr = 0; rr < n; ++rr) Pn[rr + n * c] -= KtQux[rr + n * c];
 #pragma unroll
-      for (int c = 0; c < n; ++c)
+    for (int c = 0; c < n; ++c)
 #pragma unroll
-        for (int rr = 0; rr < n; ++rr) Pn[rr + n * c] -= KtQux[c + n * rr];
+      for (int rr = 0; rr < n; ++rr) Pn[rr + n * c] -= KtQux[c + n * rr];
 #pragma unroll
-      for (int i = 0; i < n; ++i) pn[i] = Qx[i];
-      mm<n, 1, m, true, false, -1>(QuuK, d, pn);
-      mm<n, 1, m, true, false, -1>(K, Qu, pn);
-      mm<n, 1, m, true, false, 1>(Qux, d, pn);
-      store_block<n * n>(F(P.P), S, k, Pn);
-      store_block<n>(F(P.p), S, k, pn);
+    for (int i = 0; i < n; ++i) pn[i] = Qx[i];
+    mm<n, 1, m, true, false, -1>(QuuK, d, pn);
+    mm<n, 1, m, true, false, -1>(K, Qu, pn);
+    mm<n, 1, m, true, false, 1>(Qux, d, pn);
+    store_block<n * n>(F(P.P), S, k, Pn);
+    store_block<n>(F(P.p), S, k, pn);
+    return true;
+  }
+
+  // Out-of-line copy for the large-block models (n > kUnrollDim): their arrays live in local
+  // memory anyway, and keeping the step a real function keeps ptxas' register allocation of the
+  // surrounding kernel sane (13 KB of spills when inlined into k_phase_backward<Chain<12,4>>).
+  __device__ __noinline__ bool riccati_step_call(int k, const double* A, const double* Bm, double* Qx,
+                                                 double* Qu, double* Pn, double* pn) {
+    return riccati_step(k, A, Bm, Qx, Qu, Pn, pn);
+  }
+
+  ALTRO_DEV void backward_sweep() {
+    double Pn[n * n], pn[n];
+    riccati_terminal(Pn, pn);
+    for (int k = N - 1; k >= 0; --k) {
+      if (k > 0) {
+        prefetch_block<n * n>(F(P.A), S, k - 1);
+        prefetch_block<n * m>(F(P.Bm), S, k - 1);
+        prefetch_block<n>(F(P.lx), S, k - 1);
+        prefetch_block<m>(F(P.lu), S, k - 1);
+      }
+      double A[n * n], Bm[n * m], Qx[n], Qu[m];
+      load_block<n * n>(F(P.A), S, k, A);
+      load_block<n * m>(F(P.Bm), S, k, Bm);
+      load_block<n>(F(P.lx), S, k, Qx);
+      load_block<m>(F(P.lu), S, k, Qu);
+      bool ok;
+      if constexpr (n > kUnrollDim)
+        ok = riccati_step_call(k, A, Bm, Qx, Qu, Pn, pn);
+      else
+        ok = riccati_step(k, A, Bm, Qx, Qu, Pn, pn);
+      if (!ok) return;
     }
   }
 
@@ -862,53 +863,46 @@ struct TrajSolver {
   // closed-loop rollout reproduces the accepted trajectory bit for bit (dx = 0), so x_, u_, A, B
   // are already in HBM; what changes with the new gains / duals / penalty is the cost, the
   // projected duals, the gradients and the directional derivative, recomputed here in one
-  // linear scan.
-  static constexpr int kStagePhi0 = 2 * (n + m) + m * n + m + n * n + n * m;
-  template <bool STAGED = false>
-  ALTRO_DEV void phase_phi0_scan(double* phi_out, double* dphi_out, double* ring = nullptr,
-                                 int depth = 0) {
+  // linear scan.  phi0_step handles knot k < N given its blocks in registers.
+  ALTRO_DEV void phi0_step(int k, const double* x, const double* u, const double* q, const double* r,
+                           double cval, const double* K, const double* d, const double* A,
+                           const double* Bm, double* dxda, double& phi, double& dphi) {
+    double lx[n], lu[m], duda[m], dxn[n];
+    stage_gradient(k, x, u, q, r, false, lx, lu);
+    phi += stage_cost(k, x, u, q, r, false, cval) + al_terms(k, x, u, false, true, lx, lu);
+    store_block<n>(F(P.lx), S, k, lx);
+    store_block<m>(F(P.lu), S, k, lu);
+    {
+      double Kd[m];
+      mm<m, 1, n, false, false, 0>(K, dxda, Kd);
+#pragma unroll
+      for (int i = 0; i < m; ++i) duda[i] = -Kd[i] + d[i];
+    }
+    mm<n, 1, n, false, false, 0>(A, dxda, dxn);
+    mm<n, 1, m, false, false, 1>(Bm, duda, dxn);
+    dphi += dot<n>(lx, dxda);
+    dphi += dot<m>(lu, duda);
+#pragma unroll
+    for (int i = 0; i < n; ++i) dxda[i] = dxn[i];
+  }
+  ALTRO_DEV void phi0_terminal(const double* dxda, double& phi, double& dphi) {
+    double x[n], q[n], u0[m], lx[n];
+    load_block<n>(F(P.x), S, N, x);
+    load_block<n>(F(P.q), S, N, q);
+#pragma unroll
+    for (int i = 0; i < m; ++i) u0[i] = 0.0;
+    stage_gradient(N, x, u0, q, nullptr, true, lx, nullptr);
+    phi += stage_cost(N, x, u0, q, nullptr, true) + al_terms(N, x, u0, true, true, lx, nullptr);
+    store_block<n>(F(P.lx), S, N, lx);
+    dphi += dot<n>(lx, dxda);
+  }
+  ALTRO_DEV void phase_phi0_scan(double* phi_out, double* dphi_out) {
     double phi = 0.0, dphi = 0.0;
     double dxda[n];
 #pragma unroll
     for (int i = 0; i < n; ++i) dxda[i] = 0.0;
-    constexpr int oU = n, oQ = n + m, oR = 2 * n + m, oK = 2 * (n + m), oD = oK + m * n,
-                  oA = oD + m, oB = oA + n * n;
-    auto fetch = [&](int k, int stage) {  // knots 0..N-1 (the terminal knot is read directly)
-      double* st = ring + stage * (kStagePhi0 * 32);
-      stage_block<n>(st, 0, F(P.x), S, k);
-      stage_block<m>(st, oU, F(P.u), S, k);
-      stage_block<n>(st, oQ, F(P.q), S, k);
-      stage_block<m>(st, oR, F(P.r), S, k);
-      stage_block<m * n>(st, oK, F(P.K), S, k);
-      stage_block<m>(st, oD, F(P.d), S, k);
-      stage_block<n * n>(st, oA, F(P.A), S, k);
-      stage_block<n * m>(st, oB, F(P.Bm), S, k);
-    };
-    if constexpr (STAGED) {
-      for (int j = 0; j < depth; ++j) {
-        if (j < N) fetch(j, j);
-        cp_async_commit();
-      }
-    }
-    int stage = 0;
     for (int k = 0; k < N; ++k) {
-      double x[n], u[m], q[n], r[m], lx[n], lu[m];
-      double K[m * n], d[m], A[n * n], Bm[n * m], duda[m], dxn[n];
-      if constexpr (STAGED) {
-        cp_async_wait(depth - 1);
-        const double* st = ring + stage * (kStagePhi0 * 32);
-        unstage_block<n>(st, 0, x);
-        unstage_block<m>(st, oU, u);
-        unstage_block<n>(st, oQ, q);
-        unstage_block<m>(st, oR, r);
-        unstage_block<m * n>(st, oK, K);
-        unstage_block<m>(st, oD, d);
-        unstage_block<n * n>(st, oA, A);
-        unstage_block<n * m>(st, oB, Bm);
-        if (k + depth < N) fetch(k + depth, stage);
-        cp_async_commit();
-        stage = (stage + 1 == depth) ? 0 : stage + 1;
-      } else {
+      {
         const int kn = k + 1;
         prefetch_block<n>(F(P.x), S, kn);
         prefetch_block<n>(F(P.q), S, kn);
@@ -920,95 +914,65 @@ struct TrajSolver {
           prefetch_block<n * n>(F(P.A), S, kn);
           prefetch_block<n * m>(F(P.Bm), S, kn);
         }
-        load_block<n>(F(P.x), S, k, x);
-        load_block<m>(F(P.u), S, k, u);
-        load_block<n>(F(P.q), S, k, q);
-        load_block<m>(F(P.r), S, k, r);
       }
-      stage_gradient(k, x, u, q, r, false, lx, lu);
-      phi += stage_cost(k, x, u, q, r, false) + al_terms(k, x, u, false, true, lx, lu);
-      store_block<n>(F(P.lx), S, k, lx);
-      store_block<m>(F(P.lu), S, k, lu);
-      if constexpr (!STAGED) {
-        load_block<m * n>(F(P.K), S, k, K);
-        load_block<m>(F(P.d), S, k, d);
-        load_block<n * n>(F(P.A), S, k, A);
-        load_block<n * m>(F(P.Bm), S, k, Bm);
-      }
-      {
-        double Kd[m];
-        mm<m, 1, n, false, false, 0>(K, dxda, Kd);
-#pragma unroll
-        for (int i = 0; i < m; ++i) duda[i] = -Kd[i] + d[i];
-      }
-      mm<n, 1, n, false, false, 0>(A, dxda, dxn);
-      mm<n, 1, m, false, false, 1>(Bm, duda, dxn);
-      dphi += dot<n>(lx, dxda);
-      dphi += dot<m>(lu, duda);
-#pragma unroll
-      for (int i = 0; i < n; ++i) dxda[i] = dxn[i];
+      double x[n], u[m], q[n], r[m], K[m * n], d[m], A[n * n], Bm[n * m];
+      load_block<n>(F(P.x), S, k, x);
+      load_block<m>(F(P.u), S, k, u);
+      load_block<n>(F(P.q), S, k, q);
+      load_block<m>(F(P.r), S, k, r);
+      load_block<m * n>(F(P.K), S, k, K);
+      load_block<m>(F(P.d), S, k, d);
+      load_block<n * n>(F(P.A), S, k, A);
+      load_block<n * m>(F(P.Bm), S, k, Bm);
+      phi0_step(k, x, u, q, r, F(P.c)[(long)k * S], K, d, A, Bm, dxda, phi, dphi);
     }
-    {
-      double x[n], q[n], u0[m], lx[n];
-      load_block<n>(F(P.x), S, N, x);
-      load_block<n>(F(P.q), S, N, q);
-#pragma unroll
-      for (int i = 0; i < m; ++i) u0[i] = 0.0;
-      stage_gradient(N, x, u0, q, nullptr, true, lx, nullptr);
-      phi += stage_cost(N, x, u0, q, nullptr, true) + al_terms(N, x, u0, true, true, lx, nullptr);
-      store_block<n>(F(P.lx), S, N, lx);
-      dphi += dot<n>(lx, dxda);
-    }
+    phi0_terminal(dxda, phi, dphi);
     *phi_out = phi;
     *dphi_out = dphi;
   }
 
   // The simulation half of MeritFunction (solver.cpp:285-301, :319-322): closed-loop rollout at
-  // step alpha into candidate `slot`, returning the merit value.  Derivative work is left to
-  // phase_expand_knot (parallel over knots) + phase_dphi_scan; y_ is produced for the accepted
-  // point only (phase_costate_knot).  z_est is not stored here: every candidate that can be
-  // accepted is expanded afterwards, which stores it.
-  static constexpr int kStageRollout = 2 * (n + m) + m * n + m;
-  template <bool STAGED = false>
-  ALTRO_DEV double phase_rollout(double alpha, int slot, double* ring = nullptr, int depth = 0) {
+  // step alpha, returning the merit value.  Derivative work is left to phase_expand_knot
+  // (parallel over knots) + the d(phi) scan; y_ is produced for the accepted point only
+  // (phase_costate_knot).  z_est is not stored here: every candidate that can be accepted is
+  // expanded afterwards, which stores it.  rollout_step advances x from knot k to k + 1; xo/uo
+  // (may be null: merit value only) receive the trial trajectory with knot stride `so`.
+  ALTRO_DEV void rollout_step(int k, double alpha, const double* xb, const double* ub,
+                              const double* K, const double* d, const double* q, const double* r,
+                              double cval, double* x, double* xo, double* uo, long so, double& phi) {
+    double dx[n], u[m], xn[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) dx[i] = x[i] - xb[i];
+    {
+      double Kdx[m];
+      mm<m, 1, n, false, false, 0>(K, dx, Kdx);
+#pragma unroll
+      for (int i = 0; i < m; ++i) u[i] = ub[i] + (-Kdx[i] + alpha * d[i]);
+    }
+    if (xo) {
+      store_block<n>(xo, so, k, x);
+      store_block<m>(uo, so, k, u);
+    }
+    dynamics(k, x, u, xn);
+    phi += stage_cost(k, x, u, q, r, false, cval) +
+           al_terms(k, x, u, false, false, nullptr, nullptr, false);
+#pragma unroll
+    for (int i = 0; i < n; ++i) x[i] = xn[i];
+  }
+  ALTRO_DEV void rollout_terminal(const double* x, double* xo, long so, double& phi) {
+    double q[n], u0[m];
+    load_block<n>(F(P.q), S, N, q);
+#pragma unroll
+    for (int i = 0; i < m; ++i) u0[i] = 0.0;
+    phi += stage_cost(N, x, u0, q, nullptr, true) + al_terms(N, x, u0, true, false, nullptr, nullptr, false);
+    if (xo) store_block<n>(xo, so, N, x);
+  }
+  ALTRO_DEV double phase_rollout(double alpha, double* xo, double* uo, long so) {
     double phi = 0.0;
     double x[n];
-    double* xo = xw(slot);
-    double* uo = uw(slot);
-    const long so = sw(slot);
-    constexpr int oU = n, oK = n + m, oD = oK + m * n, oQ = oD + m, oR = oQ + n;
-    auto fetch = [&](int k, int stage) {
-      double* st = ring + stage * (kStageRollout * 32);
-      stage_block<n>(st, 0, F(P.xbar), S, k);
-      stage_block<m>(st, oU, F(P.ubar), S, k);
-      stage_block<m * n>(st, oK, F(P.K), S, k);
-      stage_block<m>(st, oD, F(P.d), S, k);
-      stage_block<n>(st, oQ, F(P.q), S, k);
-      stage_block<m>(st, oR, F(P.r), S, k);
-    };
-    if constexpr (STAGED) {
-      for (int j = 0; j < depth; ++j) {
-        if (j < N) fetch(j, j);
-        cp_async_commit();
-      }
-    }
-    int stage = 0;
     load_block<n>(G(P.x0, n), 0, 0, x);
     for (int k = 0; k < N; ++k) {
-      double xb[n], ub[m], K[m * n], d[m], dx[n], u[m], xn[n], q[n], r[m];
-      if constexpr (STAGED) {
-        cp_async_wait(depth - 1);
-        const double* st = ring + stage * (kStageRollout * 32);
-        unstage_block<n>(st, 0, xb);
-        unstage_block<m>(st, oU, ub);
-        unstage_block<m * n>(st, oK, K);
-        unstage_block<m>(st, oD, d);
-        unstage_block<n>(st, oQ, q);
-        unstage_block<m>(st, oR, r);
-        if (k + depth < N) fetch(k + depth, stage);
-        cp_async_commit();
-        stage = (stage + 1 == depth) ? 0 : stage + 1;
-      } else {
+      {
         const int kn = k + 1;
         prefetch_block<n>(F(P.xbar), S, kn);
         prefetch_block<n>(F(P.q), S, kn);
@@ -1018,82 +982,51 @@ struct TrajSolver {
           prefetch_block<m>(F(P.d), S, kn);
           prefetch_block<m>(F(P.r), S, kn);
         }
-        load_block<n>(F(P.xbar), S, k, xb);
-        load_block<m>(F(P.ubar), S, k, ub);
-        load_block<m * n>(F(P.K), S, k, K);
-        load_block<m>(F(P.d), S, k, d);
-        load_block<n>(F(P.q), S, k, q);
-        load_block<m>(F(P.r), S, k, r);
       }
-#pragma unroll
-      for (int i = 0; i < n; ++i) dx[i] = x[i] - xb[i];
-      {
-        double Kdx[m];
-        mm<m, 1, n, false, false, 0>(K, dx, Kdx);
-#pragma unroll
-        for (int i = 0; i < m; ++i) u[i] = ub[i] + (-Kdx[i] + alpha * d[i]);
-      }
-      store_block<n>(xo, so, k, x);
-      store_block<m>(uo, so, k, u);
-      dynamics(k, x, u, xn);
-      phi += stage_cost(k, x, u, q, r, false) +
-             al_terms(k, x, u, false, false, nullptr, nullptr, false);
-#pragma unroll
-      for (int i = 0; i < n; ++i) x[i] = xn[i];
+      double xb[n], ub[m], K[m * n], d[m], q[n], r[m];
+      load_block<n>(F(P.xbar), S, k, xb);
+      load_block<m>(F(P.ubar), S, k, ub);
+      load_block<m * n>(F(P.K), S, k, K);
+      load_block<m>(F(P.d), S, k, d);
+      load_block<n>(F(P.q), S, k, q);
+      load_block<m>(F(P.r), S, k, r);
+      rollout_step(k, alpha, xb, ub, K, d, q, r, F(P.c)[(long)k * S], x, xo, uo, so, phi);
     }
-    {
-      double q[n], u0[m];
-      load_block<n>(F(P.q), S, N, q);
-#pragma unroll
-      for (int i = 0; i < m; ++i) u0[i] = 0.0;
-      phi += stage_cost(N, x, u0, q, nullptr, true) +
-             al_terms(N, x, u0, true, false, nullptr, nullptr, false);
-      store_block<n>(xo, so, N, x);
-    }
+    rollout_terminal(x, xo, so, phi);
     return phi;
   }
 
   // The derivative half of MeritFunction (solver.cpp:303-315, :327-331) once A, B, lx, lu of the
   // trial trajectory are in HBM.
-  static constexpr int kStageDphi = m * n + m + n * n + n * m + n + m;
-  template <bool STAGED = false>
-  ALTRO_DEV double phase_dphi_scan(double* ring = nullptr, int depth = 0) {
+  ALTRO_DEV void dphi_step(const double* K, const double* d, const double* A, const double* Bm,
+                           const double* lx, const double* lu, double* dxda, double& dphi) {
+    double duda[m], dxn[n];
+    {
+      double Kd[m];
+      mm<m, 1, n, false, false, 0>(K, dxda, Kd);
+#pragma unroll
+      for (int i = 0; i < m; ++i) duda[i] = -Kd[i] + d[i];
+    }
+    mm<n, 1, n, false, false, 0>(A, dxda, dxn);
+    mm<n, 1, m, false, false, 1>(Bm, duda, dxn);
+    dphi += dot<n>(lx, dxda);
+    dphi += dot<m>(lu, duda);
+#pragma unroll
+    for (int i = 0; i < n; ++i) dxda[i] = dxn[i];
+  }
+  ALTRO_DEV double dphi_terminal(const double* dxda, double dphi) {
+    double lx[n];
+    load_block<n>(F(P.lx), S, N, lx);
+    dphi += dot<n>(lx, dxda);
+    return dphi;
+  }
+  ALTRO_DEV double phase_dphi_scan() {
     double dphi = 0.0;
     double dxda[n];
 #pragma unroll
     for (int i = 0; i < n; ++i) dxda[i] = 0.0;
-    constexpr int oD = m * n, oA = oD + m, oB = oA + n * n, oLx = oB + n * m, oLu = oLx + n;
-    auto fetch = [&](int k, int stage) {
-      double* st = ring + stage * (kStageDphi * 32);
-      stage_block<m * n>(st, 0, F(P.K), S, k);
-      stage_block<m>(st, oD, F(P.d), S, k);
-      stage_block<n * n>(st, oA, F(P.A), S, k);
-      stage_block<n * m>(st, oB, F(P.Bm), S, k);
-      stage_block<n>(st, oLx, F(P.lx), S, k);
-      stage_block<m>(st, oLu, F(P.lu), S, k);
-    };
-    if constexpr (STAGED) {
-      for (int j = 0; j < depth; ++j) {
-        if (j < N) fetch(j, j);
-        cp_async_commit();
-      }
-    }
-    int stage = 0;
     for (int k = 0; k < N; ++k) {
-      double K[m * n], d[m], A[n * n], Bm[n * m], lx[n], lu[m], duda[m], dxn[n];
-      if constexpr (STAGED) {
-        cp_async_wait(depth - 1);
-        const double* st = ring + stage * (kStageDphi * 32);
-        unstage_block<m * n>(st, 0, K);
-        unstage_block<m>(st, oD, d);
-        unstage_block<n * n>(st, oA, A);
-        unstage_block<n * m>(st, oB, Bm);
-        unstage_block<n>(st, oLx, lx);
-        unstage_block<m>(st, oLu, lu);
-        if (k + depth < N) fetch(k + depth, stage);
-        cp_async_commit();
-        stage = (stage + 1 == depth) ? 0 : stage + 1;
-      } else {
+      {
         const int kn = k + 1;
         prefetch_block<n>(F(P.lx), S, kn);
         if (kn < N) {
@@ -1103,30 +1036,17 @@ struct TrajSolver {
           prefetch_block<n * m>(F(P.Bm), S, kn);
           prefetch_block<m>(F(P.lu), S, kn);
         }
-        load_block<m * n>(F(P.K), S, k, K);
-        load_block<m>(F(P.d), S, k, d);
-        load_block<n * n>(F(P.A), S, k, A);
-        load_block<n * m>(F(P.Bm), S, k, Bm);
-        load_block<n>(F(P.lx), S, k, lx);
-        load_block<m>(F(P.lu), S, k, lu);
       }
-      {
-        double Kd[m];
-        mm<m, 1, n, false, false, 0>(K, dxda, Kd);
-#pragma unroll
-        for (int i = 0; i < m; ++i) duda[i] = -Kd[i] + d[i];
-      }
-      mm<n, 1, n, false, false, 0>(A, dxda, dxn);
-      mm<n, 1, m, false, false, 1>(Bm, duda, dxn);
-      dphi += dot<n>(lx, dxda);
-      dphi += dot<m>(lu, duda);
-#pragma unroll
-      for (int i = 0; i < n; ++i) dxda[i] = dxn[i];
+      double K[m * n], d[m], A[n * n], Bm[n * m], lx[n], lu[m];
+      load_block<m * n>(F(P.K), S, k, K);
+      load_block<m>(F(P.d), S, k, d);
+      load_block<n * n>(F(P.A), S, k, A);
+      load_block<n * m>(F(P.Bm), S, k, Bm);
+      load_block<n>(F(P.lx), S, k, lx);
+      load_block<m>(F(P.lu), S, k, lu);
+      dphi_step(K, d, A, Bm, lx, lu, dxda, dphi);
     }
-    double lx[n];
-    load_block<n>(F(P.lx), S, N, lx);
-    dphi += dot<n>(lx, dxda);
-    return dphi;
+    return dphi_terminal(dxda, dphi);
   }
 
   // y_k = P_k (x_k - xbar_k) + p_k for the accepted point (solver.cpp:293, :324)

@@ -1,81 +1,106 @@
-// solver_phases.cuh -- the AL-iLQR iteration as a pipeline of phase kernels over compacted work
-// lists (the production path; the single persistent kernel of solver_kernels.cuh stays as the
+// solver_phases.cuh -- the AL-iLQR iteration as a pipeline of phase kernels over compacted lists of
+// GROUPS (the production path; the single persistent kernel of solver_kernels.cuh stays as the
 // differential-testing twin: both must agree bit for bit).
 //
-// Why: the persistent thread-per-trajectory kernel is latency bound (ncu, profiles/r01: one warp
-// per scheduler, 12 % issue utilisation) and loses half its lanes to divergence -- trajectories of
-// one warp need different numbers of line-search evaluations and iterations.  Here
-//   * every sequential sweep (backward Riccati, rollout, d(phi) scan, convergence criteria) is its
-//     own small kernel, launched over a COMPACTED list of the trajectories that actually need it,
-//     so warps stay dense and the instruction footprint of each kernel fits the I-cache;
-//   * everything that is independent per knot -- dynamics Jacobians (the transcendental-heavy
-//     part), projected duals, cost gradients -- runs one thread per (trajectory, knot) and is
-//     throughput- instead of latency-bound;
-//   * the redundant alpha = 0 rollout of ForwardPass (solver.cpp:241, ~40 % of the reference's
+// A group is 32 consecutive problems = one warp = one stream of knot records (device_problem.h).
+//   * Every sequential sweep (backward Riccati, phi0 scan, rollout, d(phi) scan) is a kernel with
+//     one warp per group that streams the group's knot records through a shared-memory ring with
+//     TMA bulk copies (linalg.cuh, BulkRing): one cp.async.bulk per knot and contiguous range, a
+//     few knots ahead, instead of dozens of dependent 256-byte loads per knot.  The pipeline is
+//     HBM-bound (ncu r01 v2: 50-65 % of DRAM peak in every kernel at only 3.5 warps/SM), so what
+//     counts is bytes per knot and how fast a lone warp can stream them.
+//   * Lists are compacted per GROUP (a group stays listed while any of its lanes needs the
+//     phase); lanes that do not need it are predicated off.  Records are fetched whole anyway.
+//   * Everything that is independent per knot -- dynamics Jacobians (the transcendental-heavy
+//     part), projected duals, cost gradients, costates, residuals -- runs one thread per
+//     (problem, knot).
+//   * Backtracking line search: the first rollout round evaluates the requested step AND the
+//     halvings that SimpleBacktracking (linesearch.cpp:385-412) would try next, one warp per
+//     candidate in the SAME CTA, all fed from one staged copy of the knot data; only slot 0 and
+//     the first `nstore` halvings write their trajectory, the others return the merit value
+//     alone (an accepted one is rolled out once more, TF_REROLL).  The state machine is then fed
+//     the values in the order the reference would have evaluated them, so decisions and the
+//     reported evaluation counts are those of the sequential search.
+//   * The redundant alpha = 0 rollout of ForwardPass (solver.cpp:241, ~40 % of the reference's
 //     merit evaluations) is replaced by a linear scan that provably reproduces it
-//     (TrajSolver::phase_phi0_scan).
+//     (TrajSolver::phi0_step).
 // Decisions (line search, dual/penalty update, convergence) are identical to the reference.
 #pragma once
 #include "solver_kernels.cuh"
 
 namespace altro_b200 {
 
-// ------------------------------------------------------------------ list compaction
-// Ordered compaction of `in[0..count)` by (flags[in[i]] & mask) != 0 into out; writes the number
-// kept to counters[slot] (and, if mask2 != 0, the number that also has mask2 to counters[slot2]).
-// `count` bounds the input length; `dcount` (optional) is its exact device-side value.
-// One CTA; ordered so that neighbouring lanes keep touching neighbouring problems.
+// ------------------------------------------------------------------ list compaction (groups)
+// Ordered compaction of the groups in[0..count) that have at least one lane with
+// (flags & mask) != 0 into out; writes the number kept to counters[slot], and the number of kept
+// groups that also have such a lane with mask2 / mask3 to counters[slot2] / counters[slot3].
+// `count` bounds the input length; `dcount` (optional) is its exact device-side value.  One CTA.
 static __global__ void __launch_bounds__(1024) k_compact(const int* __restrict__ in, int count,
                                                   const int* dcount,
                                                   const int* __restrict__ flags, int mask,
                                                   int* __restrict__ out, int* counters, int slot,
-                                                  int mask2, int slot2) {
-  __shared__ int warp_tot[32];
-  __shared__ int warp_tot2[32];
-  __shared__ int base_s, base2_s;
+                                                  int mask2, int slot2, int mask3, int slot3) {
+  __shared__ int warp_tot[32], warp_tot2[32], warp_tot3[32];
+  __shared__ int base_s, base2_s, base3_s;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  // the input length may live on the device (possibly in the very counter this kernel rewrites
-  // at the end, hence read before the first barrier)
+  // the input length may live in the very counter this kernel rewrites at the end, hence read
+  // before the first barrier
   if (dcount) count = min(count, *dcount);
   if (tid == 0) {
     base_s = 0;
     base2_s = 0;
+    base3_s = 0;
   }
   __syncthreads();
   for (int start = 0; start < count; start += 1024) {
     const int i = start + tid;
-    int b = -1, keep = 0, keep2 = 0;
+    int g = -1, keep = 0, keep2 = 0, keep3 = 0;
     if (i < count) {
-      b = in ? in[i] : i;
-      const int f = flags[b];
+      g = in ? in[i] : i;
+      int f = 0;  // OR of the flags of the lanes that have `mask`
+      const int4* fp = reinterpret_cast<const int4*>(flags + (long)g * 32);
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        const int4 v = fp[l];
+        f |= (v.x & mask) ? v.x : 0;
+        f |= (v.y & mask) ? v.y : 0;
+        f |= (v.z & mask) ? v.z : 0;
+        f |= (v.w & mask) ? v.w : 0;
+      }
       keep = (f & mask) != 0;
       keep2 = keep && mask2 && (f & mask2) != 0;
+      keep3 = keep && mask3 && (f & mask3) != 0;
     }
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
     const unsigned bal2 = __ballot_sync(0xffffffffu, keep2);
+    const unsigned bal3 = __ballot_sync(0xffffffffu, keep3);
     if (lane == 0) {
       warp_tot[wid] = __popc(bal);
       warp_tot2[wid] = __popc(bal2);
+      warp_tot3[wid] = __popc(bal3);
     }
     __syncthreads();
     int off = base_s;
     for (int w = 0; w < wid; ++w) off += warp_tot[w];
-    if (keep) out[off + __popc(bal & ((1u << lane) - 1u))] = b;
+    if (keep) out[off + __popc(bal & ((1u << lane) - 1u))] = g;
     __syncthreads();
     if (tid == 0) {
-      int t = 0, t2 = 0;
+      int t = 0, t2 = 0, t3 = 0;
       for (int w = 0; w < 32; ++w) {
         t += warp_tot[w];
         t2 += warp_tot2[w];
+        t3 += warp_tot3[w];
       }
       base_s += t;
       base2_s += t2;
+      base3_s += t3;
     }
     __syncthreads();
   }
   if (tid == 0) {
     counters[slot] = base_s;
     if (mask2) counters[slot2] = base2_s;
+    if (mask3) counters[slot3] = base3_s;
   }
 }
 
@@ -95,9 +120,8 @@ __device__ __forceinline__ LsOptions ls_options(const DevOptions& o) {
   return lo;
 }
 
-// this lane's column of the per-warp staging ring (dynamic shared memory; CTA = one warp)
-extern __shared__ double altro_stage_ring[];
-__device__ __forceinline__ double* lane_ring() { return altro_stage_ring + (threadIdx.x & 31); }
+// dynamic shared memory of the sweep kernels: mbarriers + staging ring (linalg.cuh)
+extern __shared__ __align__(128) unsigned char altro_smem[];
 
 // K0: Solve() prologue, sequential part (solver.cpp:417-423)
 template <class Model, bool CON>
@@ -114,12 +138,12 @@ __global__ void __launch_bounds__(32) k_phase_init(const DeviceProblem P) {
   P.sel[b] = -1;
 }
 
-// Expansion, one thread per (list entry, knot).  `mask`: only trajectories whose flags have one of
-// these bits are processed (0 = all).  with_dyn: also recompute [A B].  slot_mode: -1 read the
-// main trajectory, >= 0 that candidate slot, -2 the slot recorded in sel[b].  dual_first: apply
-// the dual update z <- Pi(z_est) of this knot before recomputing the projected duals.
-// The prologue calls this BEFORE the penalty reset, which reproduces quirk Q3 (gradient with the
-// old rho, solver.cpp:424-430).
+// Expansion, one thread per (problem of a listed group, knot).  `mask`: only problems whose flags
+// have one of these bits are processed (0 = all).  with_dyn: also recompute [A B].  slot_mode: -1
+// read the main trajectory, >= 0 that candidate slot, -2 the slot recorded in sel[b].
+// dual_first: apply the dual update z <- Pi(z_est) of this knot before recomputing the projected
+// duals.  The prologue calls this BEFORE the penalty reset, which reproduces quirk Q3 (gradient
+// with the old rho, solver.cpp:424-430).
 template <class Model, bool CON>
 __global__ void __launch_bounds__(128) k_phase_expand(const DeviceProblem P, const int* list,
                                                       int count, const int* dcount, int mask,
@@ -127,8 +151,10 @@ __global__ void __launch_bounds__(128) k_phase_expand(const DeviceProblem P, con
                                                       bool dual_first) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int k = blockIdx.y;
-  if (t >= list_count(count, dcount)) return;
-  const int b = list ? list[t] : t;
+  const int gi = t >> 5;
+  if (gi >= list_count(count, dcount)) return;
+  const int b = (list ? list[gi] : gi) * 32 + (t & 31);
+  if (b >= P.B) return;
   if (mask && !(P.flags[b] & mask)) return;
   TrajSolver<Model, CON> s(P, b);
   s.rho = CON ? P.rho[b] : 1.0;
@@ -143,19 +169,99 @@ static __global__ void k_phase_set_rho(double* rho, int B, double value) {
 }
 
 // K1: CalcExpansions + BackwardPass + the alpha = 0 half of ForwardPass (solver.cpp:448-450,
-// :241-245) and the start of the line search.
+// :241-245) and the start of the line search.  One warp per listed group.
 template <class Model, bool CON>
 __global__ void __launch_bounds__(32) k_phase_backward(const DeviceProblem P, const int* list,
                                                        int count, int depth) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
-  const int b = list[t];
-  TrajSolver<Model, CON> s(P, b);
-  s.rho = CON ? P.rho[b] : 1.0;
-  constexpr bool ST = TrajSolver<Model, CON>::kStaged;
-  s.template backward_sweep<ST>(lane_ring(), depth);
-  double phi0, dphi0;
-  s.template phase_phi0_scan<ST>(&phi0, &dphi0, lane_ring(), depth);
+  using TS = TrajSolver<Model, CON>;
+  constexpr int n = Model::n, m = Model::m;
+  if ((int)blockIdx.x >= count) return;
+  const int g = list[blockIdx.x];
+  const int lane = threadIdx.x;
+  const int b = g * 32 + lane;
+  const bool active = b < P.B && (P.flags[b] & TF_ACTIVE);
+  TS s(P, active ? b : g * 32);
+  s.rho = (CON && active) ? P.rho[b] : 1.0;
+  double phi0 = 0.0, dphi0 = 0.0;
+  if constexpr (TS::kStaged) {
+    // stage contents: Riccati sweep rows [A B lx lu]; phi0 scan rows [q r c K d x u A B]
+    constexpr int kRowsBw = n * n + n * m + n + m;
+    constexpr int kRowsPhi = TS::rB + n * m - TS::rQ;
+    constexpr int kStage = (kRowsBw > kRowsPhi ? kRowsBw : kRowsPhi) * 32;
+    BulkRing ring;
+    ring.init(altro_smem, depth, kStage, lane == 0);
+    __syncwarp();
+    const double* rec = P.xbar + (long)g * P.GS;  // row 0 of the group's knot-0 record
+    auto fetch_bw = [&](int k, int st) {
+      ring.expect(st, kRowsBw * 256);
+      ring.copy(st, 0, rec + (long)k * P.R + TS::rA * 32, kRowsBw * 256);
+    };
+    if (lane == 0)
+      for (int j = 0; j < depth; ++j)
+        if (P.N - 1 - j >= 0) fetch_bw(P.N - 1 - j, (ring.s + j) % depth);
+    double Pn[n * n], pn[n];
+    if (active) s.riccati_terminal(Pn, pn);
+    bool alive = active;
+    for (int k = P.N - 1; k >= 0; --k) {
+      const double* st = ring.wait();
+      double A[n * n], Bm[n * m], Qx[n], Qu[m];
+      if (alive) {
+        unstage_block<n * n>(st, 0, lane, A);
+        unstage_block<n * m>(st, n * n, lane, Bm);
+        unstage_block<n>(st, n * n + n * m, lane, Qx);
+        unstage_block<m>(st, n * n + n * m + n, lane, Qu);
+      }
+      __syncwarp();
+      if (lane == 0 && k - depth >= 0) fetch_bw(k - depth, ring.s);
+      ring.advance();
+      if (alive) alive = s.riccati_step(k, A, Bm, Qx, Qu, Pn, pn);
+    }
+    // phi0 / dphi0 scan, knots ascending
+    auto fetch_phi = [&](int k, int st) {
+      ring.expect(st, kRowsPhi * 256);
+      ring.copy(st, 0, rec + (long)k * P.R + TS::rQ * 32, kRowsPhi * 256);
+    };
+    // K, d were just written by this warp through the generic proxy; the bulk copies read them
+    // through the async proxy
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("fence.proxy.async;" ::: "memory");
+      for (int j = 0; j < depth; ++j)
+        if (j < P.N) fetch_phi(j, (ring.s + j) % depth);
+    }
+    double dxda[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) dxda[i] = 0.0;
+    constexpr int oR = n, oC = n + m, oK = oC + 1, oD = oK + m * n, oX = oD + m, oU = oX + n,
+                  oA = oU + m, oB = oA + n * n;
+    for (int k = 0; k < P.N; ++k) {
+      const double* st = ring.wait();
+      double x[n], u[m], q[n], r[m], K[m * n], d[m], A[n * n], Bm[n * m], cval = 0.0;
+      if (active) {
+        unstage_block<n>(st, 0, lane, q);
+        unstage_block<m>(st, oR, lane, r);
+        cval = st[oC * 32 + lane];
+        unstage_block<m * n>(st, oK, lane, K);
+        unstage_block<m>(st, oD, lane, d);
+        unstage_block<n>(st, oX, lane, x);
+        unstage_block<m>(st, oU, lane, u);
+        unstage_block<n * n>(st, oA, lane, A);
+        unstage_block<n * m>(st, oB, lane, Bm);
+      }
+      __syncwarp();
+      if (lane == 0 && k + depth < P.N) fetch_phi(k + depth, ring.s);
+      ring.advance();
+      if (active) s.phi0_step(k, x, u, q, r, cval, K, d, A, Bm, dxda, phi0, dphi0);
+    }
+    if (active) s.phi0_terminal(dxda, phi0, dphi0);
+  } else {
+    if (active) {
+      s.backward_sweep();
+      s.phase_phi0_scan(&phi0, &dphi0);
+    }
+  }
+  if (!active) return;
   P.phi0[b] = phi0;
   P.dphi0[b] = dphi0;
   P.phi[b] = phi0;
@@ -163,16 +269,23 @@ __global__ void __launch_bounds__(32) k_phase_backward(const DeviceProblem P, co
   P.stat_acc[b] = 0ull;
   P.feas_acc[b] = 0ull;
   P.sel[b] = -1;
-  int f = P.flags[b] & TF_ACTIVE;
+  int f = TF_ACTIVE;
   if (fabs(dphi0) < P.opts.tol_meritfun_gradient) {
     // MeritFunctionGradientTooSmall: alpha = 0, not fatal (solver.cpp:242-245, :451)
     P.alpha_eval[b] = 0.0;
+    if (P.ls_hist) atomicAdd(P.ls_hist + 19, 1ull);
   } else {
     const LsOptions lo = ls_options(P.opts);
     LsMachine ls;
     if (ls.start(lo, 1.0, phi0, dphi0)) {
       f |= TF_NEED_EVAL | TF_WANT_DERIV;
       P.alpha_eval[b] = ls.alpha;
+      if (lo.use_backtracking && P.nslots > 1) {
+        // the halvings SimpleBacktracking(alpha0 * beta_decrease) will try if alpha0 and the
+        // cubic-first probe are rejected (linesearch.cpp:130-132, :385-412)
+        f |= TF_SPECULATE;
+        P.alpha_bt[b] = ls.alpha0 * lo.beta_decrease;
+      }
     } else {
       // NOT_DESCENT_DIRECTION: Run returns 0 without evaluating -> LineSearchFailed (:264-269)
       f |= TF_LS_FAILED;
@@ -183,70 +296,176 @@ __global__ void __launch_bounds__(32) k_phase_backward(const DeviceProblem P, co
   P.flags[b] = f;
 }
 
-// K2: rollouts.  Plain round: one candidate per trajectory (alpha_eval) into the main trajectory.
-// Speculative round (backtracking line search): candidate `blockIdx.y` of every trajectory is
-// rolled out concurrently into its own slot -- slot 0 is the step the state machine asked for,
-// slots j >= 1 are the halvings it will ask for next if it keeps rejecting
-// (SimpleBacktracking, linesearch.cpp:385-412), alpha_bt * 2^-(j-1).
+// K2: rollouts.  One CTA per listed group, one warp per candidate step of the group's problems:
+// warp 0 rolls out the step the state machine asked for (alpha_eval) into the main trajectory;
+// warps j >= 1 (launched in speculative rounds) roll out the halving alpha_bt * 2^-(j-1) for the
+// lanes flagged TF_SPECULATE -- into candidate slot j-1 when j <= nstore, merit value only
+// otherwise.  All warps consume the SAME staged copy of the knot data [xbar ubar q r c K d].
 template <class Model, bool CON>
-__global__ void __launch_bounds__(32) k_phase_rollout(const DeviceProblem P, const int* list,
-                                                      int count, const int* dcount,
-                                                      bool speculative, int depth) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= list_count(count, dcount)) return;
-  const int b = list[t];
-  TrajSolver<Model, CON> s(P, b);
-  s.rho = CON ? P.rho[b] : 1.0;
-  constexpr bool ST = TrajSolver<Model, CON>::kStaged;
-  if (!speculative) {
-    P.phi_eval[b] = s.template phase_rollout<ST>(P.alpha_eval[b], -1, lane_ring(), depth);
+__global__ void __launch_bounds__(32 * 16) k_phase_rollout(const DeviceProblem P, const int* list,
+                                                           int count, const int* dcount, int depth) {
+  using TS = TrajSolver<Model, CON>;
+  constexpr int n = Model::n, m = Model::m;
+  if ((int)blockIdx.x >= list_count(count, dcount)) return;
+  const int g = list[blockIdx.x];
+  const int lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
+  const int b = g * 32 + lane;
+  const int f = b < P.B ? P.flags[b] : 0;
+  const bool need = (slot == 0) ? (f & (TF_NEED_EVAL | TF_REROLL)) != 0
+                                : ((f & TF_NEED_EVAL) && (f & TF_SPECULATE));
+  TS s(P, need ? b : g * 32);
+  s.rho = (CON && need) ? P.rho[b] : 1.0;
+  double alpha = 0.0;
+  double *xo = nullptr, *uo = nullptr;
+  long so = 0;
+  if (need) {
+    if (slot == 0) {
+      alpha = P.alpha_eval[b];
+      xo = s.xw(-1);
+      uo = s.uw(-1);
+      so = s.sw(-1);
+    } else {
+      alpha = ldexp(P.alpha_bt[b], -(slot - 1));
+      if (slot <= P.nstore) {
+        xo = s.xw(slot - 1);
+        uo = s.uw(slot - 1);
+        so = s.sw(slot - 1);
+      }
+    }
+  }
+  double phi = 0.0;
+  if constexpr (TS::kStaged) {
+    constexpr int kRows = TS::rD + m;  // [xbar ubar q r c K d]
+    BulkRing ring;
+    ring.init(altro_smem, depth, kRows * 32, threadIdx.x == 0);
+    __syncthreads();
+    const double* rec = P.xbar + (long)g * P.GS;
+    auto fetch = [&](int k, int st) {
+      ring.expect(st, kRows * 256);
+      ring.copy(st, 0, rec + (long)k * P.R, kRows * 256);
+    };
+    if (threadIdx.x == 0)
+      for (int j = 0; j < depth; ++j)
+        if (j < P.N) fetch(j, j);
+    double x[n];
+    if (need) load_block<n>(s.G(P.x0, n), 0, 0, x);
+    for (int k = 0; k < P.N; ++k) {
+      const double* st = ring.wait();
+      double xb[n], ub[m], q[n], r[m], K[m * n], d[m], cval = 0.0;
+      if (need) {
+        unstage_block<n>(st, TS::rXbar, lane, xb);
+        unstage_block<m>(st, TS::rUbar, lane, ub);
+        unstage_block<n>(st, TS::rQ, lane, q);
+        unstage_block<m>(st, TS::rR, lane, r);
+        cval = st[TS::rC * 32 + lane];
+        unstage_block<m * n>(st, TS::rK, lane, K);
+        unstage_block<m>(st, TS::rD, lane, d);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0 && k + depth < P.N) fetch(k + depth, ring.s);
+      ring.advance();
+      if (need) s.rollout_step(k, alpha, xb, ub, K, d, q, r, cval, x, xo, uo, so, phi);
+    }
+    if (need) s.rollout_terminal(x, xo, so, phi);
   } else {
-    const int slot = blockIdx.y;
-    const double alpha = (slot == 0) ? P.alpha_eval[b] : ldexp(P.alpha_bt[b], -(slot - 1));
-    P.phi_s[(long)slot * P.Bp + b] = s.template phase_rollout<ST>(alpha, slot, lane_ring(), depth);
+    if (need) phi = s.phase_rollout(alpha, xo, uo, so);
+  }
+  if (need) {
+    if (slot == 0)
+      P.phi_eval[b] = phi;
+    else
+      P.phi_s[(long)slot * P.Bp + b] = phi;
   }
 }
 
-// K4: d(phi) scan (when requested) + the line-search state machine.  In a speculative round the
-// candidates are fed to the machine in the order the reference would have evaluated them, and
-// feeding stops at the first one it accepts, so the decisions (and the reported evaluation count)
-// are those of the sequential search.
+// K4: d(phi) scan (when requested) + the line-search state machine, one warp per listed group.
+// The machine is fed the value of the requested step and then, while it keeps backtracking, the
+// precomputed merit values of the halvings in the order the reference would have evaluated
+// them; feeding stops at the first one it accepts, so the decisions (and the reported evaluation
+// count) are those of the sequential search.
 template <class Model, bool CON>
 __global__ void __launch_bounds__(32) k_phase_lsupdate(const DeviceProblem P, const int* list,
-                                                       int count, const int* dcount,
-                                                       bool speculative, int depth) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= list_count(count, dcount)) return;
-  const int b = list[t];
-  int f = P.flags[b];
-  const bool had_deriv = (f & TF_WANT_DERIV) != 0;
+                                                       int count, const int* dcount, int depth) {
+  using TS = TrajSolver<Model, CON>;
+  constexpr int n = Model::n, m = Model::m;
+  if ((int)blockIdx.x >= list_count(count, dcount)) return;
+  const int g = list[blockIdx.x];
+  const int lane = threadIdx.x;
+  const int b = g * 32 + lane;
+  int f = b < P.B ? P.flags[b] : 0;
+  const bool pending = (f & (TF_NEED_EVAL | TF_REROLL)) != 0;
+  const bool had_deriv = (f & TF_NEED_EVAL) && (f & TF_WANT_DERIV) && !(f & TF_REROLL);
   double dphi = 0.0;
-  if (had_deriv) {
-    TrajSolver<Model, CON> s(P, b);
-    dphi = s.template phase_dphi_scan<TrajSolver<Model, CON>::kStaged>(lane_ring(), depth);
+  if (__any_sync(0xffffffffu, had_deriv)) {
+    TS s(P, had_deriv ? b : g * 32);
+    if constexpr (TS::kStaged) {
+      // stage contents: [K d] then [A B lx lu]
+      constexpr int kRows1 = m * n + m, kRows2 = n * n + n * m + n + m;
+      BulkRing ring;
+      ring.init(altro_smem, depth, (kRows1 + kRows2) * 32, lane == 0);
+      __syncwarp();
+      const double* rec = P.xbar + (long)g * P.GS;
+      auto fetch = [&](int k, int st) {
+        ring.expect(st, (kRows1 + kRows2) * 256);
+        ring.copy(st, 0, rec + (long)k * P.R + TS::rK * 32, kRows1 * 256);
+        ring.copy(st, kRows1, rec + (long)k * P.R + TS::rA * 32, kRows2 * 256);
+      };
+      if (lane == 0)
+        for (int j = 0; j < depth; ++j)
+          if (j < P.N) fetch(j, j);
+      double dxda[n];
+#pragma unroll
+      for (int i = 0; i < n; ++i) dxda[i] = 0.0;
+      for (int k = 0; k < P.N; ++k) {
+        const double* st = ring.wait();
+        double K[m * n], d[m], A[n * n], Bm[n * m], lx[n], lu[m];
+        if (had_deriv) {
+          unstage_block<m * n>(st, 0, lane, K);
+          unstage_block<m>(st, m * n, lane, d);
+          unstage_block<n * n>(st, kRows1, lane, A);
+          unstage_block<n * m>(st, kRows1 + n * n, lane, Bm);
+          unstage_block<n>(st, kRows1 + n * n + n * m, lane, lx);
+          unstage_block<m>(st, kRows1 + n * n + n * m + n, lane, lu);
+        }
+        __syncwarp();
+        if (lane == 0 && k + depth < P.N) fetch(k + depth, ring.s);
+        ring.advance();
+        if (had_deriv) s.dphi_step(K, d, A, Bm, lx, lu, dxda, dphi);
+      }
+      if (had_deriv) dphi = s.dphi_terminal(dxda, dphi);
+    } else {
+      if (had_deriv) dphi = s.phase_dphi_scan();
+    }
   }
+  if (!pending) return;
   const LsOptions lo = ls_options(P.opts);
+  if (f & TF_REROLL) {
+    // the accepted candidate has just been rolled out again into x_, u_; it still needs its
+    // expansion (TF_REFRESH_DYN stays set)
+    f &= ~(TF_REROLL | TF_NEED_EVAL | TF_WANT_DERIV | TF_SPECULATE);
+    P.sel[b] = -1;
+    P.flags[b] = f;
+    return;
+  }
   LsMachine ls = P.ls[b];
   bool last_had_deriv = had_deriv;
-  int fed = 0;
-  if (!speculative) {
-    ls.update(lo, P.phi_eval[b], dphi);
-    fed = 1;
-  } else {
-    int last_slot = -1;
-    for (int slot = 0; slot < P.nslots && !ls.done(); ++slot) {
-      const double cand = (slot == 0) ? P.alpha_eval[b] : ldexp(P.alpha_bt[b], -(slot - 1));
-      if (ls.alpha != cand) break;  // not the step the machine is asking for (cannot happen)
-      const bool want = ls.want_derivative();
-      if (want && !(slot == 0 && had_deriv)) break;
-      ls.update(lo, P.phi_s[(long)slot * P.Bp + b], want ? dphi : 0.0);
-      last_had_deriv = want;
-      last_slot = slot;
+  int fed = 1, winner_slot = 0;
+  ls.update(lo, P.phi_eval[b], dphi);
+  if (f & TF_SPECULATE) f |= TF_SPEC_VALID;  // this round also produced the halvings' merit values
+  bool exhausted = false;
+  if ((f & TF_SPEC_VALID) && !ls.done() && ls.phase == LsMachine::P_BACKTRACK) {
+    exhausted = true;
+    for (int j = 1; j < P.nslots; ++j) {
+      const double cand = ldexp(P.alpha_bt[b], -(j - 1));
+      if (ls.alpha != cand) continue;  // not the step the machine is asking for
+      ls.update(lo, P.phi_s[(long)j * P.Bp + b], 0.0);
+      last_had_deriv = false;
+      winner_slot = j;
       fed += 1;
-    }
-    if (last_slot >= 0) P.sel[b] = last_slot;
-    if (fed == 0) {  // defensive: never stall the pipeline
-      ls.finish(LS_NOERROR, ls.alpha);
+      if (ls.done() || ls.phase != LsMachine::P_BACKTRACK) {
+        exhausted = false;
+        break;
+      }
     }
   }
   P.merit_evals[b] += fed;
@@ -255,19 +474,40 @@ __global__ void __launch_bounds__(32) k_phase_lsupdate(const DeviceProblem P, co
     f |= TF_NEED_EVAL;
     if (ls.want_derivative()) f |= TF_WANT_DERIV;
     P.alpha_eval[b] = ls.alpha;
-    if (lo.use_backtracking) {
+    if (lo.use_backtracking && P.nslots > 1 && ls.phase == LsMachine::P_BACKTRACK &&
+        (exhausted || !(f & TF_SPEC_VALID))) {
+      // more halvings than were precomputed: next round evaluates ls.alpha and the ones after it
       f |= TF_SPECULATE;
-      // first halving the machine will ask for after the pending step is rejected
-      P.alpha_bt[b] = (ls.phase == LsMachine::P_CUBIC_FIRST ? ls.alpha0 : ls.alpha) * lo.beta_decrease;
+      P.alpha_bt[b] = ls.alpha * lo.beta_decrease;
     }
   } else {
     const double alpha = ls.alpha;
     P.alpha_eval[b] = alpha;
     if (ls.n_iters > 0) P.phi[b] = ls.phi;
-    // the accepted candidate lives in a slot and/or has no derivative information yet
-    // (solver.cpp:256-262): copy it into x_, u_ and expand it
-    if (P.sel[b] >= 0 || (lo.use_backtracking && fabs(alpha - 1.0) > 0 && !last_had_deriv))
+    if (P.ls_hist) {
+      int bin = 17;
+      if (!(ls.status == LS_MINIMUM_FOUND || ls.status == LS_HIT_MAX_STEPSIZE)) bin = 18;
+      else if (winner_slot > 0) bin = winner_slot < 15 ? winner_slot : 15;
+      else if (alpha == ls.alpha0) bin = 0;
+      else if (lo.use_backtracking && last_had_deriv) bin = 16;
+      else if (lo.use_backtracking) {  // a halving evaluated as the requested step of a later round
+        int j = 1;
+        double a = ls.alpha0 * lo.beta_decrease;
+        while (j < 15 && a != alpha) { a *= lo.beta_decrease; ++j; }
+        bin = j;
+      }
+      atomicAdd(P.ls_hist + bin, 1ull);
+    }
+    if (winner_slot > 0) {
+      // the step the search returns was only evaluated as a speculative candidate
+      if (winner_slot <= P.nstore)
+        P.sel[b] = winner_slot - 1;  // its trajectory is in a candidate slot: copy + expand it
+      else
+        f |= TF_REROLL;              // merit-only candidate: roll it out again, then expand
       f |= TF_REFRESH_DYN;
+    } else if (lo.use_backtracking && fabs(alpha - 1.0) > 0 && !last_had_deriv) {
+      f |= TF_REFRESH_DYN;  // accepted point has no derivative information yet (solver.cpp:256-262)
+    }
     if (isnan(alpha) || !(ls.status == LS_MINIMUM_FOUND || ls.status == LS_HIT_MAX_STEPSIZE))
       f |= TF_LS_FAILED;
   }
@@ -276,13 +516,15 @@ __global__ void __launch_bounds__(32) k_phase_lsupdate(const DeviceProblem P, co
 }
 
 // K5a/b: costates of the accepted point, then stationarity / feasibility residuals and
-// CopyTrajectory -- one thread per (trajectory, knot)
+// CopyTrajectory -- one thread per (problem of a listed group, knot)
 template <class Model, bool CON>
 __global__ void __launch_bounds__(128) k_phase_costate(const DeviceProblem P, const int* list,
                                                        int count) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
-  TrajSolver<Model, CON> s(P, list[t]);
+  if ((t >> 5) >= count) return;
+  const int b = list[t >> 5] * 32 + (t & 31);
+  if (b >= P.B || !(P.flags[b] & TF_ACTIVE)) return;
+  TrajSolver<Model, CON> s(P, b);
   s.phase_costate_knot(blockIdx.y);
 }
 
@@ -290,8 +532,10 @@ template <class Model, bool CON>
 __global__ void __launch_bounds__(128) k_phase_residual(const DeviceProblem P, const int* list,
                                                         int count) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
-  TrajSolver<Model, CON> s(P, list[t]);
+  if ((t >> 5) >= count) return;
+  const int b = list[t >> 5] * 32 + (t & 31);
+  if (b >= P.B || !(P.flags[b] & TF_ACTIVE)) return;
+  TrajSolver<Model, CON> s(P, b);
   s.phase_residual_knot(blockIdx.y);
 }
 
@@ -300,8 +544,9 @@ template <bool CON>
 __global__ void __launch_bounds__(128) k_phase_decide(const DeviceProblem P, const int* list,
                                                       int count) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
-  const int b = list[t];
+  if ((t >> 5) >= count) return;
+  const int b = list[t >> 5] * 32 + (t & 31);
+  if (b >= P.B || !(P.flags[b] & TF_ACTIVE)) return;
   const DevOptions& o = P.opts;
   const double stationarity = __longlong_as_double((long long)P.stat_acc[b]);
   const double feasibility = __longlong_as_double((long long)P.feas_acc[b]);
@@ -312,7 +557,7 @@ __global__ void __launch_bounds__(128) k_phase_decide(const DeviceProblem P, con
     stop = true;
     status = SOLVE_SUCCESS;
   }
-  f &= ~(TF_REFRESH_DYN | TF_REFRESH_GRAD);
+  f &= ~(TF_REFRESH_DYN | TF_REFRESH_GRAD | TF_SPEC_VALID);
   if (stationarity < sqrt(o.tol_stationarity)) {
     if constexpr (CON) {
       // z <- Pi(z_est) is applied knot by knot by the expansion that follows (dual_first)

@@ -97,6 +97,8 @@ def load_library():
             getattr(L, "altro_b200_" + f).argtypes = [vp, dptr]
         for f in ("get_status", "get_iterations", "get_merit_evals"):
             getattr(L, "altro_b200_" + f).argtypes = [vp, iptr]
+        L.altro_b200_get_linesearch_histogram.argtypes = [vp, C.POINTER(C.c_long), C.c_int]
+        L.altro_b200_get_field.argtypes = [vp, C.c_char_p, dptr, C.POINTER(C.c_int)]
         L.altro_b200_set_solve_mode.argtypes = [vp, C.c_int]
         L.altro_b200_set_profiling.argtypes = [vp, C.c_int]
         L.altro_b200_set_speculation.argtypes = [vp, C.c_int]
@@ -274,6 +276,11 @@ class BatchSolver:
         return {p: dict(ms=float(ms[i]), launches=int(launches[i]), units=float(units[i]))
                 for i, p in enumerate(self.PHASES)}, int(syncs.value)
 
+    def GetLinesearchHistogram(self, reset=False):
+        h = (C.c_long * 32)()
+        self._ck(self.L.altro_b200_get_linesearch_histogram(self.h, h, int(reset)), "GetLinesearchHistogram")
+        return np.array(list(h))
+
     def ResetDuals(self):
         self._ck(self.L.altro_b200_reset_duals(self.h), "ResetDuals")
 
@@ -330,6 +337,14 @@ class BatchSolver:
 
     def GetFeedforwardGains(self):
         return self._get("get_feedforward_gains", (self.B, self.N, self.m))
+
+    def GetField(self, name):
+        """KnotPointData member `name` of every problem: array [B, N+1, rows]."""
+        rows = C.c_int()
+        self._ck(self.L.altro_b200_get_field(self.h, name.encode(), None, C.byref(rows)), "GetField")
+        out = np.empty((self.B, self.N + 1, rows.value))
+        self._ck(self.L.altro_b200_get_field(self.h, name.encode(), out.ctypes.data_as(dptr), None), "GetField")
+        return out
 
     def GetStatus(self, out=None):
         return self._get("get_status", (self.B,), np.int32, out=out)

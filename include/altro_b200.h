@@ -222,7 +222,7 @@ int altro_b200_synchronize(altro_b200_solver *s);
  * trips per iteration, so solve_async returns when the last kernel is queued);
  * 1: one persistent kernel for the whole solve (thread per trajectory, no host interaction) */
 int altro_b200_set_solve_mode(altro_b200_solver *s, int mode);
-/* number of candidate step lengths rolled out concurrently per backtracking round (1..24,
+/* number of candidate step lengths rolled out concurrently per backtracking round (1..16,
  * default 10; before altro_b200_initialize).  1 reproduces the strictly sequential search. */
 int altro_b200_set_speculation(altro_b200_solver *s, int nslots);
 /* per-phase instrumentation of the pipeline.  Phases: 0 init rollout, 1 expansion (knot-parallel),
@@ -232,6 +232,10 @@ int altro_b200_set_speculation(altro_b200_solver *s, int nslots);
 int altro_b200_set_profiling(altro_b200_solver *s, int on);
 int altro_b200_get_phase_stats(altro_b200_solver *s, double *ms, long *launches, double *units,
                                long *syncs);
+/* accepted-step histogram of the line searches run so far (32 bins: 0 alpha0 accepted, 1..15
+ * halving j accepted, 16 cubic-first probe, 17 zoom/other, 18 failed, 19 merit gradient too
+ * small); reset != 0 clears it */
+int altro_b200_get_linesearch_histogram(altro_b200_solver *s, long *hist32, int reset);
 /* number of kernels this handle has launched since creation */
 long altro_b200_kernel_launches(const altro_b200_solver *s);
 
@@ -241,6 +245,10 @@ int altro_b200_get_inputs(altro_b200_solver *s, double *U);  /* [B][N][m]    Get
 int altro_b200_get_dual_dynamics(altro_b200_solver *s, double *Y); /* [B][N+1][n]             */
 int altro_b200_get_feedback_gains(altro_b200_solver *s, double *K); /* [B][N][m*n]            */
 int altro_b200_get_feedforward_gains(altro_b200_solver *s, double *d); /* [B][N][m]           */
+/* any KnotPointData member by name (knotpoint_data.hpp:160-233): "x" "u" "y" "xbar" "ubar" "A" "B"
+ * "lx" "lu" "K" "d" "P" "p" "q" "r" "c".  out: [B][N+1][rows] (column-major blocks); rows_out
+ * receives the rows per knot; out may be NULL to query rows only. */
+int altro_b200_get_field(altro_b200_solver *s, const char *name, double *out, int *rows_out);
 int altro_b200_get_status(altro_b200_solver *s, int *status);       /* [B] SolveStatus        */
 int altro_b200_get_iterations(altro_b200_solver *s, int *iters);    /* [B] GetIterations      */
 int altro_b200_get_merit_evals(altro_b200_solver *s, int *evals);   /* [B]                    */

@@ -22,6 +22,7 @@ def main():
     s = altro_b200.make_solver(P, nslots=nslots)
     for _ in range(2):
         s.ResetTrajectory(); s.ResetDuals(); s.Solve()
+    s.GetLinesearchHistogram(reset=True)
     s.SetProfiling(1)
     s.ResetTrajectory(); s.ResetDuals(); s.Solve()
     st, syncs = s.GetPhaseStats()
@@ -32,7 +33,7 @@ def main():
         v["ns_per_unit"] = 1e6 * v["ms"] / max(v["units"], 1)
     out = {"workload": wl, "B": B, "total_ms": tot, "syncs": int(syncs),
            "mean_iters": float(s.GetIterations().mean()), "mean_evals": float(s.GetMeritEvals().mean()),
-           "phases": st}
+           "ls_hist": s.GetLinesearchHistogram().tolist(), "phases": st}
     print(json.dumps(out, indent=1))
 
 
