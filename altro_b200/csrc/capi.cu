@@ -8,7 +8,9 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../../include/altro_b200.h"
@@ -200,13 +202,21 @@ struct altro_b200_solver {
   double *xs = nullptr, *us = nullptr, *phi_s = nullptr;
   int* sel = nullptr;
   unsigned long long *stat_acc = nullptr, *feas_acc = nullptr;
-  int nslots = 10;  // candidate steps per speculative line-search round (slot 0 = requested step)
-  int nstore = 1;   // halvings 1..nstore also keep their trajectory (candidate slot buffers)
+  int nslots = 4;   // candidate steps per speculative line-search round (slot 0 = requested step)
+  int nstore = 3;   // halvings 1..nstore also keep their trajectory (candidate slot buffers)
   int *flags = nullptr, *iter_count = nullptr, *list_iter = nullptr, *list_ls = nullptr,
       *list_tmp = nullptr, *list_aux = nullptr, *counters = nullptr;
   unsigned long long* ls_hist = nullptr;
   PhaseHost ph;
   int solve_mode = 0;  // 0: phase pipeline (default), 1: single persistent kernel
+  // pipelined sub-batches: the groups are cut into `nsplit` contiguous ranges, each driven by its
+  // own host thread on its own stream, so that the compute-bound rollouts of one range overlap
+  // the HBM-bound sweeps of another and host round trips of one hide behind kernels of the others
+  static constexpr int kMaxSplit = 8;
+  int nsplit = 0;  // 0: choose from the batch size
+  cudaStream_t sub_stream[kMaxSplit] = {nullptr};
+  PhaseHost sub_ph[kMaxSplit];
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxSplit] = {nullptr};
   // tracking-window cost
   double *xtab = nullptr, *utab = nullptr;
   int* offsets = nullptr;
@@ -423,6 +433,16 @@ void altro_b200_destroy(altro_b200_solver* s) {
   cudaStreamSynchronize(s->stream);
   for (void* p : s->allocs) cudaFree(p);
   if (s->stage) cudaFree(s->stage);
+  for (int i = 0; i < altro_b200_solver::kMaxSplit; ++i) {
+    if (s->sub_stream[i]) {
+      cudaStreamDestroy(s->sub_stream[i]);
+      cudaFreeHost(s->sub_ph[i].h_counters);
+      cudaEventDestroy(s->sub_ph[i].ev0);
+      cudaEventDestroy(s->sub_ph[i].ev1);
+      cudaEventDestroy(s->ev_join[i]);
+    }
+  }
+  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
   if (s->ph.h_counters) {
     cudaFreeHost(s->ph.h_counters);
     cudaEventDestroy(s->ph.ev0);
@@ -507,7 +527,7 @@ int altro_b200_set_dimension(altro_b200_solver* s, int n, int m) {  // altro_sol
   DALLOC(s, s->list_ls, S);
   DALLOC(s, s->list_tmp, S);
   DALLOC(s, s->list_aux, S);
-  DALLOC(s, s->counters, 8);
+  DALLOC(s, s->counters, 8 * altro_b200_solver::kMaxSplit);
   DALLOC(s, s->ls_hist, 32);
   memset(&s->ph, 0, sizeof(s->ph));
   {  // device limits that size the staging rings of the sequential sweeps (solve_inst.cu)
@@ -896,6 +916,7 @@ static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   P.B = s->B;
   P.Bp = s->Bp;
   P.G = s->G;
+  P.Gtot = s->G;
   P.R = s->R;
   P.GS = s->GS;
   P.Rz = s->Rz;
@@ -982,7 +1003,71 @@ int altro_b200_solve_async(altro_b200_solver* s) {  // altro_solver.cpp:257-260
   } else {
     long before = 0;
     for (int i = 0; i < PH_COUNT; ++i) before += s->ph.launches[i];
-    int e = L(P, s->con_h.ncon > 0, s->stream, &s->ph);
+    int nsplit = s->nsplit;
+    if (nsplit <= 0) nsplit = s->G >= 256 ? 2 : 1;  // see DESIGN.md "pipelined sub-batches"
+    nsplit = std::min(std::min(nsplit, (int)altro_b200_solver::kMaxSplit), s->G);
+    P.g0 = 0;
+    P.G = s->G;
+    int e = 0;
+    if (nsplit == 1) {
+      e = L(P, s->con_h.ncon > 0, s->stream, &s->ph);
+    } else {
+      if (!s->ev_fork) CUDA_OK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+      for (int i = 0; i < nsplit; ++i) {
+        if (s->sub_stream[i]) continue;
+        CUDA_OK(cudaStreamCreateWithFlags(&s->sub_stream[i], cudaStreamNonBlocking));
+        memset(&s->sub_ph[i], 0, sizeof(PhaseHost));
+        CUDA_OK(cudaMallocHost((void**)&s->sub_ph[i].h_counters, 8 * sizeof(int)));
+        CUDA_OK(cudaEventCreate(&s->sub_ph[i].ev0));
+        CUDA_OK(cudaEventCreate(&s->sub_ph[i].ev1));
+        CUDA_OK(cudaEventCreateWithFlags(&s->ev_join[i], cudaEventDisableTiming));
+      }
+      CUDA_OK(cudaEventRecord(s->ev_fork, s->stream));
+      const int per = (s->G + nsplit - 1) / nsplit;
+      int rc[altro_b200_solver::kMaxSplit] = {0};
+      std::vector<std::thread> workers;
+      const int has_con = s->con_h.ncon > 0;
+      for (int i = 0; i < nsplit; ++i) {
+        workers.emplace_back([&, i]() {
+          cudaSetDevice(s->device);
+          PhaseHost& H = s->sub_ph[i];
+          H.op = OP_SOLVE;
+          H.profile = s->ph.profile;
+          H.num_sms = s->ph.num_sms;
+          H.smem_per_sm = s->ph.smem_per_sm;
+          H.smem_per_cta = s->ph.smem_per_cta;
+          for (int j = 0; j < PH_COUNT; ++j) {
+            H.ms[j] = 0.0;
+            H.launches[j] = 0;
+            H.units[j] = 0.0;
+          }
+          H.syncs = 0;
+          DeviceProblem Pi = P;
+          Pi.g0 = i * per;
+          Pi.G = std::min(per, s->G - Pi.g0);
+          if (Pi.G <= 0) return;
+          Pi.list_iter = P.list_iter + Pi.g0;
+          Pi.list_ls = P.list_ls + Pi.g0;
+          Pi.list_tmp = P.list_tmp + Pi.g0;
+          Pi.counters = P.counters + 8 * i;
+          H.list_aux = s->list_aux + Pi.g0;
+          cudaStreamWaitEvent(s->sub_stream[i], s->ev_fork, 0);
+          rc[i] = L(Pi, has_con, s->sub_stream[i], &H);
+          cudaEventRecord(s->ev_join[i], s->sub_stream[i]);
+        });
+      }
+      for (auto& w : workers) w.join();
+      for (int i = 0; i < nsplit; ++i) {
+        CUDA_OK(cudaStreamWaitEvent(s->stream, s->ev_join[i], 0));
+        if (rc[i]) e = rc[i];
+        for (int j = 0; j < PH_COUNT; ++j) {
+          s->ph.ms[j] += s->sub_ph[i].ms[j];
+          s->ph.launches[j] += s->sub_ph[i].launches[j];
+          s->ph.units[j] += s->sub_ph[i].units[j];
+        }
+        s->ph.syncs += s->sub_ph[i].syncs;
+      }
+    }
     long after = 0;
     for (int i = 0; i < PH_COUNT; ++i) after += s->ph.launches[i];
     s->launches += after - before;
@@ -1028,6 +1113,13 @@ int altro_b200_set_solve_mode(altro_b200_solver* s, int mode) {
   if (!s) return ALTRO_B200_INVALID_POINTER;
   if (mode != 0 && mode != 1) return ALTRO_B200_BAD_INDEX;
   s->solve_mode = mode;
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_set_pipeline_split(altro_b200_solver* s, int nsplit) {
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  if (nsplit < 0 || nsplit > altro_b200_solver::kMaxSplit) return ALTRO_B200_BAD_INDEX;
+  s->nsplit = nsplit;
   return ALTRO_B200_NO_ERROR;
 }
 

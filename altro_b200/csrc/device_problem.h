@@ -66,7 +66,9 @@ struct DevOptions {
 struct DeviceProblem {
   int N, B;
   long Bp;  // batch padded to a multiple of 32 (per-problem scalar arrays)
-  int G;    // groups = Bp / 32
+  int G;    // groups this launch sequence covers (a sub-batch of the handle when pipelined)
+  int g0;   // first group of the sub-batch
+  int Gtot; // groups of the whole handle = Bp / 32
   long R, GS;    // main record stream: knot stride, group stride (doubles)
   long Rz, GSz;  // dual record stream [group][knot][z rows | z_est rows][32]
   long Rs;       // candidate-slot record stream [slot][group][knot][x rows | u rows][32]

@@ -173,7 +173,12 @@ ALTRO_DEV void prefetch_block(const double* __restrict__ base, long rec, int k) 
 // the stage's mbarrier with the byte count and issues one bulk copy per contiguous piece; every
 // thread waits on the mbarrier parity, reads ITS lane's column of the stage
 //     stage[row][lane]      (256-byte rows: conflict-free 8-byte accesses)
-// into registers, and after a warp/CTA barrier the leader refills the stage.  Measured at the
+// into registers, WORKS ON THE KNOT, and only then passes the warp/CTA barrier after which the
+// leader refills the stage: a barrier does not wait for outstanding LDS, but arithmetic that
+// consumed the values does, so the bulk copy can never overwrite a row that is still being read
+// (with 10 warps x 27 LDS queued per knot the read-out takes as long as an L2-hit bulk copy; run
+// to run differences in the last bits showed up before the order was fixed).  The refill
+// therefore runs depth - 1 knots ahead.  Measured at the
 // 3.5 warps/SM of B = 16384: 6.8 TB/s vs 3.2 TB/s for per-element LDG from the old
 // problem-fastest layout and 5.0 TB/s for per-lane cp.async (profiles/r01_microbench_layout.txt).
 constexpr int kMaxStageDepth = 4;

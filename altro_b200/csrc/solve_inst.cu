@@ -12,7 +12,6 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
   using TS = TrajSolver<Model, CON>;
   constexpr int n = Model::n, m = Model::m;
   const int B = P.B, N = P.N, G = P.G;
-  auto g32 = [](int count) { return (count + 31) / 32; };
   auto g128 = [](int count) { return (count + 127) / 128; };
   cudaError_t err = cudaSuccess;
   // launch wrapper: counts launches/units and, in profile mode, times the kernel with events
@@ -46,7 +45,7 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
                      int mask2, int slot2, int mask3, int slot3) {
     timed(PH_COMPACT, count, [&] {
       k_compact<<<1, 1024, 0, st>>>(in, count, dcount, P.flags, mask, out, P.counters, slot, mask2,
-                                    slot2, mask3, slot3);
+                                    slot2, mask3, slot3, P.g0);
     });
   };
   // TMA staging ring of the sequential sweeps (linalg.cuh): depth = knots in flight per CTA, as
@@ -89,9 +88,11 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
   };
 
   // ---- prologue (solver.cpp:417-430)
-  timed(PH_INIT, B, [&] { k_phase_init<Model, CON><<<g32(B), 32, 0, st>>>(P); });
+  const int b0 = P.g0 * 32, b1 = std::min(B, (P.g0 + G) * 32);  // problems of this sub-batch
+  timed(PH_INIT, b1 - b0, [&] { k_phase_init<Model, CON><<<G, 32, 0, st>>>(P); });
   expand(nullptr, G, nullptr, 0, true, -1, false);  // with the OLD penalty (quirk Q3) ...
-  if (CON) k_phase_set_rho<<<g128(B), 128, 0, st>>>(P.rho, B, P.opts.penalty_initial);  // ... then reset
+  if (CON)  // ... then reset
+    k_phase_set_rho<<<g128(b1 - b0), 128, 0, st>>>(P.rho, b0, b1, P.opts.penalty_initial);
   int* list_iter = P.list_iter;
   int* list_iter_next = H->list_aux;
   compact(nullptr, G, nullptr, TF_ACTIVE, list_iter, PC_ITER, 0, 0, 0, 0);

@@ -780,7 +780,7 @@ struct TrajSolver {
   ALTRO_DEV double* uw(int slot) const { return slot < 0 ? F(P.u) : P.us + slot_off(slot); }
   // candidate slots: [slot][group][knot][x rows | u rows][32]
   ALTRO_DEV long slot_off(int slot) const {
-    return ((long)slot * P.G + (b >> 5)) * (long)(N + 1) * P.Rs + (b & 31);
+    return ((long)slot * P.Gtot + (b >> 5)) * (long)(N + 1) * P.Rs + (b & 31);
   }
   ALTRO_DEV long sw(int slot) const { return slot < 0 ? S : P.Rs; }
 

@@ -39,7 +39,8 @@ static __global__ void __launch_bounds__(1024) k_compact(const int* __restrict__
                                                   const int* dcount,
                                                   const int* __restrict__ flags, int mask,
                                                   int* __restrict__ out, int* counters, int slot,
-                                                  int mask2, int slot2, int mask3, int slot3) {
+                                                  int mask2, int slot2, int mask3, int slot3,
+                                                  int gbase) {
   __shared__ int warp_tot[32], warp_tot2[32], warp_tot3[32];
   __shared__ int base_s, base2_s, base3_s;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -56,7 +57,7 @@ static __global__ void __launch_bounds__(1024) k_compact(const int* __restrict__
     const int i = start + tid;
     int g = -1, keep = 0, keep2 = 0, keep3 = 0;
     if (i < count) {
-      g = in ? in[i] : i;
+      g = in ? in[i] : gbase + i;
       int f = 0;  // OR of the flags of the lanes that have `mask`
       const int4* fp = reinterpret_cast<const int4*>(flags + (long)g * 32);
 #pragma unroll
@@ -126,7 +127,7 @@ extern __shared__ __align__(128) unsigned char altro_smem[];
 // K0: Solve() prologue, sequential part (solver.cpp:417-423)
 template <class Model, bool CON>
 __global__ void __launch_bounds__(32) k_phase_init(const DeviceProblem P) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (P.g0 + blockIdx.x) * 32 + threadIdx.x;
   if (b >= P.B) return;
   TrajSolver<Model, CON> s(P, b);
   s.phase_init_rollout();
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(128) k_phase_expand(const DeviceProblem P, con
   const int k = blockIdx.y;
   const int gi = t >> 5;
   if (gi >= list_count(count, dcount)) return;
-  const int b = (list ? list[gi] : gi) * 32 + (t & 31);
+  const int b = (list ? list[gi] : P.g0 + gi) * 32 + (t & 31);
   if (b >= P.B) return;
   if (mask && !(P.flags[b] & mask)) return;
   TrajSolver<Model, CON> s(P, b);
@@ -163,9 +164,9 @@ __global__ void __launch_bounds__(128) k_phase_expand(const DeviceProblem P, con
 }
 
 // penalty reset at the end of the prologue (SetPenalty(penalty_initial), solver.cpp:429)
-static __global__ void k_phase_set_rho(double* rho, int B, double value) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) rho[b] = value;
+static __global__ void k_phase_set_rho(double* rho, int b0, int b1, double value) {
+  const int b = b0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < b1) rho[b] = value;
 }
 
 // K1: CalcExpansions + BackwardPass + the alpha = 0 half of ForwardPass (solver.cpp:448-450,
@@ -211,22 +212,23 @@ __global__ void __launch_bounds__(32) k_phase_backward(const DeviceProblem P, co
         unstage_block<n>(st, n * n + n * m, lane, Qx);
         unstage_block<m>(st, n * n + n * m + n, lane, Qu);
       }
+      if (alive) alive = s.riccati_step(k, A, Bm, Qx, Qu, Pn, pn);
+      // release the stage only after the step has consumed what was read from it (see BulkRing)
       __syncwarp();
       if (lane == 0 && k - depth >= 0) fetch_bw(k - depth, ring.s);
       ring.advance();
-      if (alive) alive = s.riccati_step(k, A, Bm, Qx, Qu, Pn, pn);
     }
     // phi0 / dphi0 scan, knots ascending
     auto fetch_phi = [&](int k, int st) {
       ring.expect(st, kRowsPhi * 256);
       ring.copy(st, 0, rec + (long)k * P.R + TS::rQ * 32, kRowsPhi * 256);
     };
-    // K, d were just written by this warp through the generic proxy; the bulk copies read them
-    // through the async proxy
+    // K, d were just written by the lanes of this warp through the generic proxy; the bulk copies
+    // read them through the async proxy: every writer fences, then the leader issues
     __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
     __syncwarp();
     if (lane == 0) {
-      asm volatile("fence.proxy.async;" ::: "memory");
       for (int j = 0; j < depth; ++j)
         if (j < P.N) fetch_phi(j, (ring.s + j) % depth);
     }
@@ -249,10 +251,10 @@ __global__ void __launch_bounds__(32) k_phase_backward(const DeviceProblem P, co
         unstage_block<n * n>(st, oA, lane, A);
         unstage_block<n * m>(st, oB, lane, Bm);
       }
+      if (active) s.phi0_step(k, x, u, q, r, cval, K, d, A, Bm, dxda, phi0, dphi0);
       __syncwarp();
       if (lane == 0 && k + depth < P.N) fetch_phi(k + depth, ring.s);
       ring.advance();
-      if (active) s.phi0_step(k, x, u, q, r, cval, K, d, A, Bm, dxda, phi0, dphi0);
     }
     if (active) s.phi0_terminal(dxda, phi0, dphi0);
   } else {
@@ -361,10 +363,10 @@ __global__ void __launch_bounds__(32 * 16) k_phase_rollout(const DeviceProblem P
         unstage_block<m * n>(st, TS::rK, lane, K);
         unstage_block<m>(st, TS::rD, lane, d);
       }
+      if (need) s.rollout_step(k, alpha, xb, ub, K, d, q, r, cval, x, xo, uo, so, phi);
       __syncthreads();
       if (threadIdx.x == 0 && k + depth < P.N) fetch(k + depth, ring.s);
       ring.advance();
-      if (need) s.rollout_step(k, alpha, xb, ub, K, d, q, r, cval, x, xo, uo, so, phi);
     }
     if (need) s.rollout_terminal(x, xo, so, phi);
   } else {
@@ -427,10 +429,10 @@ __global__ void __launch_bounds__(32) k_phase_lsupdate(const DeviceProblem P, co
           unstage_block<n>(st, kRows1 + n * n + n * m, lane, lx);
           unstage_block<m>(st, kRows1 + n * n + n * m + n, lane, lu);
         }
+        if (had_deriv) s.dphi_step(K, d, A, Bm, lx, lu, dxda, dphi);
         __syncwarp();
         if (lane == 0 && k + depth < P.N) fetch(k + depth, ring.s);
         ring.advance();
-        if (had_deriv) s.dphi_step(K, d, A, Bm, lx, lu, dxda, dphi);
       }
       if (had_deriv) dphi = s.dphi_terminal(dxda, dphi);
     } else {

@@ -102,6 +102,7 @@ def load_library():
         L.altro_b200_set_solve_mode.argtypes = [vp, C.c_int]
         L.altro_b200_set_profiling.argtypes = [vp, C.c_int]
         L.altro_b200_set_speculation.argtypes = [vp, C.c_int]
+        L.altro_b200_set_pipeline_split.argtypes = [vp, C.c_int]
         L.altro_b200_get_phase_stats.argtypes = [vp, dptr, C.POINTER(C.c_long), dptr, C.POINTER(C.c_long)]
         L.altro_b200_tvlqr_backward_batch.argtypes = [C.c_int] * 4 + [dptr] * 8 + [C.c_double, C.c_bool] + \
             [dptr] * 5 + [iptr]
@@ -260,6 +261,10 @@ class BatchSolver:
 
     def SetSpeculation(self, nslots):
         self._ck(self.L.altro_b200_set_speculation(self.h, nslots), "SetSpeculation")
+
+    def SetPipelineSplit(self, nsplit):
+        """0: automatic; 1..8 sub-batches pipelined on their own streams/host threads."""
+        self._ck(self.L.altro_b200_set_pipeline_split(self.h, nsplit), "SetPipelineSplit")
 
     def SetProfiling(self, on):
         self._ck(self.L.altro_b200_set_profiling(self.h, int(on)), "SetProfiling")

@@ -222,8 +222,12 @@ int altro_b200_synchronize(altro_b200_solver *s);
  * trips per iteration, so solve_async returns when the last kernel is queued);
  * 1: one persistent kernel for the whole solve (thread per trajectory, no host interaction) */
 int altro_b200_set_solve_mode(altro_b200_solver *s, int mode);
+/* pipelined sub-batches: the batch is cut into `nsplit` contiguous ranges (1..8; 0 = automatic),
+ * each driven by its own host thread and stream so the compute-bound rollouts of one range
+ * overlap the HBM-bound sweeps of another.  Results do not depend on nsplit. */
+int altro_b200_set_pipeline_split(altro_b200_solver *s, int nsplit);
 /* number of candidate step lengths rolled out concurrently per backtracking round (1..16,
- * default 10; before altro_b200_initialize).  1 reproduces the strictly sequential search. */
+ * default 4; before altro_b200_initialize).  1 reproduces the strictly sequential search. */
 int altro_b200_set_speculation(altro_b200_solver *s, int nslots);
 /* per-phase instrumentation of the pipeline.  Phases: 0 init rollout, 1 expansion (knot-parallel),
  * 2 backward Riccati + alpha=0 scan, 3 rollout, 4 d(phi) scan + line-search step, 5 criteria +

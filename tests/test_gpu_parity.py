@@ -175,3 +175,27 @@ def test_phase_pipeline_equals_persistent_kernel(make):
     b = altro_b200.solve_problem(P, mode=1)
     for key in ("X", "U", "Y", "status", "iters", "merit_evals", "cost", "stat", "feas"):
         assert np.array_equal(a[key], b[key]), key
+
+
+@pytest.mark.parametrize("make", [
+    lambda: PR.bicycle(B=1000, N=100, n=5),
+    lambda: PR.scotty(B=700, N=30, n=4),
+])
+def test_results_do_not_depend_on_schedule(make):
+    """Speculation width (candidate steps rolled out per round) and the pipelined sub-batch split
+    only change WHEN work is done, never the arithmetic: results must be bit-identical, run to
+    run and schedule to schedule."""
+    P = make()
+    ref = None
+    for nslots, nsplit in [(1, 1), (4, 1), (4, 3), (10, 2), (4, 3), (16, 8)]:
+        s = altro_b200.make_solver(P, nslots=nslots)
+        s.SetPipelineSplit(nsplit)
+        s.Solve()
+        out = dict(X=s.GetStates(), U=s.GetInputs(), iters=s.GetIterations(), evals=s.GetMeritEvals(),
+                   cost=s.GetFinalObjective(), status=s.GetStatus())
+        s.close()
+        if ref is None:
+            ref = out
+            continue
+        for key in ref:
+            assert np.array_equal(out[key], ref[key]), (key, nslots, nsplit)
