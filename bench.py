@@ -56,6 +56,7 @@ def workload_desc(name, P, world):
                         f"{'backtracking' if P.options.get('use_backtracking_linesearch') else 'cubic'} "
                         f"line search",
             "batch_per_gpu": P.B, "n": P.n, "m": P.m, "horizon": P.N,
+            "timing": "CUDA events on the launching stream; max over ranks",
             "l2_policy": "working set (>= 1.4 GB of per-trajectory state) is far larger than the "
                          "126 MB L2; no flush needed"}
 
@@ -73,6 +74,32 @@ def algorithmic_bytes(P, iters, evals):
     extra = np.maximum(evals.astype(np.float64) - it, 0.0)
     per = 8.0 * (N * it * (D + 2 * rows) + N * extra * E + 2 * ((N + 1) * n + N * m))
     return float(per.sum())
+
+
+# Per-kernel split of the algorithmic bytes (DESIGN.md "Kernels"): compulsory HBM doubles per
+# trajectory-knot each phase kernel must move, and how many trajectory-knots the ALGORITHM needs
+# it to process in one solve (speculative / masked-off work is NOT counted as useful).
+def kernel_models(P, iters, evals):
+    n, m, N = P.n, P.m, P.N
+    rows = P.n_constraint_rows()
+    it = float(iters.astype(np.float64).sum())                       # backward passes
+    roll = float(np.maximum(evals.astype(np.float64) - iters, 0).sum())  # rollouts the search consumed
+    jac = n * n + n * m
+    return {
+        "backward": dict(kernel="k_phase_backward (Riccati sweep + alpha=0 scan)",
+                         doubles=(jac + n + m) + (m * n + m + n * n + n) + rows            # sweep
+                         + (2 * (n + m) + 1 + m * n + m + jac) + (n + m) + 2 * rows,       # scan
+                         units=it * N),
+        "rollout": dict(kernel="k_phase_rollout (closed-loop rollout, merit value)",
+                        doubles=(2 * (n + m) + 1 + m * n + m) + (n + m) + rows, units=roll * N),
+        "expand": dict(kernel="k_phase_expand (dynamics Jacobians, projected duals, gradients)",
+                       doubles=2 * (n + m) + (jac + n + m) + 2 * rows, units=(it + P.B) * (N + 1)),
+        "lsupdate": dict(kernel="k_phase_lsupdate (d(phi) scan + line-search machine)",
+                         doubles=m * n + m + jac + n + m, units=it * N),
+        "criteria": dict(kernel="k_phase_costate + k_phase_residual (+ decide)",
+                         doubles=(2 * n + n * n + n) + n + (2 * n + jac + 2 * (n + m)) + (n + m) + rows,
+                         units=it * (N + 1)),
+    }
 
 
 class ClockSampler:
@@ -134,12 +161,13 @@ def peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(workload_name):
-    """dram bytes per launch of the solve kernel from the committed ncu --set full capture."""
+def ncu_traffic(workload_name, phase):
+    """dram bytes per trajectory-knot of a phase kernel from the committed ncu --set full capture
+    (profiles/traffic.json, written by tools/ncu_traffic.py)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(workload_name, {}).get("dram_bytes_per_launch")
+            return json.load(open(p)).get(workload_name, {}).get(phase, {}).get("dram_bytes_per_unit")
         except Exception:
             return None
     return None
@@ -208,6 +236,8 @@ def main():
     ap.add_argument("--ref-step-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--split", type=int, default=0, help="pipelined sub-batches (0 = automatic)")
+    ap.add_argument("--slots", type=int, default=None, help="candidate steps per line-search round")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = {"bicycle": 16384, "pendulum": 4096, "scotty": 8192, "chain12": 4096,
@@ -237,8 +267,9 @@ def main():
         torch.cuda.synchronize()
 
     P = workload(args.workload, args.batch, rank, world)
-    solver = altro_b200.make_solver(P, device=local_rank)
+    solver = altro_b200.make_solver(P, device=local_rank, nslots=args.slots)
     solver.SetStream(torch.cuda.current_stream().cuda_stream)
+    solver.SetPipelineSplit(args.split)
     B, N, n, m = P.B, P.N, P.n, P.m
 
     # ------------------------------------------------------------ (1) resident-in-HBM steps
@@ -314,6 +345,24 @@ def main():
     barrier()
     e2e_ms = e_start.elapsed_time(e_end)
 
+    # ------------------------------------------------------------ (3) per-kernel times (rank 0)
+    # one extra solve, sub-batch pipelining off and every launch bracketed by CUDA events on the
+    # launching stream (the pipeline's own instrumentation): gives each phase kernel's launches
+    # and summed duration without overlap from other sub-batches
+    phase_stats = None
+    if rank == 0:
+        solver.SetPipelineSplit(1)
+        solver.ResetTrajectory()
+        solver.ResetDuals()
+        solver.Solve()                       # warm (no split) instantiation
+        solver.SetProfiling(1)
+        solver.ResetTrajectory()
+        solver.ResetDuals()
+        solver.Solve()
+        phase_stats, _ = solver.GetPhaseStats()
+        solver.SetProfiling(0)
+        solver.SetPipelineSplit(args.split)
+
     # ------------------------------------------------------------ max over ranks
     times = torch.tensor([elapsed_ms, e2e_ms, kernel_ms], dtype=torch.float64, device="cuda")
     counts = torch.tensor([float(B)], dtype=torch.float64, device="cuda")
@@ -329,7 +378,28 @@ def main():
         e2e_value = total_solves * args.steps / (e2e_ms * 1e-3)
         peak, peak_src = peak_hbm()
         alg_bytes = algorithmic_bytes(P, iters, evals)
-        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        models = kernel_models(P, iters, evals)
+        phase_map = {"backward": "backward", "rollout": "rollout", "expand": "expand",
+                     "lsupdate": "lsupdate", "criteria": "criteria"}
+        tot_ms = sum(v["ms"] for v in phase_stats.values())
+        kernels = {}
+        for ph, st_ in phase_stats.items():
+            if ph not in phase_map or st_["launches"] == 0:
+                continue
+            mdl = models[phase_map[ph]]
+            bytes_total = 8.0 * mdl["doubles"] * mdl["units"]
+            kernels[ph] = {"kernel": mdl["kernel"], "launches": st_["launches"], "ms": st_["ms"],
+                           "share_of_step": st_["ms"] / tot_ms,
+                           "us_per_launch": 1e3 * st_["ms"] / st_["launches"],
+                           "algorithmic_bytes_per_launch": bytes_total / st_["launches"],
+                           "achieved_gbs": bytes_total / (st_["ms"] * 1e-3) / 1e9,
+                           "frac": bytes_total / (st_["ms"] * 1e-3) / 1e9 / peak}
+        dom = max(kernels, key=lambda k: kernels[k]["ms"])
+        kd = kernels[dom]
+        traffic_unit = ncu_traffic(args.workload, dom)
+        traffic = None
+        if traffic_unit is not None:
+            traffic = traffic_unit * phase_stats[dom]["units"] / phase_stats[dom]["launches"]
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -338,12 +408,22 @@ def main():
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                        "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
                "gpu_launches": int(launches),
-               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
-                            "kernel": "altro_b200::solve_kernel<Model,CON> (one launch per step)",
-                            "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+               "roofline": {"bound": "hbm", "achieved": kd["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                            "frac": kd["frac"], "traffic": traffic,
+                            "kernel": kd["kernel"], "launches_per_step": kd["launches"],
+                            "kernel_us_per_launch": kd["us_per_launch"],
+                            "share_of_step": kd["share_of_step"],
+                            "algorithmic_bytes_per_launch": kd["algorithmic_bytes_per_launch"],
                             "peak_source": peak_src,
-                            "note": "latency/FP64-issue bound, not HBM bound: see DESIGN.md"},
+                            "note": "dominant kernel of the step; per-kernel algorithmic bytes = "
+                                    "DESIGN.md 'Kernels' table x the trajectory-knots the algorithm "
+                                    "needs (speculative candidates not counted); timed with CUDA "
+                                    "events around every launch, sub-batch pipelining off"},
+               "kernels": kernels,
+               "step_roofline": {"algorithmic_bytes_per_step": alg_bytes,
+                                 "achieved": alg_bytes / (elapsed_ms / args.steps * 1e-3) / 1e9,
+                                 "frac": alg_bytes / (elapsed_ms / args.steps * 1e-3) / 1e9 / peak,
+                                 "note": "SURVEY 8(d) bytes of the whole solve / step time"},
                "solve_stats": {"mean_iterations": float(iters.mean()),
                                "mean_merit_evals": float(evals.mean()),
                                "success_frac": float((status == 0).mean()),
