@@ -1195,6 +1195,8 @@ GETTER_PM(altro_b200_get_dual_dynamics, y, s->n, (s->N + 1) * s->n)
 GETTER_PM(altro_b200_get_feedback_gains, K, s->m * s->n, s->N * s->m * s->n)
 GETTER_PM(altro_b200_get_feedforward_gains, d, s->m, s->N * s->m)
 
+static int run_host_op(altro_b200_solver* s, int op, double* cost_out);
+
 // KnotPointData member of every problem by name (knotpoint_data.hpp:160-233): x u y (accepted
 // point = working copy after Solve), xbar ubar, A B, lx lu, K d, P p, q r c.  out: [B][knots][rows]
 // with knots = N + 1 (fields that do not exist at the terminal knot hold zeros / stale data there).
@@ -1212,6 +1214,21 @@ int altro_b200_get_field(altro_b200_solver* s, const char* name, double* out, in
       if (rows_out) *rows_out = t.rows;
       if (!out) return ALTRO_B200_NO_ERROR;
       CUDA_OK(cudaSetDevice(s->device));
+      if (t.p == s->A || t.p == s->Bm) {
+        // [A B] may be stored packed (models.cuh, JacPack): expand into a dense scratch stream
+        const long rows = (long)n * n + (long)n * m;
+        double* dense = nullptr;
+        CUDA_OK(cudaMalloc((void**)&dense, (size_t)s->G * (s->N + 1) * rows * 32 * 8));
+        CUDA_OK(cudaMemsetAsync(dense, 0, (size_t)s->G * (s->N + 1) * rows * 32 * 8, s->stream));
+        int e = run_host_op(s, OP_UNPACK_JAC, dense);
+        if (!e) {
+          FieldView v{dense + (t.p == s->Bm ? (long)n * n * 32 : 0), t.rows, rows * 32,
+                      (long)(s->N + 1) * rows * 32};
+          e = download_pm(s, v, (long)(s->N + 1) * t.rows, out);
+        }
+        cudaFree(dense);
+        return e;
+      }
       return download_pm(s, fview(s, t.p, t.rows), (long)(s->N + 1) * t.rows, out);
     }
   }

@@ -11,11 +11,12 @@ namespace altro_b200 {
 // Host-side state of the phase-kernel pipeline (solver_phases.cuh)
 enum Phase { PH_INIT = 0, PH_EXPAND, PH_BACKWARD, PH_ROLLOUT, PH_LSUPDATE, PH_CRITERIA, PH_COMPACT, PH_COUNT };
 
-enum HostOp { OP_SOLVE = 0, OP_OPEN_LOOP_ROLLOUT = 1, OP_CALC_COST = 2 };
+enum HostOp { OP_SOLVE = 0, OP_OPEN_LOOP_ROLLOUT = 1, OP_CALC_COST = 2, OP_UNPACK_JAC = 3 };
 
 struct PhaseHost {
   int op;              // HostOp
-  double* cost_out;    // OP_CALC_COST: device array [Bp]
+  double* cost_out;    // OP_CALC_COST: device array [Bp]; OP_UNPACK_JAC: dense [A B] stream
+                       // [group][knot][n*n + n*m][32]
   int* h_counters;     // pinned, 8 ints
   int* list_aux;       // second buffer for list_iter
   bool profile;        // record CUDA events around every launch

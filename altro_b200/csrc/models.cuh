@@ -291,4 +291,110 @@ using Bicycle5 = Midpoint<Bicycle5C>;
 template <int NS, int NI>
 using Chain = Midpoint<ChainC<NS, NI>>;
 
+// ------------------------------------------------------------------ packed Jacobian storage
+// What the kernels keep in HBM of the discrete expansion [A B] of one knot.  Generic models store
+// all n*n + n*m entries.  Models whose midpoint Jacobian has entries that are the SAME constant
+// (0, 1 or h) at every state store only the varying ones and re-create the constants on load:
+// the dense blocks the arithmetic sees are bit-identical to the computed ones (a structural zero
+// times a finite number is an exact zero), so nothing downstream changes -- only the bytes moved
+// by every HBM-bound kernel (bicycle: 15 of 35 doubles).  The one observable difference: a
+// trajectory that has already overflowed to inf/NaN would poison the "constant" entries in the
+// dense computation (0 * inf) and does not here; such a solve has failed either way.
+template <class Model>
+struct JacPack {
+  static constexpr int n = Model::n, m = Model::m;
+  static constexpr int V = n * n + n * m;
+  static constexpr bool packed = false;
+  ALTRO_DEV static void pack(const double* A, const double* B, double* J) {
+#pragma unroll
+    for (int i = 0; i < n * n; ++i) J[i] = A[i];
+#pragma unroll
+    for (int i = 0; i < n * m; ++i) J[n * n + i] = B[i];
+  }
+  ALTRO_DEV static void unpack(const double* J, float h, double* A, double* B) {
+    (void)h;
+#pragma unroll
+    for (int i = 0; i < n * n; ++i) A[i] = J[i];
+#pragma unroll
+    for (int i = 0; i < n * m; ++i) B[i] = J[n * n + i];
+  }
+};
+
+// Bicycle5 (state [x,y,theta,delta,v], input [a,delta_dot]): the continuous Jacobian has rows
+// 0..2 x columns 2..4 only and B_c = [e4 e3], so A_d = I + h Am (I + h/2 A) differs from the
+// identity in rows 0..2 x columns 2..4 and B_d = h (Am h/2 B + Bm) has rows 0..2 varying,
+// B_d[3,1] = B_d[4,0] = h.
+template <>
+struct JacPack<Midpoint<Bicycle5C>> {
+  static constexpr int n = 5, m = 2;
+  static constexpr int V = 15;
+  static constexpr bool packed = true;
+  ALTRO_DEV static void pack(const double* A, const double* B, double* J) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) J[r + 3 * c] = A[r + n * (2 + c)];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) J[9 + r + 3 * c] = B[r + n * c];
+  }
+  ALTRO_DEV static void unpack(const double* J, float h, double* A, double* B) {
+    const double hd = h;
+#pragma unroll
+    for (int c = 0; c < n; ++c)
+#pragma unroll
+      for (int r = 0; r < n; ++r) A[r + n * c] = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) A[r + n * (2 + c)] = J[r + 3 * c];
+#pragma unroll
+    for (int i = 0; i < n * m; ++i) B[i] = 0.0;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) B[r + n * c] = J[9 + r + 3 * c];
+    B[3 + n * 1] = hd;
+    B[4 + n * 0] = hd;
+  }
+};
+
+// Bicycle4 (test/test_utils.cpp:134-238; state [x,y,theta,delta], input [v,delta_dot]): A_d
+// differs from the identity in rows 0..2 x columns 2..3, B_d has rows 0..2 varying, B_d[3,1] = h.
+template <>
+struct JacPack<Midpoint<Bicycle4C>> {
+  static constexpr int n = 4, m = 2;
+  static constexpr int V = 12;
+  static constexpr bool packed = true;
+  ALTRO_DEV static void pack(const double* A, const double* B, double* J) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) J[r + 3 * c] = A[r + n * (2 + c)];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) J[6 + r + 3 * c] = B[r + n * c];
+  }
+  ALTRO_DEV static void unpack(const double* J, float h, double* A, double* B) {
+    const double hd = h;
+#pragma unroll
+    for (int c = 0; c < n; ++c)
+#pragma unroll
+      for (int r = 0; r < n; ++r) A[r + n * c] = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) A[r + n * (2 + c)] = J[r + 3 * c];
+#pragma unroll
+    for (int i = 0; i < n * m; ++i) B[i] = 0.0;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) B[r + n * c] = J[6 + r + 3 * c];
+    B[3 + n * 1] = hd;
+  }
+};
+
 }  // namespace altro_b200

@@ -68,9 +68,9 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
     cudaFuncSetAttribute(k_phase_rollout<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_phase_lsupdate<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   }
-  constexpr int kRowsBackward = std::max(n * n + n * m + n + m, TS::rB + n * m - TS::rQ);
-  constexpr int kRowsRollout = TS::rD + m;
-  constexpr int kRowsDphi = m * n + m + n * n + n * m + n + m;
+  constexpr int kRowsBackward = TS::kRowsBackwardKernel;
+  constexpr int kRowsRollout = TS::kRowsRoll;
+  constexpr int kRowsDphi = TS::kRowsDphi;
   // warps = candidate steps rolled out per group (1 = only the requested step)
   auto rollout = [&](const int* list, int count, const int* dcount, int warps) {
     int depth;
@@ -168,6 +168,10 @@ static int launch_solve(const DeviceProblem& P, int has_con, cudaStream_t st, Ph
       k_calc_cost<Model, true><<<(P.B + 31) / 32, 32, 0, st>>>(P, host->cost_out);
     else
       k_calc_cost<Model, false><<<(P.B + 31) / 32, 32, 0, st>>>(P, host->cost_out);
+    return (int)cudaGetLastError();
+  }
+  if (host && host->op == OP_UNPACK_JAC) {
+    k_unpack_jac<Model, false><<<dim3((P.B + 127) / 128, P.N), 128, 0, st>>>(P, host->cost_out);
     return (int)cudaGetLastError();
   }
   if (host) return has_con ? run_phased<Model, true>(P, st, host) : run_phased<Model, false>(P, st, host);

@@ -152,6 +152,33 @@ struct TrajSolver {
   ALTRO_DEV TrajSolver(const DeviceProblem& p, int b_)
       : P(p), S(p.R), go((long)(b_ >> 5) * p.GS + (b_ & 31)), b(b_), N(p.N), rho(1.0), merit_evals(0) {}
 
+  // [A B] of knot k <-> the packed Jacobian rows of the record (models.cuh, JacPack)
+  using JP = JacPack<Model>;
+  static constexpr int kV = JP::V;
+  ALTRO_DEV void store_jac(int k, const double* A, const double* Bm) const {
+    double J[kV];
+    JP::pack(A, Bm, J);
+    store_block<kV>(P.A + go, S, k, J);
+  }
+  ALTRO_DEV void load_jac(int k, double* A, double* Bm) const {
+    double J[kV];
+    load_block<kV>(P.A + go, S, k, J);
+    JP::unpack(J, P.h, A, Bm);
+  }
+  // the same from a landed stage of the TMA ring (J rows start at `row`)
+  ALTRO_DEV void unstage_jac(const double* stage, int row, int lane, double* A, double* Bm) const {
+    double J[kV];
+    unstage_block<kV>(stage, row, lane, J);
+    JP::unpack(J, P.h, A, Bm);
+  }
+
+  // rows per knot each sequential sweep stages through the TMA ring (solver_phases.cuh)
+  static constexpr int kRowsBw = kV + NS_ + NI_;                          // [J] [lx lu]
+  static constexpr int kRowsPhi = rA - rQ + kV;                           // [q r c K d x u J]
+  static constexpr int kRowsRoll = rD + NI_;                              // [xbar ubar q r c K d]
+  static constexpr int kRowsDphi = NI_ * NS_ + NI_ + kV + NS_ + NI_;      // [K d] [J] [lx lu]
+  static constexpr int kRowsBackwardKernel = kRowsBw > kRowsPhi ? kRowsBw : kRowsPhi;
+
   // field pointer of this problem (knot 0); knot k is k * S further, rows are 32 doubles apart
   ALTRO_DEV double* F(double* field) const { return field + go; }
   ALTRO_DEV const double* F(const double* field) const { return field + go; }
@@ -440,8 +467,7 @@ struct TrajSolver {
       load_block<n>(F(P.q), S, k, q);
       load_block<m>(F(P.r), S, k, r);
       jacobian(k, x, u, A, Bm);
-      store_block<n * n>(F(P.A), S, k, A);
-      store_block<n * m>(F(P.Bm), S, k, Bm);
+      store_jac(k, A, Bm);
       stage_gradient(k, x, u, q, r, false, lx, lu);
       al_terms(k, x, u, false, true, lx, lu);
       store_block<n>(F(P.lx), S, k, lx);
@@ -562,14 +588,12 @@ struct TrajSolver {
     riccati_terminal(Pn, pn);
     for (int k = N - 1; k >= 0; --k) {
       if (k > 0) {
-        prefetch_block<n * n>(F(P.A), S, k - 1);
-        prefetch_block<n * m>(F(P.Bm), S, k - 1);
+        prefetch_block<kV>(F(P.A), S, k - 1);
         prefetch_block<n>(F(P.lx), S, k - 1);
         prefetch_block<m>(F(P.lu), S, k - 1);
       }
       double A[n * n], Bm[n * m], Qx[n], Qu[m];
-      load_block<n * n>(F(P.A), S, k, A);
-      load_block<n * m>(F(P.Bm), S, k, Bm);
+      load_jac(k, A, Bm);
       load_block<n>(F(P.lx), S, k, Qx);
       load_block<m>(F(P.lu), S, k, Qu);
       bool ok;
@@ -621,8 +645,7 @@ struct TrajSolver {
       if (want) {
         double A[n * n], Bm[n * m], duda[m], dxn[n];
         jacobian(k, x, u, A, Bm);  // :305
-        store_block<n * n>(F(P.A), S, k, A);
-        store_block<n * m>(F(P.Bm), S, k, Bm);
+        store_jac(k, A, Bm);
         {
           double Kd[m];
           mm<m, 1, n, false, false, 0>(K, dxda, Kd);
@@ -681,8 +704,7 @@ struct TrajSolver {
         if (with_dynamics) {
           double A[n * n], Bm[n * m];
           jacobian(k, x, u, A, Bm);
-          store_block<n * n>(F(P.A), S, k, A);
-          store_block<n * m>(F(P.Bm), S, k, Bm);
+          store_jac(k, A, Bm);
         }
       } else {
 #pragma unroll
@@ -703,8 +725,7 @@ struct TrajSolver {
     for (int k = 0; k < N; ++k) {
       double yn[n], A[n * n], Bm[n * m], lx[n], lu[m], x[n], u[m];
       load_block<n>(F(P.y), S, k + 1, yn);
-      load_block<n * n>(F(P.A), S, k, A);
-      load_block<n * m>(F(P.Bm), S, k, Bm);
+      load_jac(k, A, Bm);
       load_block<n>(F(P.lx), S, k, lx);
       load_block<m>(F(P.lu), S, k, lu);
       mm<n, 1, n, true, false, 1>(A, yn, lx);  // lx + A' y+
@@ -845,8 +866,7 @@ struct TrajSolver {
       if (with_dyn) {
         double A[n * n], Bm[n * m];
         jacobian(k, x, u, A, Bm);
-        store_block<n * n>(F(P.A), S, k, A);
-        store_block<n * m>(F(P.Bm), S, k, Bm);
+        store_jac(k, A, Bm);
       }
     } else {
 #pragma unroll
@@ -911,8 +931,7 @@ struct TrajSolver {
           prefetch_block<m>(F(P.r), S, kn);
           prefetch_block<m * n>(F(P.K), S, kn);
           prefetch_block<m>(F(P.d), S, kn);
-          prefetch_block<n * n>(F(P.A), S, kn);
-          prefetch_block<n * m>(F(P.Bm), S, kn);
+          prefetch_block<kV>(F(P.A), S, kn);
         }
       }
       double x[n], u[m], q[n], r[m], K[m * n], d[m], A[n * n], Bm[n * m];
@@ -922,8 +941,7 @@ struct TrajSolver {
       load_block<m>(F(P.r), S, k, r);
       load_block<m * n>(F(P.K), S, k, K);
       load_block<m>(F(P.d), S, k, d);
-      load_block<n * n>(F(P.A), S, k, A);
-      load_block<n * m>(F(P.Bm), S, k, Bm);
+      load_jac(k, A, Bm);
       phi0_step(k, x, u, q, r, F(P.c)[(long)k * S], K, d, A, Bm, dxda, phi, dphi);
     }
     phi0_terminal(dxda, phi, dphi);
@@ -1032,16 +1050,14 @@ struct TrajSolver {
         if (kn < N) {
           prefetch_block<m * n>(F(P.K), S, kn);
           prefetch_block<m>(F(P.d), S, kn);
-          prefetch_block<n * n>(F(P.A), S, kn);
-          prefetch_block<n * m>(F(P.Bm), S, kn);
+          prefetch_block<kV>(F(P.A), S, kn);
           prefetch_block<m>(F(P.lu), S, kn);
         }
       }
       double K[m * n], d[m], A[n * n], Bm[n * m], lx[n], lu[m];
       load_block<m * n>(F(P.K), S, k, K);
       load_block<m>(F(P.d), S, k, d);
-      load_block<n * n>(F(P.A), S, k, A);
-      load_block<n * m>(F(P.Bm), S, k, Bm);
+      load_jac(k, A, Bm);
       load_block<n>(F(P.lx), S, k, lx);
       load_block<m>(F(P.lu), S, k, lu);
       dphi_step(K, d, A, Bm, lx, lu, dxda, dphi);
@@ -1073,8 +1089,7 @@ struct TrajSolver {
       double y[n], yn[n], A[n * n], Bm[n * m], lx[n], lu[m];
       load_block<n>(F(P.y), S, k, y);
       load_block<n>(F(P.y), S, k + 1, yn);
-      load_block<n * n>(F(P.A), S, k, A);
-      load_block<n * m>(F(P.Bm), S, k, Bm);
+      load_jac(k, A, Bm);
       load_block<n>(F(P.lx), S, k, lx);
       load_block<m>(F(P.lu), S, k, lu);
       load_block<m>(F(P.u), S, k, u);

@@ -185,17 +185,18 @@ __global__ void __launch_bounds__(32) k_phase_backward(const DeviceProblem P, co
   s.rho = (CON && active) ? P.rho[b] : 1.0;
   double phi0 = 0.0, dphi0 = 0.0;
   if constexpr (TS::kStaged) {
-    // stage contents: Riccati sweep rows [A B lx lu]; phi0 scan rows [q r c K d x u A B]
-    constexpr int kRowsBw = n * n + n * m + n + m;
-    constexpr int kRowsPhi = TS::rB + n * m - TS::rQ;
-    constexpr int kStage = (kRowsBw > kRowsPhi ? kRowsBw : kRowsPhi) * 32;
+    // stage contents: Riccati sweep [J | lx lu]; phi0 scan [q r c K d x u J]  (J = packed [A B])
+    constexpr int kV = TS::kV;
+    constexpr int kRowsBw = TS::kRowsBw, kRowsPhi = TS::kRowsPhi;
+    constexpr int kStage = TS::kRowsBackwardKernel * 32;
     BulkRing ring;
     ring.init(altro_smem, depth, kStage, lane == 0);
     __syncwarp();
     const double* rec = P.xbar + (long)g * P.GS;  // row 0 of the group's knot-0 record
     auto fetch_bw = [&](int k, int st) {
       ring.expect(st, kRowsBw * 256);
-      ring.copy(st, 0, rec + (long)k * P.R + TS::rA * 32, kRowsBw * 256);
+      ring.copy(st, 0, rec + (long)k * P.R + TS::rA * 32, kV * 256);
+      ring.copy(st, kV, rec + (long)k * P.R + TS::rLx * 32, (n + m) * 256);
     };
     if (lane == 0)
       for (int j = 0; j < depth; ++j)
@@ -207,10 +208,9 @@ __global__ void __launch_bounds__(32) k_phase_backward(const DeviceProblem P, co
       const double* st = ring.wait();
       double A[n * n], Bm[n * m], Qx[n], Qu[m];
       if (alive) {
-        unstage_block<n * n>(st, 0, lane, A);
-        unstage_block<n * m>(st, n * n, lane, Bm);
-        unstage_block<n>(st, n * n + n * m, lane, Qx);
-        unstage_block<m>(st, n * n + n * m + n, lane, Qu);
+        s.unstage_jac(st, 0, lane, A, Bm);
+        unstage_block<n>(st, kV, lane, Qx);
+        unstage_block<m>(st, kV + n, lane, Qu);
       }
       if (alive) alive = s.riccati_step(k, A, Bm, Qx, Qu, Pn, pn);
       // release the stage only after the step has consumed what was read from it (see BulkRing)
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(32) k_phase_backward(const DeviceProblem P, co
 #pragma unroll
     for (int i = 0; i < n; ++i) dxda[i] = 0.0;
     constexpr int oR = n, oC = n + m, oK = oC + 1, oD = oK + m * n, oX = oD + m, oU = oX + n,
-                  oA = oU + m, oB = oA + n * n;
+                  oJ = oU + m;
     for (int k = 0; k < P.N; ++k) {
       const double* st = ring.wait();
       double x[n], u[m], q[n], r[m], K[m * n], d[m], A[n * n], Bm[n * m], cval = 0.0;
@@ -248,8 +248,7 @@ __global__ void __launch_bounds__(32) k_phase_backward(const DeviceProblem P, co
         unstage_block<m>(st, oD, lane, d);
         unstage_block<n>(st, oX, lane, x);
         unstage_block<m>(st, oU, lane, u);
-        unstage_block<n * n>(st, oA, lane, A);
-        unstage_block<n * m>(st, oB, lane, Bm);
+        s.unstage_jac(st, oJ, lane, A, Bm);
       }
       if (active) s.phi0_step(k, x, u, q, r, cval, K, d, A, Bm, dxda, phi0, dphi0);
       __syncwarp();
@@ -337,7 +336,7 @@ __global__ void __launch_bounds__(32 * 16) k_phase_rollout(const DeviceProblem P
   }
   double phi = 0.0;
   if constexpr (TS::kStaged) {
-    constexpr int kRows = TS::rD + m;  // [xbar ubar q r c K d]
+    constexpr int kRows = TS::kRowsRoll;  // [xbar ubar q r c K d]
     BulkRing ring;
     ring.init(altro_smem, depth, kRows * 32, threadIdx.x == 0);
     __syncthreads();
@@ -401,16 +400,18 @@ __global__ void __launch_bounds__(32) k_phase_lsupdate(const DeviceProblem P, co
   if (__any_sync(0xffffffffu, had_deriv)) {
     TS s(P, had_deriv ? b : g * 32);
     if constexpr (TS::kStaged) {
-      // stage contents: [K d] then [A B lx lu]
-      constexpr int kRows1 = m * n + m, kRows2 = n * n + n * m + n + m;
+      // stage contents: [K d] [J] [lx lu]
+      constexpr int kV = TS::kV;
+      constexpr int kRows1 = m * n + m;
       BulkRing ring;
-      ring.init(altro_smem, depth, (kRows1 + kRows2) * 32, lane == 0);
+      ring.init(altro_smem, depth, TS::kRowsDphi * 32, lane == 0);
       __syncwarp();
       const double* rec = P.xbar + (long)g * P.GS;
       auto fetch = [&](int k, int st) {
-        ring.expect(st, (kRows1 + kRows2) * 256);
+        ring.expect(st, TS::kRowsDphi * 256);
         ring.copy(st, 0, rec + (long)k * P.R + TS::rK * 32, kRows1 * 256);
-        ring.copy(st, kRows1, rec + (long)k * P.R + TS::rA * 32, kRows2 * 256);
+        ring.copy(st, kRows1, rec + (long)k * P.R + TS::rA * 32, kV * 256);
+        ring.copy(st, kRows1 + kV, rec + (long)k * P.R + TS::rLx * 32, (n + m) * 256);
       };
       if (lane == 0)
         for (int j = 0; j < depth; ++j)
@@ -424,10 +425,9 @@ __global__ void __launch_bounds__(32) k_phase_lsupdate(const DeviceProblem P, co
         if (had_deriv) {
           unstage_block<m * n>(st, 0, lane, K);
           unstage_block<m>(st, m * n, lane, d);
-          unstage_block<n * n>(st, kRows1, lane, A);
-          unstage_block<n * m>(st, kRows1 + n * n, lane, Bm);
-          unstage_block<n>(st, kRows1 + n * n + n * m, lane, lx);
-          unstage_block<m>(st, kRows1 + n * n + n * m + n, lane, lu);
+          s.unstage_jac(st, kRows1, lane, A, Bm);
+          unstage_block<n>(st, kRows1 + kV, lane, lx);
+          unstage_block<m>(st, kRows1 + kV + n, lane, lu);
         }
         if (had_deriv) s.dphi_step(K, d, A, Bm, lx, lu, dxda, dphi);
         __syncwarp();
@@ -604,6 +604,21 @@ __global__ void __launch_bounds__(32) k_open_loop_rollout(const DeviceProblem P)
     for (int i = 0; i < n; ++i) x[i] = xn[i];
   }
   store_block<n>(s.F(P.x), s.S, P.N, x);
+}
+
+// Dense [A B] of every knot from the packed Jacobian rows (host views A_, B_ of KnotPointData)
+template <class Model, bool CON>
+__global__ void __launch_bounds__(128) k_unpack_jac(const DeviceProblem P, double* out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (b >= P.B) return;
+  TrajSolver<Model, CON> s(P, b);
+  constexpr int n = Model::n, m = Model::m, rows = n * n + n * m;
+  double A[n * n], Bm[n * m];
+  s.load_jac(k, A, Bm);
+  double* o = out + ((long)(b >> 5) * (P.N + 1) + k) * rows * 32 + (b & 31);
+  for (int e = 0; e < n * n; ++e) o[e * 32] = A[e];
+  for (int e = 0; e < n * m; ++e) o[(n * n + e) * 32] = Bm[e];
 }
 
 // ALTROSolver::CalcCost (solver.cpp:163-174): sum_k cost(k) incl. the AL terms at the working
