@@ -201,6 +201,7 @@ struct altro_b200_solver {
   double *alpha_eval = nullptr, *alpha_bt = nullptr, *phi_eval = nullptr, *phi0 = nullptr, *dphi0 = nullptr;
   double *xs = nullptr, *us = nullptr, *phi_s = nullptr;
   int* sel = nullptr;
+  int *spec_base = nullptr, *spec_known = nullptr;
   unsigned long long *stat_acc = nullptr, *feas_acc = nullptr;
   int nslots = 4;   // candidate steps per speculative line-search round (slot 0 = requested step)
   int nstore = 3;   // halvings 1..nstore also keep their trajectory (candidate slot buffers)
@@ -818,7 +819,9 @@ int altro_b200_initialize(altro_b200_solver* s) {  // altro_solver.cpp:225-229
   s->Rs = (long)(s->n + s->m) * 32;
   DALLOC(s, s->xs, (long)(s->nstore > 0 ? s->nstore : 1) * s->G * (s->N + 1) * s->Rs);
   s->us = s->xs + (long)s->n * 32;
-  DALLOC(s, s->phi_s, (long)s->nslots * s->Bp);
+  DALLOC(s, s->phi_s, (long)(kMaxHalvings + 1) * s->Bp);
+  DALLOC(s, s->spec_base, s->Bp);
+  DALLOC(s, s->spec_known, s->Bp);
   CUDA_OK(cudaStreamSynchronize(s->stream));
   s->initialized = true;
   return ALTRO_B200_NO_ERROR;
@@ -963,6 +966,8 @@ static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   P.xs = s->xs;
   P.us = s->us;
   P.phi_s = s->phi_s;
+  P.spec_base = s->spec_base;
+  P.spec_known = s->spec_known;
   P.sel = s->sel;
   P.stat_acc = s->stat_acc;
   P.feas_acc = s->feas_acc;

@@ -19,6 +19,7 @@
 
 namespace altro_b200 {
 
+constexpr int kMaxHalvings = 26;  // SimpleBacktracking tries at most max_iters - 1 = 24 halvings
 constexpr int kMaxCon = 4;       // constraint slots per problem on the device
 constexpr int kMaxConDim = 16;   // rows per constraint
 constexpr int kMaxSocDim = 6;    // rows of a second-order-cone constraint
@@ -116,7 +117,9 @@ struct DeviceProblem {
   int nslots;           // candidates per speculative round (>= 1): slot 0 = the requested step
   int nstore;           // speculative slots 1..nstore also keep their trajectory (slot buffers)
   double *xs, *us;      // slot record stream; us = xs + n * 32
-  double* phi_s;        // [nslots][Bp] merit value per candidate
+  double* phi_s;        // [kMaxHalvings + 1][Bp] merit value of halving j (alpha0 * 2^-j), j >= 1
+  int* spec_base;       // [Bp] halving index rolled out by slot 1 of the pending / last round
+  int* spec_known;      // [Bp] halvings 1..spec_known have their merit value in phi_s (this iteration)
   int* sel;             // [Bp] slot holding the working trajectory (-1: the main x, u arrays)
   unsigned long long *stat_acc, *feas_acc;  // [Bp] max-reductions over knots (bit patterns of doubles >= 0)
 
@@ -133,7 +136,7 @@ enum TrajFlags {
   TF_CONVERGED = 64,
   TF_SPECULATE = 128,       // the pending round also rolls out the halvings alpha_bt * 2^-j (merit only)
   TF_REROLL = 256,          // accepted step came from a merit-only candidate: roll it out again, storing
-  TF_SPEC_VALID = 512,      // phi_s holds merit values of alpha_bt * 2^-j for this iteration's gains
+  TF_SPEC_VALID = 512,      // (unused)
 };
 
 enum PhaseCounter { PC_LS = 0, PC_DERIV = 1, PC_SPEC = 2, PC_REFRESH_GRAD = 3, PC_ITER = 4 };

@@ -281,10 +281,12 @@ __global__ void __launch_bounds__(32) k_phase_backward(const DeviceProblem P, co
     if (ls.start(lo, 1.0, phi0, dphi0)) {
       f |= TF_NEED_EVAL | TF_WANT_DERIV;
       P.alpha_eval[b] = ls.alpha;
+      P.spec_known[b] = 0;
       if (lo.use_backtracking && P.nslots > 1) {
         // the halvings SimpleBacktracking(alpha0 * beta_decrease) will try if alpha0 and the
         // cubic-first probe are rejected (linesearch.cpp:130-132, :385-412)
         f |= TF_SPECULATE;
+        P.spec_base[b] = 1;
         P.alpha_bt[b] = ls.alpha0 * lo.beta_decrease;
       }
     } else {
@@ -326,7 +328,7 @@ __global__ void __launch_bounds__(32 * 16) k_phase_rollout(const DeviceProblem P
       uo = s.uw(-1);
       so = s.sw(-1);
     } else {
-      alpha = ldexp(P.alpha_bt[b], -(slot - 1));
+      alpha = ldexp(P.alpha_bt[b], -(slot - 1));  // halving spec_base + slot - 1
       if (slot <= P.nstore) {
         xo = s.xw(slot - 1);
         uo = s.uw(slot - 1);
@@ -375,7 +377,7 @@ __global__ void __launch_bounds__(32 * 16) k_phase_rollout(const DeviceProblem P
     if (slot == 0)
       P.phi_eval[b] = phi;
     else
-      P.phi_s[(long)slot * P.Bp + b] = phi;
+      P.phi_s[(long)min(P.spec_base[b] + slot - 1, kMaxHalvings) * P.Bp + b] = phi;
   }
 }
 
@@ -451,36 +453,63 @@ __global__ void __launch_bounds__(32) k_phase_lsupdate(const DeviceProblem P, co
   }
   LsMachine ls = P.ls[b];
   bool last_had_deriv = had_deriv;
-  int fed = 1, winner_slot = 0;
+  const int nspec = P.nslots - 1;  // halvings a speculative round rolls out besides the request
+  int known = P.spec_known[b];     // halvings 1..known have their merit value in phi_s
+  const int base = P.spec_base[b];
+  const bool was_backtrack = ls.phase == LsMachine::P_BACKTRACK;
+  int fed = 1, winner = 0;         // winner: halving index the search returned (0: the request)
   ls.update(lo, P.phi_eval[b], dphi);
-  if (f & TF_SPECULATE) f |= TF_SPEC_VALID;  // this round also produced the halvings' merit values
-  bool exhausted = false;
-  if ((f & TF_SPEC_VALID) && !ls.done() && ls.phase == LsMachine::P_BACKTRACK) {
-    exhausted = true;
-    for (int j = 1; j < P.nslots; ++j) {
-      const double cand = ldexp(P.alpha_bt[b], -(j - 1));
-      if (ls.alpha != cand) continue;  // not the step the machine is asking for
-      ls.update(lo, P.phi_s[(long)j * P.Bp + b], 0.0);
-      last_had_deriv = false;
-      winner_slot = j;
-      fed += 1;
-      if (ls.done() || ls.phase != LsMachine::P_BACKTRACK) {
-        exhausted = false;
-        break;
-      }
-    }
+  if (f & TF_SPECULATE) {
+    // this round produced halvings base .. base+nspec-1; the request itself was halving base-1
+    // when the machine was already backtracking
+    if (was_backtrack && base >= 2) P.phi_s[(long)min(base - 1, kMaxHalvings) * P.Bp + b] = P.phi_eval[b];
+    known = min(base + nspec - 1, kMaxHalvings);
   }
+  // feed the precomputed halvings in the order the sequential search would evaluate them
+  while (!ls.done() && ls.phase == LsMachine::P_BACKTRACK) {
+    // halving index of the step the machine asks for: alpha = alpha0 * 2^-j
+    int j = 1;
+    double cand = ls.alpha0 * lo.beta_decrease;
+    while (j <= known && cand != ls.alpha) {
+      cand *= lo.beta_decrease;
+      ++j;
+    }
+    if (j > known) break;  // not precomputed: needs another round
+    ls.update(lo, P.phi_s[(long)j * P.Bp + b], 0.0);
+    last_had_deriv = false;
+    winner = j;
+    fed += 1;
+  }
+  if (!ls.done()) winner = 0;
   P.merit_evals[b] += fed;
+  P.spec_known[b] = known;
   f &= ~(TF_NEED_EVAL | TF_WANT_DERIV | TF_SPECULATE);
   if (!ls.done()) {
     f |= TF_NEED_EVAL;
     if (ls.want_derivative()) f |= TF_WANT_DERIV;
     P.alpha_eval[b] = ls.alpha;
-    if (lo.use_backtracking && P.nslots > 1 && ls.phase == LsMachine::P_BACKTRACK &&
-        (exhausted || !(f & TF_SPEC_VALID))) {
-      // more halvings than were precomputed: next round evaluates ls.alpha and the ones after it
-      f |= TF_SPECULATE;
-      P.alpha_bt[b] = ls.alpha * lo.beta_decrease;
+    if (lo.use_backtracking && nspec > 0) {
+      if (ls.phase == LsMachine::P_BACKTRACK) {
+        // ran out of precomputed halvings: the request is halving known+1, speculate the next ones
+        f |= TF_SPECULATE;
+        P.spec_base[b] = known + 2;
+        P.alpha_bt[b] = ls.alpha * lo.beta_decrease;
+      } else if (ls.phase == LsMachine::P_CUBIC_FIRST) {
+        // the cubic-first probe is next (linesearch.cpp:96-127).  If it is rejected the search
+        // backtracks through the halvings; when none of the known ones passes the Armijo test the
+        // ones after them ride along with the probe
+        bool any = false;
+        double cand = ls.alpha0;
+        for (int j = 1; j <= known; ++j) {
+          cand *= lo.beta_decrease;
+          any = any || (P.phi_s[(long)j * P.Bp + b] <= ls.phi0 + lo.c1 * cand * ls.dphi0);
+        }
+        if (!any && known + 1 <= kMaxHalvings) {
+          f |= TF_SPECULATE;
+          P.spec_base[b] = known + 1;
+          P.alpha_bt[b] = cand * lo.beta_decrease;
+        }
+      }
     }
   } else {
     const double alpha = ls.alpha;
@@ -489,10 +518,10 @@ __global__ void __launch_bounds__(32) k_phase_lsupdate(const DeviceProblem P, co
     if (P.ls_hist) {
       int bin = 17;
       if (!(ls.status == LS_MINIMUM_FOUND || ls.status == LS_HIT_MAX_STEPSIZE)) bin = 18;
-      else if (winner_slot > 0) bin = winner_slot < 15 ? winner_slot : 15;
+      else if (winner > 0) bin = winner < 15 ? winner : 15;
       else if (alpha == ls.alpha0) bin = 0;
       else if (lo.use_backtracking && last_had_deriv) bin = 16;
-      else if (lo.use_backtracking) {  // a halving evaluated as the requested step of a later round
+      else if (lo.use_backtracking) {  // a halving evaluated as the request of a later round
         int j = 1;
         double a = ls.alpha0 * lo.beta_decrease;
         while (j < 15 && a != alpha) { a *= lo.beta_decrease; ++j; }
@@ -500,12 +529,15 @@ __global__ void __launch_bounds__(32) k_phase_lsupdate(const DeviceProblem P, co
       }
       atomicAdd(P.ls_hist + bin, 1ull);
     }
-    if (winner_slot > 0) {
-      // the step the search returns was only evaluated as a speculative candidate
-      if (winner_slot <= P.nstore)
-        P.sel[b] = winner_slot - 1;  // its trajectory is in a candidate slot: copy + expand it
+    if (winner > 0) {
+      // the step the search returns was only evaluated as a speculative candidate of the round
+      // that started at halving `wbase`
+      const int wbase = (winner >= base) ? base : 1;
+      const int wslot = winner - wbase + 1;
+      if (winner >= base && wslot >= 1 && wslot <= P.nstore)
+        P.sel[b] = wslot - 1;  // its trajectory is in a candidate slot: copy + expand it
       else
-        f |= TF_REROLL;              // merit-only candidate: roll it out again, then expand
+        f |= TF_REROLL;        // merit-only / overwritten candidate: roll it out again, then expand
       f |= TF_REFRESH_DYN;
     } else if (lo.use_backtracking && fabs(alpha - 1.0) > 0 && !last_had_deriv) {
       f |= TF_REFRESH_DYN;  // accepted point has no derivative information yet (solver.cpp:256-262)
@@ -559,7 +591,7 @@ __global__ void __launch_bounds__(128) k_phase_decide(const DeviceProblem P, con
     stop = true;
     status = SOLVE_SUCCESS;
   }
-  f &= ~(TF_REFRESH_DYN | TF_REFRESH_GRAD | TF_SPEC_VALID);
+  f &= ~(TF_REFRESH_DYN | TF_REFRESH_GRAD);
   if (stationarity < sqrt(o.tol_stationarity)) {
     if constexpr (CON) {
       // z <- Pi(z_est) is applied knot by knot by the expansion that follows (dual_first)
