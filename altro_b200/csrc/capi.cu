@@ -203,8 +203,8 @@ struct altro_b200_solver {
   int* sel = nullptr;
   int *spec_base = nullptr, *spec_known = nullptr;
   unsigned long long *stat_acc = nullptr, *feas_acc = nullptr;
-  int nslots = 4;   // candidate steps per speculative line-search round (slot 0 = requested step)
-  int nstore = 3;   // halvings 1..nstore also keep their trajectory (candidate slot buffers)
+  int nslots = 6;   // candidate steps per speculative line-search round (slot 0 = requested step)
+  int nstore = 15;  // speculative slots 1..nstore keep their trajectory (candidate slot buffers)
   int *flags = nullptr, *iter_count = nullptr, *list_iter = nullptr, *list_ls = nullptr,
       *list_tmp = nullptr, *list_aux = nullptr, *counters = nullptr;
   unsigned long long* ls_hist = nullptr;
@@ -817,7 +817,15 @@ int altro_b200_initialize(altro_b200_solver* s) {  // altro_solver.cpp:225-229
   CUDA_OK(cudaGetLastError());
   // candidate slots of the speculative line search
   s->Rs = (long)(s->n + s->m) * 32;
-  DALLOC(s, s->xs, (long)(s->nstore > 0 ? s->nstore : 1) * s->G * (s->N + 1) * s->Rs);
+  {
+    // candidate slot buffers: as many as fit a budget of 8 GB (at least 3)
+    const long per_slot = (long)s->G * (s->N + 1) * s->Rs;
+    const long fit = ((long)8 << 30) / 8 / per_slot;
+    if (s->nstore > s->nslots - 1) s->nstore = s->nslots - 1;
+    if (s->nstore > fit) s->nstore = (int)(fit < 3 ? 3 : fit);
+    if (s->nstore < 1) s->nstore = 1;
+  }
+  DALLOC(s, s->xs, (long)s->nstore * s->G * (s->N + 1) * s->Rs);
   s->us = s->xs + (long)s->n * 32;
   DALLOC(s, s->phi_s, (long)(kMaxHalvings + 1) * s->Bp);
   DALLOC(s, s->spec_base, s->Bp);
@@ -962,7 +970,7 @@ static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   P.alpha_eval = s->alpha_eval;
   P.alpha_bt = s->alpha_bt;
   P.nslots = s->nslots;
-  P.nstore = s->nstore < s->nslots - 1 ? s->nstore : s->nslots - 1;
+  P.nstore = s->nslots > 1 ? s->nstore : 0;
   P.xs = s->xs;
   P.us = s->us;
   P.phi_s = s->phi_s;
@@ -1009,7 +1017,7 @@ int altro_b200_solve_async(altro_b200_solver* s) {  // altro_solver.cpp:257-260
     long before = 0;
     for (int i = 0; i < PH_COUNT; ++i) before += s->ph.launches[i];
     int nsplit = s->nsplit;
-    if (nsplit <= 0) nsplit = s->G >= 256 ? 2 : 1;  // see DESIGN.md "pipelined sub-batches"
+    if (nsplit <= 0) nsplit = s->G >= 512 ? 4 : (s->G >= 128 ? 2 : 1);  // DESIGN.md "pipelined sub-batches"
     nsplit = std::min(std::min(nsplit, (int)altro_b200_solver::kMaxSplit), s->G);
     P.g0 = 0;
     P.G = s->G;

@@ -79,11 +79,11 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
       k_phase_rollout<Model, CON><<<count, 32 * warps, sm, st>>>(P, list, count, dcount, depth);
     });
   };
-  auto lsupdate = [&](const int* list, int count, const int* dcount) {
+  auto lsupdate = [&](const int* list, int count, const int* dcount, int warps) {
     int depth;
     const size_t sm = ring(count, kRowsDphi, &depth);
     timed(PH_LSUPDATE, (double)count * 32, [&] {
-      k_phase_lsupdate<Model, CON><<<count, 32, sm, st>>>(P, list, count, dcount, depth);
+      k_phase_lsupdate<Model, CON><<<count, 32, sm, st>>>(P, list, count, dcount, depth, warps - 1);
     });
   };
 
@@ -98,7 +98,11 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
   compact(nullptr, G, nullptr, TF_ACTIVE, list_iter, PC_ITER, 0, 0, 0, 0);
   int count_iter = G;
   const bool backtracking = P.opts.use_backtracking_linesearch != 0;
+  // candidate steps per round.  (Going wider in the late rounds that only serve the lanes that
+  // keep halving was measured and lost: nearly every group has such a lane, so a 16-warp tail
+  // round costs more issue slots than the round it saves -- 29.2 vs 21.9 ms of rollouts.)
   const int spec_warps = (backtracking && P.nslots > 1) ? std::min(P.nslots, 16) : 1;
+  const int tail_warps = spec_warps;
   const int LS_MASK = TF_NEED_EVAL | TF_REROLL;
 
   for (int iter = 0; iter < P.opts.iterations_max && count_iter > 0; ++iter) {
@@ -118,17 +122,20 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
     const int* dcount = P.counters + PC_LS;
     rollout(cur, count_iter, dcount, spec_warps);
     expand(cur, count_iter, dcount, TF_WANT_DERIV, true, -1, false);
-    lsupdate(cur, count_iter, dcount);
+    lsupdate(cur, count_iter, dcount, spec_warps);
     compact(cur, count_iter, dcount, LS_MASK, nxt, PC_LS, TF_WANT_DERIV, PC_DERIV, TF_SPECULATE, PC_SPEC);
     readback();
     if (err != cudaSuccess) return (int)err;
     int count_ls = H->h_counters[PC_LS], count_deriv = H->h_counters[PC_DERIV],
         count_spec = H->h_counters[PC_SPEC];
     std::swap(cur, nxt);
+    int round = 1;
     while (count_ls > 0) {  // further rounds: cubic-first probe, zoom steps, re-rollouts, deeper halvings
-      rollout(cur, count_ls, nullptr, count_spec > 0 ? spec_warps : 1);
+      const int warps = count_spec > 0 ? (round >= 2 ? tail_warps : spec_warps) : 1;
+      ++round;
+      rollout(cur, count_ls, nullptr, warps);
       if (count_deriv > 0) expand(cur, count_ls, nullptr, TF_WANT_DERIV, true, -1, false);
-      lsupdate(cur, count_ls, nullptr);
+      lsupdate(cur, count_ls, nullptr, warps);
       compact(cur, count_ls, nullptr, LS_MASK, nxt, PC_LS, TF_WANT_DERIV, PC_DERIV, TF_SPECULATE, PC_SPEC);
       readback();
       if (err != cudaSuccess) return (int)err;

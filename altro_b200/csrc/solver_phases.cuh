@@ -388,7 +388,8 @@ __global__ void __launch_bounds__(32 * 16) k_phase_rollout(const DeviceProblem P
 // count) are those of the sequential search.
 template <class Model, bool CON>
 __global__ void __launch_bounds__(32) k_phase_lsupdate(const DeviceProblem P, const int* list,
-                                                       int count, const int* dcount, int depth) {
+                                                       int count, const int* dcount, int depth,
+                                                       int nspec) {
   using TS = TrajSolver<Model, CON>;
   constexpr int n = Model::n, m = Model::m;
   if ((int)blockIdx.x >= list_count(count, dcount)) return;
@@ -453,7 +454,7 @@ __global__ void __launch_bounds__(32) k_phase_lsupdate(const DeviceProblem P, co
   }
   LsMachine ls = P.ls[b];
   bool last_had_deriv = had_deriv;
-  const int nspec = P.nslots - 1;  // halvings a speculative round rolls out besides the request
+  // nspec: halvings the round just executed rolled out besides the request (warps - 1)
   int known = P.spec_known[b];     // halvings 1..known have their merit value in phi_s
   const int base = P.spec_base[b];
   const bool was_backtrack = ls.phase == LsMachine::P_BACKTRACK;
@@ -488,7 +489,7 @@ __global__ void __launch_bounds__(32) k_phase_lsupdate(const DeviceProblem P, co
     f |= TF_NEED_EVAL;
     if (ls.want_derivative()) f |= TF_WANT_DERIV;
     P.alpha_eval[b] = ls.alpha;
-    if (lo.use_backtracking && nspec > 0) {
+    if (lo.use_backtracking && P.nslots > 1) {
       if (ls.phase == LsMachine::P_BACKTRACK) {
         // ran out of precomputed halvings: the request is halving known+1, speculate the next ones
         f |= TF_SPECULATE;

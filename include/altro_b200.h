@@ -227,7 +227,7 @@ int altro_b200_set_solve_mode(altro_b200_solver *s, int mode);
  * overlap the HBM-bound sweeps of another.  Results do not depend on nsplit. */
 int altro_b200_set_pipeline_split(altro_b200_solver *s, int nsplit);
 /* number of candidate step lengths rolled out concurrently per backtracking round (1..16,
- * default 4; before altro_b200_initialize).  1 reproduces the strictly sequential search. */
+ * default 6; before altro_b200_initialize).  1 reproduces the strictly sequential search. */
 int altro_b200_set_speculation(altro_b200_solver *s, int nslots);
 /* per-phase instrumentation of the pipeline.  Phases: 0 init rollout, 1 expansion (knot-parallel),
  * 2 backward Riccati + alpha=0 scan, 3 rollout, 4 d(phi) scan + line-search step, 5 criteria +
