@@ -32,12 +32,14 @@ def _deps():
          os.path.join(HERE, "..", "include", "altro", "altro_solver.hpp")]
 
 
-def _compile(unit, verbose):
+def _compile(unit, verbose, skip=()):
     name, src, defs = unit
     srcp = os.path.join(CSRC, src)
     if not os.path.exists(srcp):
         return name, None, ""
     obj = os.path.join(OBJ, name + ".o")
+    if name in skip:
+        return name, obj, "stale (ALTRO_ONLY)"
     newest = max(os.path.getmtime(p) for p in [srcp] + _deps())
     if os.path.exists(obj) and os.path.getmtime(obj) >= newest:
         return name, obj, "cached"
@@ -53,16 +55,17 @@ def build(verbose=False, jobs=None):
     from stale objects -- for quick kernel experiments; never commit a library built that way."""
     os.makedirs(OBJ, exist_ok=True)
     only = os.environ.get("ALTRO_ONLY")
-    units = UNITS
+    skip = set()
     if only:
         keep = {f"solve_inst_{g}" for g in only.split(",")} | {"capi", "tvlqr", "facade"}
-        for name, src, defs in UNITS:
-            if name not in keep and os.path.exists(os.path.join(OBJ, name + ".o")):
-                os.utime(os.path.join(OBJ, name + ".o"))
+        # stale objects of the other groups are linked as they are (their mtime is left alone, so
+        # the next full build recompiles them)
+        skip = {name for name, _, _ in UNITS
+                if name not in keep and os.path.exists(os.path.join(OBJ, name + ".o"))}
     jobs = jobs or min(len(UNITS), os.cpu_count() or 4)
     objs, logs = [], {}
     with cf.ThreadPoolExecutor(max_workers=jobs) as ex:
-        for name, obj, log in ex.map(lambda u: _compile(u, verbose), UNITS):
+        for name, obj, log in ex.map(lambda u: _compile(u, verbose, skip), UNITS):
             if obj:
                 objs.append(obj)
                 logs[name] = log

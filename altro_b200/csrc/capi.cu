@@ -921,6 +921,14 @@ int altro_b200_shift_trajectory(altro_b200_solver* s) {
   return ALTRO_B200_NO_ERROR;
 }
 
+// TrajSolver's constraint level: 0 none, 1 linear cones only, 2 with second-order cones
+static int con_level(const altro_b200_solver* s) {
+  int level = s->con_h.ncon > 0 ? 1 : 0;
+  for (int j = 0; j < s->con_h.ncon; ++j)
+    if (s->con_h.slot[j].cone == CONE_SOC) level = 2;
+  return level;
+}
+
 static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   memset(&P, 0, sizeof(P));
   P.N = s->N;
@@ -933,6 +941,7 @@ static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   P.Rz = s->Rz;
   P.GSz = s->GSz;
   P.Rs = s->Rs;
+  P.zrows = s->con_h.rows;
   P.h = s->h;
   memcpy(P.model_params, s->params, sizeof(P.model_params));
   P.lin = s->lin;
@@ -955,7 +964,7 @@ static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   P.d = s->d;
   P.P = s->P;
   P.p = s->p;
-  P.con = s->con_d;
+  P.contab = s->con_h;
   P.z = s->z;
   P.zest = s->zest;
   P.rho = s->rho;
@@ -1010,7 +1019,7 @@ int altro_b200_solve_async(altro_b200_solver* s) {  // altro_solver.cpp:257-260
   DeviceProblem P;
   fill_device_problem(s, P);
   if (s->solve_mode == 1) {
-    int e = L(P, s->con_h.ncon > 0, s->stream, nullptr);
+    int e = L(P, con_level(s), s->stream, nullptr);
     s->launches++;
     if (e) return ALTRO_B200_ERR_NO_DEVICE;
   } else {
@@ -1023,7 +1032,7 @@ int altro_b200_solve_async(altro_b200_solver* s) {  // altro_solver.cpp:257-260
     P.G = s->G;
     int e = 0;
     if (nsplit == 1) {
-      e = L(P, s->con_h.ncon > 0, s->stream, &s->ph);
+      e = L(P, con_level(s), s->stream, &s->ph);
     } else {
       if (!s->ev_fork) CUDA_OK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
       for (int i = 0; i < nsplit; ++i) {
@@ -1039,7 +1048,7 @@ int altro_b200_solve_async(altro_b200_solver* s) {  // altro_solver.cpp:257-260
       const int per = (s->G + nsplit - 1) / nsplit;
       int rc[altro_b200_solver::kMaxSplit] = {0};
       std::vector<std::thread> workers;
-      const int has_con = s->con_h.ncon > 0;
+      const int has_con = con_level(s);
       for (int i = 0; i < nsplit; ++i) {
         workers.emplace_back([&, i]() {
           cudaSetDevice(s->device);
@@ -1102,7 +1111,7 @@ static int run_host_op(altro_b200_solver* s, int op, double* cost_out) {
   fill_device_problem(s, P);
   s->ph.op = op;
   s->ph.cost_out = cost_out;
-  int e = L(P, s->con_h.ncon > 0, s->stream, &s->ph);
+  int e = L(P, con_level(s), s->stream, &s->ph);
   s->ph.op = OP_SOLVE;
   s->launches++;
   if (e) return ALTRO_B200_ERR_NO_DEVICE;

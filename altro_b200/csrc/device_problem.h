@@ -72,6 +72,7 @@ struct DeviceProblem {
   int Gtot; // groups of the whole handle = Bp / 32
   long R, GS;    // main record stream: knot stride, group stride (doubles)
   long Rz, GSz;  // dual record stream [group][knot][z rows | z_est rows][32]
+  int zrows;     // constraint rows per knot (0 when unconstrained)
   long Rs;       // candidate-slot record stream [slot][group][knot][x rows | u rows][32]
   float h;
   double model_params[8];
@@ -91,7 +92,9 @@ struct DeviceProblem {
   double *lx, *lu;          // cost gradient        (lx_, lu_)
   double *K, *d, *P, *p;    // gains / cost-to-go   (K_, d_, P_, p_)
 
-  const ConTable* con;      // device pointer; ncon == 0 when unconstrained
+  // constraint slots, by value: the struct is a __grid_constant__ kernel parameter, so the
+  // per-knot loops over slots and rows read them through the constant cache instead of HBM/L2
+  ConTable contab;
   double *z, *zest;         // duals z_ and estimates z_est_ (dual record stream)
   double* rho;              // penalty rho_ (uniform over knots and constraints): [Bp]
 

@@ -7,7 +7,7 @@
 
 namespace altro_b200 {
 
-template <class Model, bool CON>
+template <class Model, int CON>
 static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
   using TS = TrajSolver<Model, CON>;
   constexpr int n = Model::n, m = Model::m;
@@ -68,8 +68,9 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
     cudaFuncSetAttribute(k_phase_rollout<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_phase_lsupdate<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   }
-  constexpr int kRowsBackward = TS::kRowsBackwardKernel;
-  constexpr int kRowsRollout = TS::kRowsRoll;
+  const int zr = CON ? 2 * P.zrows : 0;  // dual record rows staged with the main rows
+  const int kRowsBackward = TS::kRowsBackwardKernel + zr;
+  const int kRowsRollout = TS::kRowsRoll + zr;
   constexpr int kRowsDphi = TS::kRowsDphi;
   // warps = candidate steps rolled out per group (1 = only the requested step)
   auto rollout = [&](const int* list, int count, const int* dcount, int warps) {
@@ -161,33 +162,40 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
   return (int)cudaGetLastError();
 }
 
+// has_con: 0 unconstrained, 1 linear cones only, 2 with second-order cones (TrajSolver's CON).
+// The secondary entry points (open-loop rollout, cost, persistent twin) only distinguish
+// unconstrained / constrained and use the general instantiation for the latter.
 template <class Model>
 static int launch_solve(const DeviceProblem& P, int has_con, cudaStream_t st, PhaseHost* host) {
   if (host && host->op == OP_OPEN_LOOP_ROLLOUT) {
     if (has_con)
-      k_open_loop_rollout<Model, true><<<(P.B + 31) / 32, 32, 0, st>>>(P);
+      k_open_loop_rollout<Model, 2><<<(P.B + 31) / 32, 32, 0, st>>>(P);
     else
-      k_open_loop_rollout<Model, false><<<(P.B + 31) / 32, 32, 0, st>>>(P);
+      k_open_loop_rollout<Model, 0><<<(P.B + 31) / 32, 32, 0, st>>>(P);
     return (int)cudaGetLastError();
   }
   if (host && host->op == OP_CALC_COST) {
     if (has_con)
-      k_calc_cost<Model, true><<<(P.B + 31) / 32, 32, 0, st>>>(P, host->cost_out);
+      k_calc_cost<Model, 2><<<(P.B + 31) / 32, 32, 0, st>>>(P, host->cost_out);
     else
-      k_calc_cost<Model, false><<<(P.B + 31) / 32, 32, 0, st>>>(P, host->cost_out);
+      k_calc_cost<Model, 0><<<(P.B + 31) / 32, 32, 0, st>>>(P, host->cost_out);
     return (int)cudaGetLastError();
   }
   if (host && host->op == OP_UNPACK_JAC) {
-    k_unpack_jac<Model, false><<<dim3((P.B + 127) / 128, P.N), 128, 0, st>>>(P, host->cost_out);
+    k_unpack_jac<Model, 0><<<dim3((P.B + 127) / 128, P.N), 128, 0, st>>>(P, host->cost_out);
     return (int)cudaGetLastError();
   }
-  if (host) return has_con ? run_phased<Model, true>(P, st, host) : run_phased<Model, false>(P, st, host);
+  if (host) {
+    if (has_con == 0) return run_phased<Model, 0>(P, st, host);
+    if (has_con == 1) return run_phased<Model, 1>(P, st, host);
+    return run_phased<Model, 2>(P, st, host);
+  }
   const int threads = 32;  // one warp per CTA: 32 consecutive problems
   const int blocks = (P.B + threads - 1) / threads;
   if (has_con)
-    solve_kernel<Model, true><<<blocks, threads, 0, st>>>(P);
+    solve_kernel<Model, 2><<<blocks, threads, 0, st>>>(P);
   else
-    solve_kernel<Model, false><<<blocks, threads, 0, st>>>(P);
+    solve_kernel<Model, 0><<<blocks, threads, 0, st>>>(P);
   return (int)cudaGetLastError();
 }
 

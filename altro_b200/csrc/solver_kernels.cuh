@@ -125,7 +125,10 @@ ALTRO_DEV void soc_hessian(int dim, const double* x, const double* b, double* H)
 }
 
 // ---------------------------------------------------------------- the per-trajectory solver
-template <class Model, bool CON>
+// CON: 0 unconstrained, 1 constraints with linear cones only (equality / identity / inequality:
+// diagonal projections, no scratch arrays), 2 also second-order cones (the SOC projection,
+// Jacobian and Hessian need local scratch that would otherwise bloat every constrained kernel).
+template <class Model, int CON>
 struct TrajSolver {
   static constexpr int n = Model::n;
   static constexpr int m = Model::m;
@@ -185,6 +188,17 @@ struct TrajSolver {
   // per-group blocks that are not per knot: [group][rows][32]
   ALTRO_DEV const double* G(const double* base, int rows) const {
     return base + (long)(b >> 5) * rows * 32 + (b & 31);
+  }
+  // Staged copy of the CURRENT knot's dual record [z rows | z_est rows] for this lane (set by the
+  // TMA-staged sweeps before they call a step; null: read HBM directly).  Row r of z is
+  // zstage[r * 32], of z_est zstage[(zrows + r) * 32].
+  const double* zstage = nullptr;
+  // zrow = zoff(k, row0): HBM offset of the slot's first row at knot k; i = row inside the slot
+  ALTRO_DEV double zread(long zrow, int row0, int i) const {
+    return zstage ? zstage[(row0 + i) * 32] : P.z[zrow + i * 32];
+  }
+  ALTRO_DEV double zest_read(long zrow, int row0, int i) const {
+    return zstage ? zstage[(P.zrows + row0 + i) * 32] : P.zest[zrow + i * 32];
   }
   // constraint duals live in their own record stream [group][knot][z rows | z_est rows][32]
   ALTRO_DEV long zoff(int k, int row0) const {
@@ -285,17 +299,17 @@ struct TrajSolver {
     if constexpr (!CON) {
       return 0.0;
     } else {
-      const ConTable& T = *P.con;
+      const ConTable& T = P.contab;
       double cost = 0.0;
       for (int j = 0; j < T.ncon; ++j) {
         const ConSlot& s = T.slot[j];
         if (k < s.k_start || k >= s.k_stop) continue;
         const long zrow = zoff(k, s.row0);
-        if (s.cone == CONE_SOC) {
+        if (CON == 2 && s.cone == CONE_SOC) {
           double zt[kMaxSocDim], zp[kMaxSocDim];
           for (int i = 0; i < s.dim; ++i) {
             const double c = row_value(s, i, x, u);
-            zt[i] = P.z[zrow + i * 32] - rho * c;
+            zt[i] = zread(zrow, s.row0, i) - rho * c;
             if (store_zest) P.zest[zrow + i * 32] = zt[i];
           }
           soc_projection(s.dim, zt, zp);
@@ -315,7 +329,7 @@ struct TrajSolver {
           double nrm = 0.0;
           for (int i = 0; i < s.dim; ++i) {
             const double c = row_value(s, i, x, u);
-            const double zt = P.z[zrow + i * 32] - rho * c;
+            const double zt = zread(zrow, s.row0, i) - rho * c;
             if (store_zest) P.zest[zrow + i * 32] = zt;
             // dual cones (cones.hpp:13-30): EQUALITY -> IDENTITY, INEQUALITY -> INEQUALITY,
             // IDENTITY -> EQUALITY (projection onto {0})
@@ -337,16 +351,16 @@ struct TrajSolver {
   // (knotpoint_data.cpp:549-570, :597-613).  Adds into lxx (n x n), luu (m x m), lux (m x n).
   ALTRO_DEV void al_hessian(int k, bool terminal, double* lxx, double* luu, double* lux) const {
     if constexpr (CON) {
-      const ConTable& T = *P.con;
+      const ConTable& T = P.contab;
       for (int j = 0; j < T.ncon; ++j) {
         const ConSlot& s = T.slot[j];
         if (k < s.k_start || k >= s.k_stop) continue;
         const long zrow = zoff(k, s.row0);
-        if (s.cone == CONE_SOC) {
+        if (CON == 2 && s.cone == CONE_SOC) {
           const int p = s.dim;
           double zt[kMaxSocDim], zp[kMaxSocDim];
           double J[kMaxSocDim * kMaxSocDim], H[kMaxSocDim * kMaxSocDim];
-          for (int i = 0; i < p; ++i) zt[i] = P.zest[zrow + i * 32];
+          for (int i = 0; i < p; ++i) zt[i] = zest_read(zrow, s.row0, i);
           soc_projection(p, zt, zp);
           soc_jacobian(p, zt, J);
           soc_hessian(p, zt, zp, H);
@@ -380,7 +394,7 @@ struct TrajSolver {
           for (int i = 0; i < s.dim; ++i) {
             const int id = s.idx[i];
             if (id < 0) continue;
-            const double zt = P.zest[zrow + i * 32];
+            const double zt = zest_read(zrow, s.row0, i);
             double act = 0.0;  // diagonal of the dual-cone projection Jacobian (cones.cpp:160-171)
             if (s.cone == CONE_EQUALITY) act = 1.0;
             if (s.cone == CONE_INEQUALITY) act = (zt <= 0) ? 1.0 : 0.0;
@@ -401,11 +415,11 @@ struct TrajSolver {
   ALTRO_DEV double al_violation(int k, const double* x, const double* u) const {
     double viol = 0.0;
     if constexpr (CON) {
-      const ConTable& T = *P.con;
+      const ConTable& T = P.contab;
       for (int j = 0; j < T.ncon; ++j) {
         const ConSlot& s = T.slot[j];
         if (k < s.k_start || k >= s.k_stop) continue;
-        if (s.cone == CONE_SOC) {
+        if (CON == 2 && s.cone == CONE_SOC) {
           double c[kMaxSocDim], pc[kMaxSocDim];
           for (int i = 0; i < s.dim; ++i) c[i] = row_value(s, i, x, u);
           soc_projection(s.dim, c, pc);
@@ -427,12 +441,12 @@ struct TrajSolver {
   // ---- DualUpdate (z <- Pi(z_est), knotpoint_data.cpp:503-510) over the whole trajectory
   ALTRO_DEV void dual_update() {
     if constexpr (CON) {
-      const ConTable& T = *P.con;
+      const ConTable& T = P.contab;
       for (int j = 0; j < T.ncon; ++j) {
         const ConSlot& s = T.slot[j];
         for (int k = s.k_start; k < s.k_stop; ++k) {
           const long zrow = zoff(k, s.row0);
-          if (s.cone == CONE_SOC) {
+          if (CON == 2 && s.cone == CONE_SOC) {
             double zt[kMaxSocDim], zp[kMaxSocDim];
             for (int i = 0; i < s.dim; ++i) zt[i] = P.zest[zrow + i * 32];
             soc_projection(s.dim, zt, zp);
@@ -826,12 +840,12 @@ struct TrajSolver {
   // z <- Pi(z_est) for the rows of knot k (KnotPointData::DualUpdate, knotpoint_data.cpp:503-510)
   ALTRO_DEV void dual_update_knot(int k) {
     if constexpr (CON) {
-      const ConTable& T = *P.con;
+      const ConTable& T = P.contab;
       for (int j = 0; j < T.ncon; ++j) {
         const ConSlot& s = T.slot[j];
         if (k < s.k_start || k >= s.k_stop) continue;
         const long zrow = zoff(k, s.row0);
-        if (s.cone == CONE_SOC) {
+        if (CON == 2 && s.cone == CONE_SOC) {
           double zt[kMaxSocDim], zp[kMaxSocDim];
           for (int i = 0; i < s.dim; ++i) zt[i] = P.zest[zrow + i * 32];
           soc_projection(s.dim, zt, zp);
@@ -1162,8 +1176,8 @@ struct TrajSolver {
   }
 };
 
-template <class Model, bool CON>
-__global__ void __launch_bounds__(32) solve_kernel(const DeviceProblem P) {
+template <class Model, int CON>
+__global__ void __launch_bounds__(32) solve_kernel(const __grid_constant__ DeviceProblem P) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= P.B) return;
   TrajSolver<Model, CON> s(P, b);

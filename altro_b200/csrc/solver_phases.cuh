@@ -125,8 +125,8 @@ __device__ __forceinline__ LsOptions ls_options(const DevOptions& o) {
 extern __shared__ __align__(128) unsigned char altro_smem[];
 
 // K0: Solve() prologue, sequential part (solver.cpp:417-423)
-template <class Model, bool CON>
-__global__ void __launch_bounds__(32) k_phase_init(const DeviceProblem P) {
+template <class Model, int CON>
+__global__ void __launch_bounds__(32) k_phase_init(const __grid_constant__ DeviceProblem P) {
   const int b = (P.g0 + blockIdx.x) * 32 + threadIdx.x;
   if (b >= P.B) return;
   TrajSolver<Model, CON> s(P, b);
@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(32) k_phase_init(const DeviceProblem P) {
 // dual_first: apply the dual update z <- Pi(z_est) of this knot before recomputing the projected
 // duals.  The prologue calls this BEFORE the penalty reset, which reproduces quirk Q3 (gradient
 // with the old rho, solver.cpp:424-430).
-template <class Model, bool CON>
-__global__ void __launch_bounds__(128) k_phase_expand(const DeviceProblem P, const int* list,
+template <class Model, int CON>
+__global__ void __launch_bounds__(128) k_phase_expand(const __grid_constant__ DeviceProblem P, const int* list,
                                                       int count, const int* dcount, int mask,
                                                       bool with_dyn, int slot_mode,
                                                       bool dual_first) {
@@ -171,8 +171,8 @@ static __global__ void k_phase_set_rho(double* rho, int b0, int b1, double value
 
 // K1: CalcExpansions + BackwardPass + the alpha = 0 half of ForwardPass (solver.cpp:448-450,
 // :241-245) and the start of the line search.  One warp per listed group.
-template <class Model, bool CON>
-__global__ void __launch_bounds__(32) k_phase_backward(const DeviceProblem P, const int* list,
+template <class Model, int CON>
+__global__ void __launch_bounds__(32) k_phase_backward(const __grid_constant__ DeviceProblem P, const int* list,
                                                        int count, int depth) {
   using TS = TrajSolver<Model, CON>;
   constexpr int n = Model::n, m = Model::m;
@@ -188,15 +188,19 @@ __global__ void __launch_bounds__(32) k_phase_backward(const DeviceProblem P, co
     // stage contents: Riccati sweep [J | lx lu]; phi0 scan [q r c K d x u J]  (J = packed [A B])
     constexpr int kV = TS::kV;
     constexpr int kRowsBw = TS::kRowsBw, kRowsPhi = TS::kRowsPhi;
-    constexpr int kStage = TS::kRowsBackwardKernel * 32;
+    // constrained problems also stage the knot's dual record [z | z_est] behind the main rows
+    const int zr = CON ? 2 * P.zrows : 0;
+    const int kStage = (TS::kRowsBackwardKernel + zr) * 32;
     BulkRing ring;
     ring.init(altro_smem, depth, kStage, lane == 0);
     __syncwarp();
     const double* rec = P.xbar + (long)g * P.GS;  // row 0 of the group's knot-0 record
+    const double* zrec = CON ? P.z + (long)g * P.GSz : nullptr;
     auto fetch_bw = [&](int k, int st) {
-      ring.expect(st, kRowsBw * 256);
+      ring.expect(st, (kRowsBw + zr) * 256);
       ring.copy(st, 0, rec + (long)k * P.R + TS::rA * 32, kV * 256);
       ring.copy(st, kV, rec + (long)k * P.R + TS::rLx * 32, (n + m) * 256);
+      if (zr) ring.copy(st, kRowsBw, zrec + (long)k * P.Rz, zr * 256);
     };
     if (lane == 0)
       for (int j = 0; j < depth; ++j)
@@ -212,7 +216,9 @@ __global__ void __launch_bounds__(32) k_phase_backward(const DeviceProblem P, co
         unstage_block<n>(st, kV, lane, Qx);
         unstage_block<m>(st, kV + n, lane, Qu);
       }
+      if (zr) s.zstage = st + kRowsBw * 32 + lane;
       if (alive) alive = s.riccati_step(k, A, Bm, Qx, Qu, Pn, pn);
+      s.zstage = nullptr;
       // release the stage only after the step has consumed what was read from it (see BulkRing)
       __syncwarp();
       if (lane == 0 && k - depth >= 0) fetch_bw(k - depth, ring.s);
@@ -220,8 +226,9 @@ __global__ void __launch_bounds__(32) k_phase_backward(const DeviceProblem P, co
     }
     // phi0 / dphi0 scan, knots ascending
     auto fetch_phi = [&](int k, int st) {
-      ring.expect(st, kRowsPhi * 256);
+      ring.expect(st, (kRowsPhi + zr) * 256);
       ring.copy(st, 0, rec + (long)k * P.R + TS::rQ * 32, kRowsPhi * 256);
+      if (zr) ring.copy(st, kRowsPhi, zrec + (long)k * P.Rz, zr * 256);
     };
     // K, d were just written by the lanes of this warp through the generic proxy; the bulk copies
     // read them through the async proxy: every writer fences, then the leader issues
@@ -250,7 +257,9 @@ __global__ void __launch_bounds__(32) k_phase_backward(const DeviceProblem P, co
         unstage_block<m>(st, oU, lane, u);
         s.unstage_jac(st, oJ, lane, A, Bm);
       }
+      if (zr) s.zstage = st + kRowsPhi * 32 + lane;
       if (active) s.phi0_step(k, x, u, q, r, cval, K, d, A, Bm, dxda, phi0, dphi0);
+      s.zstage = nullptr;
       __syncwarp();
       if (lane == 0 && k + depth < P.N) fetch_phi(k + depth, ring.s);
       ring.advance();
@@ -304,8 +313,8 @@ __global__ void __launch_bounds__(32) k_phase_backward(const DeviceProblem P, co
 // warps j >= 1 (launched in speculative rounds) roll out the halving alpha_bt * 2^-(j-1) for the
 // lanes flagged TF_SPECULATE -- into candidate slot j-1 when j <= nstore, merit value only
 // otherwise.  All warps consume the SAME staged copy of the knot data [xbar ubar q r c K d].
-template <class Model, bool CON>
-__global__ void __launch_bounds__(32 * 16) k_phase_rollout(const DeviceProblem P, const int* list,
+template <class Model, int CON>
+__global__ void __launch_bounds__(32 * 16) k_phase_rollout(const __grid_constant__ DeviceProblem P, const int* list,
                                                            int count, const int* dcount, int depth) {
   using TS = TrajSolver<Model, CON>;
   constexpr int n = Model::n, m = Model::m;
@@ -338,14 +347,17 @@ __global__ void __launch_bounds__(32 * 16) k_phase_rollout(const DeviceProblem P
   }
   double phi = 0.0;
   if constexpr (TS::kStaged) {
-    constexpr int kRows = TS::kRowsRoll;  // [xbar ubar q r c K d]
+    constexpr int kRows = TS::kRowsRoll;  // [xbar ubar q r c K d] (+ the dual record)
+    const int zr = CON ? 2 * P.zrows : 0;
     BulkRing ring;
-    ring.init(altro_smem, depth, kRows * 32, threadIdx.x == 0);
+    ring.init(altro_smem, depth, (kRows + zr) * 32, threadIdx.x == 0);
     __syncthreads();
     const double* rec = P.xbar + (long)g * P.GS;
+    const double* zrec = CON ? P.z + (long)g * P.GSz : nullptr;
     auto fetch = [&](int k, int st) {
-      ring.expect(st, kRows * 256);
+      ring.expect(st, (kRows + zr) * 256);
       ring.copy(st, 0, rec + (long)k * P.R, kRows * 256);
+      if (zr) ring.copy(st, kRows, zrec + (long)k * P.Rz, zr * 256);
     };
     if (threadIdx.x == 0)
       for (int j = 0; j < depth; ++j)
@@ -364,7 +376,9 @@ __global__ void __launch_bounds__(32 * 16) k_phase_rollout(const DeviceProblem P
         unstage_block<m * n>(st, TS::rK, lane, K);
         unstage_block<m>(st, TS::rD, lane, d);
       }
+      if (zr) s.zstage = st + kRows * 32 + lane;
       if (need) s.rollout_step(k, alpha, xb, ub, K, d, q, r, cval, x, xo, uo, so, phi);
+      s.zstage = nullptr;
       __syncthreads();
       if (threadIdx.x == 0 && k + depth < P.N) fetch(k + depth, ring.s);
       ring.advance();
@@ -386,8 +400,8 @@ __global__ void __launch_bounds__(32 * 16) k_phase_rollout(const DeviceProblem P
 // precomputed merit values of the halvings in the order the reference would have evaluated
 // them; feeding stops at the first one it accepts, so the decisions (and the reported evaluation
 // count) are those of the sequential search.
-template <class Model, bool CON>
-__global__ void __launch_bounds__(32) k_phase_lsupdate(const DeviceProblem P, const int* list,
+template <class Model, int CON>
+__global__ void __launch_bounds__(32) k_phase_lsupdate(const __grid_constant__ DeviceProblem P, const int* list,
                                                        int count, const int* dcount, int depth,
                                                        int nspec) {
   using TS = TrajSolver<Model, CON>;
@@ -552,8 +566,8 @@ __global__ void __launch_bounds__(32) k_phase_lsupdate(const DeviceProblem P, co
 
 // K5a/b: costates of the accepted point, then stationarity / feasibility residuals and
 // CopyTrajectory -- one thread per (problem of a listed group, knot)
-template <class Model, bool CON>
-__global__ void __launch_bounds__(128) k_phase_costate(const DeviceProblem P, const int* list,
+template <class Model, int CON>
+__global__ void __launch_bounds__(128) k_phase_costate(const __grid_constant__ DeviceProblem P, const int* list,
                                                        int count) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if ((t >> 5) >= count) return;
@@ -563,8 +577,8 @@ __global__ void __launch_bounds__(128) k_phase_costate(const DeviceProblem P, co
   s.phase_costate_knot(blockIdx.y);
 }
 
-template <class Model, bool CON>
-__global__ void __launch_bounds__(128) k_phase_residual(const DeviceProblem P, const int* list,
+template <class Model, int CON>
+__global__ void __launch_bounds__(128) k_phase_residual(const __grid_constant__ DeviceProblem P, const int* list,
                                                         int count) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if ((t >> 5) >= count) return;
@@ -575,8 +589,8 @@ __global__ void __launch_bounds__(128) k_phase_residual(const DeviceProblem P, c
 }
 
 // K5c: convergence test, dual / penalty update decision (solver.cpp:459-489, :503-506)
-template <bool CON>
-__global__ void __launch_bounds__(128) k_phase_decide(const DeviceProblem P, const int* list,
+template <int CON>
+__global__ void __launch_bounds__(128) k_phase_decide(const __grid_constant__ DeviceProblem P, const int* list,
                                                       int count) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if ((t >> 5) >= count) return;
@@ -621,8 +635,8 @@ __global__ void __launch_bounds__(128) k_phase_decide(const DeviceProblem P, con
 }
 
 // ALTROSolver::OpenLoopRollout (solver.cpp:116-131): x_[k+1] = f(x_[k], u_[k]) from the initial state
-template <class Model, bool CON>
-__global__ void __launch_bounds__(32) k_open_loop_rollout(const DeviceProblem P) {
+template <class Model, int CON>
+__global__ void __launch_bounds__(32) k_open_loop_rollout(const __grid_constant__ DeviceProblem P) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= P.B) return;
   TrajSolver<Model, CON> s(P, b);
@@ -640,8 +654,8 @@ __global__ void __launch_bounds__(32) k_open_loop_rollout(const DeviceProblem P)
 }
 
 // Dense [A B] of every knot from the packed Jacobian rows (host views A_, B_ of KnotPointData)
-template <class Model, bool CON>
-__global__ void __launch_bounds__(128) k_unpack_jac(const DeviceProblem P, double* out) {
+template <class Model, int CON>
+__global__ void __launch_bounds__(128) k_unpack_jac(const __grid_constant__ DeviceProblem P, double* out) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const int k = blockIdx.y;
   if (b >= P.B) return;
@@ -656,8 +670,8 @@ __global__ void __launch_bounds__(128) k_unpack_jac(const DeviceProblem P, doubl
 
 // ALTROSolver::CalcCost (solver.cpp:163-174): sum_k cost(k) incl. the AL terms at the working
 // trajectory; refreshes the projected duals like the reference does.
-template <class Model, bool CON>
-__global__ void __launch_bounds__(32) k_calc_cost(const DeviceProblem P, double* out) {
+template <class Model, int CON>
+__global__ void __launch_bounds__(32) k_calc_cost(const __grid_constant__ DeviceProblem P, double* out) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= P.B) return;
   TrajSolver<Model, CON> s(P, b);
