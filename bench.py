@@ -173,10 +173,19 @@ def ncu_traffic(workload_name, phase):
     return None
 
 
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which is not what
+    the CPU arm is meant to measure, so the count is taken from the affinity mask)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_oracle_rate(P, target_seconds, threads=None):
     """Times the CPU oracle on a bounded prefix of the workload.  Returns dict for the JSON."""
     from oracle import oracle as O
-    threads = threads or O.lib().oracle_max_threads()
+    threads = threads or host_threads()
     probe = min(P.B, 4 * threads)
     r = O.solve_batch(P, 0, probe, nthreads=threads)
     rate = probe / max(r["seconds"], 1e-9)
@@ -196,7 +205,7 @@ def run_reference(args, rank, world):
     from oracle import oracle as O
     O.build()
     P = workload(args.workload, args.batch, 0, 1)
-    threads = O.lib().oracle_max_threads()
+    threads = host_threads()
     probe = min(P.B, 4 * threads)
     r = O.solve_batch(P, 0, probe, nthreads=threads)
     rate = probe / max(r["seconds"], 1e-9)
