@@ -139,12 +139,15 @@ struct Bicycle4C {  // prm[0]=L, prm[1]=lr
 struct Bicycle5C {  // state [x,y,theta,delta,v], input [a, delta_dot]
   static constexpr int n = 5;
   static constexpr int m = 2;
-  // Defined (here and in oracle/models.c, identically) in the algebraic form that avoids atan2:
-  // with beta = atan(lr*delta/L): cos(beta) = L/hyp, sin(beta) = lr*delta/hyp,
+  // Defined (here and in oracle/models.c, in exactly this operation order) in the algebraic form
+  // that avoids atan2: with beta = atan(lr*delta/L): cos(beta) = L/hyp, sin(beta) = lr*delta/hyp,
   // hyp = sqrt(L^2 + (lr*delta)^2); sin/cos(theta+beta) by angle addition.  Two independent
-  // sincos per evaluation instead of a chain of five transcendental calls.
+  // sincos per evaluation instead of a chain of five transcendental calls, and reciprocals so that
+  // an evaluation costs two IEEE divisions (1/hyp, 1/cos delta; 1/L is loop-invariant) instead of
+  // six -- the rollout kernels are bound by instruction issue (ncu r01 v9) and a double division
+  // is ~25 instructions.
   struct Trig {
-    double sb, cb, tand, s_tb, c_tb, cd, dbeta;
+    double sb, cb, tand, s_tb, c_tb, icd, dbeta;
   };
   ALTRO_DEV static Trig trig(const double* prm, const double* x) {
     const double L = prm[0], lr = prm[1];
@@ -154,34 +157,51 @@ struct Bicycle5C {  // state [x,y,theta,delta,v], input [a, delta_dot]
     const double by = lr * x[3];
     const double h2 = L * L + by * by;
     const double hyp = sqrt(h2);
+    const double inv = 1.0 / hyp;
+    const double icd = 1.0 / cd;
     Trig t;
-    t.cb = L / hyp;
-    t.sb = by / hyp;
-    t.tand = sd / cd;
+    t.cb = L * inv;
+    t.sb = by * inv;
+    t.tand = sd * icd;
     t.s_tb = st * t.cb + ct * t.sb;
     t.c_tb = ct * t.cb - st * t.sb;
-    t.cd = cd;
-    t.dbeta = L / h2 * lr;
+    t.icd = icd;
+    t.dbeta = (L * lr) * (inv * inv);
     return t;
   }
   ALTRO_DEV static void xdot(const double* prm, const double* x, const double* u, double* f) {
-    const double L = prm[0];
+    const double invL = 1.0 / prm[0];
     const double v = x[4];
     const Trig t = trig(prm, x);
     f[0] = v * t.c_tb;
     f[1] = v * t.s_tb;
-    f[2] = v * t.cb * t.tand / L;
+    f[2] = v * t.cb * t.tand * invL;
     f[3] = u[1];
     f[4] = u[0];
+  }
+  // f(x,u) and its Jacobian at the same point from ONE trig evaluation (the midpoint Jacobian
+  // needs both at x; same values as xdot() and jac())
+  ALTRO_DEV static void xdot_jac(const double* prm, const double* x, const double* u, double* f,
+                                 double* A, double* B) {
+    const double invL = 1.0 / prm[0];
+    const double v = x[4];
+    const Trig t = trig(prm, x);
+    f[0] = v * t.c_tb;
+    f[1] = v * t.s_tb;
+    f[2] = v * t.cb * t.tand * invL;
+    f[3] = u[1];
+    f[4] = u[0];
+    fill_jac(t, v, invL, A, B);
   }
   ALTRO_DEV static void jac(const double* prm, const double* x, const double* u, double* A,
                             double* B) {
     (void)u;
-    const double L = prm[0];
-    const double v = x[4];
-    const Trig t = trig(prm, x);
-    const double domega_ddelta = v / L * (-t.sb * t.tand * t.dbeta + t.cb / (t.cd * t.cd));
-    const double domega_dv = t.cb * t.tand / L;
+    const double invL = 1.0 / prm[0];
+    fill_jac(trig(prm, x), x[4], invL, A, B);
+  }
+  ALTRO_DEV static void fill_jac(const Trig& t, double v, double invL, double* A, double* B) {
+    const double domega_ddelta = (v * invL) * (-t.sb * t.tand * t.dbeta + t.cb * (t.icd * t.icd));
+    const double domega_dv = t.cb * t.tand * invL;
 #pragma unroll
     for (int i = 0; i < n * n; ++i) A[i] = 0.0;
 #pragma unroll
@@ -236,6 +256,16 @@ struct ChainC {  // q_i'' = -g sin q_i - b q_i' + kc (q_{i-1} - 2 q_i + q_{i+1})
   }
 };
 
+// detects an optional fused CM::xdot_jac
+template <class CM, class = void>
+struct has_xdot_jac {
+  static constexpr bool value = false;
+};
+template <class CM>
+struct has_xdot_jac<CM, decltype(CM::xdot_jac(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr), void())> {
+  static constexpr bool value = true;
+};
+
 // ------------------------------------------------------------------ explicit midpoint
 template <class CM>
 struct Midpoint {
@@ -261,11 +291,15 @@ struct Midpoint {
     const double hh = h / 2;
     const double hd = h;
     double xm[n];
-    CM::xdot(prm, x, u, xm);
+    double T[n * n], Bc[n * m], Am[n * n], Bm[n * m];
+    if constexpr (has_xdot_jac<CM>::value) {
+      CM::xdot_jac(prm, x, u, xm, T, Bc);
+    } else {
+      CM::xdot(prm, x, u, xm);
+      CM::jac(prm, x, u, T, Bc);
+    }
 #pragma unroll
     for (int i = 0; i < n; ++i) xm[i] = fma(hh, xm[i], x[i]);
-    double T[n * n], Bc[n * m], Am[n * n], Bm[n * m];
-    CM::jac(prm, x, u, T, Bc);
     CM::jac(prm, xm, u, Am, Bm);
     // T = I + h/2 A ; Bc = h/2 B
 #pragma unroll

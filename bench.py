@@ -84,7 +84,8 @@ def kernel_models(P, iters, evals):
     rows = P.n_constraint_rows()
     it = float(iters.astype(np.float64).sum())                       # backward passes
     roll = float(np.maximum(evals.astype(np.float64) - iters, 0).sum())  # rollouts the search consumed
-    jac = n * n + n * m
+    # Jacobian entries kept in HBM: dense n^2 + nm unless the model packs them (models.cuh, JacPack)
+    jac = {PR.MODEL_BICYCLE5: 15, PR.MODEL_BICYCLE4: 12}.get(P.model_id, n * n + n * m)
     return {
         "backward": dict(kernel="k_phase_backward (Riccati sweep + alpha=0 scan)",
                          doubles=(jac + n + m) + (m * n + m + n * n + n) + rows            # sweep

@@ -129,42 +129,46 @@ static void bicycle4_cjac(const double *prm, double *jac, const double *x, const
  *   cos(beta) = L / hypot,  sin(beta) = lr*delta / hypot,  hypot = sqrt(L^2 + (lr*delta)^2),
  * and sin/cos(theta+beta) by the angle-addition formulas. */
 static void bicycle5_trig(const double *prm, const double *x, double *sb, double *cb, double *tand,
-                          double *s_tb, double *c_tb, double *cd_out, double *dbeta) {
+                          double *s_tb, double *c_tb, double *icd_out, double *dbeta) {
+  /* Written with reciprocals so that one evaluation costs two divisions (1/hyp, 1/cos(delta))
+   * instead of six: the rollout kernels are bound by instruction issue, and an IEEE double
+   * division is ~25 instructions on the GPU.  altro_b200/csrc/models.cuh (Bicycle5C::trig) uses
+   * exactly this operation order. */
   double L = prm[0], lr = prm[1];
   double theta = x[2], delta = x[3];
   double sd = sin(delta), cd = cos(delta), st = sin(theta), ct = cos(theta);
   double by = lr * delta;
   double h2 = L * L + by * by;
   double hyp = sqrt(h2);
-  *cb = L / hyp;
-  *sb = by / hyp;
-  *tand = sd / cd;
+  double inv = 1.0 / hyp;
+  double icd = 1.0 / cd;
+  *cb = L * inv;
+  *sb = by * inv;
+  *tand = sd * icd;
   *s_tb = st * (*cb) + ct * (*sb);
   *c_tb = ct * (*cb) - st * (*sb);
-  *cd_out = cd;
-  *dbeta = L / h2 * lr;
+  *icd_out = icd;
+  *dbeta = (L * lr) * (inv * inv);
 }
-
 static void bicycle5_xdot(const double *prm, double *xdot, const double *x, const double *u) {
-  double L = prm[0];
+  double invL = 1.0 / prm[0];
   double v = x[4];
-  double sb, cb, tand, s_tb, c_tb, cd, dbeta;
-  bicycle5_trig(prm, x, &sb, &cb, &tand, &s_tb, &c_tb, &cd, &dbeta);
+  double sb, cb, tand, s_tb, c_tb, icd, dbeta;
+  bicycle5_trig(prm, x, &sb, &cb, &tand, &s_tb, &c_tb, &icd, &dbeta);
   xdot[0] = v * c_tb;
   xdot[1] = v * s_tb;
-  xdot[2] = v * cb * tand / L;
+  xdot[2] = v * cb * tand * invL;
   xdot[3] = u[1];
   xdot[4] = u[0];
 }
-
 static void bicycle5_cjac(const double *prm, double *jac, const double *x, const double *u) {
   (void)u;
-  double L = prm[0];
+  double invL = 1.0 / prm[0];
   double v = x[4];
-  double sb, cb, tand, s_tb, c_tb, cd, dbeta;
-  bicycle5_trig(prm, x, &sb, &cb, &tand, &s_tb, &c_tb, &cd, &dbeta);
-  double domega_ddelta = v / L * (-sb * tand * dbeta + cb / (cd * cd));
-  double domega_dv = cb * tand / L;
+  double sb, cb, tand, s_tb, c_tb, icd, dbeta;
+  bicycle5_trig(prm, x, &sb, &cb, &tand, &s_tb, &c_tb, &icd, &dbeta);
+  double domega_ddelta = (v * invL) * (-sb * tand * dbeta + cb * (icd * icd));
+  double domega_dv = cb * tand * invL;
   const int n = 5;
   memset(jac, 0, sizeof(double) * 5 * 7);
 #define J(i, j) jac[(i) + n * (j)]

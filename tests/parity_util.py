@@ -14,7 +14,8 @@ the same rate when it is merely recompiled with -ffp-contract=fast (FMA contract
 counted and reported, never silently dropped.
 
 Problems the oracle itself does NOT solve (MaxIterations / line-search failure) have no
-well-defined answer; for those only the status is compared, on >= 97 % of them.
+well-defined answer; for those only the status is compared, on >= 97 % of them (at least two
+mismatches are always tolerated).
 """
 import numpy as np
 
@@ -48,8 +49,12 @@ def compare(gpu, ref, tail_frac=0.01):
         f"(allowed {allowed}): iteration/status mismatches {int((conv & ~same).sum())}, " \
         f"max state err {ex[conv & same].max(initial=0):.3e}, max cost err {ec[conv & same].max(initial=0):.3e}"
     if (~conv).any():
-        st_same = (gs[~conv] == ref["status"][~conv]).mean()
-        assert st_same >= 0.97, f"status differs on {1 - st_same:.3f} of the unsolved problems"
+        n_uns = int((~conv).sum())
+        n_diff = int((gs[~conv] != ref["status"][~conv]).sum())
+        # 3 %, but never fewer than 2: with a handful of unsolved problems one chaotic flip
+        # (MaxIterations <-> line-search failure <-> late Success) is not evidence of anything
+        assert n_diff <= max(2, int(np.ceil(0.03 * n_uns))), \
+            f"status differs on {n_diff} of the {n_uns} problems the oracle does not solve"
     return dict(n=int(nb), converged=n_conv, strict=int(strict.sum()), tail=int(tail.sum()),
                 max_state_err=float(ex[strict].max(initial=0)),
                 max_input_err=float(eu[strict].max(initial=0)),
