@@ -163,12 +163,12 @@ def peak_hbm():
 
 
 def ncu_traffic(workload_name, phase):
-    """dram bytes per trajectory-knot of a phase kernel from the committed ncu --set full capture
-    (profiles/traffic.json, written by tools/ncu_traffic.py)."""
+    """dram read+write bytes per launch of a phase kernel from the committed ncu --set full capture
+    of full-batch launches of this workload (profiles/traffic.json, tools/ncu_traffic.py)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(workload_name, {}).get(phase, {}).get("dram_bytes_per_unit")
+            return json.load(open(p)).get(workload_name, {}).get(phase, {}).get("dram_bytes_per_launch")
         except Exception:
             return None
     return None
@@ -406,10 +406,7 @@ def main():
                            "frac": bytes_total / (st_["ms"] * 1e-3) / 1e9 / peak}
         dom = max(kernels, key=lambda k: kernels[k]["ms"])
         kd = kernels[dom]
-        traffic_unit = ncu_traffic(args.workload, dom)
-        traffic = None
-        if traffic_unit is not None:
-            traffic = traffic_unit * phase_stats[dom]["units"] / phase_stats[dom]["launches"]
+        traffic = ncu_traffic(args.workload, dom)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",

@@ -40,6 +40,7 @@ def main():
                     d["kernels"].append(name)
     for d in out.values():
         d["dram_bytes_per_unit"] = d["dram_bytes"] / d["units"]
+        d["dram_bytes_per_launch"] = d["dram_bytes"] / d["launches"]  # captured launches: full batch
     print(json.dumps({wl: out}, indent=1))
 
 
