@@ -320,11 +320,33 @@ __global__ void __launch_bounds__(32 * 16) k_phase_rollout(const __grid_constant
   constexpr int n = Model::n, m = Model::m;
   if ((int)blockIdx.x >= list_count(count, dcount)) return;
   const int g = list[blockIdx.x];
-  const int lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
+  // Work assignment.  Warp 0: thread = problem lane, candidate 0 (the requested step).  Warps
+  // >= 1: the (lane, halving) pairs of the lanes flagged TF_SPECULATE, PACKED densely over the
+  // threads -- in the first round every lane speculates and warp j is simply halving j, but in the
+  // later rounds only a few lanes per group still need halvings and all their candidates fit in
+  // one or two warps instead of keeping nslots-1 mostly idle warps busy for the whole sweep.
+  // Pair p -> lane rank p % nneedy (consecutive threads = different lanes: conflict-free smem
+  // columns, neighbouring global stores), halving p / nneedy + 1.
+  int lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
+  const int nspec = (int)(blockDim.x >> 5) - 1;
+  bool need;
+  {
+    const int bl = g * 32 + lane;
+    const int fl = bl < P.B ? P.flags[bl] : 0;
+    const unsigned needy = __ballot_sync(0xffffffffu, (fl & TF_NEED_EVAL) && (fl & TF_SPECULATE));
+    if (slot == 0) {
+      need = (fl & (TF_NEED_EVAL | TF_REROLL)) != 0;
+    } else {
+      const int nneedy = __popc(needy);
+      const int p = (slot - 1) * 32 + lane;
+      need = nneedy > 0 && p < nneedy * nspec;
+      if (need) {
+        lane = __fns(needy, 0, p % nneedy + 1);  // the (p % nneedy)-th flagged lane
+        slot = p / nneedy + 1;
+      }
+    }
+  }
   const int b = g * 32 + lane;
-  const int f = b < P.B ? P.flags[b] : 0;
-  const bool need = (slot == 0) ? (f & (TF_NEED_EVAL | TF_REROLL)) != 0
-                                : ((f & TF_NEED_EVAL) && (f & TF_SPECULATE));
   TS s(P, need ? b : g * 32);
   s.rho = (CON && need) ? P.rho[b] : 1.0;
   double alpha = 0.0;
