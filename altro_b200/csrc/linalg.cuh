@@ -239,7 +239,9 @@ struct BulkRing {
       parity ^= 1u;
     }
   }
-  static size_t bytes(int depth, int stage_doubles) { return 128 + (size_t)depth * stage_doubles * 8; }
+  __host__ __device__ static size_t bytes(int depth, int stage_doubles) {
+    return 128 + (size_t)depth * stage_doubles * 8;
+  }
 };
 
 // this lane's element e of a block that starts at `row` of a landed stage

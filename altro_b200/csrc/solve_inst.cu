@@ -50,17 +50,21 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
   };
   // TMA staging ring of the sequential sweeps (linalg.cuh): depth = knots in flight per CTA, as
   // deep as shared memory allows with every CTA of the launch resident (<= kMaxStageDepth).
-  auto ring = [&](int ctas, int stage_rows, int* depth) -> size_t {
+  // cost weights staged in shared memory behind the ring (stage_weights) when they are small
+  const int wdoubles = (N + 1) * n + N * m;
+  const int wcount = (TS::kStaged && wdoubles * 8 <= 16 * 1024) ? wdoubles : 0;
+  auto ring = [&](int ctas, int stage_rows, int* depth, bool weights) -> size_t {
     if (!TS::kStaged) {
       *depth = 0;
       return 0;
     }
+    const size_t wbytes = weights ? (size_t)wcount * 8 : 0;
     const size_t stage_bytes = (size_t)stage_rows * 256;
     const int per_sm = (ctas + H->num_sms - 1) / H->num_sms;
     const size_t budget =
-        std::min<size_t>(H->smem_per_sm / std::max(per_sm, 1) - 1024, H->smem_per_cta) - 128;
+        std::min<size_t>(H->smem_per_sm / std::max(per_sm, 1) - 1024, H->smem_per_cta) - 128 - wbytes;
     *depth = (int)std::max<size_t>(2, std::min<size_t>(kMaxStageDepth, budget / stage_bytes));
-    return BulkRing::bytes(*depth, stage_rows * 32);
+    return BulkRing::bytes(*depth, stage_rows * 32) + wbytes;
   };
   if (TS::kStaged) {
     const int mx = (int)H->smem_per_cta;
@@ -75,14 +79,14 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
   // warps = candidate steps rolled out per group (1 = only the requested step)
   auto rollout = [&](const int* list, int count, const int* dcount, int warps) {
     int depth;
-    const size_t sm = ring(count, kRowsRollout, &depth);
+    const size_t sm = ring(count, kRowsRollout, &depth, true);
     timed(PH_ROLLOUT, (double)count * 32 * warps, [&] {
-      k_phase_rollout<Model, CON><<<count, 32 * warps, sm, st>>>(P, list, count, dcount, depth);
+      k_phase_rollout<Model, CON><<<count, 32 * warps, sm, st>>>(P, list, count, dcount, depth, wcount);
     });
   };
   auto lsupdate = [&](const int* list, int count, const int* dcount, int warps) {
     int depth;
-    const size_t sm = ring(count, kRowsDphi, &depth);
+    const size_t sm = ring(count, kRowsDphi, &depth, false);
     timed(PH_LSUPDATE, (double)count * 32, [&] {
       k_phase_lsupdate<Model, CON><<<count, 32, sm, st>>>(P, list, count, dcount, depth, warps - 1);
     });
@@ -109,9 +113,9 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
   for (int iter = 0; iter < P.opts.iterations_max && count_iter > 0; ++iter) {
     {
       int depth;
-      const size_t sm = ring(count_iter, kRowsBackward, &depth);
+      const size_t sm = ring(count_iter, kRowsBackward, &depth, true);
       timed(PH_BACKWARD, (double)count_iter * 32, [&] {
-        k_phase_backward<Model, CON><<<count_iter, 32, sm, st>>>(P, list_iter, count_iter, depth);
+        k_phase_backward<Model, CON><<<count_iter, 32, sm, st>>>(P, list_iter, count_iter, depth, wcount);
       });
     }
     int* cur = P.list_ls;

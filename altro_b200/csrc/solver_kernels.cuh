@@ -145,6 +145,10 @@ struct TrajSolver {
                        rP = rY + NS_, rPv = rP + NS_ * NS_, rUinit = rPv + NS_, kRecordRows = rUinit + NI_;
 
   const DeviceProblem& P;
+  // diagonal cost weights of every knot (shared by the batch): HBM by default, the sweep kernels
+  // point these at a shared-memory copy so the per-knot reads are LDS broadcasts, not L2 round trips
+  const double* Qd;
+  const double* Rd;
   const long S;   // knot-record stride (doubles) of the main record stream
   const long go;  // this problem's offset inside a field: group * group_stride + lane
   const int b;   // this thread's problem
@@ -153,7 +157,7 @@ struct TrajSolver {
   int merit_evals;
 
   ALTRO_DEV TrajSolver(const DeviceProblem& p, int b_)
-      : P(p), S(p.R), go((long)(b_ >> 5) * p.GS + (b_ & 31)), b(b_), N(p.N), rho(1.0), merit_evals(0) {}
+      : P(p), Qd(p.Qd), Rd(p.Rd), S(p.R), go((long)(b_ >> 5) * p.GS + (b_ & 31)), b(b_), N(p.N), rho(1.0), merit_evals(0) {}
 
   // [A B] of knot k <-> the packed Jacobian rows of the record (models.cuh, JacPack)
   using JP = JacPack<Model>;
@@ -268,13 +272,13 @@ struct TrajSolver {
     double J = 0.0;
     double a = 0.0;
 #pragma unroll
-    for (int i = 0; i < n; ++i) a += (0.5 * x[i]) * P.Qd[k * n + i] * x[i];
+    for (int i = 0; i < n; ++i) a += (0.5 * x[i]) * Qd[k * n + i] * x[i];
     J = a;
     J += dot<n>(q, x);
     if (!terminal) {
       double bb = 0.0;
 #pragma unroll
-      for (int i = 0; i < m; ++i) bb += (0.5 * u[i]) * P.Rd[k * m + i] * u[i];
+      for (int i = 0; i < m; ++i) bb += (0.5 * u[i]) * Rd[k * m + i] * u[i];
       J += bb;
       J += dot<m>(r, u);
     }
@@ -284,10 +288,10 @@ struct TrajSolver {
   ALTRO_DEV void stage_gradient(int k, const double* x, const double* u, const double* q,
                                 const double* r, bool terminal, double* lx, double* lu) const {
 #pragma unroll
-    for (int i = 0; i < n; ++i) lx[i] = P.Qd[k * n + i] * x[i] + q[i];
+    for (int i = 0; i < n; ++i) lx[i] = Qd[k * n + i] * x[i] + q[i];
     if (!terminal) {
 #pragma unroll
-      for (int i = 0; i < m; ++i) lu[i] = P.Rd[k * m + i] * u[i] + r[i];
+      for (int i = 0; i < m; ++i) lu[i] = Rd[k * m + i] * u[i] + r[i];
     }
   }
 
@@ -509,7 +513,7 @@ struct TrajSolver {
 #pragma unroll
     for (int i = 0; i < n * n; ++i) Pn[i] = 0.0;
 #pragma unroll
-    for (int i = 0; i < n; ++i) Pn[i + n * i] = P.Qd[N * n + i];
+    for (int i = 0; i < n; ++i) Pn[i + n * i] = Qd[N * n + i];
     al_hessian(N, true, Pn, nullptr, nullptr);
     load_block<n>(F(P.lx), S, N, pn);
     store_block<n * n>(F(P.P), S, N, Pn);
@@ -526,11 +530,11 @@ struct TrajSolver {
 #pragma unroll
     for (int i = 0; i < n * n; ++i) Qxx[i] = 0.0;
 #pragma unroll
-    for (int i = 0; i < n; ++i) Qxx[i + n * i] = P.Qd[k * n + i];
+    for (int i = 0; i < n; ++i) Qxx[i + n * i] = Qd[k * n + i];
 #pragma unroll
     for (int i = 0; i < m * m; ++i) Quu[i] = 0.0;
 #pragma unroll
-    for (int i = 0; i < m; ++i) Quu[i + m * i] = P.Rd[k * m + i];
+    for (int i = 0; i < m; ++i) Quu[i + m * i] = Rd[k * m + i];
 #pragma unroll
     for (int i = 0; i < m * n; ++i) Qux[i] = 0.0;
     al_hessian(k, false, Qxx, Quu, Qux);

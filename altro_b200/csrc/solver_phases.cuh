@@ -124,6 +124,19 @@ __device__ __forceinline__ LsOptions ls_options(const DevOptions& o) {
 // dynamic shared memory of the sweep kernels: mbarriers + staging ring (linalg.cuh)
 extern __shared__ __align__(128) unsigned char altro_smem[];
 
+// Copies the cost weights Qd [(N+1) n], Rd [N m] into shared memory behind the staging ring (when
+// the launch reserved room for them: wcount > 0) and points the solver at the copy.  All threads
+// of the CTA call it; the caller synchronises afterwards.
+template <class TS>
+__device__ __forceinline__ void stage_weights(TS& s, const DeviceProblem& P, double* wsm, int wcount) {
+  if (wcount <= 0) return;
+  const int nq = (P.N + 1) * TS::n, nr = P.N * TS::m;
+  for (int i = threadIdx.x; i < nq; i += blockDim.x) wsm[i] = P.Qd[i];
+  for (int i = threadIdx.x; i < nr; i += blockDim.x) wsm[nq + i] = P.Rd[i];
+  s.Qd = wsm;
+  s.Rd = wsm + nq;
+}
+
 // K0: Solve() prologue, sequential part (solver.cpp:417-423)
 template <class Model, int CON>
 __global__ void __launch_bounds__(32) k_phase_init(const __grid_constant__ DeviceProblem P) {
@@ -173,7 +186,7 @@ static __global__ void k_phase_set_rho(double* rho, int b0, int b1, double value
 // :241-245) and the start of the line search.  One warp per listed group.
 template <class Model, int CON>
 __global__ void __launch_bounds__(32) k_phase_backward(const __grid_constant__ DeviceProblem P, const int* list,
-                                                       int count, int depth) {
+                                                       int count, int depth, int wcount) {
   using TS = TrajSolver<Model, CON>;
   constexpr int n = Model::n, m = Model::m;
   if ((int)blockIdx.x >= count) return;
@@ -193,6 +206,7 @@ __global__ void __launch_bounds__(32) k_phase_backward(const __grid_constant__ D
     const int kStage = (TS::kRowsBackwardKernel + zr) * 32;
     BulkRing ring;
     ring.init(altro_smem, depth, kStage, lane == 0);
+    stage_weights(s, P, reinterpret_cast<double*>(altro_smem + BulkRing::bytes(depth, kStage)), wcount);
     __syncwarp();
     const double* rec = P.xbar + (long)g * P.GS;  // row 0 of the group's knot-0 record
     const double* zrec = CON ? P.z + (long)g * P.GSz : nullptr;
@@ -315,7 +329,8 @@ __global__ void __launch_bounds__(32) k_phase_backward(const __grid_constant__ D
 // otherwise.  All warps consume the SAME staged copy of the knot data [xbar ubar q r c K d].
 template <class Model, int CON>
 __global__ void __launch_bounds__(32 * 16) k_phase_rollout(const __grid_constant__ DeviceProblem P, const int* list,
-                                                           int count, const int* dcount, int depth) {
+                                                           int count, const int* dcount, int depth,
+                                                           int wcount) {
   using TS = TrajSolver<Model, CON>;
   constexpr int n = Model::n, m = Model::m;
   if ((int)blockIdx.x >= list_count(count, dcount)) return;
@@ -373,6 +388,7 @@ __global__ void __launch_bounds__(32 * 16) k_phase_rollout(const __grid_constant
     const int zr = CON ? 2 * P.zrows : 0;
     BulkRing ring;
     ring.init(altro_smem, depth, (kRows + zr) * 32, threadIdx.x == 0);
+    stage_weights(s, P, reinterpret_cast<double*>(altro_smem + BulkRing::bytes(depth, (kRows + zr) * 32)), wcount);
     __syncthreads();
     const double* rec = P.xbar + (long)g * P.GS;
     const double* zrec = CON ? P.z + (long)g * P.GSz : nullptr;
