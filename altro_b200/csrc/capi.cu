@@ -1026,7 +1026,14 @@ int altro_b200_solve_async(altro_b200_solver* s) {  // altro_solver.cpp:257-260
     long before = 0;
     for (int i = 0; i < PH_COUNT; ++i) before += s->ph.launches[i];
     int nsplit = s->nsplit;
-    if (nsplit <= 0) nsplit = s->G >= 512 ? 4 : (s->G >= 128 ? 2 : 1);  // DESIGN.md "pipelined sub-batches"
+    if (nsplit <= 0) {
+      // DESIGN.md "pipelined sub-batches": splitting pays when there is a compute-bound phase to
+      // overlap with the HBM-bound sweeps, i.e. the speculative rollouts of the backtracking
+      // search (bicycle 16384: 56 -> 48 ms); with the cubic search it only shrinks the kernels
+      // (pendulum 4096: 2.8 -> 3.0 ms, chain 32768: no gain)
+      const bool spec = s->opts.use_backtracking_linesearch && s->nslots > 1;
+      nsplit = !spec ? 1 : (s->G >= 512 ? 4 : (s->G >= 128 ? 2 : 1));
+    }
     nsplit = std::min(std::min(nsplit, (int)altro_b200_solver::kMaxSplit), s->G);
     P.g0 = 0;
     P.G = s->G;
