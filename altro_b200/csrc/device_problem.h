@@ -139,7 +139,6 @@ enum TrajFlags {
   TF_CONVERGED = 64,
   TF_SPECULATE = 128,       // the pending round also rolls out the halvings alpha_bt * 2^-j (merit only)
   TF_REROLL = 256,          // accepted step came from a merit-only candidate: roll it out again, storing
-  TF_SPEC_VALID = 512,      // (unused)
 };
 
 enum PhaseCounter { PC_LS = 0, PC_DERIV = 1, PC_SPEC = 2, PC_REFRESH_GRAD = 3, PC_ITER = 4 };

@@ -107,7 +107,6 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
   // keep halving was measured and lost: nearly every group has such a lane, so a 16-warp tail
   // round costs more issue slots than the round it saves -- 29.2 vs 21.9 ms of rollouts.)
   const int spec_warps = (backtracking && P.nslots > 1) ? std::min(P.nslots, 16) : 1;
-  const int tail_warps = spec_warps;
   const int LS_MASK = TF_NEED_EVAL | TF_REROLL;
 
   for (int iter = 0; iter < P.opts.iterations_max && count_iter > 0; ++iter) {
@@ -134,10 +133,8 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
     int count_ls = H->h_counters[PC_LS], count_deriv = H->h_counters[PC_DERIV],
         count_spec = H->h_counters[PC_SPEC];
     std::swap(cur, nxt);
-    int round = 1;
     while (count_ls > 0) {  // further rounds: cubic-first probe, zoom steps, re-rollouts, deeper halvings
-      const int warps = count_spec > 0 ? (round >= 2 ? tail_warps : spec_warps) : 1;
-      ++round;
+      const int warps = count_spec > 0 ? spec_warps : 1;
       rollout(cur, count_ls, nullptr, warps);
       if (count_deriv > 0) expand(cur, count_ls, nullptr, TF_WANT_DERIV, true, -1, false);
       lsupdate(cur, count_ls, nullptr, warps);

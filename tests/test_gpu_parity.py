@@ -199,3 +199,32 @@ def test_results_do_not_depend_on_schedule(make):
             continue
         for key in ref:
             assert np.array_equal(out[key], ref[key]), (key, nslots, nsplit)
+
+
+@pytest.mark.parametrize("make,model", [
+    (lambda: PR.bicycle(B=40, N=20, n=5, iterations_max=3), PR.MODEL_BICYCLE5),
+    (lambda: PR.scotty(B=40, N=15, n=4, iterations_max=3), PR.MODEL_BICYCLE4),
+    (lambda: PR.pendulum(B=33, N=20, iterations_max=3), PR.MODEL_PENDULUM),
+])
+def test_knotpoint_views_match_oracle_model(oracle, make, model):
+    """KnotPointData host views (altro_b200_get_field): A_, B_ of the accepted trajectory are the
+    discrete Jacobians of the oracle's model at (x_k, u_k) -- also for the models whose Jacobian is
+    stored packed and re-expanded on load -- and x_{k+1} = f(x_k, u_k)."""
+    P = make()
+    s = altro_b200.make_solver(P)
+    s.Solve()
+    X, U, A, B = s.GetField("x"), s.GetField("u"), s.GetField("A"), s.GetField("B")
+    n, m = P.n, P.m
+    assert A.shape == (P.B, P.N + 1, n * n) and B.shape == (P.B, P.N + 1, n * m)
+    for b in (0, 7, P.B - 1):
+        for k in (0, P.N // 2, P.N - 1):
+            J = oracle.model_jacobian(model, P.model_params, X[b, k], U[b, k], P.h)  # n x (n+m)
+            Ak = A[b, k].reshape(n, n, order="F")
+            Bk = B[b, k].reshape(n, m, order="F")
+            np.testing.assert_allclose(Ak, J[:, :n], rtol=1e-12, atol=1e-14)
+            np.testing.assert_allclose(Bk, J[:, n:], rtol=1e-12, atol=1e-14)
+            xn = oracle.model_dynamics(model, P.model_params, X[b, k], U[b, k], P.h)
+            np.testing.assert_allclose(X[b, k + 1], xn, rtol=1e-12, atol=1e-13)
+    hist = s.GetLinesearchHistogram()
+    assert hist.sum() > 0
+    s.close()
