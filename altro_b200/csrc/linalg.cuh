@@ -16,6 +16,12 @@ constexpr int kUnrollDim = 6;
 
 #define ALTRO_DEV __device__ __forceinline__
 
+// register-tile edge for the large-block path of mm: the largest of 6, 4, 3, 2, 1 dividing d
+template <int D>
+struct TileDim {
+  static constexpr int v = D % 6 == 0 ? 6 : (D % 4 == 0 ? 4 : (D % 3 == 0 ? 3 : (D % 2 == 0 ? 2 : 1)));
+};
+
 // C (RA x CB) (=, +=, -=) op(A) * op(B);  op(A) is RA x KK, op(B) is KK x CB.
 // ACC: 0 assign, 1 add, -1 subtract.
 template <int RA, int CB, int KK, bool TA, bool TB, int ACC>
@@ -41,20 +47,39 @@ ALTRO_DEV void mm(const double* __restrict__ A, const double* __restrict__ B, do
       }
     }
   } else {
+    // Large blocks: operands live in local memory, so a rolled dot product costs two loads per
+    // FMA.  Register tiles of TR x TC accumulators cut that to (TR + TC) loads per TR * TC FMAs;
+    // every output element still accumulates over l in ascending order, i.e. the result is
+    // bit-identical to the plain triple loop.
+    constexpr int TR = TileDim<RA>::v, TC = TileDim<CB>::v;
 #pragma unroll 1
-    for (int j = 0; j < CB; ++j) {
+    for (int j0 = 0; j0 < CB; j0 += TC) {
 #pragma unroll 1
-      for (int i = 0; i < RA; ++i) {
-        double s = 0.0;
-#pragma unroll 4
+      for (int i0 = 0; i0 < RA; i0 += TR) {
+        double acc[TR * TC];
+#pragma unroll
+        for (int t = 0; t < TR * TC; ++t) acc[t] = 0.0;
+#pragma unroll 2
         for (int l = 0; l < KK; ++l) {
-          const double a = TA ? A[l + lda * i] : A[i + lda * l];
-          const double b = TB ? B[j + ldb * l] : B[l + ldb * j];
-          s = fma(a, b, s);
+          double av[TR], bv[TC];
+#pragma unroll
+          for (int i = 0; i < TR; ++i) av[i] = TA ? A[l + lda * (i0 + i)] : A[(i0 + i) + lda * l];
+#pragma unroll
+          for (int j = 0; j < TC; ++j) bv[j] = TB ? B[(j0 + j) + ldb * l] : B[l + ldb * (j0 + j)];
+#pragma unroll
+          for (int j = 0; j < TC; ++j)
+#pragma unroll
+            for (int i = 0; i < TR; ++i) acc[i + TR * j] = fma(av[i], bv[j], acc[i + TR * j]);
         }
-        if (ACC == 0) C[i + RA * j] = s;
-        if (ACC == 1) C[i + RA * j] += s;
-        if (ACC == -1) C[i + RA * j] -= s;
+#pragma unroll
+        for (int j = 0; j < TC; ++j)
+#pragma unroll
+          for (int i = 0; i < TR; ++i) {
+            const double sum = acc[i + TR * j];
+            if (ACC == 0) C[(i0 + i) + RA * (j0 + j)] = sum;
+            if (ACC == 1) C[(i0 + i) + RA * (j0 + j)] += sum;
+            if (ACC == -1) C[(i0 + i) + RA * (j0 + j)] -= sum;
+          }
       }
     }
   }
