@@ -114,7 +114,8 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
       int depth;
       const size_t sm = ring(count_iter, kRowsBackward, &depth, true);
       timed(PH_BACKWARD, (double)count_iter * 32, [&] {
-        k_phase_backward<Model, CON><<<count_iter, 32, sm, st>>>(P, list_iter, count_iter, depth, wcount);
+        k_phase_backward<Model, CON><<<count_iter, 32, sm, st>>>(P, list_iter, count_iter, depth, wcount,
+                                                                 iter == 0);
       });
     }
     int* cur = P.list_ls;

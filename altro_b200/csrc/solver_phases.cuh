@@ -186,7 +186,7 @@ static __global__ void k_phase_set_rho(double* rho, int b0, int b1, double value
 // :241-245) and the start of the line search.  One warp per listed group.
 template <class Model, int CON>
 __global__ void __launch_bounds__(32) k_phase_backward(const __grid_constant__ DeviceProblem P, const int* list,
-                                                       int count, int depth, int wcount) {
+                                                       int count, int depth, int wcount, int first) {
   using TS = TrajSolver<Model, CON>;
   constexpr int n = Model::n, m = Model::m;
   if ((int)blockIdx.x >= count) return;
@@ -239,16 +239,55 @@ __global__ void __launch_bounds__(32) k_phase_backward(const __grid_constant__ D
       ring.advance();
     }
     // phi0 / dphi0 scan, knots ascending
-    auto fetch_phi = [&](int k, int st) {
-      ring.expect(st, (kRowsPhi + zr) * 256);
-      ring.copy(st, 0, rec + (long)k * P.R + TS::rQ * 32, kRowsPhi * 256);
-      if (zr) ring.copy(st, kRowsPhi, zrec + (long)k * P.Rz, zr * 256);
-    };
     // K, d were just written by the lanes of this warp through the generic proxy; the bulk copies
     // read them through the async proxy: every writer fences, then the leader issues
     __threadfence();
     asm volatile("fence.proxy.async;" ::: "memory");
     __syncwarp();
+    if (CON == 0 && !first) {
+      // Unconstrained problems after the first iteration: merit(0) at the accepted point IS the
+      // merit value the line search accepted it with (same stage costs summed in the same
+      // order), and lx, lu in HBM are already those of the accepted point; only the directional
+      // derivative depends on the new gains.  Scan [K d] [J] [lx lu] instead of
+      // [q r c K d x u J] and skip the lx, lu write-back.
+      constexpr int kRows1 = m * n + m;
+      auto fetch_d = [&](int k, int st) {
+        ring.expect(st, TS::kRowsDphi * 256);
+        ring.copy(st, 0, rec + (long)k * P.R + TS::rK * 32, kRows1 * 256);
+        ring.copy(st, kRows1, rec + (long)k * P.R + TS::rA * 32, kV * 256);
+        ring.copy(st, kRows1 + kV, rec + (long)k * P.R + TS::rLx * 32, (n + m) * 256);
+      };
+      if (lane == 0)
+        for (int j = 0; j < depth; ++j)
+          if (j < P.N) fetch_d(j, (ring.s + j) % depth);
+      double dxda[n];
+#pragma unroll
+      for (int i = 0; i < n; ++i) dxda[i] = 0.0;
+      for (int k = 0; k < P.N; ++k) {
+        const double* st = ring.wait();
+        double K[m * n], d[m], A[n * n], Bm[n * m], lx[n], lu[m];
+        if (active) {
+          unstage_block<m * n>(st, 0, lane, K);
+          unstage_block<m>(st, m * n, lane, d);
+          s.unstage_jac(st, kRows1, lane, A, Bm);
+          unstage_block<n>(st, kRows1 + kV, lane, lx);
+          unstage_block<m>(st, kRows1 + kV + n, lane, lu);
+          s.dphi_step(K, d, A, Bm, lx, lu, dxda, dphi0);
+        }
+        __syncwarp();
+        if (lane == 0 && k + depth < P.N) fetch_d(k + depth, ring.s);
+        ring.advance();
+      }
+      if (active) {
+        dphi0 = s.dphi_terminal(dxda, dphi0);
+        phi0 = P.phi[b];
+      }
+    } else {
+    auto fetch_phi = [&](int k, int st) {
+      ring.expect(st, (kRowsPhi + zr) * 256);
+      ring.copy(st, 0, rec + (long)k * P.R + TS::rQ * 32, kRowsPhi * 256);
+      if (zr) ring.copy(st, kRowsPhi, zrec + (long)k * P.Rz, zr * 256);
+    };
     if (lane == 0) {
       for (int j = 0; j < depth; ++j)
         if (j < P.N) fetch_phi(j, (ring.s + j) % depth);
@@ -279,6 +318,7 @@ __global__ void __launch_bounds__(32) k_phase_backward(const __grid_constant__ D
       ring.advance();
     }
     if (active) s.phi0_terminal(dxda, phi0, dphi0);
+    }
   } else {
     if (active) {
       s.backward_sweep();
