@@ -87,10 +87,14 @@ def kernel_models(P, iters, evals):
     # Jacobian entries kept in HBM: dense n^2 + nm unless the model packs them (models.cuh, JacPack)
     jac = {PR.MODEL_BICYCLE5: 15, PR.MODEL_BICYCLE4: 12}.get(P.model_id, n * n + n * m)
     return {
+        # sweep: r J,lx,lu  w K,d,P,p (+ z_est rows).  scan: r q,r,c,K,d,x,u,J  w lx,lu (+ duals);
+        # unconstrained problems after their first iteration scan only K,d,J,lx,lu and write nothing
         "backward": dict(kernel="k_phase_backward (Riccati sweep + alpha=0 scan)",
-                         doubles=(jac + n + m) + (m * n + m + n * n + n) + rows            # sweep
-                         + (2 * (n + m) + 1 + m * n + m + jac) + (n + m) + 2 * rows,       # scan
-                         units=it * N),
+                         doubles=(jac + n + m) + (m * n + m + n * n + n) + rows
+                         + ((2 * (n + m) + 1 + m * n + m + jac) + (n + m) + 2 * rows if rows
+                            else (m * n + m + jac + n + m)),
+                         units=it * N,
+                         extra_bytes=0.0 if rows else 8.0 * (n + m + 1 + n + m) * P.B * N),
         "rollout": dict(kernel="k_phase_rollout (closed-loop rollout, merit value)",
                         doubles=(2 * (n + m) + 1 + m * n + m) + (n + m) + rows, units=roll * N),
         "expand": dict(kernel="k_phase_expand (dynamics Jacobians, projected duals, gradients)",
@@ -397,7 +401,7 @@ def main():
             if ph not in phase_map or st_["launches"] == 0:
                 continue
             mdl = models[phase_map[ph]]
-            bytes_total = 8.0 * mdl["doubles"] * mdl["units"]
+            bytes_total = 8.0 * mdl["doubles"] * mdl["units"] + mdl.get("extra_bytes", 0.0)
             kernels[ph] = {"kernel": mdl["kernel"], "launches": st_["launches"], "ms": st_["ms"],
                            "share_of_step": st_["ms"] / tot_ms,
                            "us_per_launch": 1e3 * st_["ms"] / st_["launches"],

@@ -39,7 +39,7 @@ def main():
                 ker = {}
                 for ph in ("backward", "rollout", "expand", "lsupdate", "criteria"):
                     if st[ph]["launches"]:
-                        by = 8.0 * models[ph]["doubles"] * models[ph]["units"]
+                        by = 8.0 * models[ph]["doubles"] * models[ph]["units"] + models[ph].get("extra_bytes", 0.0)
                         ker[ph] = dict(ms=st[ph]["ms"], gbs=by / (st[ph]["ms"] * 1e-3) / 1e9)
                 dom = max(ker, key=lambda k: ker[k]["ms"])
                 t = min(ts)
