@@ -929,6 +929,24 @@ static int con_level(const altro_b200_solver* s) {
   return level;
 }
 
+// One receding-horizon step without a host round trip (test/bicycle_test.cpp:302-337 with the
+// plant equal to the model): the next initial state is x_[1] = f(x0, u_[0]) of the solved
+// trajectory, then ShiftTrajectory, then the tracking window moves one row (on-device
+// UpdateLinearCosts).  Duals and penalties carry over like in the reference (quirk Q14).
+int altro_b200_mpc_step(altro_b200_solver* s) {
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;
+  CUDA_OK(cudaSetDevice(s->device));
+  dim3 grid((unsigned)((s->B + 127) / 128), (unsigned)s->n);
+  k_copy_field<<<grid, 128, 0, s->stream>>>(fview(s, s->x, s->n, 1), gview(s->x0, s->n), s->B, s->n);
+  s->launches++;
+  CUDA_OK(cudaGetLastError());
+  int e = altro_b200_shift_trajectory(s);
+  if (e) return e;
+  if (s->xtab) e = altro_b200_advance_window(s, 1);
+  return e;
+}
+
 static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   memset(&P, 0, sizeof(P));
   P.N = s->N;

@@ -89,7 +89,7 @@ def load_library():
         L.altro_b200_set_options.argtypes = [vp, C.POINTER(Options)]
         L.altro_b200_calc_cost.argtypes = [vp, dptr]
         for f in ("reset_duals", "reset_trajectory", "shift_trajectory", "solve", "solve_async", "synchronize",
-                  "open_loop_rollout"):
+                  "open_loop_rollout", "mpc_step"):
             getattr(L, "altro_b200_" + f).argtypes = [vp]
         for f in ("get_states", "get_inputs", "get_dual_dynamics", "get_feedback_gains",
                   "get_feedforward_gains", "get_final_objective", "get_stationarity",
@@ -291,6 +291,10 @@ class BatchSolver:
 
     def ResetTrajectory(self):
         self._ck(self.L.altro_b200_reset_trajectory(self.h), "ResetTrajectory")
+
+    def MpcStep(self):
+        """x0 <- x_[1], ShiftTrajectory, advance the tracking window: one MPC step on the device."""
+        self._ck(self.L.altro_b200_mpc_step(self.h), "MpcStep")
 
     def ShiftTrajectory(self):
         self._ck(self.L.altro_b200_shift_trajectory(self.h), "ShiftTrajectory")

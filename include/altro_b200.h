@@ -205,6 +205,10 @@ int altro_b200_set_options(altro_b200_solver *s, const altro_b200_options *o);
 /* reset duals (z = 0) and penalties (rho = 1) to their post-Initialize values */
 int altro_b200_reset_duals(altro_b200_solver *s);
 int altro_b200_shift_trajectory(altro_b200_solver *s); /* ShiftTrajectory, altro_solver.cpp:283 */
+/* one receding-horizon (MPC) step entirely on the device, plant = model: x0 <- x_[1] of the solved
+ * trajectory, ShiftTrajectory, and (tracking-window cost) advance the window by one row; duals and
+ * penalties carry over (test/bicycle_test.cpp:302-337).  Call altro_b200_solve again afterwards. */
+int altro_b200_mpc_step(altro_b200_solver *s);
 /* restore the working inputs u_ to the last SetInput guess (device-to-device; lets a resident
  * batch be re-solved from the same starting point without a host round trip) */
 int altro_b200_reset_trajectory(altro_b200_solver *s);

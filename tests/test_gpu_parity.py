@@ -228,3 +228,25 @@ def test_knotpoint_views_match_oracle_model(oracle, make, model):
     hist = s.GetLinesearchHistogram()
     assert hist.sum() > 0
     s.close()
+
+
+def test_on_device_mpc_step_equals_host_driven_loop():
+    """altro_b200_mpc_step (x0 <- x_[1], ShiftTrajectory, window + 1, all on the device) against the
+    same receding-horizon loop driven from the host through SetInitialState / ShiftTrajectory /
+    AdvanceWindow: bit-identical over several warm-started solves of a scotty batch."""
+    P = PR.scotty(B=96, N=30, n=4)
+    a = altro_b200.make_solver(P)
+    b = altro_b200.make_solver(P)
+    for step in range(6):
+        sa, sb = a.Solve(), b.Solve()
+        assert np.array_equal(sa, sb)
+        Xa, Xb = a.GetStates(), b.GetStates()
+        assert np.array_equal(Xa, Xb) and np.array_equal(a.GetIterations(), b.GetIterations())
+        assert np.array_equal(a.GetInputs(), b.GetInputs())
+        a.MpcStep()
+        b.SetInitialState(Xb[:, 1].copy())
+        b.ShiftTrajectory()
+        b.AdvanceWindow(1)
+    assert (a.GetStatus() == 0).mean() > 0.9
+    a.close()
+    b.close()
