@@ -11,8 +11,11 @@ A step = one batched Solve() of the whole per-GPU batch.
 
 Prints ONE JSON line (rank 0).  `value` = solves/s with inputs resident in HBM; `e2e` = the same
 through the public C ABI with host buffers (H2D of problem data and D2H of the solution inside
-the timed region); `roofline` = algorithmic HBM bytes of the solve kernel / its CUDA-event time
-against the measured copy bandwidth; `cpu_baseline` = the CPU oracle (restatement of the
+the timed region); `roofline` = the dominant phase kernel of the step: its algorithmic HBM bytes
+per launch / its CUDA-event time, measured live in one extra solve with
+every launch bracketed by events, against the measured copy bandwidth (MEASURED_PEAKS.json, else
+the 6.65 TB/s fallback), `traffic` = its ncu DRAM bytes per launch (profiles/traffic.json);
+`kernels` = the same for every phase; `cpu_baseline` = the CPU oracle (restatement of the
 reference, oracle/) timed on this box's host cores on a bounded sample of the same workload.
 """
 import argparse
