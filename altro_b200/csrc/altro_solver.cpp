@@ -593,6 +593,27 @@ ErrorCodes ALTROSolver::GetFeedbackGain(a_float* K, int k) const {
   std::memcpy(K, &solver_->K[static_cast<size_t>(k) * mn], sizeof(double) * mn);
   return ErrorCodes::NoError;
 }
+ErrorCodes ALTROSolver::MpcStep() {
+  REQUIRE_HANDLE();
+  solver_->Invalidate();
+  return EC(altro_b200_mpc_step(solver_->handle));
+}
+ErrorCodes ALTROSolver::GetKnotPointField(const char* name, a_float* out, int k) const {
+  REQUIRE_HANDLE();
+  if (!name || !out) return ErrorCodes::InvalidPointer;
+  int k_stop = k + 1;
+  ErrorCodes err = CheckKnotPointIndices(k, k_stop, LastIndexMode::Inclusive);
+  if (err != ErrorCodes::NoError) return err;
+  int rows = 0;
+  int e = altro_b200_get_field(solver_->handle, name, nullptr, &rows);
+  if (e) return EC(e);
+  const size_t N = solver_->horizon_length_, B = solver_->batch_;
+  std::vector<double> all(B * (N + 1) * static_cast<size_t>(rows));
+  e = altro_b200_get_field(solver_->handle, name, all.data(), nullptr);
+  if (e) return EC(e);
+  std::memcpy(out, &all[static_cast<size_t>(k) * rows], sizeof(double) * rows);
+  return ErrorCodes::NoError;
+}
 ErrorCodes ALTROSolver::GetFeedforwardGain(a_float* d, int k) const {
   REQUIRE_HANDLE();
   int k_stop = k + 1;

@@ -257,6 +257,9 @@ class ALTROSolver {
   ErrorCodes UpdateLinearCosts(const a_float* q, const a_float* r, a_float c,
                                int k_start = AllIndices, int k_stop = 0);
   ErrorCodes ShiftTrajectory();
+  // One receding-horizon step on the device (plant = model): x0 <- x_[1], ShiftTrajectory and, for
+  // a tracking-window cost, the window moves one row (test/bicycle_test.cpp:302-337).
+  ErrorCodes MpcStep();
 
   void SetOptions(const AltroOptions& opts);
   AltroOptions& GetOptions();
@@ -282,6 +285,10 @@ class ALTROSolver {
   ErrorCodes GetDualDynamics(a_float* y, int k) const;
   ErrorCodes GetFeedbackGain(a_float* K, int k) const;
   ErrorCodes GetFeedforwardGain(a_float* d, int k) const;
+  // KnotPointData member `name` of knot k of the first problem (the views the reference's tests
+  // reach through solver_->data_[k]): "x" "u" "y" "xbar" "ubar" "A" "B" "lx" "lu" "K" "d" "P" "p"
+  // "q" "r" "c"; `out` holds the column-major block.
+  ErrorCodes GetKnotPointField(const char* name, a_float* out, int k) const;
 
   void PrintStateTrajectory() const;
   void PrintInputTrajectory() const;

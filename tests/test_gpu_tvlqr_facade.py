@@ -203,6 +203,14 @@ int double_integrator(bool control_bounds) {
   CHECK(solver.GetStatus() == SolveStatus::Success);
   std::vector<double> K(m * n);
   CHECK(solver.GetFeedbackGain(K.data(), 0) == ErrorCodes::NoError);
+  // KnotPointData-named views (what the reference's tests read through solver_->data_[k])
+  std::vector<double> Kf(m * n), A(n * n), Bk(n * m);
+  CHECK(solver.GetKnotPointField("K", Kf.data(), 0) == ErrorCodes::NoError);
+  for (int i = 0; i < m * n; ++i) CHECK(Kf[i] == K[i]);
+  CHECK(solver.GetKnotPointField("A", A.data(), 0) == ErrorCodes::NoError);
+  CHECK(solver.GetKnotPointField("B", Bk.data(), 0) == ErrorCodes::NoError);
+  CHECK(A[0] == 1.0 && std::fabs(A[0 + n * 2] - h) < 1e-7 && std::fabs(Bk[2 + n * 0] - h) < 1e-7);  // test_utils.cpp:18-41
+  CHECK(solver.GetKnotPointField("nope", A.data(), 0) == ErrorCodes::BadIndex);
   // error conventions
   CHECK(solver.SetDimension(n, m) == ErrorCodes::SolverAlreadyInitialized);
   CHECK(solver.GetState(xN.data(), N + 5) == ErrorCodes::BadIndex);
