@@ -10,7 +10,6 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstring>
-#include <thread>
 #include <vector>
 
 #include "../../include/altro_b200.h"
@@ -148,6 +147,30 @@ __global__ void k_lqr_cost(int n, int m, int N, int B, int k0, int k1,
   }
 }
 
+// The reference's receding-horizon cost update (test/bicycle_test.cpp:317-328): for every knot k
+// UpdateLinearCosts(q, nullptr, c, k) with q = -(Qd .* xref[row]), c = -(1/2 q . xref[row]) and
+// the FROZEN input part c_u added for k < N; r_k keeps the value of the original SetLQRCost
+// (altro_solver.cpp:266-281 leaves r alone when the pointer is null).  row = offsets[b] + k.
+__global__ void k_window_linear_update(int n, int N, int B, const double* __restrict__ Qd,
+                                       const double* __restrict__ xtab,
+                                       const int* __restrict__ offsets, FieldView q, FieldView c,
+                                       double c_u) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  for (int k = blockIdx.y; k <= N; k += gridDim.y) {
+    const double* xr = xtab + ((long)offsets[b] + k) * n;
+    double dot = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double qi = -(Qd[k * n + i] * xr[i]);
+      q.p[fv_index(q, (long)k * n + i, b)] = qi;
+      dot += qi * xr[i];
+    }
+    double cc = -(0.5 * dot);
+    if (k < N) cc += c_u;
+    c.p[fv_index(c, k, b)] = cc;
+  }
+}
+
 __global__ void k_add_int(int* v, int B, int add) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) v[b] += add;
@@ -205,23 +228,29 @@ struct altro_b200_solver {
   unsigned long long *stat_acc = nullptr, *feas_acc = nullptr;
   int nslots = 6;   // candidate steps per speculative line-search round (slot 0 = requested step)
   int nstore = 15;  // speculative slots 1..nstore keep their trajectory (candidate slot buffers)
-  int *flags = nullptr, *iter_count = nullptr, *list_iter = nullptr, *list_ls = nullptr,
-      *list_tmp = nullptr, *list_aux = nullptr, *counters = nullptr;
+  int nstore_alloc = 0;  // slot buffers allocated by Initialize
+  int *flags = nullptr, *iter_count = nullptr;
+  int* d_done = nullptr;                 // [kMaxSplit] stopped problems per sub-batch
+  unsigned long long* d_prof = nullptr;  // [kMaxSplit][8] sub-phase clocks of k_phase_forward
   unsigned long long* ls_hist = nullptr;
-  PhaseHost ph;
+  PhaseHost ph;        // accumulated statistics + device limits
   int solve_mode = 0;  // 0: phase pipeline (default), 1: single persistent kernel
-  // pipelined sub-batches: the groups are cut into `nsplit` contiguous ranges, each driven by its
-  // own host thread on its own stream, so that the compute-bound rollouts of one range overlap
-  // the HBM-bound sweeps of another and host round trips of one hide behind kernels of the others
+  // pipelined sub-batches: the groups are cut into `nsplit` contiguous ranges, each on its own
+  // stream, so that the sweeps of one range (one busy warp per group) overlap the rollouts and
+  // knot-parallel phases of another.  One host thread enqueues all of them.
   static constexpr int kMaxSplit = 8;
   int nsplit = 0;  // 0: choose from the batch size
   cudaStream_t sub_stream[kMaxSplit] = {nullptr};
   PhaseHost sub_ph[kMaxSplit];
+  bool sub_ready[kMaxSplit] = {false};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxSplit] = {nullptr};
   // tracking-window cost
   double *xtab = nullptr, *utab = nullptr;
   int* offsets = nullptr;
-  int T = 0;
+  int T = 0, T_alloc = 0;
+  int off_min = 0, off_max = 0;  // host-side range of the window offsets (bounds checks)
+  int mpc_mode = 1;     // cost update of altro_b200_mpc_step: 1 reference (q, c; r frozen), 0 re-window q, r, c
+  double mpc_cu = 0.0;  // frozen input part of c_k, k < N (mode 1)
   // constraints
   ConTable con_h;
   ConTable* con_d = nullptr;
@@ -240,6 +269,15 @@ static int dalloc(altro_b200_solver* s, void** p, size_t bytes, bool zero = true
   s->allocs.push_back(*p);
   s->bytes += (long)bytes;
   return 0;
+}
+// frees one tracked allocation
+static void release(altro_b200_solver* s, void* p) {
+  for (size_t i = 0; i < s->allocs.size(); ++i)
+    if (s->allocs[i] == p) {
+      cudaFree(p);
+      s->allocs.erase(s->allocs.begin() + (long)i);
+      return;
+    }
 }
 #define DALLOC(s, ptr, count)                                                      \
   do {                                                                             \
@@ -318,6 +356,9 @@ static int resolve_range(const altro_b200_solver* s, int& k_start, int& k_stop, 
   if (k_stop > terminal_index + 1) return ALTRO_B200_BAD_INDEX;
   return ALTRO_B200_NO_ERROR;
 }
+// 0 < k_stop <= k_start: the reference only warns and loops over nothing (altro_solver.cpp:423-427);
+// callers return NoError without touching anything
+static bool empty_range(int k_start, int k_stop) { return k_stop <= k_start; }
 
 // ------------------------------------------------------------------ model dispatch
 // The per-model kernels are instantiated in solve_inst.cu (one translation unit per group so the
@@ -435,20 +476,16 @@ void altro_b200_destroy(altro_b200_solver* s) {
   for (void* p : s->allocs) cudaFree(p);
   if (s->stage) cudaFree(s->stage);
   for (int i = 0; i < altro_b200_solver::kMaxSplit; ++i) {
-    if (s->sub_stream[i]) {
+    if (s->sub_ready[i]) {
       cudaStreamDestroy(s->sub_stream[i]);
-      cudaFreeHost(s->sub_ph[i].h_counters);
+      cudaFreeHost(s->sub_ph[i].h_done);
       cudaEventDestroy(s->sub_ph[i].ev0);
       cudaEventDestroy(s->sub_ph[i].ev1);
+      for (int j = 0; j < PhaseHost::kDoneRing; ++j) cudaEventDestroy(s->sub_ph[i].ev_done[j]);
       cudaEventDestroy(s->ev_join[i]);
     }
   }
   if (s->ev_fork) cudaEventDestroy(s->ev_fork);
-  if (s->ph.h_counters) {
-    cudaFreeHost(s->ph.h_counters);
-    cudaEventDestroy(s->ph.ev0);
-    cudaEventDestroy(s->ph.ev1);
-  }
   delete s;
 }
 
@@ -524,11 +561,8 @@ int altro_b200_set_dimension(altro_b200_solver* s, int n, int m) {  // altro_sol
   DALLOC(s, s->dphi0, S);
   DALLOC(s, s->flags, S);
   DALLOC(s, s->iter_count, S);
-  DALLOC(s, s->list_iter, S);
-  DALLOC(s, s->list_ls, S);
-  DALLOC(s, s->list_tmp, S);
-  DALLOC(s, s->list_aux, S);
-  DALLOC(s, s->counters, 8 * altro_b200_solver::kMaxSplit);
+  DALLOC(s, s->d_done, altro_b200_solver::kMaxSplit);
+  DALLOC(s, s->d_prof, 8 * altro_b200_solver::kMaxSplit);
   DALLOC(s, s->ls_hist, 32);
   memset(&s->ph, 0, sizeof(s->ph));
   {  // device limits that size the staging rings of the sequential sweeps (solve_inst.cu)
@@ -540,10 +574,6 @@ int altro_b200_set_dimension(altro_b200_solver* s, int n, int m) {  // altro_sol
     cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device);
     s->ph.smem_per_cta = v > 0 ? (size_t)v : (size_t)227 * 1024;
   }
-  CUDA_OK(cudaMallocHost((void**)&s->ph.h_counters, 8 * sizeof(int)));
-  CUDA_OK(cudaEventCreate(&s->ph.ev0));
-  CUDA_OK(cudaEventCreate(&s->ph.ev1));
-  s->ph.list_aux = s->list_aux;
   s->dims_set = true;
   return ALTRO_B200_NO_ERROR;
 }
@@ -572,6 +602,7 @@ int altro_b200_set_linear_dynamics(altro_b200_solver* s, const double* A, const 
   if (!s->dims_set) return ALTRO_B200_DIMENSION_UNKNOWN;
   int e = resolve_range(s, k_start, k_stop, false);
   if (e) return e;
+  if (empty_range(k_start, k_stop)) return ALTRO_B200_NO_ERROR;
   const int n = s->n, m = s->m;
   const int W = n * n + n * m + n;
   for (int k = k_start; k < k_stop; ++k) {
@@ -604,6 +635,7 @@ int altro_b200_set_lqr_cost(altro_b200_solver* s, const double* Qd, const double
   CUDA_OK(cudaSetDevice(s->device));
   int e = resolve_range(s, k_start, k_stop, true);
   if (e) return e;
+  if (empty_range(k_start, k_stop)) return ALTRO_B200_NO_ERROR;
   e = store_weights(s, Qd, Rd, k_start, k_stop);
   if (e) return e;
   const int n = s->n, m = s->m;
@@ -645,12 +677,28 @@ int altro_b200_set_lqr_cost_window(altro_b200_solver* s, const double* Qd, const
   CUDA_OK(cudaSetDevice(s->device));
   int e = store_weights(s, Qd, Rd, 0, s->N + 1);
   if (e) return e;
-  if (!s->xtab || s->T != T) {
+  if (T < s->N + 1) return ALTRO_B200_BAD_INDEX;
+  int omin = offsets[0], omax = offsets[0];
+  for (int b = 1; b < s->B; ++b) {
+    omin = std::min(omin, offsets[b]);
+    omax = std::max(omax, offsets[b]);
+  }
+  // every knot 0..N of every problem must read a row of the tables
+  if (omin < 0 || omax + s->N >= T) return ALTRO_B200_BAD_INDEX;
+  if (!s->xtab || T > s->T_alloc) {  // (re)allocate only when the tables grow; old ones are released
+    if (s->xtab) {
+      CUDA_OK(cudaStreamSynchronize(s->stream));
+      release(s, s->xtab);
+      release(s, s->utab);
+    }
     DALLOC(s, s->xtab, (long)T * s->n);
     DALLOC(s, s->utab, (long)T * s->m);
-    DALLOC(s, s->offsets, s->Bp);
-    s->T = T;
+    if (!s->offsets) DALLOC(s, s->offsets, s->Bp);
+    s->T_alloc = T;
   }
+  s->T = T;
+  s->off_min = omin;
+  s->off_max = omax;
   CUDA_OK(cudaMemcpyAsync(s->xtab, xtab, sizeof(double) * (size_t)T * s->n, cudaMemcpyHostToDevice, s->stream));
   CUDA_OK(cudaMemcpyAsync(s->utab, utab, sizeof(double) * (size_t)T * s->m, cudaMemcpyHostToDevice, s->stream));
   CUDA_OK(cudaMemcpyAsync(s->offsets, offsets, sizeof(int) * (size_t)s->B, cudaMemcpyHostToDevice, s->stream));
@@ -661,13 +709,45 @@ int altro_b200_set_lqr_cost_window(altro_b200_solver* s, const double* Qd, const
   return ALTRO_B200_NO_ERROR;
 }
 
-int altro_b200_advance_window(altro_b200_solver* s, int steps) {
-  if (!s) return ALTRO_B200_INVALID_POINTER;
+static int move_window(altro_b200_solver* s, int steps) {
   if (!s->xtab) return ALTRO_B200_COST_FUN_NOT_SET;
+  // the moved window must stay inside the reference tables for every problem
+  if (s->off_min + steps < 0 || s->off_max + steps + s->N >= s->T) return ALTRO_B200_BAD_INDEX;
+  s->off_min += steps;
+  s->off_max += steps;
   CUDA_OK(cudaSetDevice(s->device));
   k_add_int<<<(s->B + 127) / 128, 128, 0, s->stream>>>(s->offsets, s->B, steps);
   s->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int altro_b200_advance_window(altro_b200_solver* s, int steps) {
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  int e = move_window(s, steps);
+  if (e) return e;
   return apply_window(s);
+}
+
+int altro_b200_advance_window_linear(altro_b200_solver* s, int steps, double c_u) {
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;  // UpdateLinearCosts, altro_solver.cpp:268
+  int e = move_window(s, steps);
+  if (e) return e;
+  dim3 grid((s->B + 127) / 128, (unsigned)(s->N + 1));
+  k_window_linear_update<<<grid, 128, 0, s->stream>>>(s->n, s->N, s->B, s->Qd, s->xtab, s->offsets,
+                                                      fview(s, s->q, s->n), fview(s, s->c, 1), c_u);
+  s->launches++;
+  CUDA_OK(cudaGetLastError());
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_set_mpc_cost_update(altro_b200_solver* s, int mode, double c_u) {
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  if (mode != 0 && mode != 1) return ALTRO_B200_BAD_INDEX;
+  s->mpc_mode = mode;
+  s->mpc_cu = c_u;
+  return ALTRO_B200_NO_ERROR;
 }
 
 static int set_linear_terms(altro_b200_solver* s, const double* q, const double* r, const double* c,
@@ -721,6 +801,7 @@ int altro_b200_set_diagonal_cost(altro_b200_solver* s, const double* Qd, const d
   CUDA_OK(cudaSetDevice(s->device));
   int e = resolve_range(s, k_start, k_stop, true);
   if (e) return e;
+  if (empty_range(k_start, k_stop)) return ALTRO_B200_NO_ERROR;
   e = store_weights(s, Qd, Rd, k_start, k_stop);
   if (e) return e;
   e = set_linear_terms(s, q, r, c, per_problem, k_start, k_stop);
@@ -736,6 +817,7 @@ int altro_b200_update_linear_costs(altro_b200_solver* s, const double* q, const 
   CUDA_OK(cudaSetDevice(s->device));
   int e = resolve_range(s, k_start, k_stop, true);
   if (e) return e;
+  if (empty_range(k_start, k_stop)) return ALTRO_B200_NO_ERROR;
   if (r && k_stop > s->N && k_stop - k_start == 1) return ALTRO_B200_INVALID_OPT_AT_TERMINAL;
   return set_linear_terms(s, q, r, c, per_problem, k_start, k_stop);
 }
@@ -752,6 +834,7 @@ int altro_b200_set_constraint(altro_b200_solver* s, int cone, int dim, const int
   CUDA_OK(cudaSetDevice(s->device));
   int e = resolve_range(s, k_start, k_stop, true);
   if (e) return e;
+  if (empty_range(k_start, k_stop)) return ALTRO_B200_NO_ERROR;
   ConSlot& c = s->con_h.slot[s->con_h.ncon];
   memset(&c, 0, sizeof(c));
   c.k_start = k_start;
@@ -760,7 +843,9 @@ int altro_b200_set_constraint(altro_b200_solver* s, int cone, int dim, const int
   c.dim = dim;
   c.row0 = s->con_h.rows;
   for (int i = 0; i < dim; ++i) {
-    if (idx[i] >= s->n + s->m) return ALTRO_B200_BAD_INDEX;
+    if (idx[i] < -1 || idx[i] >= s->n + s->m) return ALTRO_B200_BAD_INDEX;
+    // a row that reads an input cannot live on the terminal knot (it has no input)
+    if (idx[i] >= s->n && k_stop > s->N) return ALTRO_B200_INVALID_OPT_AT_TERMINAL;
     c.idx[i] = idx[i];
     c.scale[i] = scale[i];
     c.off[i] = off[i];
@@ -825,6 +910,7 @@ int altro_b200_initialize(altro_b200_solver* s) {  // altro_solver.cpp:225-229
     if (s->nstore > fit) s->nstore = (int)(fit < 3 ? 3 : fit);
     if (s->nstore < 1) s->nstore = 1;
   }
+  s->nstore_alloc = s->nstore;
   DALLOC(s, s->xs, (long)s->nstore * s->G * (s->N + 1) * s->Rs);
   s->us = s->xs + (long)s->n * 32;
   DALLOC(s, s->phi_s, (long)(kMaxHalvings + 1) * s->Bp);
@@ -860,6 +946,7 @@ int altro_b200_set_input(altro_b200_solver* s, const double* u, int layout, int 
   CUDA_OK(cudaSetDevice(s->device));
   int e = resolve_range(s, k_start, k_stop, false);
   if (e) return e;
+  if (empty_range(k_start, k_stop)) return ALTRO_B200_NO_ERROR;
   e = set_traj(s, u, layout, k_start, k_stop, s->m, s->u);
   if (e) return e;
   const long W = (long)(k_stop - k_start) * s->m;
@@ -890,6 +977,7 @@ int altro_b200_set_state(altro_b200_solver* s, const double* x, int layout, int 
   CUDA_OK(cudaSetDevice(s->device));
   int e = resolve_range(s, k_start, k_stop, true);
   if (e) return e;
+  if (empty_range(k_start, k_stop)) return ALTRO_B200_NO_ERROR;
   return set_traj(s, x, layout, k_start, k_stop, s->n, s->x);
 }
 
@@ -929,13 +1017,17 @@ static int con_level(const altro_b200_solver* s) {
   return level;
 }
 
-// One receding-horizon step without a host round trip (test/bicycle_test.cpp:302-337 with the
-// plant equal to the model): the next initial state is x_[1] = f(x0, u_[0]) of the solved
-// trajectory, then ShiftTrajectory, then the tracking window moves one row (on-device
-// UpdateLinearCosts).  Duals and penalties carry over like in the reference (quirk Q14).
+// One receding-horizon step without a host round trip (test/bicycle_test.cpp:302-337; the plant
+// there is the model itself, :312): the tracking window moves one row with the reference's cost
+// update -- UpdateLinearCosts(q, nullptr, c): q and c follow the window, r stays, c's input part
+// is the frozen c_u (:317-328; altro_b200_set_mpc_cost_update selects the full re-windowing
+// instead) --, the next initial state is x_[1] = f(x0, u_[0]) of the solved trajectory (:312,
+// :331), then ShiftTrajectory (:334).  Duals and penalties carry over (quirk Q14).
 int altro_b200_mpc_step(altro_b200_solver* s) {
   if (!s) return ALTRO_B200_INVALID_POINTER;
   if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;
+  // refuse BEFORE touching anything when the moved window would leave the reference tables
+  if (s->xtab && (s->off_min + 1 < 0 || s->off_max + 1 + s->N >= s->T)) return ALTRO_B200_BAD_INDEX;
   CUDA_OK(cudaSetDevice(s->device));
   dim3 grid((unsigned)((s->B + 127) / 128), (unsigned)s->n);
   k_copy_field<<<grid, 128, 0, s->stream>>>(fview(s, s->x, s->n, 1), gview(s->x0, s->n), s->B, s->n);
@@ -943,7 +1035,8 @@ int altro_b200_mpc_step(altro_b200_solver* s) {
   CUDA_OK(cudaGetLastError());
   int e = altro_b200_shift_trajectory(s);
   if (e) return e;
-  if (s->xtab) e = altro_b200_advance_window(s, 1);
+  if (s->xtab)
+    e = s->mpc_mode == 1 ? altro_b200_advance_window_linear(s, 1, s->mpc_cu) : altro_b200_advance_window(s, 1);
   return e;
 }
 
@@ -1011,10 +1104,7 @@ static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   P.dphi0 = s->dphi0;
   P.flags = s->flags;
   P.iter_count = s->iter_count;
-  P.list_iter = s->list_iter;
-  P.list_ls = s->list_ls;
-  P.list_tmp = s->list_tmp;
-  P.counters = s->counters;
+  P.prof = nullptr;
   P.ls_hist = s->ls_hist;
   P.opts.iterations_max = s->opts.iterations_max;
   P.opts.tol_primal_feasibility = s->opts.tol_primal_feasibility;
@@ -1028,6 +1118,22 @@ static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   P.opts.ls_c2 = s->opts.linesearch_c2;
 }
 
+// per-sub-batch stream, pinned stop-counter ring and events, created on first use
+static int ensure_sub(altro_b200_solver* s, int i) {
+  if (s->sub_ready[i]) return 0;
+  PhaseHost& H = s->sub_ph[i];
+  memset(&H, 0, sizeof(PhaseHost));
+  CUDA_OK(cudaStreamCreateWithFlags(&s->sub_stream[i], cudaStreamNonBlocking));
+  CUDA_OK(cudaMallocHost((void**)&H.h_done, PhaseHost::kDoneRing * sizeof(int)));
+  CUDA_OK(cudaEventCreate(&H.ev0));
+  CUDA_OK(cudaEventCreate(&H.ev1));
+  for (int j = 0; j < PhaseHost::kDoneRing; ++j)
+    CUDA_OK(cudaEventCreateWithFlags(&H.ev_done[j], cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&s->ev_join[i], cudaEventDisableTiming));
+  s->sub_ready[i] = true;
+  return 0;
+}
+
 int altro_b200_solve_async(altro_b200_solver* s) {  // altro_solver.cpp:257-260
   if (!s) return ALTRO_B200_INVALID_POINTER;
   if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;
@@ -1036,92 +1142,107 @@ int altro_b200_solve_async(altro_b200_solver* s) {  // altro_solver.cpp:257-260
   if (!L) return ALTRO_B200_ERR_UNSUPPORTED;
   DeviceProblem P;
   fill_device_problem(s, P);
+  const int has_con = con_level(s);
   if (s->solve_mode == 1) {
-    int e = L(P, con_level(s), s->stream, nullptr);
+    int e = L(P, has_con, s->stream, nullptr);
     s->launches++;
     if (e) return ALTRO_B200_ERR_NO_DEVICE;
-  } else {
-    long before = 0;
-    for (int i = 0; i < PH_COUNT; ++i) before += s->ph.launches[i];
-    int nsplit = s->nsplit;
-    if (nsplit <= 0) {
-      // DESIGN.md "pipelined sub-batches": splitting pays when there is a compute-bound phase to
-      // overlap with the HBM-bound sweeps, i.e. the speculative rollouts of the backtracking
-      // search (bicycle 16384: 56 -> 48 ms); with the cubic search it only shrinks the kernels
-      // (pendulum 4096: 2.8 -> 3.0 ms, chain 32768: no gain)
-      const bool spec = s->opts.use_backtracking_linesearch && s->nslots > 1;
-      nsplit = !spec ? 1 : (s->G >= 512 ? 4 : (s->G >= 128 ? 2 : 1));
+    return ALTRO_B200_NO_ERROR;
+  }
+  long before = 0;  // kernel launches so far (the PH_FWD_* entries are sub-phases, not launches)
+  for (int i = 0; i <= PH_FORWARD; ++i) before += s->ph.launches[i];
+  int nsplit = s->nsplit;
+  // DESIGN.md "pipelined sub-batches": the Riccati sweep keeps one warp per group busy, the
+  // forward kernel up to eight; sub-batches on separate streams let the two overlap
+  if (nsplit <= 0) nsplit = s->G >= 512 ? 4 : (s->G >= 128 ? 2 : 1);
+  nsplit = std::min(std::min(nsplit, (int)altro_b200_solver::kMaxSplit), s->G);
+  const int per = (s->G + nsplit - 1) / nsplit;
+  nsplit = (s->G + per - 1) / per;  // no empty sub-batch
+  if (!s->ev_fork) CUDA_OK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+  CUDA_OK(cudaEventRecord(s->ev_fork, s->stream));
+  struct Sub {
+    DeviceProblem P;
+    cudaStream_t st;
+    PhaseHost* H;
+    int total;
+    bool done;
+  } subs[altro_b200_solver::kMaxSplit];
+  int e = 0;
+  for (int i = 0; i < nsplit; ++i) {
+    int err = ensure_sub(s, i);
+    if (err) return err;
+    Sub& sb = subs[i];
+    sb.P = P;
+    sb.P.g0 = i * per;
+    sb.P.G = std::min(per, s->G - sb.P.g0);
+    sb.st = s->sub_stream[i];
+    sb.H = &s->sub_ph[i];
+    sb.total = std::min(s->B, (sb.P.g0 + sb.P.G) * 32) - sb.P.g0 * 32;
+    sb.done = false;
+    PhaseHost& H = *sb.H;
+    H.profile = s->ph.profile;
+    H.num_sms = s->ph.num_sms;
+    H.smem_per_sm = s->ph.smem_per_sm;
+    H.smem_per_cta = s->ph.smem_per_cta;
+    H.d_done = s->d_done + i;
+    H.d_prof = s->d_prof + 8 * i;
+    H.fwd_warps = std::max(4, s->nslots);
+    for (int j = 0; j < PH_COUNT; ++j) {
+      H.ms[j] = 0.0;
+      H.launches[j] = 0;
+      H.units[j] = 0.0;
     }
-    nsplit = std::min(std::min(nsplit, (int)altro_b200_solver::kMaxSplit), s->G);
-    P.g0 = 0;
-    P.G = s->G;
-    int e = 0;
-    if (nsplit == 1) {
-      e = L(P, con_level(s), s->stream, &s->ph);
-    } else {
-      if (!s->ev_fork) CUDA_OK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
-      for (int i = 0; i < nsplit; ++i) {
-        if (s->sub_stream[i]) continue;
-        CUDA_OK(cudaStreamCreateWithFlags(&s->sub_stream[i], cudaStreamNonBlocking));
-        memset(&s->sub_ph[i], 0, sizeof(PhaseHost));
-        CUDA_OK(cudaMallocHost((void**)&s->sub_ph[i].h_counters, 8 * sizeof(int)));
-        CUDA_OK(cudaEventCreate(&s->sub_ph[i].ev0));
-        CUDA_OK(cudaEventCreate(&s->sub_ph[i].ev1));
-        CUDA_OK(cudaEventCreateWithFlags(&s->ev_join[i], cudaEventDisableTiming));
-      }
-      CUDA_OK(cudaEventRecord(s->ev_fork, s->stream));
-      const int per = (s->G + nsplit - 1) / nsplit;
-      int rc[altro_b200_solver::kMaxSplit] = {0};
-      std::vector<std::thread> workers;
-      const int has_con = con_level(s);
-      for (int i = 0; i < nsplit; ++i) {
-        workers.emplace_back([&, i]() {
-          cudaSetDevice(s->device);
-          PhaseHost& H = s->sub_ph[i];
-          H.op = OP_SOLVE;
-          H.profile = s->ph.profile;
-          H.num_sms = s->ph.num_sms;
-          H.smem_per_sm = s->ph.smem_per_sm;
-          H.smem_per_cta = s->ph.smem_per_cta;
-          for (int j = 0; j < PH_COUNT; ++j) {
-            H.ms[j] = 0.0;
-            H.launches[j] = 0;
-            H.units[j] = 0.0;
-          }
-          H.syncs = 0;
-          DeviceProblem Pi = P;
-          Pi.g0 = i * per;
-          Pi.G = std::min(per, s->G - Pi.g0);
-          if (Pi.G <= 0) return;
-          Pi.list_iter = P.list_iter + Pi.g0;
-          Pi.list_ls = P.list_ls + Pi.g0;
-          Pi.list_tmp = P.list_tmp + Pi.g0;
-          Pi.counters = P.counters + 8 * i;
-          H.list_aux = s->list_aux + Pi.g0;
-          cudaStreamWaitEvent(s->sub_stream[i], s->ev_fork, 0);
-          rc[i] = L(Pi, has_con, s->sub_stream[i], &H);
-          cudaEventRecord(s->ev_join[i], s->sub_stream[i]);
-        });
-      }
-      for (auto& w : workers) w.join();
-      for (int i = 0; i < nsplit; ++i) {
-        CUDA_OK(cudaStreamWaitEvent(s->stream, s->ev_join[i], 0));
-        if (rc[i]) e = rc[i];
-        for (int j = 0; j < PH_COUNT; ++j) {
-          s->ph.ms[j] += s->sub_ph[i].ms[j];
-          s->ph.launches[j] += s->sub_ph[i].launches[j];
-          s->ph.units[j] += s->sub_ph[i].units[j];
+    H.syncs = 0;
+    CUDA_OK(cudaStreamWaitEvent(sb.st, s->ev_fork, 0));
+    H.op = OP_SOLVE_PROLOGUE;
+    const int rc = L(sb.P, has_con, sb.st, &H);
+    if (rc) e = rc;
+  }
+  // Iterations are enqueued back to back; the stop counter of iteration i is copied to pinned
+  // memory right behind it and looked at kLag iterations later, so the device always has work
+  // queued while the host decides whether the sub-batch still needs another iteration.
+  constexpr int kLag = 2;
+  int live = nsplit;
+  for (int iter = 0; iter < s->opts.iterations_max && live > 0 && !e; ++iter) {
+    for (int i = 0; i < nsplit; ++i) {
+      Sub& sb = subs[i];
+      if (sb.done) continue;
+      PhaseHost& H = *sb.H;
+      if (iter >= kLag) {
+        const int slot = (iter - kLag) % PhaseHost::kDoneRing;
+        CUDA_OK(cudaEventSynchronize(H.ev_done[slot]));
+        H.syncs += 1;
+        if (H.h_done[slot] >= sb.total) {
+          sb.done = true;
+          live -= 1;
+          continue;
         }
-        s->ph.syncs += s->sub_ph[i].syncs;
       }
+      H.op = OP_SOLVE_ITERATION;
+      H.iter = iter;
+      const int rc = L(sb.P, has_con, sb.st, &H);
+      if (rc) e = rc;
+      const int slot = iter % PhaseHost::kDoneRing;
+      CUDA_OK(cudaMemcpyAsync(&H.h_done[slot], H.d_done, sizeof(int), cudaMemcpyDeviceToHost, sb.st));
+      CUDA_OK(cudaEventRecord(H.ev_done[slot], sb.st));
     }
-    long after = 0;
-    for (int i = 0; i < PH_COUNT; ++i) after += s->ph.launches[i];
-    s->launches += after - before;
-    if (e) {
-      fprintf(stderr, "altro_b200: CUDA error %d in the phase pipeline\n", e);
-      return ALTRO_B200_ERR_NO_DEVICE;
+  }
+  for (int i = 0; i < nsplit; ++i) {
+    CUDA_OK(cudaEventRecord(s->ev_join[i], subs[i].st));
+    CUDA_OK(cudaStreamWaitEvent(s->stream, s->ev_join[i], 0));
+    for (int j = 0; j < PH_COUNT; ++j) {
+      s->ph.ms[j] += s->sub_ph[i].ms[j];
+      s->ph.launches[j] += s->sub_ph[i].launches[j];
+      s->ph.units[j] += s->sub_ph[i].units[j];
     }
+    s->ph.syncs += s->sub_ph[i].syncs;
+  }
+  long after = 0;
+  for (int i = 0; i <= PH_FORWARD; ++i) after += s->ph.launches[i];
+  s->launches += after - before;
+  if (e) {
+    fprintf(stderr, "altro_b200: CUDA error %d in the phase pipeline\n", e);
+    return ALTRO_B200_ERR_NO_DEVICE;
   }
   return ALTRO_B200_NO_ERROR;
 }
@@ -1137,7 +1258,7 @@ static int run_host_op(altro_b200_solver* s, int op, double* cost_out) {
   s->ph.op = op;
   s->ph.cost_out = cost_out;
   int e = L(P, con_level(s), s->stream, &s->ph);
-  s->ph.op = OP_SOLVE;
+  s->ph.op = OP_SOLVE_PROLOGUE;
   s->launches++;
   if (e) return ALTRO_B200_ERR_NO_DEVICE;
   return ALTRO_B200_NO_ERROR;
@@ -1173,8 +1294,16 @@ int altro_b200_set_pipeline_split(altro_b200_solver* s, int nsplit) {
 int altro_b200_set_speculation(altro_b200_solver* s, int nslots) {
   if (!s) return ALTRO_B200_INVALID_POINTER;
   if (s->initialized) return ALTRO_B200_SOLVER_ALREADY_INITIALIZED;
-  if (nslots < 1 || nslots > 16) return ALTRO_B200_BAD_INDEX;
+  if (nslots < 1 || nslots > 8) return ALTRO_B200_BAD_INDEX;
   s->nslots = nslots;
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_set_candidate_store(altro_b200_solver* s, int nstore) {
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;
+  if (nstore < 0) return ALTRO_B200_BAD_INDEX;
+  s->nstore = std::min(nstore, s->nstore_alloc);
   return ALTRO_B200_NO_ERROR;
 }
 

@@ -102,7 +102,7 @@ struct DeviceProblem {
   int *status, *iters, *merit_evals, *ls_fail;
   double *phi, *stat, *feas;
 
-  // ---- phase-kernel pipeline (solver_phases.cuh): per-trajectory scalar state + work lists
+  // ---- phase-kernel pipeline (solver_phases.cuh): per-trajectory scalar state
   LsMachine* ls;        // [B] line-search state machines
   double *alpha_eval;   // [Bp] step length of the pending merit evaluation
   double *alpha_bt;     // [Bp] first backtracking step after alpha_eval (speculative rounds)
@@ -110,8 +110,8 @@ struct DeviceProblem {
   double *phi0, *dphi0; // [Bp]
   int* flags;           // [Bp] bit mask, see TrajFlags
   int* iter_count;      // [Bp] iLQR iterations done so far
-  int *list_iter, *list_ls, *list_tmp;  // compacted GROUP indices (a group = 32 problems = 1 warp)
-  int* counters;        // [8] device-side counts (see PhaseCounter)
+  // [FS_COUNT + 1] profile mode only (else null): nanoseconds per sub-phase of k_phase_forward
+  unsigned long long* prof;
   // [32] accepted-step histogram of the line search: 0 alpha0 accepted, 1..15 halving j accepted,
   // 16 cubic-first probe accepted, 17 zoom/other, 18 failed, 19 merit gradient too small
   unsigned long long* ls_hist;
@@ -140,7 +140,5 @@ enum TrajFlags {
   TF_SPECULATE = 128,       // the pending round also rolls out the halvings alpha_bt * 2^-j (merit only)
   TF_REROLL = 256,          // accepted step came from a merit-only candidate: roll it out again, storing
 };
-
-enum PhaseCounter { PC_LS = 0, PC_DERIV = 1, PC_SPEC = 2, PC_REFRESH_GRAD = 3, PC_ITER = 4 };
 
 }  // namespace altro_b200

@@ -8,30 +8,48 @@
 
 namespace altro_b200 {
 
-// Host-side state of the phase-kernel pipeline (solver_phases.cuh)
-enum Phase { PH_INIT = 0, PH_EXPAND, PH_BACKWARD, PH_ROLLOUT, PH_LSUPDATE, PH_CRITERIA, PH_COMPACT, PH_COUNT };
+// Host-side state of the phase-kernel pipeline (solver_phases.cuh).  One PhaseHost per sub-batch.
+// Phases: kernels timed with CUDA events in profile mode (INIT, EXPAND = prologue expansion,
+// BACKWARD, FORWARD) followed by the sub-phases of k_phase_forward, whose `ms` is the forward
+// kernel's time split by the in-kernel %globaltimer shares (rollout passes, expansions, d(phi)
+// scan + line-search machines, criteria + AL update).
+enum Phase {
+  PH_INIT = 0, PH_EXPAND, PH_BACKWARD, PH_FORWARD, PH_FWD_ROLLOUT, PH_FWD_EXPAND, PH_FWD_DPHI_LS,
+  PH_FWD_CRITERIA, PH_COUNT
+};
 
-enum HostOp { OP_SOLVE = 0, OP_OPEN_LOOP_ROLLOUT = 1, OP_CALC_COST = 2, OP_UNPACK_JAC = 3 };
+enum HostOp {
+  OP_SOLVE_PROLOGUE = 0,   // Solve() up to the loop (solver.cpp:417-430) for the sub-batch [g0, g0+G)
+  OP_OPEN_LOOP_ROLLOUT = 1,
+  OP_CALC_COST = 2,
+  OP_UNPACK_JAC = 3,
+  OP_SOLVE_ITERATION = 4,  // one iLQR iteration: k_phase_backward + k_phase_forward (iter = PhaseHost::iter)
+};
 
 struct PhaseHost {
   int op;              // HostOp
+  int iter;            // OP_SOLVE_ITERATION: iteration number (0 = first)
   double* cost_out;    // OP_CALC_COST: device array [Bp]; OP_UNPACK_JAC: dense [A B] stream
                        // [group][knot][n*n + n*m][32]
-  int* h_counters;     // pinned, 8 ints
-  int* list_aux;       // second buffer for list_iter
+  int* d_done;         // device: problems of the sub-batch that have stopped (zeroed by the prologue)
+  int* h_done;         // pinned [kDoneRing]: copies of *d_done taken after each iteration
+  unsigned long long* d_prof;  // device [8]: sub-phase nanoseconds of k_phase_forward (profile mode)
   bool profile;        // record CUDA events around every launch
   double ms[PH_COUNT];         // accumulated kernel time per phase (profile mode)
   long launches[PH_COUNT];     // launches per phase
   double units[PH_COUNT];      // trajectories (or trajectory-knots for PH_EXPAND) processed
-  long syncs;                  // host<->device count readbacks
+  long syncs;                  // host waits on the device (lagged stop-counter checks)
+  int fwd_warps;               // warps per CTA of k_phase_forward (1 + speculative candidates)
   cudaEvent_t ev0, ev1;
+  static constexpr int kDoneRing = 4;
+  cudaEvent_t ev_done[kDoneRing];  // recorded after the h_done copy of iteration i % kDoneRing
   // device limits that size the shared-memory staging rings of the sequential sweeps
   int num_sms;
   size_t smem_per_sm, smem_per_cta;
 };
 
 // has_constraints selects the AL-enabled instantiation.  host == nullptr: the single persistent
-// kernel (solver_kernels.cuh); otherwise the phase pipeline.  Returns 0 or a cudaError_t.
+// kernel (solver_kernels.cuh); otherwise the operation host->op.  Returns 0 or a cudaError_t.
 typedef int (*solve_launcher)(const DeviceProblem&, int has_constraints, cudaStream_t, PhaseHost* host);
 
 #define ALTRO_DECLARE_LAUNCHER(name) \

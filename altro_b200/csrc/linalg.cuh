@@ -269,6 +269,90 @@ struct BulkRing {
   }
 };
 
+// ---- The same staging for SEVERAL consumer warps that are NOT kept in lockstep (k_phase_forward):
+// a classic full/empty mbarrier pipeline.  `full[s]` completes when the bulk copies of a stage have
+// landed (1 arrival + transaction bytes); `empty[s]` completes when every participating warp has
+// released the stage (one elected arrival per warp, issued after the warp consumed what it read).
+// The producer thread refills a stage only after its `empty` phase completed, so fast warps run up
+// to depth - 1 knots ahead of slow ones instead of meeting at a CTA barrier every knot (ncu r01:
+// 9 barrier stalls per issue in the late line-search rounds).  A pass = one sweep over the knots;
+// the barriers are re-armed per pass for the warps that take part in it (begin_pass), so stage and
+// parity are functions of the pass-local knot counter.
+struct BulkPipe {
+  unsigned long long* full;   // [depth]
+  unsigned long long* empty;  // [depth]
+  double* data;               // [depth][stage_doubles], 128-byte aligned
+  int depth, stage_doubles;
+
+  __host__ __device__ static size_t bytes(int depth, int stage_doubles) {
+    return 256 + (size_t)depth * stage_doubles * 8;
+  }
+  // pointer carving only; all threads
+  ALTRO_DEV void setup(unsigned char* smem, int depth_, int stage_doubles_) {
+    full = reinterpret_cast<unsigned long long*>(smem);
+    empty = full + 16;
+    data = reinterpret_cast<double*>(smem + 256);
+    depth = depth_;
+    stage_doubles = stage_doubles_;
+  }
+  // ONE thread, with a CTA barrier before (nobody still uses the previous pass) and after.
+  // `used`: the barriers hold valid objects from an earlier pass and must be invalidated first.
+  ALTRO_DEV void begin_pass(int consumer_warps, bool used) const {
+    for (int j = 0; j < depth; ++j) {
+      const unsigned f = (unsigned)__cvta_generic_to_shared(full + j);
+      const unsigned e = (unsigned)__cvta_generic_to_shared(empty + j);
+      if (used) {
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(f) : "memory");
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(e) : "memory");
+      }
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(f) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(e), "r"(consumer_warps) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  ALTRO_DEV static void spin(unsigned addr, unsigned parity) {
+    unsigned ok = 0;
+    while (!ok) {
+      asm volatile(
+          "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+          : "=r"(ok)
+          : "r"(addr), "r"(parity)
+          : "memory");
+    }
+  }
+  // producer thread: make stage k % depth writable for pass-local knot k, announce `bytes`
+  ALTRO_DEV int acquire(int k, unsigned bytes) const {
+    const int st = k % depth;
+    const int use = k / depth;
+    if (use > 0) spin((unsigned)__cvta_generic_to_shared(empty + st), (unsigned)((use - 1) & 1));
+    const unsigned a = (unsigned)__cvta_generic_to_shared(full + st);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+    return st;
+  }
+  ALTRO_DEV void copy(int stage, int row, const double* src, unsigned bytes) const {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(full + stage);
+    const unsigned d = (unsigned)__cvta_generic_to_shared(data + (long)stage * stage_doubles + row * 32);
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+        "l"(src), "r"(bytes), "r"(a)
+        : "memory");
+  }
+  // consumer, all lanes: wait for pass-local knot k; returns the stage's first row
+  ALTRO_DEV const double* wait(int k) const {
+    const int st = k % depth;
+    spin((unsigned)__cvta_generic_to_shared(full + st), (unsigned)((k / depth) & 1));
+    return data + (long)st * stage_doubles;
+  }
+  // consumer, all lanes of the warp, AFTER the arithmetic that consumed the stage's values
+  ALTRO_DEV void release(int k, int lane) const {
+    __syncwarp();
+    if (lane == 0) {
+      const unsigned a = (unsigned)__cvta_generic_to_shared(empty + (k % depth));
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+    }
+  }
+};
+
 // this lane's element e of a block that starts at `row` of a landed stage
 template <int E>
 ALTRO_DEV void unstage_block(const double* stage, int row, int lane, double* out) {

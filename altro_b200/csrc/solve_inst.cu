@@ -7,13 +7,15 @@
 
 namespace altro_b200 {
 
+// One operation of the phase pipeline for the sub-batch [P.g0, P.g0 + P.G): the Solve() prologue
+// (OP_SOLVE_PROLOGUE) or iLQR iteration H->iter (OP_SOLVE_ITERATION = two launches).  Nothing here
+// waits for the device; capi.cu enqueues iterations back to back and reads the stop counter late.
 template <class Model, int CON>
 static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
   using TS = TrajSolver<Model, CON>;
   constexpr int n = Model::n, m = Model::m;
   const int B = P.B, N = P.N, G = P.G;
   auto g128 = [](int count) { return (count + 127) / 128; };
-  cudaError_t err = cudaSuccess;
   // launch wrapper: counts launches/units and, in profile mode, times the kernel with events
   auto timed = [&](int phase, double units, auto&& launch) {
     if (H->profile) cudaEventRecord(H->ev0, st);
@@ -28,138 +30,77 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
     H->launches[phase] += 1;
     H->units[phase] += units;
   };
-  auto readback = [&]() {
-    cudaMemcpyAsync(H->h_counters, P.counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, st);
-    err = cudaStreamSynchronize(st);
-    H->syncs += 1;
-  };
-  // lists hold GROUP ids; `count` = groups
-  auto expand = [&](const int* list, int count, const int* dcount, int mask, bool with_dyn,
-                    int slot_mode, bool dual_first) {
-    timed(PH_EXPAND, (double)count * 32 * (N + 1), [&] {
-      k_phase_expand<Model, CON><<<dim3(g128(count * 32), N + 1), 128, 0, st>>>(
-          P, list, count, dcount, mask, with_dyn, slot_mode, dual_first);
+  const int b0 = P.g0 * 32, b1 = std::min(B, (P.g0 + G) * 32);  // problems of this sub-batch
+
+  if (H->op == OP_SOLVE_PROLOGUE) {  // solver.cpp:417-430
+    if (TS::kStaged) {
+      const int mx = (int)H->smem_per_cta;
+      cudaFuncSetAttribute(k_phase_backward<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+      cudaFuncSetAttribute(k_phase_forward<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    }
+    cudaMemsetAsync(H->d_done, 0, sizeof(int), st);
+    timed(PH_INIT, b1 - b0, [&] { k_phase_init<Model, CON><<<G, 32, 0, st>>>(P); });
+    timed(PH_EXPAND, (double)G * 32 * (N + 1), [&] {  // with the OLD penalty (quirk Q3) ...
+      k_phase_expand<Model, CON><<<dim3(g128(G * 32), N + 1), 128, 0, st>>>(P, G);
     });
-  };
-  auto compact = [&](const int* in, int count, const int* dcount, int mask, int* out, int slot,
-                     int mask2, int slot2, int mask3, int slot3) {
-    timed(PH_COMPACT, count, [&] {
-      k_compact<<<1, 1024, 0, st>>>(in, count, dcount, P.flags, mask, out, P.counters, slot, mask2,
-                                    slot2, mask3, slot3, P.g0);
-    });
-  };
-  // TMA staging ring of the sequential sweeps (linalg.cuh): depth = knots in flight per CTA, as
-  // deep as shared memory allows with every CTA of the launch resident (<= kMaxStageDepth).
-  // cost weights staged in shared memory behind the ring (stage_weights) when they are small
+    if (CON)  // ... then reset
+      k_phase_set_rho<<<g128(b1 - b0), 128, 0, st>>>(P.rho, b0, b1, P.opts.penalty_initial);
+    return (int)cudaGetLastError();
+  }
+
+  // ---- OP_SOLVE_ITERATION
+  // TMA staging of the sequential sweeps (linalg.cuh): depth = knots in flight per CTA, as deep as
+  // shared memory allows with `per_sm` CTAs of the launch resident (<= kMaxStageDepth); the cost
+  // weights ride in shared memory behind the ring (stage_weights) when they are small.
   const int wdoubles = (N + 1) * n + N * m;
   const int wcount = (TS::kStaged && wdoubles * 8 <= 16 * 1024) ? wdoubles : 0;
-  auto ring = [&](int ctas, int stage_rows, int* depth, bool weights) -> size_t {
-    if (!TS::kStaged) {
-      *depth = 0;
-      return 0;
-    }
-    const size_t wbytes = weights ? (size_t)wcount * 8 : 0;
-    const size_t stage_bytes = (size_t)stage_rows * 256;
-    const int per_sm = (ctas + H->num_sms - 1) / H->num_sms;
+  const size_t wbytes = (size_t)wcount * 8;
+  auto ring_depth = [&](int per_sm, size_t stage_bytes, size_t fixed) -> int {
     const size_t budget =
-        std::min<size_t>(H->smem_per_sm / std::max(per_sm, 1) - 1024, H->smem_per_cta) - 128 - wbytes;
-    *depth = (int)std::max<size_t>(2, std::min<size_t>(kMaxStageDepth, budget / stage_bytes));
-    return BulkRing::bytes(*depth, stage_rows * 32) + wbytes;
+        std::min<size_t>(H->smem_per_sm / std::max(per_sm, 1) - 1024, H->smem_per_cta) - fixed - wbytes;
+    return (int)std::max<size_t>(2, std::min<size_t>(kMaxStageDepth, budget / stage_bytes));
   };
-  if (TS::kStaged) {
-    const int mx = (int)H->smem_per_cta;
-    cudaFuncSetAttribute(k_phase_backward<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(k_phase_rollout<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(k_phase_lsupdate<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-  }
   const int zr = CON ? 2 * P.zrows : 0;  // dual record rows staged with the main rows
-  const int kRowsBackward = TS::kRowsBackwardKernel + zr;
-  const int kRowsRollout = TS::kRowsRoll + zr;
-  constexpr int kRowsDphi = TS::kRowsDphi;
-  // warps = candidate steps rolled out per group (1 = only the requested step)
-  auto rollout = [&](const int* list, int count, const int* dcount, int warps) {
-    int depth;
-    const size_t sm = ring(count, kRowsRollout, &depth, true);
-    timed(PH_ROLLOUT, (double)count * 32 * warps, [&] {
-      k_phase_rollout<Model, CON><<<count, 32 * warps, sm, st>>>(P, list, count, dcount, depth, wcount);
-    });
-  };
-  auto lsupdate = [&](const int* list, int count, const int* dcount, int warps) {
-    int depth;
-    const size_t sm = ring(count, kRowsDphi, &depth, false);
-    timed(PH_LSUPDATE, (double)count * 32, [&] {
-      k_phase_lsupdate<Model, CON><<<count, 32, sm, st>>>(P, list, count, dcount, depth, warps - 1);
-    });
-  };
-
-  // ---- prologue (solver.cpp:417-430)
-  const int b0 = P.g0 * 32, b1 = std::min(B, (P.g0 + G) * 32);  // problems of this sub-batch
-  timed(PH_INIT, b1 - b0, [&] { k_phase_init<Model, CON><<<G, 32, 0, st>>>(P); });
-  expand(nullptr, G, nullptr, 0, true, -1, false);  // with the OLD penalty (quirk Q3) ...
-  if (CON)  // ... then reset
-    k_phase_set_rho<<<g128(b1 - b0), 128, 0, st>>>(P.rho, b0, b1, P.opts.penalty_initial);
-  int* list_iter = P.list_iter;
-  int* list_iter_next = H->list_aux;
-  compact(nullptr, G, nullptr, TF_ACTIVE, list_iter, PC_ITER, 0, 0, 0, 0);
-  int count_iter = G;
-  const bool backtracking = P.opts.use_backtracking_linesearch != 0;
-  // candidate steps per round.  (Going wider in the late rounds that only serve the lanes that
-  // keep halving was measured and lost: nearly every group has such a lane, so a 16-warp tail
-  // round costs more issue slots than the round it saves -- 29.2 vs 21.9 ms of rollouts.)
-  const int spec_warps = (backtracking && P.nslots > 1) ? std::min(P.nslots, 16) : 1;
-  const int LS_MASK = TF_NEED_EVAL | TF_REROLL;
-
-  for (int iter = 0; iter < P.opts.iterations_max && count_iter > 0; ++iter) {
-    {
-      int depth;
-      const size_t sm = ring(count_iter, kRowsBackward, &depth, true);
-      timed(PH_BACKWARD, (double)count_iter * 32, [&] {
-        k_phase_backward<Model, CON><<<count_iter, 32, sm, st>>>(P, list_iter, count_iter, depth, wcount,
-                                                                 iter == 0);
-      });
+  {
+    int depth = 0;
+    size_t sm = 0;
+    if (TS::kStaged) {
+      const int rows = TS::kRowsBackwardKernel + zr;
+      // budget for every group of the HANDLE resident at once (other sub-batches' kernels share
+      // the SMs)
+      depth = ring_depth((P.Gtot + H->num_sms - 1) / H->num_sms, (size_t)rows * 256, 128);
+      sm = BulkRing::bytes(depth, rows * 32) + wbytes;
     }
-    int* cur = P.list_ls;
-    int* nxt = P.list_tmp;
-    compact(list_iter, count_iter, nullptr, LS_MASK, cur, PC_LS, TF_WANT_DERIV, PC_DERIV, TF_SPECULATE, PC_SPEC);
-    // round 1: the requested step (alpha0 = 1, with derivative) for every problem still searching,
-    // plus, for the backtracking search, the halvings it would try next.  The exact list length
-    // stays on the device (no host round trip); count_iter bounds the grid.
-    const int* dcount = P.counters + PC_LS;
-    rollout(cur, count_iter, dcount, spec_warps);
-    expand(cur, count_iter, dcount, TF_WANT_DERIV, true, -1, false);
-    lsupdate(cur, count_iter, dcount, spec_warps);
-    compact(cur, count_iter, dcount, LS_MASK, nxt, PC_LS, TF_WANT_DERIV, PC_DERIV, TF_SPECULATE, PC_SPEC);
-    readback();
-    if (err != cudaSuccess) return (int)err;
-    int count_ls = H->h_counters[PC_LS], count_deriv = H->h_counters[PC_DERIV],
-        count_spec = H->h_counters[PC_SPEC];
-    std::swap(cur, nxt);
-    while (count_ls > 0) {  // further rounds: cubic-first probe, zoom steps, re-rollouts, deeper halvings
-      const int warps = count_spec > 0 ? spec_warps : 1;
-      rollout(cur, count_ls, nullptr, warps);
-      if (count_deriv > 0) expand(cur, count_ls, nullptr, TF_WANT_DERIV, true, -1, false);
-      lsupdate(cur, count_ls, nullptr, warps);
-      compact(cur, count_ls, nullptr, LS_MASK, nxt, PC_LS, TF_WANT_DERIV, PC_DERIV, TF_SPECULATE, PC_SPEC);
-      readback();
-      if (err != cudaSuccess) return (int)err;
-      count_ls = H->h_counters[PC_LS];
-      count_deriv = H->h_counters[PC_DERIV];
-      count_spec = H->h_counters[PC_SPEC];
-      std::swap(cur, nxt);
-    }
-    if (backtracking) expand(list_iter, count_iter, nullptr, TF_REFRESH_DYN, true, -2, false);  // solver.cpp:256-262
-    timed(PH_CRITERIA, (double)count_iter * 32 * (N + 1), [&] {
-      k_phase_costate<Model, CON><<<dim3(g128(count_iter * 32), N + 1), 128, 0, st>>>(P, list_iter, count_iter);
-      k_phase_residual<Model, CON><<<dim3(g128(count_iter * 32), N + 1), 128, 0, st>>>(P, list_iter, count_iter);
-      k_phase_decide<CON><<<g128(count_iter * 32), 128, 0, st>>>(P, list_iter, count_iter);
+    timed(PH_BACKWARD, (double)G * 32, [&] {
+      k_phase_backward<Model, CON><<<G, 32, sm, st>>>(P, depth, wcount, H->iter == 0);
     });
-    H->launches[PH_CRITERIA] += 2;
-    if (CON) expand(list_iter, count_iter, nullptr, TF_REFRESH_GRAD, false, -1, true);  // solver.cpp:475-486
-    compact(list_iter, count_iter, nullptr, TF_ACTIVE, list_iter_next, PC_ITER, 0, 0, 0, 0);
-    readback();
-    if (err != cudaSuccess) return (int)err;
-    count_iter = H->h_counters[PC_ITER];
-    std::swap(list_iter, list_iter_next);
+  }
+  {
+    int depth = 0, rows = 0;
+    size_t sm = 0;
+    if (TS::kStaged) {
+      rows = std::max(TS::kRowsRoll + zr, TS::kRowsDphi);
+      depth = ring_depth((P.Gtot + H->num_sms - 1) / H->num_sms, (size_t)rows * 256, 256);
+      sm = BulkPipe::bytes(depth, rows * 32) + wbytes;
+    }
+    const int warps = std::max(1, std::min(H->fwd_warps, 8));
+    DeviceProblem Pf = P;
+    Pf.prof = H->profile ? H->d_prof : nullptr;
+    if (H->profile) cudaMemsetAsync(H->d_prof, 0, 8 * sizeof(unsigned long long), st);
+    const double ms_before = H->ms[PH_FORWARD];
+    timed(PH_FORWARD, (double)G * 32, [&] {
+      k_phase_forward<Model, CON><<<G, 32 * warps, sm, st>>>(Pf, depth, rows, wcount, H->d_done);
+    });
+    if (H->profile) {  // split the kernel's time by the in-kernel sub-phase clocks
+      unsigned long long ns[8];
+      cudaMemcpy(ns, H->d_prof, sizeof(ns), cudaMemcpyDeviceToHost);
+      const double tot = (double)(ns[0] + ns[1] + ns[2] + ns[3]);
+      const double ms = H->ms[PH_FORWARD] - ms_before;
+      for (int i = 0; i < 4; ++i) {
+        if (tot > 0) H->ms[PH_FWD_ROLLOUT + i] += ms * (double)ns[i] / tot;
+        H->launches[PH_FWD_ROLLOUT + i] += 1;
+      }
+    }
   }
   return (int)cudaGetLastError();
 }

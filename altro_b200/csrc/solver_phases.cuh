@@ -1,116 +1,27 @@
-// solver_phases.cuh -- the AL-iLQR iteration as a pipeline of phase kernels over compacted lists of
-// GROUPS (the production path; the single persistent kernel of solver_kernels.cuh stays as the
-// differential-testing twin: both must agree bit for bit).
+// solver_phases.cuh -- the AL-iLQR iteration as TWO kernels per iteration over the GROUPS of the
+// batch, with no host in the loop (the production path; the single thread-per-trajectory kernel of
+// solver_kernels.cuh stays as the differential-testing twin: both must agree bit for bit).
 //
-// A group is 32 consecutive problems = one warp = one stream of knot records (device_problem.h).
-//   * Every sequential sweep (backward Riccati, phi0 scan, rollout, d(phi) scan) is a kernel with
-//     one warp per group that streams the group's knot records through a shared-memory ring with
-//     TMA bulk copies (linalg.cuh, BulkRing): one cp.async.bulk per knot and contiguous range, a
-//     few knots ahead, instead of dozens of dependent 256-byte loads per knot.  The pipeline is
-//     HBM-bound (ncu r01 v2: 50-65 % of DRAM peak in every kernel at only 3.5 warps/SM), so what
-//     counts is bytes per knot and how fast a lone warp can stream them.
-//   * Lists are compacted per GROUP (a group stays listed while any of its lanes needs the
-//     phase); lanes that do not need it are predicated off.  Records are fetched whole anyway.
-//   * Everything that is independent per knot -- dynamics Jacobians (the transcendental-heavy
-//     part), projected duals, cost gradients, costates, residuals -- runs one thread per
-//     (problem, knot).
-//   * Backtracking line search: the first rollout round evaluates the requested step AND the
-//     halvings that SimpleBacktracking (linesearch.cpp:385-412) would try next, one warp per
-//     candidate in the SAME CTA, all fed from one staged copy of the knot data; only slot 0 and
-//     the first `nstore` halvings write their trajectory, the others return the merit value
-//     alone (an accepted one is rolled out once more, TF_REROLL).  The state machine is then fed
-//     the values in the order the reference would have evaluated them, so decisions and the
-//     reported evaluation counts are those of the sequential search.
-//   * The redundant alpha = 0 rollout of ForwardPass (solver.cpp:241, ~40 % of the reference's
-//     merit evaluations) is replaced by a linear scan that provably reproduces it
-//     (TrajSolver::phi0_step).
+// A group is 32 consecutive problems = one stream of knot records (device_problem.h).  Groups never
+// exchange data, so every kernel is launched over all groups of a sub-batch and a CTA whose
+// problems have all stopped returns at once: no work lists, no compaction, no counter read-back.
+//   k_phase_backward  one warp per group: CalcExpansions + the Riccati sweep + the alpha = 0 merit
+//                     evaluation of ForwardPass as a linear scan (solver.cpp:241 re-simulates the
+//                     accepted trajectory, ~40 % of the reference's merit evaluations; the scan
+//                     provably reproduces it, TrajSolver::phi0_step), streaming the knot records
+//                     through a shared-memory ring of TMA bulk copies (linalg.cuh, BulkRing).
+//   k_phase_forward   one CTA per group: the whole line search (rounds of speculative rollouts,
+//                     knot-parallel expansion, d(phi) scan, state machines), then costates,
+//                     residuals, the convergence / AL decision and the post-update expansion.
+// The host enqueues iterations back to back on the sub-batch's stream and looks at a stop counter
+// two iterations late (an asynchronous 4-byte copy), so the GPU never waits for the host.
 // Decisions (line search, dual/penalty update, convergence) are identical to the reference.
 #pragma once
 #include "solver_kernels.cuh"
 
 namespace altro_b200 {
 
-// ------------------------------------------------------------------ list compaction (groups)
-// Ordered compaction of the groups in[0..count) that have at least one lane with
-// (flags & mask) != 0 into out; writes the number kept to counters[slot], and the number of kept
-// groups that also have such a lane with mask2 / mask3 to counters[slot2] / counters[slot3].
-// `count` bounds the input length; `dcount` (optional) is its exact device-side value.  One CTA.
-static __global__ void __launch_bounds__(1024) k_compact(const int* __restrict__ in, int count,
-                                                  const int* dcount,
-                                                  const int* __restrict__ flags, int mask,
-                                                  int* __restrict__ out, int* counters, int slot,
-                                                  int mask2, int slot2, int mask3, int slot3,
-                                                  int gbase) {
-  __shared__ int warp_tot[32], warp_tot2[32], warp_tot3[32];
-  __shared__ int base_s, base2_s, base3_s;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  // the input length may live in the very counter this kernel rewrites at the end, hence read
-  // before the first barrier
-  if (dcount) count = min(count, *dcount);
-  if (tid == 0) {
-    base_s = 0;
-    base2_s = 0;
-    base3_s = 0;
-  }
-  __syncthreads();
-  for (int start = 0; start < count; start += 1024) {
-    const int i = start + tid;
-    int g = -1, keep = 0, keep2 = 0, keep3 = 0;
-    if (i < count) {
-      g = in ? in[i] : gbase + i;
-      int f = 0;  // OR of the flags of the lanes that have `mask`
-      const int4* fp = reinterpret_cast<const int4*>(flags + (long)g * 32);
-#pragma unroll
-      for (int l = 0; l < 8; ++l) {
-        const int4 v = fp[l];
-        f |= (v.x & mask) ? v.x : 0;
-        f |= (v.y & mask) ? v.y : 0;
-        f |= (v.z & mask) ? v.z : 0;
-        f |= (v.w & mask) ? v.w : 0;
-      }
-      keep = (f & mask) != 0;
-      keep2 = keep && mask2 && (f & mask2) != 0;
-      keep3 = keep && mask3 && (f & mask3) != 0;
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    const unsigned bal2 = __ballot_sync(0xffffffffu, keep2);
-    const unsigned bal3 = __ballot_sync(0xffffffffu, keep3);
-    if (lane == 0) {
-      warp_tot[wid] = __popc(bal);
-      warp_tot2[wid] = __popc(bal2);
-      warp_tot3[wid] = __popc(bal3);
-    }
-    __syncthreads();
-    int off = base_s;
-    for (int w = 0; w < wid; ++w) off += warp_tot[w];
-    if (keep) out[off + __popc(bal & ((1u << lane) - 1u))] = g;
-    __syncthreads();
-    if (tid == 0) {
-      int t = 0, t2 = 0, t3 = 0;
-      for (int w = 0; w < 32; ++w) {
-        t += warp_tot[w];
-        t2 += warp_tot2[w];
-        t3 += warp_tot3[w];
-      }
-      base_s += t;
-      base2_s += t2;
-      base3_s += t3;
-    }
-    __syncthreads();
-  }
-  if (tid == 0) {
-    counters[slot] = base_s;
-    if (mask2) counters[slot2] = base2_s;
-    if (mask3) counters[slot3] = base3_s;
-  }
-}
-
 // ------------------------------------------------------------------ phase kernels
-// Every list kernel takes an upper bound `count` (sizes the grid) and an optional device-side
-// exact count, so a freshly compacted list can be consumed without a host round trip.
-__device__ __forceinline__ int list_count(int count, const int* dcount) {
-  return dcount ? min(count, *dcount) : count;
-}
 
 __device__ __forceinline__ LsOptions ls_options(const DevOptions& o) {
   LsOptions lo;
@@ -152,28 +63,20 @@ __global__ void __launch_bounds__(32) k_phase_init(const __grid_constant__ Devic
   P.sel[b] = -1;
 }
 
-// Expansion, one thread per (problem of a listed group, knot).  `mask`: only problems whose flags
-// have one of these bits are processed (0 = all).  with_dyn: also recompute [A B].  slot_mode: -1
-// read the main trajectory, >= 0 that candidate slot, -2 the slot recorded in sel[b].
-// dual_first: apply the dual update z <- Pi(z_est) of this knot before recomputing the projected
-// duals.  The prologue calls this BEFORE the penalty reset, which reproduces quirk Q3 (gradient
-// with the old rho, solver.cpp:424-430).
+// Expansion of the Solve() prologue (solver.cpp:425-428), one thread per (problem, knot): [A B],
+// projected duals, cost gradients at the initial rollout.  Launched BEFORE the penalty reset,
+// which reproduces quirk Q3 (gradient with the old rho, solver.cpp:424-430).
 template <class Model, int CON>
-__global__ void __launch_bounds__(128) k_phase_expand(const __grid_constant__ DeviceProblem P, const int* list,
-                                                      int count, const int* dcount, int mask,
-                                                      bool with_dyn, int slot_mode,
-                                                      bool dual_first) {
+__global__ void __launch_bounds__(128) k_phase_expand(const __grid_constant__ DeviceProblem P, int count) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int k = blockIdx.y;
   const int gi = t >> 5;
-  if (gi >= list_count(count, dcount)) return;
-  const int b = (list ? list[gi] : P.g0 + gi) * 32 + (t & 31);
+  if (gi >= count) return;
+  const int b = (P.g0 + gi) * 32 + (t & 31);
   if (b >= P.B) return;
-  if (mask && !(P.flags[b] & mask)) return;
   TrajSolver<Model, CON> s(P, b);
   s.rho = CON ? P.rho[b] : 1.0;
-  const int slot = (slot_mode == -2) ? P.sel[b] : slot_mode;
-  s.phase_expand_knot(k, with_dyn, slot, dual_first);
+  s.phase_expand_knot(k, true, -1, false);
 }
 
 // penalty reset at the end of the prologue (SetPenalty(penalty_initial), solver.cpp:429)
@@ -183,17 +86,17 @@ static __global__ void k_phase_set_rho(double* rho, int b0, int b1, double value
 }
 
 // K1: CalcExpansions + BackwardPass + the alpha = 0 half of ForwardPass (solver.cpp:448-450,
-// :241-245) and the start of the line search.  One warp per listed group.
+// :241-245) and the start of the line search.  One warp per group of the sub-batch.
 template <class Model, int CON>
-__global__ void __launch_bounds__(32) k_phase_backward(const __grid_constant__ DeviceProblem P, const int* list,
-                                                       int count, int depth, int wcount, int first) {
+__global__ void __launch_bounds__(32) k_phase_backward(const __grid_constant__ DeviceProblem P, int depth,
+                                                       int wcount, int first) {
   using TS = TrajSolver<Model, CON>;
   constexpr int n = Model::n, m = Model::m;
-  if ((int)blockIdx.x >= count) return;
-  const int g = list[blockIdx.x];
+  const int g = P.g0 + blockIdx.x;
   const int lane = threadIdx.x;
   const int b = g * 32 + lane;
   const bool active = b < P.B && (P.flags[b] & TF_ACTIVE);
+  if (!__any_sync(0xffffffffu, active)) return;  // every problem of the group has stopped
   TS s(P, active ? b : g * 32);
   s.rho = (CON && active) ? P.rho[b] : 1.0;
   double phi0 = 0.0, dphi0 = 0.0;
@@ -362,354 +265,475 @@ __global__ void __launch_bounds__(32) k_phase_backward(const __grid_constant__ D
   P.flags[b] = f;
 }
 
-// K2: rollouts.  One CTA per listed group, one warp per candidate step of the group's problems:
-// warp 0 rolls out the step the state machine asked for (alpha_eval) into the main trajectory;
-// warps j >= 1 (launched in speculative rounds) roll out the halving alpha_bt * 2^-(j-1) for the
-// lanes flagged TF_SPECULATE -- into candidate slot j-1 when j <= nstore, merit value only
-// otherwise.  All warps consume the SAME staged copy of the knot data [xbar ubar q r c K d].
+// Sub-phases of k_phase_forward, timed per CTA with %globaltimer when DeviceProblem::prof is set
+// (profile mode): prof[s] accumulates the nanoseconds thread 0 of every CTA spent in sub-phase s,
+// prof[FS_COUNT] the CTAs that did work.
+enum FwdSub { FS_ROLLOUT = 0, FS_EXPAND = 1, FS_DPHI_LS = 2, FS_CRITERIA = 3, FS_COUNT = 4 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Work items of the knot-parallel sub-phases of k_phase_forward: one item per (flagged lane of
+// the group, knot).  Consecutive threads take different lanes of the same knot, so a warp's loads
+// and stores stay inside one or two 256-byte rows of the knot record.
+template <class Fn>
+__device__ __forceinline__ void for_knot_items(unsigned lanemask, int g, int knots, Fn&& fn) {
+  const int nl = __popc(lanemask);
+  if (nl == 0) return;
+  const int items = nl * knots;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int k = i / nl;
+    const int l = __fns(lanemask, 0, i % nl + 1);  // the (i % nl)-th flagged lane
+    fn(g * 32 + l, k);
+  }
+}
+
+// K2: everything of one iLQR iteration after the backward pass -- ForwardPass (solver.cpp:237-271)
+// with the whole line search (linesearch.cpp:37-412), Stationarity / Feasibility / CopyTrajectory
+// (:207-231, :148-157), the convergence test and the dual / penalty update (:459-489) -- for ONE
+// group of 32 problems per CTA, with no host in the loop.  The CTA iterates line-search ROUNDS
+// until every lane's state machine is done:
+//   rollout pass    warp 0 rolls out the step each lane's machine asked for (alpha_eval) into the
+//                   working trajectory x_, u_; warps >= 1 roll out, for the lanes whose search is
+//                   (or is about to be) backtracking, the halvings SimpleBacktracking would try
+//                   next (linesearch.cpp:385-412) -- the (lane, halving) pairs are packed densely
+//                   over their threads; halvings <= nstore keep their trajectory in a candidate
+//                   slot, deeper ones return the merit value only (an accepted one is rolled out
+//                   again, TF_REROLL).  All warps consume ONE staged copy of the knot rows
+//                   [xbar ubar q r c K d] through a full/empty mbarrier pipeline (BulkPipe): no
+//                   CTA barrier per knot, warps drift up to depth - 1 knots apart.
+//   expansion       knot-parallel over the whole CTA: [A B], projected duals, lx, lu of the trial
+//                   point of the lanes that asked for the derivative (solver.cpp:303-312).
+//   d(phi) + update warp 0: the phi' recurrence (solver.cpp:306-315) as a staged scan, then every
+//                   lane's LsMachine is fed the value of its request and, while it keeps
+//                   backtracking, the precomputed halvings in the order the reference would have
+//                   evaluated them; feeding stops at the first accept, so decisions and evaluation
+//                   counts are those of the sequential search.
+// then, still in the same launch: the post-search expansion of an accepted backtracking step
+// (:256-262), costates, residuals, the decision, and the expansion after a dual update (:483-486).
+// active_out: incremented by the number of problems of the group that stopped in this iteration.
 template <class Model, int CON>
-__global__ void __launch_bounds__(32 * 16) k_phase_rollout(const __grid_constant__ DeviceProblem P, const int* list,
-                                                           int count, const int* dcount, int depth,
-                                                           int wcount) {
+__global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_forward(const __grid_constant__ DeviceProblem P, int depth,
+                                                          int stage_rows, int wcount, int* done_out) {
   using TS = TrajSolver<Model, CON>;
   constexpr int n = Model::n, m = Model::m;
-  if ((int)blockIdx.x >= list_count(count, dcount)) return;
-  const int g = list[blockIdx.x];
-  // Work assignment.  Warp 0: thread = problem lane, candidate 0 (the requested step).  Warps
-  // >= 1: the (lane, halving) pairs of the lanes flagged TF_SPECULATE, PACKED densely over the
-  // threads -- in the first round every lane speculates and warp j is simply halving j, but in the
-  // later rounds only a few lanes per group still need halvings and all their candidates fit in
-  // one or two warps instead of keeping nslots-1 mostly idle warps busy for the whole sweep.
-  // Pair p -> lane rank p % nneedy (consecutive threads = different lanes: conflict-free smem
-  // columns, neighbouring global stores), halving p / nneedy + 1.
-  int lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
-  const int nspec = (int)(blockDim.x >> 5) - 1;
-  bool need;
-  {
-    const int bl = g * 32 + lane;
-    const int fl = bl < P.B ? P.flags[bl] : 0;
-    const unsigned needy = __ballot_sync(0xffffffffu, (fl & TF_NEED_EVAL) && (fl & TF_SPECULATE));
-    if (slot == 0) {
+  constexpr unsigned kAll = 0xffffffffu;
+  const int g = P.g0 + blockIdx.x;
+  const int tid = threadIdx.x, lid = tid & 31, wid = tid >> 5;
+  // speculative candidates per round: one warp each, at most what SetSpeculation asked for (extra
+  // warps only serve the knot-parallel sub-phases)
+  const int nspec = min((int)(blockDim.x >> 5) - 1, P.nslots - 1);
+  const int bl = g * 32 + lid;                   // the problem this thread's lane index names
+  const bool valid = bl < P.B;
+  int fl = valid ? P.flags[bl] : 0;
+  // every warp reads the same 32 flags before anyone writes them: CTA-uniform
+  const unsigned act_mask = __ballot_sync(kAll, (fl & TF_ACTIVE) != 0);
+  if (!act_mask) return;
+
+  BulkPipe pipe;
+  pipe.setup(altro_smem, depth, stage_rows * 32);
+  double* wsm = reinterpret_cast<double*>(altro_smem + BulkPipe::bytes(depth, stage_rows * 32));
+  const int nq = (P.N + 1) * n, nr = P.N * m;
+  if (wcount > 0) {
+    for (int i = tid; i < nq; i += blockDim.x) wsm[i] = P.Qd[i];
+    for (int i = tid; i < nr; i += blockDim.x) wsm[nq + i] = P.Rd[i];
+  }
+  // cost weights of the solver objects below come from shared memory when they were staged
+  auto weights = [&](TS& s) {
+    if (wcount > 0) {
+      s.Qd = wsm;
+      s.Rd = wsm + nq;
+    }
+  };
+  unsigned long long t_prev = 0;
+  const bool prof = P.prof != nullptr && tid == 0;
+  if (prof) t_prev = global_ns();
+  auto tick = [&](int sub) {
+    if (prof) {
+      const unsigned long long t = global_ns();
+      atomicAdd(P.prof + sub, t - t_prev);
+      t_prev = t;
+    }
+  };
+  const int zr = CON ? 2 * P.zrows : 0;
+  const double* rec = P.xbar + (long)g * P.GS;  // row 0 of the group's knot-0 record
+  const double* zrec = CON ? P.z + (long)g * P.GSz : nullptr;
+  const LsOptions lo = ls_options(P.opts);
+  bool pipe_used = false;
+  __syncthreads();
+
+  // ================================================================= line-search rounds
+  for (;;) {
+    fl = valid ? P.flags[bl] : 0;
+    const unsigned pend = __ballot_sync(kAll, (fl & (TF_NEED_EVAL | TF_REROLL)) != 0);
+    if (!pend) break;
+    const unsigned needy = __ballot_sync(kAll, (fl & TF_NEED_EVAL) && (fl & TF_SPECULATE));
+    const unsigned dmask = __ballot_sync(kAll, (fl & TF_WANT_DERIV) != 0);
+    const int nneedy = nspec > 0 ? __popc(needy) : 0;
+
+    // ---- rollout pass.  Warp 0: thread = problem lane, candidate 0 (the requested step).  Warps
+    // >= 1: pair p -> lane rank p % nneedy (consecutive threads = different lanes: conflict-free
+    // shared-memory columns, neighbouring global stores), halving p / nneedy + 1.
+    int lane = lid, slot = 0;
+    bool need;
+    if (wid == 0) {
       need = (fl & (TF_NEED_EVAL | TF_REROLL)) != 0;
     } else {
-      const int nneedy = __popc(needy);
-      const int p = (slot - 1) * 32 + lane;
-      need = nneedy > 0 && p < nneedy * nspec;
+      const int p = (wid - 1) * 32 + lid;
+      need = p < nneedy * nspec;
       if (need) {
-        lane = __fns(needy, 0, p % nneedy + 1);  // the (p % nneedy)-th flagged lane
+        lane = __fns(needy, 0, p % nneedy + 1);
         slot = p / nneedy + 1;
       }
     }
-  }
-  const int b = g * 32 + lane;
-  TS s(P, need ? b : g * 32);
-  s.rho = (CON && need) ? P.rho[b] : 1.0;
-  double alpha = 0.0;
-  double *xo = nullptr, *uo = nullptr;
-  long so = 0;
-  if (need) {
-    if (slot == 0) {
-      alpha = P.alpha_eval[b];
-      xo = s.xw(-1);
-      uo = s.uw(-1);
-      so = s.sw(-1);
-    } else {
-      alpha = ldexp(P.alpha_bt[b], -(slot - 1));  // halving spec_base + slot - 1
-      if (slot <= P.nstore) {
-        xo = s.xw(slot - 1);
-        uo = s.uw(slot - 1);
-        so = s.sw(slot - 1);
-      }
-    }
-  }
-  double phi = 0.0;
-  if constexpr (TS::kStaged) {
-    constexpr int kRows = TS::kRowsRoll;  // [xbar ubar q r c K d] (+ the dual record)
-    const int zr = CON ? 2 * P.zrows : 0;
-    BulkRing ring;
-    ring.init(altro_smem, depth, (kRows + zr) * 32, threadIdx.x == 0);
-    stage_weights(s, P, reinterpret_cast<double*>(altro_smem + BulkRing::bytes(depth, (kRows + zr) * 32)), wcount);
-    __syncthreads();
-    const double* rec = P.xbar + (long)g * P.GS;
-    const double* zrec = CON ? P.z + (long)g * P.GSz : nullptr;
-    auto fetch = [&](int k, int st) {
-      ring.expect(st, (kRows + zr) * 256);
-      ring.copy(st, 0, rec + (long)k * P.R, kRows * 256);
-      if (zr) ring.copy(st, kRows, zrec + (long)k * P.Rz, zr * 256);
-    };
-    if (threadIdx.x == 0)
-      for (int j = 0; j < depth; ++j)
-        if (j < P.N) fetch(j, j);
-    double x[n];
-    if (need) load_block<n>(s.G(P.x0, n), 0, 0, x);
-    for (int k = 0; k < P.N; ++k) {
-      const double* st = ring.wait();
-      double xb[n], ub[m], q[n], r[m], K[m * n], d[m], cval = 0.0;
-      if (need) {
-        unstage_block<n>(st, TS::rXbar, lane, xb);
-        unstage_block<m>(st, TS::rUbar, lane, ub);
-        unstage_block<n>(st, TS::rQ, lane, q);
-        unstage_block<m>(st, TS::rR, lane, r);
-        cval = st[TS::rC * 32 + lane];
-        unstage_block<m * n>(st, TS::rK, lane, K);
-        unstage_block<m>(st, TS::rD, lane, d);
-      }
-      if (zr) s.zstage = st + kRows * 32 + lane;
-      if (need) s.rollout_step(k, alpha, xb, ub, K, d, q, r, cval, x, xo, uo, so, phi);
-      s.zstage = nullptr;
+    const int np = 1 + (nneedy * nspec + 31) / 32;  // warps that take part in the pass
+    const bool warp_in = wid < np;
+    if (TS::kStaged) {
+      if (tid == 0) pipe.begin_pass(np, pipe_used);
+      pipe_used = true;
       __syncthreads();
-      if (threadIdx.x == 0 && k + depth < P.N) fetch(k + depth, ring.s);
-      ring.advance();
     }
-    if (need) s.rollout_terminal(x, xo, so, phi);
-  } else {
-    if (need) phi = s.phase_rollout(alpha, xo, uo, so);
-  }
-  if (need) {
-    if (slot == 0)
-      P.phi_eval[b] = phi;
-    else
-      P.phi_s[(long)min(P.spec_base[b] + slot - 1, kMaxHalvings) * P.Bp + b] = phi;
-  }
-}
+    if (warp_in) {
+      const int b = g * 32 + lane;
+      TS s(P, need ? b : g * 32);
+      weights(s);
+      s.rho = (CON && need) ? P.rho[b] : 1.0;
+      double alpha = 0.0;
+      double *xo = nullptr, *uo = nullptr;
+      long so = 0;
+      if (need) {
+        if (slot == 0) {
+          alpha = P.alpha_eval[b];
+          xo = s.xw(-1);
+          uo = s.uw(-1);
+          so = s.sw(-1);
+        } else {
+          alpha = ldexp(P.alpha_bt[b], -(slot - 1));  // halving spec_base + slot - 1
+          if (slot <= P.nstore) {
+            xo = s.xw(slot - 1);
+            uo = s.uw(slot - 1);
+            so = s.sw(slot - 1);
+          }
+        }
+      }
+      double phi = 0.0;
+      if constexpr (TS::kStaged) {
+        constexpr int kRows = TS::kRowsRoll;  // [xbar ubar q r c K d] (+ the dual record)
+        auto fetch = [&](int k) {
+          const int st = pipe.acquire(k, (unsigned)(kRows + zr) * 256u);
+          pipe.copy(st, 0, rec + (long)k * P.R, kRows * 256);
+          if (zr) pipe.copy(st, kRows, zrec + (long)k * P.Rz, zr * 256);
+        };
+        if (tid == 0)
+          for (int j = 0; j < depth && j < P.N; ++j) fetch(j);
+        double x[n];
+        if (need) load_block<n>(s.G(P.x0, n), 0, 0, x);
+        for (int k = 0; k < P.N; ++k) {
+          const double* st = pipe.wait(k);
+          double xb[n], ub[m], q[n], r[m], K[m * n], d[m], cval = 0.0;
+          if (need) {
+            unstage_block<n>(st, TS::rXbar, lane, xb);
+            unstage_block<m>(st, TS::rUbar, lane, ub);
+            unstage_block<n>(st, TS::rQ, lane, q);
+            unstage_block<m>(st, TS::rR, lane, r);
+            cval = st[TS::rC * 32 + lane];
+            unstage_block<m * n>(st, TS::rK, lane, K);
+            unstage_block<m>(st, TS::rD, lane, d);
+          }
+          if (zr) s.zstage = st + kRows * 32 + lane;
+          if (need) s.rollout_step(k, alpha, xb, ub, K, d, q, r, cval, x, xo, uo, so, phi);
+          s.zstage = nullptr;
+          // release only after the step consumed what was read from the stage (see BulkRing)
+          pipe.release(k, lid);
+          // the refill runs one knot behind warp 0, so warp 0 never waits for the knot it just
+          // released to be released by the slower warps
+          if (tid == 0 && k >= 1 && k - 1 + depth < P.N) fetch(k - 1 + depth);
+        }
+        if (need) s.rollout_terminal(x, xo, so, phi);
+      } else {
+        if (need) phi = s.phase_rollout(alpha, xo, uo, so);
+      }
+      if (need) {
+        if (slot == 0)
+          P.phi_eval[b] = phi;
+        else
+          P.phi_s[(long)min(P.spec_base[b] + slot - 1, kMaxHalvings) * P.Bp + b] = phi;
+      }
+    }
+    __syncthreads();
+    tick(FS_ROLLOUT);
 
-// K4: d(phi) scan (when requested) + the line-search state machine, one warp per listed group.
-// The machine is fed the value of the requested step and then, while it keeps backtracking, the
-// precomputed merit values of the halvings in the order the reference would have evaluated
-// them; feeding stops at the first one it accepts, so the decisions (and the reported evaluation
-// count) are those of the sequential search.
-template <class Model, int CON>
-__global__ void __launch_bounds__(32) k_phase_lsupdate(const __grid_constant__ DeviceProblem P, const int* list,
-                                                       int count, const int* dcount, int depth,
-                                                       int nspec) {
-  using TS = TrajSolver<Model, CON>;
-  constexpr int n = Model::n, m = Model::m;
-  if ((int)blockIdx.x >= list_count(count, dcount)) return;
-  const int g = list[blockIdx.x];
-  const int lane = threadIdx.x;
-  const int b = g * 32 + lane;
-  int f = b < P.B ? P.flags[b] : 0;
-  const bool pending = (f & (TF_NEED_EVAL | TF_REROLL)) != 0;
-  const bool had_deriv = (f & TF_NEED_EVAL) && (f & TF_WANT_DERIV) && !(f & TF_REROLL);
-  double dphi = 0.0;
-  if (__any_sync(0xffffffffu, had_deriv)) {
-    TS s(P, had_deriv ? b : g * 32);
-    if constexpr (TS::kStaged) {
-      // stage contents: [K d] [J] [lx lu]
-      constexpr int kV = TS::kV;
-      constexpr int kRows1 = m * n + m;
-      BulkRing ring;
-      ring.init(altro_smem, depth, TS::kRowsDphi * 32, lane == 0);
-      __syncwarp();
-      const double* rec = P.xbar + (long)g * P.GS;
-      auto fetch = [&](int k, int st) {
-        ring.expect(st, TS::kRowsDphi * 256);
-        ring.copy(st, 0, rec + (long)k * P.R + TS::rK * 32, kRows1 * 256);
-        ring.copy(st, kRows1, rec + (long)k * P.R + TS::rA * 32, kV * 256);
-        ring.copy(st, kRows1 + kV, rec + (long)k * P.R + TS::rLx * 32, (n + m) * 256);
-      };
-      if (lane == 0)
-        for (int j = 0; j < depth; ++j)
-          if (j < P.N) fetch(j, j);
-      double dxda[n];
+    // ---- expansion of the trial point of the lanes that asked for the derivative
+    if (dmask) {
+      for_knot_items(dmask, g, P.N + 1, [&](int b, int k) {
+        TS s(P, b);
+        weights(s);
+        s.rho = CON ? P.rho[b] : 1.0;
+        s.phase_expand_knot(k, true, -1, false);
+      });
+      // [J] [lx lu] were written through the generic proxy; the d(phi) scan reads them with bulk
+      // copies (async proxy)
+      __threadfence();
+      asm volatile("fence.proxy.async;" ::: "memory");
+      __syncthreads();
+    }
+    tick(FS_EXPAND);
+
+    // ---- d(phi) scan + line-search machines: warp 0, lane = problem
+    if (wid == 0) {
+      const int b = bl;
+      int f = fl;
+      const bool pending = (f & (TF_NEED_EVAL | TF_REROLL)) != 0;
+      const bool had_deriv = (f & TF_NEED_EVAL) && (f & TF_WANT_DERIV) && !(f & TF_REROLL);
+      double dphi = 0.0;
+      if (dmask) {
+        TS s(P, had_deriv ? b : g * 32);
+        if constexpr (TS::kStaged) {
+          // stage contents: [K d] [J] [lx lu]
+          constexpr int kV = TS::kV;
+          constexpr int kRows1 = m * n + m;
+          if (lid == 0) pipe.begin_pass(1, true);
+          __syncwarp();
+          auto fetch = [&](int k) {
+            const int st = pipe.acquire(k, (unsigned)TS::kRowsDphi * 256u);
+            pipe.copy(st, 0, rec + (long)k * P.R + TS::rK * 32, kRows1 * 256);
+            pipe.copy(st, kRows1, rec + (long)k * P.R + TS::rA * 32, kV * 256);
+            pipe.copy(st, kRows1 + kV, rec + (long)k * P.R + TS::rLx * 32, (n + m) * 256);
+          };
+          if (lid == 0)
+            for (int j = 0; j < depth && j < P.N; ++j) fetch(j);
+          double dxda[n];
 #pragma unroll
-      for (int i = 0; i < n; ++i) dxda[i] = 0.0;
-      for (int k = 0; k < P.N; ++k) {
-        const double* st = ring.wait();
-        double K[m * n], d[m], A[n * n], Bm[n * m], lx[n], lu[m];
-        if (had_deriv) {
-          unstage_block<m * n>(st, 0, lane, K);
-          unstage_block<m>(st, m * n, lane, d);
-          s.unstage_jac(st, kRows1, lane, A, Bm);
-          unstage_block<n>(st, kRows1 + kV, lane, lx);
-          unstage_block<m>(st, kRows1 + kV + n, lane, lu);
-        }
-        if (had_deriv) s.dphi_step(K, d, A, Bm, lx, lu, dxda, dphi);
-        __syncwarp();
-        if (lane == 0 && k + depth < P.N) fetch(k + depth, ring.s);
-        ring.advance();
-      }
-      if (had_deriv) dphi = s.dphi_terminal(dxda, dphi);
-    } else {
-      if (had_deriv) dphi = s.phase_dphi_scan();
-    }
-  }
-  if (!pending) return;
-  const LsOptions lo = ls_options(P.opts);
-  if (f & TF_REROLL) {
-    // the accepted candidate has just been rolled out again into x_, u_; it still needs its
-    // expansion (TF_REFRESH_DYN stays set)
-    f &= ~(TF_REROLL | TF_NEED_EVAL | TF_WANT_DERIV | TF_SPECULATE);
-    P.sel[b] = -1;
-    P.flags[b] = f;
-    return;
-  }
-  LsMachine ls = P.ls[b];
-  bool last_had_deriv = had_deriv;
-  // nspec: halvings the round just executed rolled out besides the request (warps - 1)
-  int known = P.spec_known[b];     // halvings 1..known have their merit value in phi_s
-  const int base = P.spec_base[b];
-  const bool was_backtrack = ls.phase == LsMachine::P_BACKTRACK;
-  int fed = 1, winner = 0;         // winner: halving index the search returned (0: the request)
-  ls.update(lo, P.phi_eval[b], dphi);
-  if (f & TF_SPECULATE) {
-    // this round produced halvings base .. base+nspec-1; the request itself was halving base-1
-    // when the machine was already backtracking
-    if (was_backtrack && base >= 2) P.phi_s[(long)min(base - 1, kMaxHalvings) * P.Bp + b] = P.phi_eval[b];
-    known = min(base + nspec - 1, kMaxHalvings);
-  }
-  // feed the precomputed halvings in the order the sequential search would evaluate them
-  while (!ls.done() && ls.phase == LsMachine::P_BACKTRACK) {
-    // halving index of the step the machine asks for: alpha = alpha0 * 2^-j
-    int j = 1;
-    double cand = ls.alpha0 * lo.beta_decrease;
-    while (j <= known && cand != ls.alpha) {
-      cand *= lo.beta_decrease;
-      ++j;
-    }
-    if (j > known) break;  // not precomputed: needs another round
-    ls.update(lo, P.phi_s[(long)j * P.Bp + b], 0.0);
-    last_had_deriv = false;
-    winner = j;
-    fed += 1;
-  }
-  if (!ls.done()) winner = 0;
-  P.merit_evals[b] += fed;
-  P.spec_known[b] = known;
-  f &= ~(TF_NEED_EVAL | TF_WANT_DERIV | TF_SPECULATE);
-  if (!ls.done()) {
-    f |= TF_NEED_EVAL;
-    if (ls.want_derivative()) f |= TF_WANT_DERIV;
-    P.alpha_eval[b] = ls.alpha;
-    if (lo.use_backtracking && P.nslots > 1) {
-      if (ls.phase == LsMachine::P_BACKTRACK) {
-        // ran out of precomputed halvings: the request is halving known+1, speculate the next ones
-        f |= TF_SPECULATE;
-        P.spec_base[b] = known + 2;
-        P.alpha_bt[b] = ls.alpha * lo.beta_decrease;
-      } else if (ls.phase == LsMachine::P_CUBIC_FIRST) {
-        // the cubic-first probe is next (linesearch.cpp:96-127).  If it is rejected the search
-        // backtracks through the halvings; when none of the known ones passes the Armijo test the
-        // ones after them ride along with the probe
-        bool any = false;
-        double cand = ls.alpha0;
-        for (int j = 1; j <= known; ++j) {
-          cand *= lo.beta_decrease;
-          any = any || (P.phi_s[(long)j * P.Bp + b] <= ls.phi0 + lo.c1 * cand * ls.dphi0);
-        }
-        if (!any && known + 1 <= kMaxHalvings) {
-          f |= TF_SPECULATE;
-          P.spec_base[b] = known + 1;
-          P.alpha_bt[b] = cand * lo.beta_decrease;
+          for (int i = 0; i < n; ++i) dxda[i] = 0.0;
+          for (int k = 0; k < P.N; ++k) {
+            const double* st = pipe.wait(k);
+            double K[m * n], d[m], A[n * n], Bm[n * m], lx[n], lu[m];
+            if (had_deriv) {
+              unstage_block<m * n>(st, 0, lid, K);
+              unstage_block<m>(st, m * n, lid, d);
+              s.unstage_jac(st, kRows1, lid, A, Bm);
+              unstage_block<n>(st, kRows1 + kV, lid, lx);
+              unstage_block<m>(st, kRows1 + kV + n, lid, lu);
+              s.dphi_step(K, d, A, Bm, lx, lu, dxda, dphi);
+            }
+            pipe.release(k, lid);
+            if (lid == 0 && k >= 1 && k - 1 + depth < P.N) fetch(k - 1 + depth);
+          }
+          if (had_deriv) dphi = s.dphi_terminal(dxda, dphi);
+        } else {
+          if (had_deriv) dphi = s.phase_dphi_scan();
         }
       }
-    }
-  } else {
-    const double alpha = ls.alpha;
-    P.alpha_eval[b] = alpha;
-    if (ls.n_iters > 0) P.phi[b] = ls.phi;
-    if (P.ls_hist) {
-      int bin = 17;
-      if (!(ls.status == LS_MINIMUM_FOUND || ls.status == LS_HIT_MAX_STEPSIZE)) bin = 18;
-      else if (winner > 0) bin = winner < 15 ? winner : 15;
-      else if (alpha == ls.alpha0) bin = 0;
-      else if (lo.use_backtracking && last_had_deriv) bin = 16;
-      else if (lo.use_backtracking) {  // a halving evaluated as the request of a later round
-        int j = 1;
-        double a = ls.alpha0 * lo.beta_decrease;
-        while (j < 15 && a != alpha) { a *= lo.beta_decrease; ++j; }
-        bin = j;
+      if (pending) {
+        if (f & TF_REROLL) {
+          // the accepted candidate has just been rolled out again into x_, u_; it still needs its
+          // expansion (TF_REFRESH_DYN stays set)
+          f &= ~(TF_REROLL | TF_NEED_EVAL | TF_WANT_DERIV | TF_SPECULATE);
+          P.sel[b] = -1;
+          P.flags[b] = f;
+        } else {
+          LsMachine ls = P.ls[b];
+          bool last_had_deriv = had_deriv;
+          int known = P.spec_known[b];  // halvings 1..known have their merit value in phi_s
+          const int base = P.spec_base[b];
+          const bool was_backtrack = ls.phase == LsMachine::P_BACKTRACK;
+          int fed = 1, winner = 0;  // winner: halving index the search returned (0: the request)
+          ls.update(lo, P.phi_eval[b], dphi);
+          if (f & TF_SPECULATE) {
+            // this round produced halvings base .. base+nspec-1; the request itself was halving
+            // base-1 when the machine was already backtracking
+            if (was_backtrack && base >= 2)
+              P.phi_s[(long)min(base - 1, kMaxHalvings) * P.Bp + b] = P.phi_eval[b];
+            known = min(base + nspec - 1, kMaxHalvings);
+          }
+          // feed the precomputed halvings in the order the sequential search would evaluate them
+          while (!ls.done() && ls.phase == LsMachine::P_BACKTRACK) {
+            // halving index of the step the machine asks for: alpha = alpha0 * 2^-j
+            int j = 1;
+            double cand = ls.alpha0 * lo.beta_decrease;
+            while (j <= known && cand != ls.alpha) {
+              cand *= lo.beta_decrease;
+              ++j;
+            }
+            if (j > known) break;  // not precomputed: needs another round
+            ls.update(lo, P.phi_s[(long)j * P.Bp + b], 0.0);
+            last_had_deriv = false;
+            winner = j;
+            fed += 1;
+          }
+          if (!ls.done()) winner = 0;
+          P.merit_evals[b] += fed;
+          P.spec_known[b] = known;
+          f &= ~(TF_NEED_EVAL | TF_WANT_DERIV | TF_SPECULATE);
+          if (!ls.done()) {
+            f |= TF_NEED_EVAL;
+            if (ls.want_derivative()) f |= TF_WANT_DERIV;
+            P.alpha_eval[b] = ls.alpha;
+            if (lo.use_backtracking && nspec > 0) {
+              if (ls.phase == LsMachine::P_BACKTRACK) {
+                // ran out of precomputed halvings: the request is halving known+1, speculate the
+                // next ones
+                f |= TF_SPECULATE;
+                P.spec_base[b] = known + 2;
+                P.alpha_bt[b] = ls.alpha * lo.beta_decrease;
+              } else if (ls.phase == LsMachine::P_CUBIC_FIRST) {
+                // the cubic-first probe is next (linesearch.cpp:96-127).  If it is rejected the
+                // search backtracks through the halvings; when none of the known ones passes the
+                // Armijo test the ones after them ride along with the probe
+                bool any = false;
+                double cand = ls.alpha0;
+                for (int j = 1; j <= known; ++j) {
+                  cand *= lo.beta_decrease;
+                  any = any || (P.phi_s[(long)j * P.Bp + b] <= ls.phi0 + lo.c1 * cand * ls.dphi0);
+                }
+                if (!any && known + 1 <= kMaxHalvings) {
+                  f |= TF_SPECULATE;
+                  P.spec_base[b] = known + 1;
+                  P.alpha_bt[b] = cand * lo.beta_decrease;
+                }
+              }
+            }
+          } else {
+            const double alpha = ls.alpha;
+            P.alpha_eval[b] = alpha;
+            if (ls.n_iters > 0) P.phi[b] = ls.phi;
+            if (P.ls_hist) {
+              int bin = 17;
+              if (!(ls.status == LS_MINIMUM_FOUND || ls.status == LS_HIT_MAX_STEPSIZE)) bin = 18;
+              else if (winner > 0) bin = winner < 15 ? winner : 15;
+              else if (alpha == ls.alpha0) bin = 0;
+              else if (lo.use_backtracking && last_had_deriv) bin = 16;
+              else if (lo.use_backtracking) {  // a halving evaluated as the request of a later round
+                int j = 1;
+                double a = ls.alpha0 * lo.beta_decrease;
+                while (j < 15 && a != alpha) { a *= lo.beta_decrease; ++j; }
+                bin = j;
+              }
+              atomicAdd(P.ls_hist + bin, 1ull);
+            }
+            if (winner > 0) {
+              // the step the search returns was only evaluated as a speculative candidate of the
+              // round that started at halving `wbase`
+              const int wbase = (winner >= base) ? base : 1;
+              const int wslot = winner - wbase + 1;
+              if (winner >= base && wslot >= 1 && wslot <= P.nstore)
+                P.sel[b] = wslot - 1;  // its trajectory is in a candidate slot: copy + expand it
+              else
+                f |= TF_REROLL;        // merit-only / overwritten candidate: roll it out again
+              f |= TF_REFRESH_DYN;
+            } else if (lo.use_backtracking && fabs(alpha - 1.0) > 0 && !last_had_deriv) {
+              f |= TF_REFRESH_DYN;  // accepted point has no derivative information yet (:256-262)
+            }
+            if (isnan(alpha) || !(ls.status == LS_MINIMUM_FOUND || ls.status == LS_HIT_MAX_STEPSIZE))
+              f |= TF_LS_FAILED;
+          }
+          P.ls[b] = ls;
+          P.flags[b] = f;
+        }
       }
-      atomicAdd(P.ls_hist + bin, 1ull);
     }
-    if (winner > 0) {
-      // the step the search returns was only evaluated as a speculative candidate of the round
-      // that started at halving `wbase`
-      const int wbase = (winner >= base) ? base : 1;
-      const int wslot = winner - wbase + 1;
-      if (winner >= base && wslot >= 1 && wslot <= P.nstore)
-        P.sel[b] = wslot - 1;  // its trajectory is in a candidate slot: copy + expand it
-      else
-        f |= TF_REROLL;        // merit-only / overwritten candidate: roll it out again, then expand
-      f |= TF_REFRESH_DYN;
-    } else if (lo.use_backtracking && fabs(alpha - 1.0) > 0 && !last_had_deriv) {
-      f |= TF_REFRESH_DYN;  // accepted point has no derivative information yet (solver.cpp:256-262)
-    }
-    if (isnan(alpha) || !(ls.status == LS_MINIMUM_FOUND || ls.status == LS_HIT_MAX_STEPSIZE))
-      f |= TF_LS_FAILED;
+    __syncthreads();
+    tick(FS_DPHI_LS);
   }
-  P.ls[b] = ls;
-  P.flags[b] = f;
-}
 
-// K5a/b: costates of the accepted point, then stationarity / feasibility residuals and
-// CopyTrajectory -- one thread per (problem of a listed group, knot)
-template <class Model, int CON>
-__global__ void __launch_bounds__(128) k_phase_costate(const __grid_constant__ DeviceProblem P, const int* list,
-                                                       int count) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if ((t >> 5) >= count) return;
-  const int b = list[t >> 5] * 32 + (t & 31);
-  if (b >= P.B || !(P.flags[b] & TF_ACTIVE)) return;
-  TrajSolver<Model, CON> s(P, b);
-  s.phase_costate_knot(blockIdx.y);
-}
-
-template <class Model, int CON>
-__global__ void __launch_bounds__(128) k_phase_residual(const __grid_constant__ DeviceProblem P, const int* list,
-                                                        int count) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if ((t >> 5) >= count) return;
-  const int b = list[t >> 5] * 32 + (t & 31);
-  if (b >= P.B || !(P.flags[b] & TF_ACTIVE)) return;
-  TrajSolver<Model, CON> s(P, b);
-  s.phase_residual_knot(blockIdx.y);
-}
-
-// K5c: convergence test, dual / penalty update decision (solver.cpp:459-489, :503-506)
-template <int CON>
-__global__ void __launch_bounds__(128) k_phase_decide(const __grid_constant__ DeviceProblem P, const int* list,
-                                                      int count) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if ((t >> 5) >= count) return;
-  const int b = list[t >> 5] * 32 + (t & 31);
-  if (b >= P.B || !(P.flags[b] & TF_ACTIVE)) return;
-  const DevOptions& o = P.opts;
-  const double stationarity = __longlong_as_double((long long)P.stat_acc[b]);
-  const double feasibility = __longlong_as_double((long long)P.feas_acc[b]);
-  int f = P.flags[b];
-  bool stop = (f & TF_LS_FAILED) != 0;
-  int status = SOLVE_UNSOLVED;
-  if (fabs(stationarity) < o.tol_stationarity && feasibility < o.tol_primal_feasibility) {
-    stop = true;
-    status = SOLVE_SUCCESS;
-  }
-  f &= ~(TF_REFRESH_DYN | TF_REFRESH_GRAD);
-  if (stationarity < sqrt(o.tol_stationarity)) {
-    if constexpr (CON) {
-      // z <- Pi(z_est) is applied knot by knot by the expansion that follows (dual_first)
-      if (feasibility > o.tol_primal_feasibility)
-        P.rho[b] = fmin(P.rho[b] * o.penalty_scaling, o.penalty_max);
-      f |= TF_REFRESH_GRAD;
+  // ================================================================= after the search
+  // accepted backtracking step: A, B, lx, lu at the accepted point, read from the candidate slot
+  // that holds it (solver.cpp:256-262)
+  {
+    const unsigned rmask = __ballot_sync(kAll, (fl & TF_REFRESH_DYN) != 0);
+    if (rmask) {
+      for_knot_items(rmask, g, P.N + 1, [&](int b, int k) {
+        TS s(P, b);
+        weights(s);
+        s.rho = CON ? P.rho[b] : 1.0;
+        s.phase_expand_knot(k, true, P.sel[b], false);
+      });
+      __syncthreads();
     }
   }
-  const int iter = P.iter_count[b] + 1;  // iterations completed
-  P.iter_count[b] = iter;
-  if (!stop && iter >= o.iterations_max) {
-    stop = true;
-    status = SOLVE_MAX_ITERATIONS;
+  tick(FS_EXPAND);
+  // costates of the accepted point, then stationarity / feasibility residuals + CopyTrajectory
+  for_knot_items(act_mask, g, P.N + 1, [&](int b, int k) {
+    TS s(P, b);
+    s.phase_costate_knot(k);
+  });
+  __syncthreads();
+  for_knot_items(act_mask, g, P.N + 1, [&](int b, int k) {
+    TS s(P, b);
+    s.phase_residual_knot(k);
+  });
+  __syncthreads();
+  // convergence test, dual / penalty update decision (solver.cpp:459-489, :503-506)
+  if (wid == 0) {
+    const int b = bl;
+    bool stopped = false;
+    if (valid && (fl & TF_ACTIVE)) {
+      const DevOptions& o = P.opts;
+      const double stationarity = __longlong_as_double((long long)P.stat_acc[b]);
+      const double feasibility = __longlong_as_double((long long)P.feas_acc[b]);
+      int f = fl;
+      bool stop = (f & TF_LS_FAILED) != 0;
+      int status = SOLVE_UNSOLVED;
+      if (fabs(stationarity) < o.tol_stationarity && feasibility < o.tol_primal_feasibility) {
+        stop = true;
+        status = SOLVE_SUCCESS;
+      }
+      f &= ~(TF_REFRESH_DYN | TF_REFRESH_GRAD);
+      if (stationarity < sqrt(o.tol_stationarity)) {
+        if constexpr (CON) {
+          // z <- Pi(z_est) is applied knot by knot by the expansion below (dual_first)
+          if (feasibility > o.tol_primal_feasibility)
+            P.rho[b] = fmin(P.rho[b] * o.penalty_scaling, o.penalty_max);
+          f |= TF_REFRESH_GRAD;
+        }
+      }
+      const int iter = P.iter_count[b] + 1;  // iterations completed
+      P.iter_count[b] = iter;
+      if (!stop && iter >= o.iterations_max) {
+        stop = true;
+        status = SOLVE_MAX_ITERATIONS;
+      }
+      P.stat[b] = stationarity;
+      P.feas[b] = feasibility;
+      if (stop) {
+        f &= ~TF_ACTIVE;
+        P.status[b] = status;
+        // stats.iterations = iter + 1 with the loop counter at exit (quirk Q4): a loop that ran to
+        // exhaustion reports iterations_max + 1
+        P.iters[b] = (status == SOLVE_MAX_ITERATIONS) ? iter + 1 : iter;
+        P.ls_fail[b] = (f & TF_LS_FAILED) ? 1 : 0;
+        stopped = true;
+      }
+      P.flags[b] = f;
+      fl = f;
+    }
+    const unsigned smask = __ballot_sync(kAll, stopped);
+    if (lid == 0 && smask && done_out) atomicAdd(done_out, __popc(smask));
   }
-  P.stat[b] = stationarity;
-  P.feas[b] = feasibility;
-  if (stop) {
-    f &= ~TF_ACTIVE;
-    P.status[b] = status;
-    // stats.iterations = iter + 1 with the loop counter at exit (quirk Q4): a loop that ran to
-    // exhaustion reports iterations_max + 1
-    P.iters[b] = (status == SOLVE_MAX_ITERATIONS) ? iter + 1 : iter;
-    P.ls_fail[b] = (f & TF_LS_FAILED) ? 1 : 0;
+  __syncthreads();
+  if constexpr (CON) {
+    // CalcProjectedDuals + CalcCostGradient after the dual / penalty update (solver.cpp:475-486),
+    // for the problems that just stopped as well (the reference updates, then leaves the loop).
+    // The flag is consumed here: a stopped problem must not be updated again while its group
+    // mates keep iterating.
+    fl = valid ? P.flags[bl] : 0;
+    const unsigned gmask = __ballot_sync(kAll, (fl & TF_REFRESH_GRAD) != 0);
+    if (gmask) {
+      for_knot_items(gmask, g, P.N + 1, [&](int b, int k) {
+        TS s(P, b);
+        weights(s);
+        s.rho = P.rho[b];
+        s.phase_expand_knot(k, false, -1, true);
+      });
+      __syncthreads();
+      if (wid == 0 && (fl & TF_REFRESH_GRAD)) P.flags[bl] = fl & ~TF_REFRESH_GRAD;
+    }
   }
-  P.flags[b] = f;
+  tick(FS_CRITERIA);
+  if (prof) atomicAdd(P.prof + FS_COUNT, 1ull);
 }
 
 // ALTROSolver::OpenLoopRollout (solver.cpp:116-131): x_[k+1] = f(x_[k], u_[k]) from the initial state

@@ -81,6 +81,8 @@ def load_library():
         L.altro_b200_set_diagonal_cost.argtypes = [vp, dptr, dptr, dptr, dptr, dptr, C.c_int, C.c_int, C.c_int]
         L.altro_b200_update_linear_costs.argtypes = [vp, dptr, dptr, dptr, C.c_int, C.c_int, C.c_int]
         L.altro_b200_advance_window.argtypes = [vp, C.c_int]
+        L.altro_b200_advance_window_linear.argtypes = [vp, C.c_int, C.c_double]
+        L.altro_b200_set_mpc_cost_update.argtypes = [vp, C.c_int, C.c_double]
         L.altro_b200_set_constraint.argtypes = [vp, C.c_int, C.c_int, iptr, dptr, dptr, dptr, C.c_int, C.c_int]
         L.altro_b200_set_initial_state.argtypes = [vp, dptr, C.c_int]
         L.altro_b200_initialize.argtypes = [vp]
@@ -102,6 +104,7 @@ def load_library():
         L.altro_b200_set_solve_mode.argtypes = [vp, C.c_int]
         L.altro_b200_set_profiling.argtypes = [vp, C.c_int]
         L.altro_b200_set_speculation.argtypes = [vp, C.c_int]
+        L.altro_b200_set_candidate_store.argtypes = [vp, C.c_int]
         L.altro_b200_set_pipeline_split.argtypes = [vp, C.c_int]
         L.altro_b200_get_phase_stats.argtypes = [vp, dptr, C.POINTER(C.c_long), dptr, C.POINTER(C.c_long)]
         L.altro_b200_tvlqr_backward_batch.argtypes = [C.c_int] * 4 + [dptr] * 8 + [C.c_double, C.c_bool] + \
@@ -220,6 +223,13 @@ class BatchSolver:
     def AdvanceWindow(self, steps=1):
         self._ck(self.L.altro_b200_advance_window(self.h, steps), "AdvanceWindow")
 
+    def AdvanceWindowLinear(self, steps, c_u):
+        """The reference's MPC cost update (UpdateLinearCosts(q, nullptr, c) on the moved window)."""
+        self._ck(self.L.altro_b200_advance_window_linear(self.h, steps, C.c_double(c_u)), "AdvanceWindowLinear")
+
+    def SetMpcCostUpdate(self, mode, c_u=0.0):
+        self._ck(self.L.altro_b200_set_mpc_cost_update(self.h, mode, C.c_double(c_u)), "SetMpcCostUpdate")
+
     def SetConstraint(self, cone, idx, scale, off, k_start, k_stop=0, off_b=None):
         dim = len(idx)
         ia = (C.c_int * dim)(*[int(i) for i in idx])
@@ -256,25 +266,29 @@ class BatchSolver:
         self._ck(self.L.altro_b200_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "SetStream")
 
     def SetSolveMode(self, mode):
-        """0: phase-kernel pipeline (default); 1: single persistent kernel."""
+        """0: two-kernel-per-iteration pipeline (default); 1: single persistent kernel (test twin)."""
         self._ck(self.L.altro_b200_set_solve_mode(self.h, mode), "SetSolveMode")
 
     def SetSpeculation(self, nslots):
         self._ck(self.L.altro_b200_set_speculation(self.h, nslots), "SetSpeculation")
 
+    def SetCandidateStore(self, nstore):
+        self._ck(self.L.altro_b200_set_candidate_store(self.h, nstore), "SetCandidateStore")
+
     def SetPipelineSplit(self, nsplit):
-        """0: automatic; 1..8 sub-batches pipelined on their own streams/host threads."""
+        """0: automatic; 1..8 sub-batches pipelined on their own streams."""
         self._ck(self.L.altro_b200_set_pipeline_split(self.h, nsplit), "SetPipelineSplit")
 
     def SetProfiling(self, on):
         self._ck(self.L.altro_b200_set_profiling(self.h, int(on)), "SetProfiling")
 
-    PHASES = ("init_rollout", "expand", "backward", "rollout", "lsupdate", "criteria", "compact")
+    PHASES = ("init_rollout", "expand", "backward", "forward", "fwd_rollout", "fwd_expand",
+              "fwd_dphi_ls", "fwd_criteria")
 
     def GetPhaseStats(self):
-        ms = np.zeros(7)
-        units = np.zeros(7)
-        launches = (C.c_long * 7)()
+        ms = np.zeros(8)
+        units = np.zeros(8)
+        launches = (C.c_long * 8)()
         syncs = C.c_long()
         self._ck(self.L.altro_b200_get_phase_stats(self.h, ms.ctypes.data_as(dptr), launches,
                                                    units.ctypes.data_as(dptr), C.byref(syncs)), "GetPhaseStats")

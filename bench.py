@@ -89,7 +89,20 @@ def kernel_models(P, iters, evals):
     roll = float(np.maximum(evals.astype(np.float64) - iters, 0).sum())  # rollouts the search consumed
     # Jacobian entries kept in HBM: dense n^2 + nm unless the model packs them (models.cuh, JacPack)
     jac = {PR.MODEL_BICYCLE5: 15, PR.MODEL_BICYCLE4: 12}.get(P.model_id, n * n + n * m)
-    return {
+    # sub-phases of k_phase_forward
+    sub = {
+        # r [xbar ubar q r c K d] (+ z rows)   w x,u
+        "fwd_rollout": dict(doubles=(2 * (n + m) + 1 + m * n + m) + (n + m) + rows, units=roll * N),
+        # one expansion per iteration (the point the search accepts): r x,u,q,r  w J,lx,lu (+ z, z_est)
+        "fwd_expand": dict(doubles=2 * (n + m) + (jac + n + m) + 2 * rows, units=it * (N + 1)),
+        # d(phi) scan: r K,d,J,lx,lu
+        "fwd_dphi_ls": dict(doubles=m * n + m + jac + n + m, units=it * N),
+        # costates r x,xbar,P,p  w y;  residuals r x,u,y,y+,J,lx,lu  w xbar,ubar
+        "fwd_criteria": dict(doubles=(2 * n + n * n + n) + n + (2 * n + jac + 2 * (n + m)) + (n + m) + rows,
+                             units=it * (N + 1)),
+    }
+    fwd_bytes = sum(8.0 * v["doubles"] * v["units"] for v in sub.values())
+    models = {
         # sweep: r J,lx,lu  w K,d,P,p (+ z_est rows).  scan: r q,r,c,K,d,x,u,J  w lx,lu (+ duals);
         # unconstrained problems after their first iteration scan only K,d,J,lx,lu and write nothing
         "backward": dict(kernel="k_phase_backward (Riccati sweep + alpha=0 scan)",
@@ -98,16 +111,15 @@ def kernel_models(P, iters, evals):
                             else (m * n + m + jac + n + m)),
                          units=it * N,
                          extra_bytes=0.0 if rows else 8.0 * (n + m + 1 + n + m) * P.B * N),
-        "rollout": dict(kernel="k_phase_rollout (closed-loop rollout, merit value)",
-                        doubles=(2 * (n + m) + 1 + m * n + m) + (n + m) + rows, units=roll * N),
-        "expand": dict(kernel="k_phase_expand (dynamics Jacobians, projected duals, gradients)",
-                       doubles=2 * (n + m) + (jac + n + m) + 2 * rows, units=(it + P.B) * (N + 1)),
-        "lsupdate": dict(kernel="k_phase_lsupdate (d(phi) scan + line-search machine)",
-                         doubles=m * n + m + jac + n + m, units=it * N),
-        "criteria": dict(kernel="k_phase_costate + k_phase_residual (+ decide)",
-                         doubles=(2 * n + n * n + n) + n + (2 * n + jac + 2 * (n + m)) + (n + m) + rows,
-                         units=it * (N + 1)),
+        "forward": dict(kernel="k_phase_forward (line search: rollouts + expansion + d(phi) scan + "
+                               "state machines; costates, residuals, AL update)",
+                        doubles=0.0, units=0.0, extra_bytes=fwd_bytes),
+        "expand": dict(kernel="k_phase_expand (prologue: Jacobians, projected duals, gradients)",
+                       doubles=2 * (n + m) + (jac + n + m) + 2 * rows, units=P.B * (N + 1)),
     }
+    for k, v in sub.items():
+        models[k] = dict(kernel=f"k_phase_forward / {k[4:]}", **v)
+    return models
 
 
 class ClockSampler:
@@ -396,14 +408,13 @@ def main():
         peak, peak_src = peak_hbm()
         alg_bytes = algorithmic_bytes(P, iters, evals)
         models = kernel_models(P, iters, evals)
-        phase_map = {"backward": "backward", "rollout": "rollout", "expand": "expand",
-                     "lsupdate": "lsupdate", "criteria": "criteria"}
-        tot_ms = sum(v["ms"] for v in phase_stats.values())
+        whole = ("init_rollout", "expand", "backward", "forward")   # launches; fwd_* are shares of forward
+        tot_ms = sum(phase_stats[k]["ms"] for k in whole)
         kernels = {}
         for ph, st_ in phase_stats.items():
-            if ph not in phase_map or st_["launches"] == 0:
+            if ph not in models or st_["launches"] == 0 or st_["ms"] <= 0:
                 continue
-            mdl = models[phase_map[ph]]
+            mdl = models[ph]
             bytes_total = 8.0 * mdl["doubles"] * mdl["units"] + mdl.get("extra_bytes", 0.0)
             kernels[ph] = {"kernel": mdl["kernel"], "launches": st_["launches"], "ms": st_["ms"],
                            "share_of_step": st_["ms"] / tot_ms,
@@ -411,7 +422,7 @@ def main():
                            "algorithmic_bytes_per_launch": bytes_total / st_["launches"],
                            "achieved_gbs": bytes_total / (st_["ms"] * 1e-3) / 1e9,
                            "frac": bytes_total / (st_["ms"] * 1e-3) / 1e9 / peak}
-        dom = max(kernels, key=lambda k: kernels[k]["ms"])
+        dom = max((k for k in kernels if k in whole), key=lambda k: kernels[k]["ms"])
         kd = kernels[dom]
         traffic = ncu_traffic(args.workload, dom)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -432,7 +443,9 @@ def main():
                             "note": "dominant kernel of the step; per-kernel algorithmic bytes = "
                                     "DESIGN.md 'Kernels' table x the trajectory-knots the algorithm "
                                     "needs (speculative candidates not counted); timed with CUDA "
-                                    "events around every launch, sub-batch pipelining off"},
+                                    "events around every launch, sub-batch pipelining off; the "
+                                    "fwd_* entries of `kernels` split k_phase_forward by its "
+                                    "in-kernel %globaltimer sub-phase clocks"},
                "kernels": kernels,
                "step_roofline": {"algorithmic_bytes_per_step": alg_bytes,
                                  "achieved": alg_bytes / (elapsed_ms / args.steps * 1e-3) / 1e9,
@@ -443,17 +456,39 @@ def main():
                                "success_frac": float((status == 0).mean()),
                                "max_iterations_frac": float((status == 2).mean()),
                                "hbm_bytes_resident": int(solver.DeviceBytes())}}
+        # solves that reach the reference's convergence criteria (status Success), per second
+        out["converged_solves_per_sec"] = value * float((status == 0).mean())
         if not args.no_cpu_baseline and world == 1:
             cb, ref, nb = cpu_oracle_rate(P, args.cpu_seconds)
             out["cpu_baseline"] = cb
+            # the same port on ONE host core ("on 1 core and on all cores")
+            cb1, _, _ = cpu_oracle_rate(P, max(2.0, args.cpu_seconds / 3), threads=1)
+            out["cpu_baseline_1core"] = {k: cb1[k] for k in ("value", "unit", "cores", "kind", "sample")}
             if not args.no_check:
-                from parity_util import compare
+                from parity_util import compare, compare_all
                 gpu = {"X": X_h, "U": U_h, "status": st_h, "iters": iters, "cost": phi_h}
                 try:
                     rep = compare(gpu, ref)
                     out["parity_check"] = {"ok": True, **rep}
                 except AssertionError as e:
                     out["parity_check"] = {"ok": False, "error": str(e)[:300]}
+                # EVERY problem of the sample, converged or not, after 1 / 3 / 10 iterations: the
+                # same iteration count and status, and how far states / inputs / cost are apart
+                from oracle import oracle as O
+                low = {}
+                for itmax in (1, 3, 10):
+                    Pl = P.subset(0, P.B)
+                    Pl.options = dict(P.options, iterations_max=itmax)
+                    solver.SetOptions(altro_b200.default_options(**Pl.options))
+                    solver.ResetTrajectory()
+                    solver.ResetDuals()
+                    solver.Solve()
+                    g = {"X": solver.GetStates(), "U": solver.GetInputs(), "status": solver.GetStatus(),
+                         "iters": solver.GetIterations(), "cost": solver.GetFinalObjective()}
+                    r = O.solve_batch(Pl, 0, min(nb, P.B), nthreads=host_threads())
+                    low[str(itmax)] = compare_all(g, r)
+                solver.SetOptions(altro_b200.default_options(**P.options))
+                out["parity_check"]["all_problems_low_iteration"] = low
         print(json.dumps(out), flush=True)
     if dist is not None:
         dist.barrier()

@@ -185,6 +185,14 @@ int altro_b200_update_linear_costs(altro_b200_solver *s, const double *q, const 
 /* advance every problem's tracking window by `steps` rows (on-device UpdateLinearCosts for the
  * receding-horizon loop of test/bicycle_test.cpp:320-331) */
 int altro_b200_advance_window(altro_b200_solver *s, int steps);
+/* the reference's own MPC cost update on the moved window (test/bicycle_test.cpp:317-328):
+ * UpdateLinearCosts(q, nullptr, c, k) for every knot with q_k = -(Qd .* xref[row]),
+ * c_k = 1/2 xref' Qd xref (+ c_u for k < N); r_k is left as the original SetLQRCost set it. */
+int altro_b200_advance_window_linear(altro_b200_solver *s, int steps, double c_u);
+/* which of the two altro_b200_mpc_step applies: mode 1 (default) the reference's update above with
+ * the frozen input-cost constant c_u = 1/2 u0' R u0 (test/bicycle_test.cpp:296), mode 0 the full
+ * re-windowing of altro_b200_advance_window (q, r and c all follow the window). */
+int altro_b200_set_mpc_cost_update(altro_b200_solver *s, int mode, double c_u);
 
 /* SetConstraint with a built-in row family instead of callbacks:
  *   c_i = scale_i * [x;u][idx_i] + off_i   (idx_i = -1: c_i = off_i),   i < dim
@@ -205,9 +213,10 @@ int altro_b200_set_options(altro_b200_solver *s, const altro_b200_options *o);
 /* reset duals (z = 0) and penalties (rho = 1) to their post-Initialize values */
 int altro_b200_reset_duals(altro_b200_solver *s);
 int altro_b200_shift_trajectory(altro_b200_solver *s); /* ShiftTrajectory, altro_solver.cpp:283 */
-/* one receding-horizon (MPC) step entirely on the device, plant = model: x0 <- x_[1] of the solved
- * trajectory, ShiftTrajectory, and (tracking-window cost) advance the window by one row; duals and
- * penalties carry over (test/bicycle_test.cpp:302-337).  Call altro_b200_solve again afterwards. */
+/* one receding-horizon (MPC) step entirely on the device (test/bicycle_test.cpp:302-337, whose
+ * plant is the model): x0 <- x_[1] of the solved trajectory, ShiftTrajectory, the tracking window
+ * moves one row with the cost update selected by altro_b200_set_mpc_cost_update; duals and
+ * penalties carry over.  Call altro_b200_solve again afterwards. */
 int altro_b200_mpc_step(altro_b200_solver *s);
 /* restore the working inputs u_ to the last SetInput guess (device-to-device; lets a resident
  * batch be re-solved from the same starting point without a host round trip) */
@@ -222,21 +231,30 @@ int altro_b200_calc_cost(altro_b200_solver *s, double *cost);
 int altro_b200_solve(altro_b200_solver *s);
 int altro_b200_solve_async(altro_b200_solver *s); /* no wait; use altro_b200_synchronize */
 int altro_b200_synchronize(altro_b200_solver *s);
-/* 0 (default): pipeline of phase kernels over compacted work lists (needs a few host round
- * trips per iteration, so solve_async returns when the last kernel is queued);
- * 1: one persistent kernel for the whole solve (thread per trajectory, no host interaction) */
+/* 0 (default): two kernels per iLQR iteration (backward sweep; forward = whole line search +
+ * criteria + AL update), enqueued back to back with no host decision in the loop -- the host only
+ * looks at a stop counter two iterations late, so solve_async returns once the last iterations
+ * are queued;
+ * 1: one persistent kernel for the whole solve (thread per trajectory; the bit-exact twin the
+ * tests compare mode 0 against) */
 int altro_b200_set_solve_mode(altro_b200_solver *s, int mode);
 /* pipelined sub-batches: the batch is cut into `nsplit` contiguous ranges (1..8; 0 = automatic),
- * each driven by its own host thread and stream so the compute-bound rollouts of one range
- * overlap the HBM-bound sweeps of another.  Results do not depend on nsplit. */
+ * each on its own stream (one host thread enqueues all) so the sweeps of one range overlap the
+ * rollouts of another.  Results do not depend on nsplit. */
 int altro_b200_set_pipeline_split(altro_b200_solver *s, int nsplit);
-/* number of candidate step lengths rolled out concurrently per backtracking round (1..16,
+/* number of candidate step lengths rolled out concurrently per backtracking round (1..8,
  * default 6; before altro_b200_initialize).  1 reproduces the strictly sequential search. */
 int altro_b200_set_speculation(altro_b200_solver *s, int nslots);
-/* per-phase instrumentation of the pipeline.  Phases: 0 init rollout, 1 expansion (knot-parallel),
- * 2 backward Riccati + alpha=0 scan, 3 rollout, 4 d(phi) scan + line-search step, 5 criteria +
- * AL update, 6 list compaction.  on=1 additionally times every launch with CUDA events
- * (serialises the pipeline; not for throughput runs).  Arrays of 7 entries. */
+/* how many of the speculative candidates keep their trajectory in HBM (0..nslots-1, after
+ * altro_b200_initialize; default all).  An accepted candidate that did not is rolled out once
+ * more.  Results do not depend on it. */
+int altro_b200_set_candidate_store(altro_b200_solver *s, int nstore);
+/* per-phase instrumentation of the pipeline.  Entries: 0 init rollout, 1 prologue expansion,
+ * 2 k_phase_backward (Riccati + alpha=0 scan), 3 k_phase_forward, and the forward kernel's time
+ * split by its in-kernel sub-phase clocks: 4 rollout passes, 5 expansions, 6 d(phi) scan +
+ * line-search machines, 7 criteria + AL update.  on=1 times every launch with CUDA events
+ * (serialises the pipeline; not for throughput runs).  Arrays of 8 entries; *syncs = host waits
+ * on the device (lagged stop-counter checks, at most one per iteration and sub-batch). */
 int altro_b200_set_profiling(altro_b200_solver *s, int on);
 int altro_b200_get_phase_stats(altro_b200_solver *s, double *ms, long *launches, double *units,
                                long *syncs);

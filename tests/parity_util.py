@@ -60,3 +60,31 @@ def compare(gpu, ref, tail_frac=0.01):
                 max_input_err=float(eu[strict].max(initial=0)),
                 max_cost_rel=float(ec[strict].max(initial=0)),
                 mean_iters=float(ref["iters"].mean()), mean_evals=float(ref["merit_evals"].mean()))
+
+
+def compare_all(gpu, ref):
+    """Every problem of the sample regardless of its status (used with a small iterations_max, before
+    the chaotic amplification of the unregularised iteration has had time to act): fraction with the
+    same status and iteration count, and the worst state / input / cost differences over ALL of them
+    (relative to max(1, |.|_inf) per problem; NaN-producing problems compare equal when both sides
+    are non-finite in the same places)."""
+    nb = ref["X"].shape[0]
+    gi, gs = gpu["iters"][:nb], gpu["status"][:nb]
+    same = (gi == ref["iters"]) & (gs == ref["status"])
+    gx, gu, gc = gpu["X"][:nb], gpu["U"][:nb], gpu["cost"][:nb]
+    fin = np.isfinite(ref["X"]).reshape(nb, -1).all(axis=1) & np.isfinite(ref["U"]).reshape(nb, -1).all(axis=1) \
+        & np.isfinite(ref["cost"])
+    gfin = np.isfinite(gx).reshape(nb, -1).all(axis=1) & np.isfinite(gu).reshape(nb, -1).all(axis=1) \
+        & np.isfinite(gc)
+    both = fin & gfin
+    sub = {"X": gx[both], "U": gu[both], "cost": gc[both]}
+    rsub = {"X": ref["X"][both], "U": ref["U"][both], "cost": ref["cost"][both]}
+    if both.any():
+        ex, eu, ec = errors(sub, rsub)
+    else:
+        ex = eu = ec = np.zeros(0)
+    return dict(n=int(nb), same_status_and_iterations=int(same.sum()),
+                finite_both=int(both.sum()), finite_mismatch=int((fin != gfin).sum()),
+                max_state_err=float(ex.max(initial=0)), max_input_err=float(eu.max(initial=0)),
+                max_cost_rel=float(ec.max(initial=0)),
+                p99_state_err=float(np.quantile(ex, 0.99)) if ex.size else 0.0)

@@ -167,9 +167,9 @@ def test_results_do_not_depend_on_batch_neighbours(oracle):
     lambda: PR.chain(B=64, n=6, m=2, N=50, control_box=True),
 ])
 def test_phase_pipeline_equals_persistent_kernel(make):
-    """The production path (phase kernels over compacted lists, knot-parallel expansion, alpha=0
-    scan instead of a re-rollout) and the single persistent kernel are two schedules of the same
-    arithmetic: results must be bit-identical."""
+    """The production path (two kernels per iteration: staged sweeps, speculative line-search rounds,
+    knot-parallel expansion, alpha=0 scan instead of a re-rollout) and the single persistent kernel
+    are two schedules of the same arithmetic: results must be bit-identical."""
     P = make()
     a = altro_b200.solve_problem(P, mode=0)
     b = altro_b200.solve_problem(P, mode=1)
@@ -187,9 +187,10 @@ def test_results_do_not_depend_on_schedule(make):
     run and schedule to schedule."""
     P = make()
     ref = None
-    for nslots, nsplit in [(1, 1), (4, 1), (4, 3), (10, 2), (4, 3), (16, 8)]:
+    for nslots, nsplit, nstore in [(1, 1, 0), (4, 1, 3), (4, 3, 0), (8, 2, 2), (4, 3, 1), (8, 8, 7), (6, 4, 5)]:
         s = altro_b200.make_solver(P, nslots=nslots)
         s.SetPipelineSplit(nsplit)
+        s.SetCandidateStore(nstore)
         s.Solve()
         out = dict(X=s.GetStates(), U=s.GetInputs(), iters=s.GetIterations(), evals=s.GetMeritEvals(),
                    cost=s.GetFinalObjective(), status=s.GetStatus())
@@ -198,7 +199,7 @@ def test_results_do_not_depend_on_schedule(make):
             ref = out
             continue
         for key in ref:
-            assert np.array_equal(out[key], ref[key]), (key, nslots, nsplit)
+            assert np.array_equal(out[key], ref[key]), (key, nslots, nsplit, nstore)
 
 
 @pytest.mark.parametrize("make,model", [
