@@ -89,6 +89,17 @@ DeviceConstraint DeviceConstraint::InputNormBound(int n, int m, double u_max) {
 DeviceConstraint DeviceConstraint::StateBound(int index, double lo, double hi) {
   return DeviceConstraint({index, index}, {1.0, -1.0}, {-hi, lo});  // bicycle_test.cpp:189-196
 }
+DeviceConstraint DeviceConstraint::Affine(int dim, std::vector<double> J_colmajor, std::vector<double> e) {
+  DeviceConstraint c(std::vector<int>(dim, -1), std::vector<double>(dim, 0.0), std::move(e));
+  c.kind = AffineRows;
+  c.jac = std::move(J_colmajor);
+  return c;
+}
+DeviceConstraint DeviceConstraint::KeepOutDisc(int idx_a, int idx_b, double cx, double cy, double r) {
+  DeviceConstraint c({idx_a, idx_b}, {1.0, 1.0}, {cx, cy, r});
+  c.kind = Disc;
+  return c;
+}
 
 }  // namespace b200
 
@@ -261,8 +272,9 @@ ErrorCodes ALTROSolver::SetDiagonalCost(int num_states, int num_inputs, const a_
   return EC(altro_b200_set_diagonal_cost(solver_->handle, Q_diag, R_diag, q, r, &c, 0, k_start, k_stop));
 }
 
-// altro_solver.cpp:118-136.  Dense Q, R, H: accepted when they are diagonal / zero (the device
-// cost is diagonal-LQR, like every reference test); anything else is reported, not approximated.
+// altro_solver.cpp:118-136 -> KnotPointData::SetQuadraticCost (knotpoint_data.cpp:64-85): dense Q,
+// R and the cross term H.  Diagonal Q, R with H = 0 keep the diagonal device path (fewer bytes per
+// knot); anything else selects the general instantiation of the kernels.
 ErrorCodes ALTROSolver::SetQuadraticCost(int num_states, int num_inputs, const a_float* Q,
                                          const a_float* R, const a_float* H, const a_float* q,
                                          const a_float* r, a_float c, int k_start, int k_stop) {
@@ -271,21 +283,24 @@ ErrorCodes ALTROSolver::SetQuadraticCost(int num_states, int num_inputs, const a
   if (err != ErrorCodes::NoError) return err;
   const int n = solver_->n, m = solver_->m;
   if (num_states != n || num_inputs != m) return ErrorCodes::DimensionMismatch;
+  bool diagonal = true;
   std::vector<double> Qd(n), Rd(m);
   for (int j = 0; j < n; ++j)
     for (int i = 0; i < n; ++i) {
       if (i == j) Qd[i] = Q[i + n * j];
-      else if (Q[i + n * j] != 0.0) return ALTRO_THROW("Only diagonal Q is supported on the device.", ErrorCodes::Unsupported);
+      else if (Q[i + n * j] != 0.0) diagonal = false;
     }
-  for (int j = 0; j < m; ++j)
+  for (int j = 0; j < m && R; ++j)
     for (int i = 0; i < m; ++i) {
       if (i == j) Rd[i] = R[i + m * j];
-      else if (R[i + m * j] != 0.0) return ALTRO_THROW("Only diagonal R is supported on the device.", ErrorCodes::Unsupported);
+      else if (R[i + m * j] != 0.0) diagonal = false;
     }
-  for (int i = 0; i < m * n; ++i)
-    if (H && H[i] != 0.0) return ALTRO_THROW("Cross term H must be zero on the device.", ErrorCodes::Unsupported);
+  for (int i = 0; i < m * n && H; ++i)
+    if (H[i] != 0.0) diagonal = false;
   solver_->Invalidate();
-  return EC(altro_b200_set_diagonal_cost(solver_->handle, Qd.data(), Rd.data(), q, r, &c, 0, k_start, k_stop));
+  if (diagonal)
+    return EC(altro_b200_set_diagonal_cost(solver_->handle, Qd.data(), Rd.data(), q, r, &c, 0, k_start, k_stop));
+  return EC(altro_b200_set_quadratic_cost(solver_->handle, Q, R, H, q, r, &c, 0, k_start, k_stop));
 }
 
 // altro_solver.cpp:138-172
@@ -359,10 +374,23 @@ ErrorCodes ALTROSolver::SetConstraint(ConstraintFunction constraint_function,
         "Host callbacks cannot run on the device: pass altro::b200::DeviceConstraint::Function()/Jacobian().",
         ErrorCodes::Unsupported);
   }
-  if (static_cast<int>(c->idx.size()) != dim) return ErrorCodes::InvalidConstraintDim;
   const double* off_b = c->off_batch.empty() ? nullptr : c->off_batch.data();
-  int e = altro_b200_set_constraint(solver_->handle, static_cast<int>(constraint_type), dim,
-                                    c->idx.data(), c->scale.data(), c->off.data(), off_b, k_start, k_stop);
+  int e = 0;
+  if (c->kind == b200::DeviceConstraint::AffineRows) {
+    if (static_cast<int>(c->off.size()) != dim ||
+        static_cast<int>(c->jac.size()) != dim * (solver_->n + solver_->m))
+      return ErrorCodes::InvalidConstraintDim;
+    e = altro_b200_set_constraint_affine(solver_->handle, static_cast<int>(constraint_type), dim,
+                                         c->jac.data(), c->off.data(), off_b, k_start, k_stop);
+  } else if (c->kind == b200::DeviceConstraint::Disc) {
+    if (dim != 1 || constraint_type != ConstraintType::INEQUALITY) return ErrorCodes::InvalidConstraintDim;
+    e = altro_b200_set_constraint_disc(solver_->handle, c->idx[0], c->idx[1], c->off.data(), off_b,
+                                       k_start, k_stop);
+  } else {
+    if (static_cast<int>(c->idx.size()) != dim) return ErrorCodes::InvalidConstraintDim;
+    e = altro_b200_set_constraint(solver_->handle, static_cast<int>(constraint_type), dim,
+                                  c->idx.data(), c->scale.data(), c->off.data(), off_b, k_start, k_stop);
+  }
   if (e) return EC(e);
   if (con_inds) {
     con_inds->reserve(k_stop - k_start);
@@ -598,12 +626,35 @@ ErrorCodes ALTROSolver::MpcStep() {
   solver_->Invalidate();
   return EC(altro_b200_mpc_step(solver_->handle));
 }
+ErrorCodes ALTROSolver::SetDualGeneric(const a_float* z, const ConstraintIndex& ci) {
+  REQUIRE_HANDLE();
+  if (!z) return ErrorCodes::InvalidPointer;
+  if (!IsInitialized()) return ErrorCodes::SolverNotInitialized;
+  return EC(altro_b200_set_dual_general(solver_->handle, ci.i, ci.k, z, 0));
+}
+ErrorCodes ALTROSolver::GetDualGeneral(a_float* z, const ConstraintIndex& ci) const {
+  REQUIRE_HANDLE();
+  if (!z) return ErrorCodes::InvalidPointer;
+  if (!solver_->is_initialized_) return ErrorCodes::SolverNotInitialized;
+  const int dim = altro_b200_get_constraint_dim(solver_->handle, ci.i);
+  if (dim <= 0) return ErrorCodes::BadIndex;
+  std::vector<double> all(static_cast<size_t>(solver_->batch_) * dim);
+  int e = altro_b200_get_dual_general(solver_->handle, ci.i, ci.k, all.data());
+  if (e) return EC(e);
+  std::memcpy(z, all.data(), sizeof(double) * static_cast<size_t>(dim));  // the first problem
+  return ErrorCodes::NoError;
+}
+
 ErrorCodes ALTROSolver::GetKnotPointField(const char* name, a_float* out, int k) const {
   REQUIRE_HANDLE();
   if (!name || !out) return ErrorCodes::InvalidPointer;
   int k_stop = k + 1;
   ErrorCodes err = CheckKnotPointIndices(k, k_stop, LastIndexMode::Inclusive);
   if (err != ErrorCodes::NoError) return err;
+  // the reference spells members with a trailing underscore (knotpoint_data.hpp:160-233)
+  std::string nm(name);
+  if (nm.size() > 1 && nm.back() == '_') nm.pop_back();
+  name = nm.c_str();
   int rows = 0;
   int e = altro_b200_get_field(solver_->handle, name, nullptr, &rows);
   if (e) return EC(e);

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -235,6 +236,7 @@ struct altro_b200_solver {
   unsigned long long* ls_hist = nullptr;
   PhaseHost ph;        // accumulated statistics + device limits
   int solve_mode = 0;  // 0: phase pipeline (default), 1: single persistent kernel
+  int backward_team = 0;  // Riccati sweep: 0 one warp per group, 1 the warps of a CTA (solver_team.cuh)
   // pipelined sub-batches: the groups are cut into `nsplit` contiguous ranges, each on its own
   // stream, so that the sweeps of one range (one busy warp per group) overlap the rollouts and
   // knot-parallel phases of another.  One host thread enqueues all of them.
@@ -257,9 +259,16 @@ struct altro_b200_solver {
   std::vector<double*> off_b;
   // host mirrors of the shared weights
   std::vector<double> Qd_h, Rd_h, lin_h;
+  // dense quadratic cost (SetQuadraticCost): host mirrors of every knot's Q, R, H (diagonal-cost
+  // knots hold diag(Qd), diag(Rd), 0) and their device copies, uploaded once a dense knot exists
+  std::vector<double> Qf_h, Rf_h, Hf_h;
+  double *Qf = nullptr, *Rf = nullptr, *Hf = nullptr;
+  bool dense_cost = false;
   // staging
   double* stage = nullptr;
   long stage_count = 0;
+  double* view_buf = nullptr;  // scratch stream of the derived KnotPointData views
+  long view_count = 0;
   std::vector<void*> allocs;
 };
 
@@ -466,6 +475,8 @@ altro_b200_solver* altro_b200_create(int horizon_length, int batch, int device) 
   s->device = device;
   altro_b200_default_options(&s->opts);
   memset(&s->con_h, 0, sizeof(s->con_h));
+  // test hook: run a whole test suite with the other Riccati schedule (results are bit-identical)
+  if (const char* env = getenv("ALTRO_B200_BACKWARD_TEAM")) s->backward_team = atoi(env) != 0;
   return s;
 }
 
@@ -475,6 +486,7 @@ void altro_b200_destroy(altro_b200_solver* s) {
   cudaStreamSynchronize(s->stream);
   for (void* p : s->allocs) cudaFree(p);
   if (s->stage) cudaFree(s->stage);
+  if (s->view_buf) cudaFree(s->view_buf);
   for (int i = 0; i < altro_b200_solver::kMaxSplit; ++i) {
     if (s->sub_ready[i]) {
       cudaStreamDestroy(s->sub_stream[i]);
@@ -506,6 +518,9 @@ int altro_b200_set_dimension(altro_b200_solver* s, int n, int m) {  // altro_sol
   const long N = s->N, S = s->Bp;
   s->Qd_h.assign((size_t)(N + 1) * n, 0.0);
   s->Rd_h.assign((size_t)N * m, 0.0);
+  s->Qf_h.assign((size_t)(N + 1) * n * n, 0.0);
+  s->Rf_h.assign((size_t)N * m * m, 0.0);
+  s->Hf_h.assign((size_t)N * m * n, 0.0);
   s->lin_h.assign((size_t)N * (n * n + n * m + n), 0.0);
   DALLOC(s, s->Qd, (N + 1) * n);
   DALLOC(s, s->Rd, N * m);
@@ -615,12 +630,37 @@ int altro_b200_set_linear_dynamics(altro_b200_solver* s, const double* A, const 
   return ALTRO_B200_NO_ERROR;
 }
 
+// device copies of the dense cost blocks (only once a dense knot exists)
+static int upload_dense_cost(altro_b200_solver* s) {
+  if (!s->dense_cost) return 0;
+  if (!s->Qf) {
+    DALLOC(s, s->Qf, (long)s->Qf_h.size());
+    DALLOC(s, s->Rf, (long)s->Rf_h.size());
+    DALLOC(s, s->Hf, (long)s->Hf_h.size());
+  }
+  CUDA_OK(cudaMemcpyAsync(s->Qf, s->Qf_h.data(), s->Qf_h.size() * 8, cudaMemcpyHostToDevice, s->stream));
+  CUDA_OK(cudaMemcpyAsync(s->Rf, s->Rf_h.data(), s->Rf_h.size() * 8, cudaMemcpyHostToDevice, s->stream));
+  CUDA_OK(cudaMemcpyAsync(s->Hf, s->Hf_h.data(), s->Hf_h.size() * 8, cudaMemcpyHostToDevice, s->stream));
+  CUDA_OK(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
 static int store_weights(altro_b200_solver* s, const double* Qd, const double* Rd, int k0, int k1) {
   const int n = s->n, m = s->m;
   for (int k = k0; k < k1; ++k) {
     memcpy(&s->Qd_h[(size_t)k * n], Qd, sizeof(double) * n);
-    if (k < s->N && Rd) memcpy(&s->Rd_h[(size_t)k * m], Rd, sizeof(double) * m);
+    double* Qk = &s->Qf_h[(size_t)k * n * n];
+    memset(Qk, 0, sizeof(double) * n * n);
+    for (int i = 0; i < n; ++i) Qk[i + n * i] = Qd[i];
+    if (k < s->N && Rd) {
+      memcpy(&s->Rd_h[(size_t)k * m], Rd, sizeof(double) * m);
+      double* Rk = &s->Rf_h[(size_t)k * m * m];
+      memset(Rk, 0, sizeof(double) * m * m);
+      for (int i = 0; i < m; ++i) Rk[i + m * i] = Rd[i];
+      memset(&s->Hf_h[(size_t)k * m * n], 0, sizeof(double) * m * n);
+    }
   }
+  if (int e = upload_dense_cost(s)) return e;
   CUDA_OK(cudaMemcpyAsync(s->Qd, s->Qd_h.data(), s->Qd_h.size() * 8, cudaMemcpyHostToDevice, s->stream));
   CUDA_OK(cudaMemcpyAsync(s->Rd, s->Rd_h.data(), s->Rd_h.size() * 8, cudaMemcpyHostToDevice, s->stream));
   CUDA_OK(cudaStreamSynchronize(s->stream));  // the host mirrors may change right after
@@ -810,6 +850,42 @@ int altro_b200_set_diagonal_cost(altro_b200_solver* s, const double* Qd, const d
   return ALTRO_B200_NO_ERROR;
 }
 
+// SetQuadraticCost (altro_solver.cpp:118-136, knotpoint_data.cpp:64-85): dense Q [n*n], R [m*m],
+// H [m*n] (column-major, shared by the batch); q, r, c as in SetDiagonalCost.
+int altro_b200_set_quadratic_cost(altro_b200_solver* s, const double* Q, const double* R,
+                                  const double* H, const double* q, const double* r,
+                                  const double* c, int per_problem, int k_start, int k_stop) {
+  if (!s || !Q || !q || !c) return ALTRO_B200_INVALID_POINTER;
+  if (!s->dims_set) return ALTRO_B200_DIMENSION_UNKNOWN;
+  CUDA_OK(cudaSetDevice(s->device));
+  int e = resolve_range(s, k_start, k_stop, true);
+  if (e) return e;
+  if (empty_range(k_start, k_stop)) return ALTRO_B200_NO_ERROR;
+  if (k_start < s->N && (!R || !r)) return ALTRO_B200_INVALID_POINTER;
+  const int n = s->n, m = s->m;
+  for (int k = k_start; k < k_stop; ++k) {
+    memcpy(&s->Qf_h[(size_t)k * n * n], Q, sizeof(double) * n * n);
+    for (int i = 0; i < n; ++i) s->Qd_h[(size_t)k * n + i] = Q[i + n * i];
+    if (k < s->N) {
+      memcpy(&s->Rf_h[(size_t)k * m * m], R, sizeof(double) * m * m);
+      for (int i = 0; i < m; ++i) s->Rd_h[(size_t)k * m + i] = R[i + m * i];
+      if (H)
+        memcpy(&s->Hf_h[(size_t)k * m * n], H, sizeof(double) * m * n);
+      else
+        memset(&s->Hf_h[(size_t)k * m * n], 0, sizeof(double) * m * n);
+    }
+  }
+  s->dense_cost = true;
+  CUDA_OK(cudaMemcpyAsync(s->Qd, s->Qd_h.data(), s->Qd_h.size() * 8, cudaMemcpyHostToDevice, s->stream));
+  CUDA_OK(cudaMemcpyAsync(s->Rd, s->Rd_h.data(), s->Rd_h.size() * 8, cudaMemcpyHostToDevice, s->stream));
+  e = upload_dense_cost(s);
+  if (e) return e;
+  e = set_linear_terms(s, q, r, c, per_problem, k_start, k_stop);
+  if (e) return e;
+  s->cost_set = true;
+  return ALTRO_B200_NO_ERROR;
+}
+
 int altro_b200_update_linear_costs(altro_b200_solver* s, const double* q, const double* r,
                                    const double* c, int per_problem, int k_start, int k_stop) {
   if (!s || !c) return ALTRO_B200_INVALID_POINTER;
@@ -861,6 +937,90 @@ int altro_b200_set_constraint(altro_b200_solver* s, int cone, int dim, const int
   }
   s->con_h.rows += dim;
   s->con_h.ncon += 1;
+  return ALTRO_B200_NO_ERROR;
+}
+
+// shared part of the family setters: slot bookkeeping + optional per-problem parameters
+static int add_slot(altro_b200_solver* s, int cone, int dim, int family, int nparam,
+                    const double* param_b, int k_start, int k_stop, ConSlot** out) {
+  if (s->initialized) return ALTRO_B200_SOLVER_ALREADY_INITIALIZED;
+  if (!s->dims_set) return ALTRO_B200_DIMENSION_UNKNOWN;
+  if (dim <= 0 || dim > kMaxConDim) return ALTRO_B200_INVALID_CONSTRAINT_DIM;
+  if (cone == CONE_SOC && dim > kMaxSocDim) return ALTRO_B200_INVALID_CONSTRAINT_DIM;
+  if (cone < CONE_EQUALITY || cone > CONE_SOC) return ALTRO_B200_BAD_INDEX;
+  if (s->con_h.ncon >= kMaxCon) return ALTRO_B200_MAX_CONSTRAINTS_EXCEEDED;
+  CUDA_OK(cudaSetDevice(s->device));
+  int e = resolve_range(s, k_start, k_stop, true);
+  if (e) return e;
+  if (empty_range(k_start, k_stop)) {
+    *out = nullptr;
+    return ALTRO_B200_NO_ERROR;
+  }
+  ConSlot& c = s->con_h.slot[s->con_h.ncon];
+  memset(&c, 0, sizeof(c));
+  c.k_start = k_start;
+  c.k_stop = k_stop;
+  c.cone = cone;
+  c.dim = dim;
+  c.family = family;
+  c.row0 = s->con_h.rows;
+  if (param_b) {
+    double* dptr = nullptr;
+    DALLOC(s, dptr, (long)nparam * s->Bp);
+    e = upload_pm(s, param_b, nparam, gview(dptr, nparam));
+    if (e) return e;
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    c.off_per_problem = 1;
+    c.off_b = dptr;
+  }
+  *out = &c;
+  return ALTRO_B200_NO_ERROR;
+}
+static void commit_slot(altro_b200_solver* s, const ConSlot& c) {
+  s->con_h.rows += c.dim;
+  s->con_h.ncon += 1;
+}
+
+// SetConstraint with general affine rows c = J [x;u] + e (dense J [dim x (n+m)], column-major,
+// shared by the batch; e [dim] shared or e_b [B][dim] per problem).
+int altro_b200_set_constraint_affine(altro_b200_solver* s, int cone, int dim, const double* J,
+                                     const double* e, const double* e_b, int k_start,
+                                     int k_stop) {
+  if (!s || !J || !e) return ALTRO_B200_INVALID_POINTER;
+  ConSlot* c = nullptr;
+  int err = add_slot(s, cone, dim, CON_FAMILY_AFFINE, dim, e_b, k_start, k_stop, &c);
+  if (err || !c) return err;
+  const int nm = s->n + s->m;
+  // rows that read an input cannot live on the terminal knot (it has no input)
+  if (c->k_stop > s->N)
+    for (int j = s->n; j < nm; ++j)
+      for (int i = 0; i < dim; ++i)
+        if (J[i + dim * j] != 0.0) return ALTRO_B200_INVALID_OPT_AT_TERMINAL;
+  double* Jd = nullptr;
+  DALLOC(s, Jd, (long)dim * nm);
+  CUDA_OK(cudaMemcpyAsync(Jd, J, sizeof(double) * (size_t)dim * nm, cudaMemcpyHostToDevice, s->stream));
+  CUDA_OK(cudaStreamSynchronize(s->stream));
+  c->Jd = Jd;
+  for (int i = 0; i < dim; ++i) c->off[i] = e[i];
+  commit_slot(s, *c);
+  return ALTRO_B200_NO_ERROR;
+}
+
+// SetConstraint with the nonlinear keep-out disc c = r^2 - (v_a - cx)^2 - (v_b - cy)^2 <= 0 on
+// the variables v_a = [x;u][idx_a], v_b = [x;u][idx_b]; (cx, cy, r) shared or per problem [B][3].
+int altro_b200_set_constraint_disc(altro_b200_solver* s, int idx_a, int idx_b, const double* disc,
+                                   const double* disc_b, int k_start, int k_stop) {
+  if (!s || !disc) return ALTRO_B200_INVALID_POINTER;
+  if (s->dims_set && (idx_a < 0 || idx_b < 0 || idx_a >= s->n + s->m || idx_b >= s->n + s->m))
+    return ALTRO_B200_BAD_INDEX;
+  ConSlot* c = nullptr;
+  int err = add_slot(s, CONE_INEQUALITY, 1, CON_FAMILY_DISC, 3, disc_b, k_start, k_stop, &c);
+  if (err || !c) return err;
+  if (c->k_stop > s->N && (idx_a >= s->n || idx_b >= s->n)) return ALTRO_B200_INVALID_OPT_AT_TERMINAL;
+  c->idx[0] = idx_a;
+  c->idx[1] = idx_b;
+  for (int i = 0; i < 3; ++i) c->off[i] = disc[i];
+  commit_slot(s, *c);
   return ALTRO_B200_NO_ERROR;
 }
 
@@ -1013,7 +1173,8 @@ int altro_b200_shift_trajectory(altro_b200_solver* s) {
 static int con_level(const altro_b200_solver* s) {
   int level = s->con_h.ncon > 0 ? 1 : 0;
   for (int j = 0; j < s->con_h.ncon; ++j)
-    if (s->con_h.slot[j].cone == CONE_SOC) level = 2;
+    if (s->con_h.slot[j].cone == CONE_SOC || s->con_h.slot[j].family != CON_FAMILY_SELECTOR) level = 2;
+  if (s->dense_cost) level = 2;  // dense Q, R, H live in the general instantiation
   return level;
 }
 
@@ -1040,6 +1201,8 @@ int altro_b200_mpc_step(altro_b200_solver* s) {
   return e;
 }
 
+static int run_host_op(altro_b200_solver* s, int op, double* cost_out);
+
 static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   memset(&P, 0, sizeof(P));
   P.N = s->N;
@@ -1058,6 +1221,9 @@ static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   P.lin = s->lin;
   P.Qd = s->Qd;
   P.Rd = s->Rd;
+  P.Qf = s->dense_cost ? s->Qf : nullptr;
+  P.Rf = s->dense_cost ? s->Rf : nullptr;
+  P.Hf = s->dense_cost ? s->Hf : nullptr;
   P.q = s->q;
   P.r = s->r;
   P.c = s->c;
@@ -1187,6 +1353,7 @@ int altro_b200_solve_async(altro_b200_solver* s) {  // altro_solver.cpp:257-260
     H.d_done = s->d_done + i;
     H.d_prof = s->d_prof + 8 * i;
     H.fwd_warps = std::max(4, s->nslots);
+    H.backward_team = s->backward_team;
     for (int j = 0; j < PH_COUNT; ++j) {
       H.ms[j] = 0.0;
       H.launches[j] = 0;
@@ -1264,6 +1431,25 @@ static int run_host_op(altro_b200_solver* s, int op, double* cost_out) {
   return ALTRO_B200_NO_ERROR;
 }
 
+// The per-knot expansions of KnotPointData at the WORKING trajectory x_, u_ (as set by SetState /
+// SetInput or left by Solve), for every knot of every problem: CalcDynamicsExpansion,
+// CalcConstraints, CalcConstraintJacobians, CalcProjectedDuals (z_est = z - rho c), CalcCostGradient
+// (knotpoint_data.cpp:406-437, :473-487, :523-595) with the current duals and penalty.  Results are
+// read back through altro_b200_get_field ("A" "B" "lx" "lu" "z_est" and the derived views).
+int altro_b200_knot_eval(altro_b200_solver* s) { return run_host_op(s, OP_KNOT_EVAL, nullptr); }
+
+// KnotPointData::SetPenalty (knotpoint_data.cpp:180-191) for every constraint of every problem
+int altro_b200_set_penalty(altro_b200_solver* s, double rho) {
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;
+  if (!(rho > 0.0)) return ALTRO_B200_NON_POSITIVE_PENALTY;
+  CUDA_OK(cudaSetDevice(s->device));
+  k_fill<<<64, 256, 0, s->stream>>>(s->rho, s->Bp, rho);
+  s->launches++;
+  CUDA_OK(cudaGetLastError());
+  return ALTRO_B200_NO_ERROR;
+}
+
 int altro_b200_open_loop_rollout(altro_b200_solver* s) {  // altro_solver.cpp:253
   return run_host_op(s, OP_OPEN_LOOP_ROLLOUT, nullptr);
 }
@@ -1281,6 +1467,13 @@ int altro_b200_set_solve_mode(altro_b200_solver* s, int mode) {
   if (!s) return ALTRO_B200_INVALID_POINTER;
   if (mode != 0 && mode != 1) return ALTRO_B200_BAD_INDEX;
   s->solve_mode = mode;
+  return ALTRO_B200_NO_ERROR;
+}
+
+int altro_b200_set_backward_mode(altro_b200_solver* s, int team) {
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  if (team != 0 && team != 1) return ALTRO_B200_BAD_INDEX;
+  s->backward_team = team;
   return ALTRO_B200_NO_ERROR;
 }
 
@@ -1373,13 +1566,32 @@ GETTER_PM(altro_b200_get_feedforward_gains, d, s->m, s->N * s->m)
 
 static int run_host_op(altro_b200_solver* s, int op, double* cost_out);
 
-// KnotPointData member of every problem by name (knotpoint_data.hpp:160-233): x u y (accepted
-// point = working copy after Solve), xbar ubar, A B, lx lu, K d, P p, q r c.  out: [B][knots][rows]
-// with knots = N + 1 (fields that do not exist at the terminal knot hold zeros / stale data there).
+// scratch stream [G][N+1][rows][32] for the derived views, grown on demand and kept
+static int ensure_view(altro_b200_solver* s, long rows) {
+  const long need = (long)s->G * (s->N + 1) * rows * 32;
+  if (need <= s->view_count) return 0;
+  if (s->view_buf) {
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    CUDA_OK(cudaFree(s->view_buf));
+    s->bytes -= s->view_count * 8;
+  }
+  CUDA_OK(cudaMalloc((void**)&s->view_buf, (size_t)need * 8));
+  s->view_count = need;
+  s->bytes += need * 8;
+  return 0;
+}
+
+// KnotPointData member of every problem by name (knotpoint_data.hpp:160-233).  Stored members:
+// x u y (x_, u_, y_: the accepted point after Solve), xbar ubar (x, u), A B, lx lu, K d, P p, q r c,
+// z z_est (duals and estimates of all constraints of the knot, slot after slot).  Re-created on
+// demand: constraint_val z_proj (same row layout as z), lxx luu lux (CalcCostHessian at the working
+// trajectory), rho (uniform over the problem's constraints).  out: [B][knots][rows] with knots =
+// N + 1 (fields that do not exist at the terminal knot, and rows of constraints that do not apply
+// at a knot, hold zeros / stale data there).
 int altro_b200_get_field(altro_b200_solver* s, const char* name, double* out, int* rows_out) {
   if (!s || !name) return ALTRO_B200_INVALID_POINTER;
   if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;
-  const int n = s->n, m = s->m;
+  const int n = s->n, m = s->m, zrows = s->con_h.rows;
   struct { const char* nm; double* p; int rows; } tab[] = {
       {"x", s->x, n}, {"u", s->u, m}, {"y", s->y, n}, {"xbar", s->xbar, n}, {"ubar", s->ubar, m},
       {"A", s->A, n * n}, {"B", s->Bm, n * m}, {"lx", s->lx, n}, {"lu", s->lu, m},
@@ -1391,24 +1603,87 @@ int altro_b200_get_field(altro_b200_solver* s, const char* name, double* out, in
       if (!out) return ALTRO_B200_NO_ERROR;
       CUDA_OK(cudaSetDevice(s->device));
       if (t.p == s->A || t.p == s->Bm) {
-        // [A B] may be stored packed (models.cuh, JacPack): expand into a dense scratch stream
+        // [A B] may be stored packed (models.cuh, JacPack): expand into the dense scratch stream
         const long rows = (long)n * n + (long)n * m;
-        double* dense = nullptr;
-        CUDA_OK(cudaMalloc((void**)&dense, (size_t)s->G * (s->N + 1) * rows * 32 * 8));
-        CUDA_OK(cudaMemsetAsync(dense, 0, (size_t)s->G * (s->N + 1) * rows * 32 * 8, s->stream));
-        int e = run_host_op(s, OP_UNPACK_JAC, dense);
-        if (!e) {
-          FieldView v{dense + (t.p == s->Bm ? (long)n * n * 32 : 0), t.rows, rows * 32,
-                      (long)(s->N + 1) * rows * 32};
-          e = download_pm(s, v, (long)(s->N + 1) * t.rows, out);
-        }
-        cudaFree(dense);
-        return e;
+        int e = ensure_view(s, rows);
+        if (e) return e;
+        CUDA_OK(cudaMemsetAsync(s->view_buf, 0, (size_t)s->G * (s->N + 1) * rows * 32 * 8, s->stream));
+        e = run_host_op(s, OP_UNPACK_JAC, s->view_buf);
+        if (e) return e;
+        FieldView v{s->view_buf + (t.p == s->Bm ? (long)n * n * 32 : 0), t.rows, rows * 32,
+                    (long)(s->N + 1) * rows * 32};
+        return download_pm(s, v, (long)(s->N + 1) * t.rows, out);
       }
       return download_pm(s, fview(s, t.p, t.rows), (long)(s->N + 1) * t.rows, out);
     }
   }
+  // duals live in their own record stream [group][knot][z rows | z_est rows][32]
+  if (strcmp(name, "z") == 0 || strcmp(name, "z_est") == 0) {
+    if (rows_out) *rows_out = zrows;
+    if (!out || zrows == 0) return ALTRO_B200_NO_ERROR;
+    CUDA_OK(cudaSetDevice(s->device));
+    FieldView v{name[1] == 0 ? s->z : s->zest, zrows, s->Rz, s->GSz};
+    return download_pm(s, v, (long)(s->N + 1) * zrows, out);
+  }
+  struct { const char* nm; int view, rows; } derived[] = {
+      {"constraint_val", KV_CONSTRAINT_VAL, zrows}, {"z_proj", KV_Z_PROJ, zrows},
+      {"lxx", KV_LXX, n * n}, {"luu", KV_LUU, m * m}, {"lux", KV_LUX, m * n}, {"rho", KV_RHO, 1}};
+  for (auto& t : derived) {
+    if (strcmp(t.nm, name) == 0) {
+      if (rows_out) *rows_out = t.rows;
+      if (!out || t.rows == 0) return ALTRO_B200_NO_ERROR;
+      CUDA_OK(cudaSetDevice(s->device));
+      int e = ensure_view(s, t.rows);
+      if (e) return e;
+      CUDA_OK(cudaMemsetAsync(s->view_buf, 0, (size_t)s->G * (s->N + 1) * t.rows * 32 * 8, s->stream));
+      s->ph.view = t.view;
+      s->ph.view_rows = t.rows;
+      e = run_host_op(s, OP_KNOT_VIEW, s->view_buf);
+      if (e) return e;
+      FieldView v{s->view_buf, t.rows, (long)t.rows * 32, (long)(s->N + 1) * t.rows * 32};
+      return download_pm(s, v, (long)(s->N + 1) * t.rows, out);
+    }
+  }
   return ALTRO_B200_BAD_INDEX;
+}
+
+// SetDualGeneric / GetDualGeneral (altro_solver.hpp:359, :416; declared, never defined in the
+// reference): the dual z of constraint slot `constraint` at knot k for every problem, [B][dim].
+static int dual_view(altro_b200_solver* s, int constraint, int k, FieldView* v, int* dim) {
+  if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;
+  if (constraint < 0 || constraint >= s->con_h.ncon) return ALTRO_B200_BAD_INDEX;
+  const ConSlot& c = s->con_h.slot[constraint];
+  if (k < c.k_start || k >= c.k_stop) return ALTRO_B200_BAD_INDEX;
+  *dim = c.dim;
+  *v = FieldView{s->z + (long)k * s->Rz + (long)c.row0 * 32, c.dim, 0, s->GSz};
+  return 0;
+}
+int altro_b200_get_dual_general(altro_b200_solver* s, int constraint, int k, double* z) {
+  if (!s || !z) return ALTRO_B200_INVALID_POINTER;
+  FieldView v;
+  int dim = 0;
+  int e = dual_view(s, constraint, k, &v, &dim);
+  if (e) return e;
+  CUDA_OK(cudaSetDevice(s->device));
+  return download_pm(s, v, dim, z);
+}
+int altro_b200_set_dual_general(altro_b200_solver* s, int constraint, int k, const double* z,
+                                int per_problem) {
+  if (!s || !z) return ALTRO_B200_INVALID_POINTER;
+  FieldView v;
+  int dim = 0;
+  int e = dual_view(s, constraint, k, &v, &dim);
+  if (e) return e;
+  CUDA_OK(cudaSetDevice(s->device));
+  e = per_problem ? upload_pm(s, z, dim, v) : upload_shared(s, z, dim, v);
+  if (e) return e;
+  CUDA_OK(cudaStreamSynchronize(s->stream));
+  return ALTRO_B200_NO_ERROR;
+}
+int altro_b200_get_num_constraints(const altro_b200_solver* s) { return s ? s->con_h.ncon : 0; }
+int altro_b200_get_constraint_dim(const altro_b200_solver* s, int constraint) {
+  if (!s || constraint < 0 || constraint >= s->con_h.ncon) return 0;
+  return s->con_h.slot[constraint].dim;
 }
 
 #define GETTER_VEC(name, field, type)                                                       \

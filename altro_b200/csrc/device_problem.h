@@ -30,19 +30,34 @@ enum Cone { CONE_EQUALITY = 0, CONE_IDENTITY = 1, CONE_INEQUALITY = 2, CONE_SOC 
 // SolveStatus, typedefs.hpp:19-27
 enum DevSolveStatus { SOLVE_SUCCESS = 0, SOLVE_UNSOLVED = 1, SOLVE_MAX_ITERATIONS = 2 };
 
-// One constraint slot: rows c_i = scale_i * [x;u][idx_i] + off_i on knots [k_start, k_stop).
-// (idx_i = -1: constant row.)  This "selector-affine" family covers every constraint the
-// reference's end-to-end tests use: goal, control box, control-norm SOC, steering bound.
+// Constraint FAMILIES: what replaces the reference's constraint callbacks c(x,u), dc/d[x;u]
+// (typedefs.hpp:48-52) on the device, the way ModelId replaces the dynamics callbacks.
+enum ConFamily {
+  // rows c_i = scale_i * [x;u][idx_i] + off_i  (idx_i = -1: constant row): one variable per row.
+  // Covers every constraint of the reference's end-to-end tests (goal, control box, control-norm
+  // SOC, steering bound) and has a diagonal fast path for the linear cones (TrajSolver CON = 1).
+  CON_FAMILY_SELECTOR = 0,
+  // general affine rows c = J [x;u] + e with a dense dim x (n+m) Jacobian shared by the batch
+  // (column-major, in HBM) and e from off[] or per problem from off_b
+  CON_FAMILY_AFFINE = 1,
+  // nonlinear: keep-out disc, c = r^2 - (s_a - cx)^2 - (s_b - cy)^2 (dim 1, INEQUALITY: c <= 0)
+  // with s_a = [x;u][idx[0]], s_b = [x;u][idx[1]], (cx, cy, r) = off[0..2] or per problem off_b
+  CON_FAMILY_DISC = 2,
+};
+
+// One constraint slot on knots [k_start, k_stop).
 struct ConSlot {
   int k_start, k_stop;
   int cone;
   int dim;
   int row0;             // first row of this slot in the packed per-knot dual arrays
   int off_per_problem;  // 1: offsets come from off_b (per problem) instead of off[]
+  int family;           // ConFamily
   int idx[kMaxConDim];
   double scale[kMaxConDim];
   double off[kMaxConDim];
-  const double* off_b;  // [G][dim][32]
+  const double* off_b;  // [G][nparam][32]  (nparam = dim, or 3 for CON_FAMILY_DISC)
+  const double* Jd;     // CON_FAMILY_AFFINE: [dim x (n+m)] column-major, device memory
 };
 
 struct ConTable {
@@ -81,6 +96,11 @@ struct DeviceProblem {
   // cost (KnotPointData Q_, R_, q_, r_, c_): diagonal weights shared per knot, linear terms per problem
   const double* Qd;  // [(N+1)*n]
   const double* Rd;  // [N*m]
+  // dense quadratic cost (KnotPointData::SetQuadraticCost, knotpoint_data.cpp:64-85), shared per
+  // knot, column-major; null = diagonal.  Only the general instantiation (CON = 2) reads them.
+  const double* Qf;  // [(N+1)][n*n]
+  const double* Rf;  // [N][m*m]
+  const double* Hf;  // [N][m*n]
   const double* q;   // record field, n rows
   const double* r;   // record field, m rows
   const double* c;   // record field, 1 row

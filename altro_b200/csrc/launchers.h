@@ -24,11 +24,17 @@ enum HostOp {
   OP_CALC_COST = 2,
   OP_UNPACK_JAC = 3,
   OP_SOLVE_ITERATION = 4,  // one iLQR iteration: k_phase_backward + k_phase_forward (iter = PhaseHost::iter)
+  OP_KNOT_VIEW = 5,        // derived KnotPointData member PhaseHost::view into cost_out
+  OP_KNOT_EVAL = 6,        // expansions of every knot at the working trajectory (k_phase_expand)
 };
+
+// derived KnotPointData views served by k_knot_view (solver_phases.cuh)
+enum KnotView { KV_CONSTRAINT_VAL = 0, KV_Z_PROJ = 1, KV_LXX = 2, KV_LUU = 3, KV_LUX = 4, KV_RHO = 5 };
 
 struct PhaseHost {
   int op;              // HostOp
   int iter;            // OP_SOLVE_ITERATION: iteration number (0 = first)
+  int view, view_rows; // OP_KNOT_VIEW: KnotView id and rows per knot of the output stream
   double* cost_out;    // OP_CALC_COST: device array [Bp]; OP_UNPACK_JAC: dense [A B] stream
                        // [group][knot][n*n + n*m][32]
   int* d_done;         // device: problems of the sub-batch that have stopped (zeroed by the prologue)
@@ -40,6 +46,7 @@ struct PhaseHost {
   double units[PH_COUNT];      // trajectories (or trajectory-knots for PH_EXPAND) processed
   long syncs;                  // host waits on the device (lagged stop-counter checks)
   int fwd_warps;               // warps per CTA of k_phase_forward (1 + speculative candidates)
+  int backward_team;           // 1: Riccati sweep by the warps of a CTA (solver_team.cuh), 0: one warp
   cudaEvent_t ev0, ev1;
   static constexpr int kDoneRing = 4;
   cudaEvent_t ev_done[kDoneRing];  // recorded after the h_done copy of iteration i % kDoneRing

@@ -7,6 +7,7 @@
 // altro_solver.hpp:185) and sizes are template parameters so loops unroll into straight-line
 // DFMA code with no indexing.
 #pragma once
+#include <cstdio>
 
 namespace altro_b200 {
 
@@ -249,12 +250,18 @@ struct BulkRing {
   ALTRO_DEV const double* wait() const {
     const unsigned a = (unsigned)__cvta_generic_to_shared(bar + s);
     unsigned ok = 0;
+    unsigned long long spins = 0;
     while (!ok) {
       asm volatile(
           "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
           : "=r"(ok)
           : "r"(a), "r"(parity)
           : "memory");
+      if (!ok && ++spins > (1ull << 24)) {  // a protocol bug must fail the launch, not hang the device
+        printf("altro_b200: ring wait stuck (block %d thread %d stage %d parity %u)\n", (int)blockIdx.x,
+               (int)threadIdx.x, s, parity);
+        __trap();
+      }
     }
     return data + (long)s * stage_doubles;
   }
@@ -310,15 +317,31 @@ struct BulkPipe {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // A wait that cannot complete is a protocol bug; it must surface as a kernel error (trap -> the
+  // launch fails, the C ABI returns an error), never as a hung device.
   ALTRO_DEV static void spin(unsigned addr, unsigned parity) {
     unsigned ok = 0;
+    unsigned long long spins = 0;
     while (!ok) {
       asm volatile(
           "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
           : "=r"(ok)
           : "r"(addr), "r"(parity)
           : "memory");
+      if (!ok && ++spins > (1ull << 24)) {
+        printf("altro_b200: mbarrier wait stuck (block %d thread %d addr %u parity %u)\n", (int)blockIdx.x,
+               (int)threadIdx.x, addr, parity);
+        __trap();
+      }
     }
+  }
+  // ALL lanes of the producer's warp, before the producer thread calls acquire(k): wait until every
+  // consumer warp has released the stage's previous use.  Waiting as a whole warp keeps the
+  // producer thread converged with its warp (a lone spinning lane would make the warp execute the
+  // next knot twice: once without it, once for it).
+  ALTRO_DEV void wait_writable(int k) const {
+    const int use = k / depth;
+    if (use > 0) spin((unsigned)__cvta_generic_to_shared(empty + k % depth), (unsigned)((use - 1) & 1));
   }
   // producer thread: make stage k % depth writable for pass-local knot k, announce `bytes`
   ALTRO_DEV int acquire(int k, unsigned bytes) const {

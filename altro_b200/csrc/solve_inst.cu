@@ -33,10 +33,13 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
   const int b0 = P.g0 * 32, b1 = std::min(B, (P.g0 + G) * 32);  // problems of this sub-batch
 
   if (H->op == OP_SOLVE_PROLOGUE) {  // solver.cpp:417-430
-    if (TS::kStaged) {
+    {
       const int mx = (int)H->smem_per_cta;
-      cudaFuncSetAttribute(k_phase_backward<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-      cudaFuncSetAttribute(k_phase_forward<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+      if (TS::kStaged) {
+        cudaFuncSetAttribute(k_phase_backward<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k_phase_forward<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+      }
+      cudaFuncSetAttribute(k_phase_backward_team<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     }
     cudaMemsetAsync(H->d_done, 0, sizeof(int), st);
     timed(PH_INIT, b1 - b0, [&] { k_phase_init<Model, CON><<<G, 32, 0, st>>>(P); });
@@ -61,7 +64,29 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
     return (int)std::max<size_t>(2, std::min<size_t>(kMaxStageDepth, budget / stage_bytes));
   };
   const int zr = CON ? 2 * P.zrows : 0;  // dual record rows staged with the main rows
-  {
+  if (H->backward_team) {
+    // Riccati sweep by the W warps of a CTA per group (solver_team.cuh)
+    using Shape = TeamShape<n, m>;
+    const int per_sm = (P.Gtot + H->num_sms - 1) / H->num_sms;
+    const size_t xch = (size_t)Shape::kXchRows * 256;
+    const size_t sweep_stage = (size_t)(TS::kRowsBw + zr) * 256;
+    const size_t scan_stage = (size_t)(TS::kRowsBackwardKernel + zr) * 256;
+    int depth, rdepth = 0;
+    size_t stage_bytes;
+    if (TS::kStaged) {
+      depth = ring_depth(per_sm, sweep_stage, 256 + xch);
+      rdepth = ring_depth(per_sm, scan_stage, 256 + 128 + xch);
+      stage_bytes = std::max(BulkPipe::bytes(depth, (TS::kRowsBw + zr) * 32),
+                             256 + BulkRing::bytes(rdepth, (TS::kRowsBackwardKernel + zr) * 32));
+    } else {
+      depth = ring_depth(1, sweep_stage, 256 + xch);  // one CTA per SM
+      stage_bytes = BulkPipe::bytes(depth, (TS::kRowsBw + zr) * 32);
+    }
+    const size_t sm = stage_bytes + xch + wbytes;
+    timed(PH_BACKWARD, (double)G * 32, [&] {
+      k_phase_backward_team<Model, CON><<<G, 32 * Shape::W, sm, st>>>(P, depth, rdepth, wcount, H->iter == 0);
+    });
+  } else {
     int depth = 0;
     size_t sm = 0;
     if (TS::kStaged) {
@@ -122,6 +147,26 @@ static int launch_solve(const DeviceProblem& P, int has_con, cudaStream_t st, Ph
       k_calc_cost<Model, 2><<<(P.B + 31) / 32, 32, 0, st>>>(P, host->cost_out);
     else
       k_calc_cost<Model, 0><<<(P.B + 31) / 32, 32, 0, st>>>(P, host->cost_out);
+    return (int)cudaGetLastError();
+  }
+  if (host && host->op == OP_KNOT_EVAL) {
+    const dim3 grid((P.G * 32 + 127) / 128, P.N + 1);
+    if (has_con == 0)
+      k_phase_expand<Model, 0><<<grid, 128, 0, st>>>(P, P.G);
+    else if (has_con == 1)
+      k_phase_expand<Model, 1><<<grid, 128, 0, st>>>(P, P.G);
+    else
+      k_phase_expand<Model, 2><<<grid, 128, 0, st>>>(P, P.G);
+    return (int)cudaGetLastError();
+  }
+  if (host && host->op == OP_KNOT_VIEW) {
+    const dim3 grid((P.B + 127) / 128, P.N + 1);
+    if (has_con == 0)
+      k_knot_view<Model, 0><<<grid, 128, 0, st>>>(P, host->view, host->view_rows, host->cost_out);
+    else if (has_con == 1)
+      k_knot_view<Model, 1><<<grid, 128, 0, st>>>(P, host->view, host->view_rows, host->cost_out);
+    else
+      k_knot_view<Model, 2><<<grid, 128, 0, st>>>(P, host->view, host->view_rows, host->cost_out);
     return (int)cudaGetLastError();
   }
   if (host && host->op == OP_UNPACK_JAC) {

@@ -134,6 +134,7 @@ struct TrajSolver {
   static constexpr int m = Model::m;
   static constexpr int NS_ = Model::n, NI_ = Model::m;
   static constexpr bool kLinear = ModelTraits<Model>::is_linear;
+  static constexpr int kCon = CON;
   // TMA staging of the sequential sweeps (solver_phases.cuh) when the blocks are small enough to
   // live in registers (larger n keeps rolled loops over local-memory arrays, is bound by
   // arithmetic rather than by load latency, and a stage would not fit shared memory).
@@ -269,6 +270,23 @@ struct TrajSolver {
   // cval: the constant term c_k of this problem (already loaded / staged)
   ALTRO_DEV double stage_cost(int k, const double* x, const double* u, const double* q,
                               const double* r, bool terminal, double cval) const {
+    if constexpr (CON == 2) {
+      if (P.Qf) {  // dense Q, R, H: knotpoint_data.cpp:620-634
+        double t[n > m ? n : m];
+        mm<n, 1, n, false, false, 0>(P.Qf + (long)k * n * n, x, t);
+        double J = 0.5 * dot<n>(x, t);
+        J += dot<n>(q, x);
+        if (!terminal) {
+          mm<m, 1, m, false, false, 0>(P.Rf + (long)k * m * m, u, t);
+          J += 0.5 * dot<m>(u, t);
+          J += dot<m>(r, u);
+          mm<m, 1, n, false, false, 0>(P.Hf + (long)k * m * n, x, t);
+          J += dot<m>(u, t);
+        }
+        J += cval;
+        return J;
+      }
+    }
     double J = 0.0;
     double a = 0.0;
 #pragma unroll
@@ -287,11 +305,263 @@ struct TrajSolver {
   }
   ALTRO_DEV void stage_gradient(int k, const double* x, const double* u, const double* q,
                                 const double* r, bool terminal, double* lx, double* lu) const {
+    if constexpr (CON == 2) {
+      if (P.Qf) {  // knotpoint_data.cpp:654-668
+        mm<n, 1, n, false, false, 0>(P.Qf + (long)k * n * n, x, lx);
+#pragma unroll
+        for (int i = 0; i < n; ++i) lx[i] += q[i];
+        if (!terminal) {
+          mm<m, 1, m, false, false, 0>(P.Rf + (long)k * m * m, u, lu);
+#pragma unroll
+          for (int i = 0; i < m; ++i) lu[i] += r[i];
+          mm<m, 1, n, false, false, 1>(P.Hf + (long)k * m * n, x, lu);
+          mm<n, 1, m, true, false, 1>(P.Hf + (long)k * m * n, u, lx);
+        }
+        return;
+      }
+    }
 #pragma unroll
     for (int i = 0; i < n; ++i) lx[i] = Qd[k * n + i] * x[i] + q[i];
     if (!terminal) {
 #pragma unroll
       for (int i = 0; i < m; ++i) lu[i] = Rd[k * m + i] * u[i] + r[i];
+    }
+  }
+
+  // ---- general constraint slots (CON == 2 only): any family, any cone, dense Jacobian.
+  // A slot takes this path when its cone is the second-order cone or its family is not the
+  // selector family; selector rows with a linear cone keep the diagonal fast path below.
+  ALTRO_DEV static bool general_slot(const ConSlot& s) {
+    return CON == 2 && (s.cone == CONE_SOC || s.family != CON_FAMILY_SELECTOR);
+  }
+  // c(x,u) [p] and, when J != null, dc/d[x;u] [p x (n+m)] column-major (typedefs.hpp:48-52)
+  ALTRO_DEV void con_eval(const ConSlot& s, const double* x, const double* u, double* c, double* J) const {
+    constexpr int nm = n + m;
+    const int p = s.dim;
+    double xu[nm];
+#pragma unroll
+    for (int i = 0; i < n; ++i) xu[i] = x[i];
+#pragma unroll
+    for (int i = 0; i < m; ++i) xu[n + i] = u[i];
+    if (J)
+      for (int i = 0; i < p * nm; ++i) J[i] = 0.0;
+    if (s.family == CON_FAMILY_AFFINE) {
+      for (int i = 0; i < p; ++i) {
+        double v = row_offset(s, i);
+        for (int j = 0; j < nm; ++j) v = fma(s.Jd[i + p * j], xu[j], v);
+        c[i] = v;
+      }
+      if (J)
+        for (int i = 0; i < p * nm; ++i) J[i] = s.Jd[i];
+    } else if (s.family == CON_FAMILY_DISC) {
+      const double cx = s.off_per_problem ? G(s.off_b, 3)[0] : s.off[0];
+      const double cy = s.off_per_problem ? G(s.off_b, 3)[32] : s.off[1];
+      const double rad = s.off_per_problem ? G(s.off_b, 3)[64] : s.off[2];
+      const double da = xu[s.idx[0]] - cx, db = xu[s.idx[1]] - cy;
+      c[0] = rad * rad - da * da - db * db;
+      if (J) {
+        J[p * s.idx[0]] = -2.0 * da;
+        J[p * s.idx[1]] = -2.0 * db;
+      }
+    } else {  // selector rows
+      for (int i = 0; i < p; ++i) {
+        const int id = s.idx[i];
+        const double off = row_offset(s, i);
+        c[i] = (id < 0) ? off : fma(s.scale[i], xu[id], off);
+        if (J && id >= 0) J[i + p * id] = s.scale[i];
+      }
+    }
+  }
+  // projection onto the DUAL cone of `cone` (cones.hpp:13-30, cones.cpp:125-150)
+  ALTRO_DEV static void project_dual(int cone, int p, const double* zt, double* zp) {
+    if (cone == CONE_SOC) {
+      soc_projection(p, zt, zp);
+    } else {
+      for (int i = 0; i < p; ++i) {
+        double v = 0.0;  // IDENTITY -> dual EQUALITY: {0}
+        if (cone == CONE_EQUALITY) v = zt[i];
+        if (cone == CONE_INEQUALITY) v = fmin(0.0, zt[i]);
+        zp[i] = v;
+      }
+    }
+  }
+  // || Pi_K(c) - c ||_inf of one general slot (knotpoint_data.cpp:489-501)
+  __device__ __noinline__ double al_violation_general(const ConSlot& s, const double* x, const double* u) const {
+    double c[kMaxConDim], pc[kMaxConDim];
+    con_eval(s, x, u, c, nullptr);
+    if (s.cone == CONE_SOC) {
+      soc_projection(s.dim, c, pc);
+    } else {
+      for (int i = 0; i < s.dim; ++i) {
+        double v = 0.0;  // EQUALITY: projection onto {0}
+        if (s.cone == CONE_IDENTITY) v = c[i];
+        if (s.cone == CONE_INEQUALITY) v = fmin(0.0, c[i]);
+        pc[i] = v;
+      }
+    }
+    double viol = 0.0;
+    for (int i = 0; i < s.dim; ++i) viol = fmax(viol, fabs(pc[i] - c[i]));
+    return viol;
+  }
+  // AL cost and gradient of one general slot (knotpoint_data.cpp:523-547, :572-595)
+  __device__ __noinline__ double al_terms_general(const ConSlot& s, long zrow, const double* x, const double* u,
+                                    bool terminal, bool want_grad, double* lx, double* lu,
+                                    bool store_zest) {
+    constexpr int nm = n + m;
+    const int p = s.dim;
+    double c[kMaxConDim], zt[kMaxConDim], zp[kMaxConDim], v[kMaxConDim];
+    double J[kMaxConDim * nm];
+    con_eval(s, x, u, c, want_grad ? J : nullptr);
+    for (int i = 0; i < p; ++i) {
+      zt[i] = zread(zrow, s.row0, i) - rho * c[i];
+      if (store_zest) P.zest[zrow + i * 32] = zt[i];
+    }
+    project_dual(s.cone, p, zt, zp);
+    double nrm = 0.0;
+    for (int i = 0; i < p; ++i) nrm += zp[i] * zp[i];
+    if (want_grad) {
+      if (s.cone == CONE_SOC) {  // v = dPi^T zp
+        double Jp[kMaxSocDim * kMaxSocDim];
+        soc_jacobian(p, zt, Jp);
+        for (int i = 0; i < p; ++i) {
+          double a = 0.0;
+          for (int l = 0; l < p; ++l) a += Jp[l + p * i] * zp[l];
+          v[i] = a;
+        }
+      } else {  // dPi is diagonal with entries {1 | zt<=0 | 0}: dPi^T zp == zp
+        for (int i = 0; i < p; ++i) v[i] = zp[i];
+      }
+#pragma unroll
+      for (int j = 0; j < n; ++j) {
+        double a = 0.0;
+        for (int i = 0; i < p; ++i) a = fma(J[i + p * j], v[i], a);
+        lx[j] -= a;
+      }
+      if (!terminal) {
+#pragma unroll
+        for (int j = 0; j < m; ++j) {
+          double a = 0.0;
+          for (int i = 0; i < p; ++i) a = fma(J[i + p * (n + j)], v[i], a);
+          lu[j] -= a;
+        }
+      }
+    }
+    return nrm / (2 * rho);
+  }
+  // Gauss-Newton AL Hessian of one general slot from the stored z_est, the current rho and the
+  // constraint Jacobian at the accepted point (knotpoint_data.cpp:549-570, :597-613):
+  // G = rho (dPi J)^T (dPi J)  [+ rho J^T (d/dz (dPi^T zp)) J for the second-order cone]
+  __device__ __noinline__ void al_hessian_general(const ConSlot& s, int k, long zrow, bool terminal, double* lxx,
+                                    double* luu, double* lux) const {
+    constexpr int nm = n + m;
+    const int p = s.dim;
+    double zt[kMaxConDim], c[kMaxConDim];
+    double J[kMaxConDim * nm], M[kMaxConDim * nm], Gm[nm * nm];
+    {
+      double x[n], u[m];
+      if (s.family == CON_FAMILY_DISC) {  // state-dependent Jacobian: the accepted point
+        load_block<n>(F(P.x), S, k, x);
+        if (!terminal) load_block<m>(F(P.u), S, k, u);
+      } else {
+#pragma unroll
+        for (int i = 0; i < n; ++i) x[i] = 0.0;
+      }
+      if (terminal || s.family != CON_FAMILY_DISC) {
+#pragma unroll
+        for (int i = 0; i < m; ++i) u[i] = 0.0;
+      }
+      con_eval(s, x, u, c, J);
+    }
+    for (int i = 0; i < p; ++i) zt[i] = zest_read(zrow, s.row0, i);
+    if (s.cone == CONE_SOC) {
+      double zp[kMaxSocDim], Jp[kMaxSocDim * kMaxSocDim], Hs[kMaxSocDim * kMaxSocDim];
+      soc_projection(p, zt, zp);
+      soc_jacobian(p, zt, Jp);
+      soc_hessian(p, zt, zp, Hs);
+      for (int j = 0; j < nm; ++j)
+        for (int i = 0; i < p; ++i) {
+          double a = 0.0;
+          for (int l = 0; l < p; ++l) a = fma(Jp[i + p * l], J[l + p * j], a);
+          M[i + p * j] = a;
+        }
+      for (int b = 0; b < nm; ++b)
+        for (int a = 0; a < nm; ++a) {
+          double g = 0.0;
+          for (int i = 0; i < p; ++i) g = fma(M[i + p * a], M[i + p * b], g);
+          Gm[a + nm * b] = rho * g;
+        }
+      // + rho J^T Hs J
+      for (int j = 0; j < nm; ++j)
+        for (int i = 0; i < p; ++i) {
+          double a = 0.0;
+          for (int l = 0; l < p; ++l) a = fma(Hs[i + p * l], J[l + p * j], a);
+          M[i + p * j] = a;
+        }
+      for (int b = 0; b < nm; ++b)
+        for (int a = 0; a < nm; ++a) {
+          double g = 0.0;
+          for (int i = 0; i < p; ++i) g = fma(J[i + p * a], M[i + p * b], g);
+          Gm[a + nm * b] += rho * g;
+        }
+    } else {
+      for (int i = 0; i < p; ++i) {
+        double act = 0.0;  // diagonal of the dual-cone projection Jacobian (cones.cpp:160-171)
+        if (s.cone == CONE_EQUALITY) act = 1.0;
+        if (s.cone == CONE_INEQUALITY) act = (zt[i] <= 0) ? 1.0 : 0.0;
+        for (int j = 0; j < nm; ++j) M[i + p * j] = act * J[i + p * j];
+      }
+      for (int b = 0; b < nm; ++b)
+        for (int a = 0; a < nm; ++a) {
+          double g = 0.0;
+          for (int i = 0; i < p; ++i) g = fma(M[i + p * a], M[i + p * b], g);
+          Gm[a + nm * b] = rho * g;
+        }
+    }
+#pragma unroll
+    for (int cc = 0; cc < n; ++cc)
+#pragma unroll
+      for (int r = 0; r < n; ++r) lxx[r + n * cc] += Gm[r + nm * cc];
+    if (!terminal) {
+#pragma unroll
+      for (int cc = 0; cc < m; ++cc)
+#pragma unroll
+        for (int r = 0; r < m; ++r) luu[r + m * cc] += Gm[(n + r) + nm * (n + cc)];
+#pragma unroll
+      for (int cc = 0; cc < n; ++cc)
+#pragma unroll
+        for (int r = 0; r < m; ++r) lux[r + m * cc] += Gm[(n + r) + nm * cc];
+    }
+  }
+
+  // ---- CalcOriginalCostHessian (knotpoint_data.cpp:683-708): lxx = Q, luu = R, lux = H | 0
+  ALTRO_DEV void cost_hessian(int k, bool terminal, double* lxx, double* luu, double* lux) const {
+    if constexpr (CON == 2) {
+      if (P.Qf) {
+        const double* Q = P.Qf + (long)k * n * n;
+#pragma unroll
+        for (int i = 0; i < n * n; ++i) lxx[i] = Q[i];
+        if (!terminal) {
+          const double* R = P.Rf + (long)k * m * m;
+          const double* H = P.Hf + (long)k * m * n;
+#pragma unroll
+          for (int i = 0; i < m * m; ++i) luu[i] = R[i];
+#pragma unroll
+          for (int i = 0; i < m * n; ++i) lux[i] = H[i];
+        }
+        return;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < n * n; ++i) lxx[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) lxx[i + n * i] = Qd[k * n + i];
+    if (!terminal) {
+#pragma unroll
+      for (int i = 0; i < m * m; ++i) luu[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < m; ++i) luu[i + m * i] = Rd[k * m + i];
+#pragma unroll
+      for (int i = 0; i < m * n; ++i) lux[i] = 0.0;
     }
   }
 
@@ -309,27 +579,12 @@ struct TrajSolver {
         const ConSlot& s = T.slot[j];
         if (k < s.k_start || k >= s.k_stop) continue;
         const long zrow = zoff(k, s.row0);
-        if (CON == 2 && s.cone == CONE_SOC) {
-          double zt[kMaxSocDim], zp[kMaxSocDim];
-          for (int i = 0; i < s.dim; ++i) {
-            const double c = row_value(s, i, x, u);
-            zt[i] = zread(zrow, s.row0, i) - rho * c;
-            if (store_zest) P.zest[zrow + i * 32] = zt[i];
-          }
-          soc_projection(s.dim, zt, zp);
-          double nrm = 0.0;
-          for (int i = 0; i < s.dim; ++i) nrm += zp[i] * zp[i];
-          cost += nrm / (2 * rho);
-          if (want_grad) {
-            double J[kMaxSocDim * kMaxSocDim];
-            soc_jacobian(s.dim, zt, J);
-            for (int i = 0; i < s.dim; ++i) {
-              double v = 0.0;  // (dPi^T zp)_i
-              for (int l = 0; l < s.dim; ++l) v += J[l + s.dim * i] * zp[l];
-              scatter_sub(s.idx[i], s.scale[i] * v, lx, lu, terminal);
-            }
-          }
-        } else {
+        bool general = false;
+        if constexpr (CON == 2) {
+          general = general_slot(s);
+          if (general) cost += al_terms_general(s, zrow, x, u, terminal, want_grad, lx, lu, store_zest);
+        }
+        if (!general) {
           double nrm = 0.0;
           for (int i = 0; i < s.dim; ++i) {
             const double c = row_value(s, i, x, u);
@@ -360,41 +615,12 @@ struct TrajSolver {
         const ConSlot& s = T.slot[j];
         if (k < s.k_start || k >= s.k_stop) continue;
         const long zrow = zoff(k, s.row0);
-        if (CON == 2 && s.cone == CONE_SOC) {
-          const int p = s.dim;
-          double zt[kMaxSocDim], zp[kMaxSocDim];
-          double J[kMaxSocDim * kMaxSocDim], H[kMaxSocDim * kMaxSocDim];
-          for (int i = 0; i < p; ++i) zt[i] = zest_read(zrow, s.row0, i);
-          soc_projection(p, zt, zp);
-          soc_jacobian(p, zt, J);
-          soc_hessian(p, zt, zp, H);
-          // W = dPi^T dPi + H ; G[idx_i, idx_j] += rho s_i s_j W_ij
-          double G[(n + m) * (n + m)];
-          for (int i = 0; i < (n + m) * (n + m); ++i) G[i] = 0.0;
-          for (int i = 0; i < p; ++i) {
-            if (s.idx[i] < 0) continue;
-            for (int jj = 0; jj < p; ++jj) {
-              if (s.idx[jj] < 0) continue;
-              double w = H[i + p * jj];
-              for (int l = 0; l < p; ++l) w += J[l + p * i] * J[l + p * jj];
-              G[s.idx[i] + (n + m) * s.idx[jj]] += rho * s.scale[i] * s.scale[jj] * w;
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < n; ++c)
-#pragma unroll
-            for (int r = 0; r < n; ++r) lxx[r + n * c] += G[r + (n + m) * c];
-          if (!terminal) {
-#pragma unroll
-            for (int c = 0; c < m; ++c)
-#pragma unroll
-              for (int r = 0; r < m; ++r) luu[r + m * c] += G[(n + r) + (n + m) * (n + c)];
-#pragma unroll
-            for (int c = 0; c < n; ++c)
-#pragma unroll
-              for (int r = 0; r < m; ++r) lux[r + m * c] += G[(n + r) + (n + m) * c];
-          }
-        } else {
+        bool general = false;
+        if constexpr (CON == 2) {
+          general = general_slot(s);
+          if (general) al_hessian_general(s, k, zrow, terminal, lxx, luu, lux);
+        }
+        if (!general) {
           for (int i = 0; i < s.dim; ++i) {
             const int id = s.idx[i];
             if (id < 0) continue;
@@ -423,12 +649,12 @@ struct TrajSolver {
       for (int j = 0; j < T.ncon; ++j) {
         const ConSlot& s = T.slot[j];
         if (k < s.k_start || k >= s.k_stop) continue;
-        if (CON == 2 && s.cone == CONE_SOC) {
-          double c[kMaxSocDim], pc[kMaxSocDim];
-          for (int i = 0; i < s.dim; ++i) c[i] = row_value(s, i, x, u);
-          soc_projection(s.dim, c, pc);
-          for (int i = 0; i < s.dim; ++i) viol = fmax(viol, fabs(pc[i] - c[i]));
-        } else {
+        bool general = false;
+        if constexpr (CON == 2) {
+          general = general_slot(s);
+          if (general) viol = fmax(viol, al_violation_general(s, x, u));
+        }
+        if (!general) {
           for (int i = 0; i < s.dim; ++i) {
             const double c = row_value(s, i, x, u);
             double pc = 0.0;  // EQUALITY: projection onto {0}
@@ -510,10 +736,7 @@ struct TrajSolver {
   // terminal part and a per-knot step so that the plain sweep below (direct loads) and the
   // TMA-staged group kernel (solver_phases.cuh) run the identical arithmetic.
   ALTRO_DEV void riccati_terminal(double* Pn, double* pn) {  // tvlqr.cpp:85-90
-#pragma unroll
-    for (int i = 0; i < n * n; ++i) Pn[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < n; ++i) Pn[i + n * i] = Qd[N * n + i];
+    cost_hessian(N, true, Pn, nullptr, nullptr);
     al_hessian(N, true, Pn, nullptr, nullptr);
     load_block<n>(F(P.lx), S, N, pn);
     store_block<n * n>(F(P.P), S, N, Pn);
@@ -527,16 +750,7 @@ struct TrajSolver {
   ALTRO_DEV bool riccati_step(int k, const double* A, const double* Bm, double* Qx, double* Qu,
                               double* Pn, double* pn) {
     double Qxx[n * n], Quu[m * m], Qux[m * n];
-#pragma unroll
-    for (int i = 0; i < n * n; ++i) Qxx[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < n; ++i) Qxx[i + n * i] = Qd[k * n + i];
-#pragma unroll
-    for (int i = 0; i < m * m; ++i) Quu[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < m; ++i) Quu[i + m * i] = Rd[k * m + i];
-#pragma unroll
-    for (int i = 0; i < m * n; ++i) Qux[i] = 0.0;
+    cost_hessian(k, false, Qxx, Quu, Qux);
     al_hessian(k, false, Qxx, Quu, Qux);
     {
       double T1[n * n];

@@ -85,62 +85,21 @@ static __global__ void k_phase_set_rho(double* rho, int b0, int b1, double value
   if (b < b1) rho[b] = value;
 }
 
-// K1: CalcExpansions + BackwardPass + the alpha = 0 half of ForwardPass (solver.cpp:448-450,
-// :241-245) and the start of the line search.  One warp per group of the sub-batch.
+// The alpha = 0 half of ForwardPass (solver.cpp:241) as a linear scan over the knots, by ONE warp
+// (lane = problem) behind the Riccati sweep of either backward kernel; `ring` continues the sweep's
+// stage / parity state.
 template <class Model, int CON>
-__global__ void __launch_bounds__(32) k_phase_backward(const __grid_constant__ DeviceProblem P, int depth,
-                                                       int wcount, int first) {
+__device__ __forceinline__ void backward_scans(const DeviceProblem& P, TrajSolver<Model, CON>& s, BulkRing& ring,
+                                               int depth, int g, int lane, int b, bool active, int first,
+                                               double& phi0, double& dphi0) {
   using TS = TrajSolver<Model, CON>;
   constexpr int n = Model::n, m = Model::m;
-  const int g = P.g0 + blockIdx.x;
-  const int lane = threadIdx.x;
-  const int b = g * 32 + lane;
-  const bool active = b < P.B && (P.flags[b] & TF_ACTIVE);
-  if (!__any_sync(0xffffffffu, active)) return;  // every problem of the group has stopped
-  TS s(P, active ? b : g * 32);
-  s.rho = (CON && active) ? P.rho[b] : 1.0;
-  double phi0 = 0.0, dphi0 = 0.0;
-  if constexpr (TS::kStaged) {
-    // stage contents: Riccati sweep [J | lx lu]; phi0 scan [q r c K d x u J]  (J = packed [A B])
-    constexpr int kV = TS::kV;
-    constexpr int kRowsBw = TS::kRowsBw, kRowsPhi = TS::kRowsPhi;
-    // constrained problems also stage the knot's dual record [z | z_est] behind the main rows
-    const int zr = CON ? 2 * P.zrows : 0;
-    const int kStage = (TS::kRowsBackwardKernel + zr) * 32;
-    BulkRing ring;
-    ring.init(altro_smem, depth, kStage, lane == 0);
-    stage_weights(s, P, reinterpret_cast<double*>(altro_smem + BulkRing::bytes(depth, kStage)), wcount);
-    __syncwarp();
-    const double* rec = P.xbar + (long)g * P.GS;  // row 0 of the group's knot-0 record
-    const double* zrec = CON ? P.z + (long)g * P.GSz : nullptr;
-    auto fetch_bw = [&](int k, int st) {
-      ring.expect(st, (kRowsBw + zr) * 256);
-      ring.copy(st, 0, rec + (long)k * P.R + TS::rA * 32, kV * 256);
-      ring.copy(st, kV, rec + (long)k * P.R + TS::rLx * 32, (n + m) * 256);
-      if (zr) ring.copy(st, kRowsBw, zrec + (long)k * P.Rz, zr * 256);
-    };
-    if (lane == 0)
-      for (int j = 0; j < depth; ++j)
-        if (P.N - 1 - j >= 0) fetch_bw(P.N - 1 - j, (ring.s + j) % depth);
-    double Pn[n * n], pn[n];
-    if (active) s.riccati_terminal(Pn, pn);
-    bool alive = active;
-    for (int k = P.N - 1; k >= 0; --k) {
-      const double* st = ring.wait();
-      double A[n * n], Bm[n * m], Qx[n], Qu[m];
-      if (alive) {
-        s.unstage_jac(st, 0, lane, A, Bm);
-        unstage_block<n>(st, kV, lane, Qx);
-        unstage_block<m>(st, kV + n, lane, Qu);
-      }
-      if (zr) s.zstage = st + kRowsBw * 32 + lane;
-      if (alive) alive = s.riccati_step(k, A, Bm, Qx, Qu, Pn, pn);
-      s.zstage = nullptr;
-      // release the stage only after the step has consumed what was read from it (see BulkRing)
-      __syncwarp();
-      if (lane == 0 && k - depth >= 0) fetch_bw(k - depth, ring.s);
-      ring.advance();
-    }
+  constexpr int kV = TS::kV;
+  constexpr int kRowsPhi = TS::kRowsPhi;
+  const int zr = CON ? 2 * P.zrows : 0;
+  const double* rec = P.xbar + (long)g * P.GS;  // row 0 of the group's knot-0 record
+  const double* zrec = CON ? P.z + (long)g * P.GSz : nullptr;
+  {
     // phi0 / dphi0 scan, knots ascending
     // K, d were just written by the lanes of this warp through the generic proxy; the bulk copies
     // read them through the async proxy: every writer fences, then the leader issues
@@ -222,12 +181,12 @@ __global__ void __launch_bounds__(32) k_phase_backward(const __grid_constant__ D
     }
     if (active) s.phi0_terminal(dxda, phi0, dphi0);
     }
-  } else {
-    if (active) {
-      s.backward_sweep();
-      s.phase_phi0_scan(&phi0, &dphi0);
-    }
   }
+}
+
+// Start of the line search from (phi0, dphi0) (solver.cpp:242-252) and the per-iteration resets
+__device__ __forceinline__ void backward_finish(const DeviceProblem& P, int b, bool active, double phi0,
+                                                double dphi0) {
   if (!active) return;
   P.phi0[b] = phi0;
   P.dphi0[b] = dphi0;
@@ -263,6 +222,72 @@ __global__ void __launch_bounds__(32) k_phase_backward(const __grid_constant__ D
     P.ls[b] = ls;
   }
   P.flags[b] = f;
+}
+
+// K1: CalcExpansions + BackwardPass + the alpha = 0 half of ForwardPass (solver.cpp:448-450,
+// :241-245) and the start of the line search.  One warp per group of the sub-batch.
+template <class Model, int CON>
+__global__ void __launch_bounds__(32) k_phase_backward(const __grid_constant__ DeviceProblem P, int depth,
+                                                       int wcount, int first) {
+  using TS = TrajSolver<Model, CON>;
+  constexpr int n = Model::n, m = Model::m;
+  const int g = P.g0 + blockIdx.x;
+  const int lane = threadIdx.x;
+  const int b = g * 32 + lane;
+  const bool active = b < P.B && (P.flags[b] & TF_ACTIVE);
+  if (!__any_sync(0xffffffffu, active)) return;  // every problem of the group has stopped
+  TS s(P, active ? b : g * 32);
+  s.rho = (CON && active) ? P.rho[b] : 1.0;
+  double phi0 = 0.0, dphi0 = 0.0;
+  if constexpr (TS::kStaged) {
+    // stage contents: Riccati sweep [J | lx lu]; phi0 scan [q r c K d x u J]  (J = packed [A B])
+    constexpr int kV = TS::kV;
+    constexpr int kRowsBw = TS::kRowsBw, kRowsPhi = TS::kRowsPhi;
+    // constrained problems also stage the knot's dual record [z | z_est] behind the main rows
+    const int zr = CON ? 2 * P.zrows : 0;
+    const int kStage = (TS::kRowsBackwardKernel + zr) * 32;
+    BulkRing ring;
+    ring.init(altro_smem, depth, kStage, lane == 0);
+    stage_weights(s, P, reinterpret_cast<double*>(altro_smem + BulkRing::bytes(depth, kStage)), wcount);
+    __syncwarp();
+    const double* rec = P.xbar + (long)g * P.GS;  // row 0 of the group's knot-0 record
+    const double* zrec = CON ? P.z + (long)g * P.GSz : nullptr;
+    auto fetch_bw = [&](int k, int st) {
+      ring.expect(st, (kRowsBw + zr) * 256);
+      ring.copy(st, 0, rec + (long)k * P.R + TS::rA * 32, kV * 256);
+      ring.copy(st, kV, rec + (long)k * P.R + TS::rLx * 32, (n + m) * 256);
+      if (zr) ring.copy(st, kRowsBw, zrec + (long)k * P.Rz, zr * 256);
+    };
+    if (lane == 0)
+      for (int j = 0; j < depth; ++j)
+        if (P.N - 1 - j >= 0) fetch_bw(P.N - 1 - j, (ring.s + j) % depth);
+    double Pn[n * n], pn[n];
+    if (active) s.riccati_terminal(Pn, pn);
+    bool alive = active;
+    for (int k = P.N - 1; k >= 0; --k) {
+      const double* st = ring.wait();
+      double A[n * n], Bm[n * m], Qx[n], Qu[m];
+      if (alive) {
+        s.unstage_jac(st, 0, lane, A, Bm);
+        unstage_block<n>(st, kV, lane, Qx);
+        unstage_block<m>(st, kV + n, lane, Qu);
+      }
+      if (zr) s.zstage = st + kRowsBw * 32 + lane;
+      if (alive) alive = s.riccati_step(k, A, Bm, Qx, Qu, Pn, pn);
+      s.zstage = nullptr;
+      // release the stage only after the step has consumed what was read from it (see BulkRing)
+      __syncwarp();
+      if (lane == 0 && k - depth >= 0) fetch_bw(k - depth, ring.s);
+      ring.advance();
+    }
+    backward_scans<Model, CON>(P, s, ring, depth, g, lane, b, active, first, phi0, dphi0);
+  } else {
+    if (active) {
+      s.backward_sweep();
+      s.phase_phi0_scan(&phi0, &dphi0);
+    }
+  }
+  backward_finish(P, b, active, phi0, dphi0);
 }
 
 // Sub-phases of k_phase_forward, timed per CTA with %globaltimer when DeviceProblem::prof is set
@@ -366,7 +391,11 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
   __syncthreads();
 
   // ================================================================= line-search rounds
-  for (;;) {
+  for (int round = 0;; ++round) {
+    if (round > 4 * kMaxHalvings + 64) {  // a search takes <= 25 evaluations (+ re-rollouts)
+      if (tid == 0) printf("altro_b200: line search of group %d does not terminate\n", g);
+      __trap();
+    }
     fl = valid ? P.flags[bl] : 0;
     const unsigned pend = __ballot_sync(kAll, (fl & (TF_NEED_EVAL | TF_REROLL)) != 0);
     if (!pend) break;
@@ -450,7 +479,10 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
           pipe.release(k, lid);
           // the refill runs one knot behind warp 0, so warp 0 never waits for the knot it just
           // released to be released by the slower warps
-          if (tid == 0 && k >= 1 && k - 1 + depth < P.N) fetch(k - 1 + depth);
+          if (wid == 0 && k >= 1 && k - 1 + depth < P.N) {
+            pipe.wait_writable(k - 1 + depth);
+            if (lid == 0) fetch(k - 1 + depth);
+          }
         }
         if (need) s.rollout_terminal(x, xo, so, phi);
       } else {
@@ -520,7 +552,10 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
               s.dphi_step(K, d, A, Bm, lx, lu, dxda, dphi);
             }
             pipe.release(k, lid);
-            if (lid == 0 && k >= 1 && k - 1 + depth < P.N) fetch(k - 1 + depth);
+            if (k >= 1 && k - 1 + depth < P.N) {
+              pipe.wait_writable(k - 1 + depth);
+              if (lid == 0) fetch(k - 1 + depth);
+            }
           }
           if (had_deriv) dphi = s.dphi_terminal(dxda, dphi);
         } else {
@@ -770,6 +805,76 @@ __global__ void __launch_bounds__(128) k_unpack_jac(const __grid_constant__ Devi
   for (int e = 0; e < n * m; ++e) o[(n * n + e) * 32] = Bm[e];
 }
 
+// KnotPointData members that are not kept in HBM, re-created on demand for the host views
+// (altro_b200_get_field): constraint_val_, z_proj_ (knotpoint_data.hpp:187-198) and the cost
+// expansion lxx_, luu_, lux_ = CalcCostHessian (knotpoint_data.cpp:439-448) at the working
+// trajectory with the stored z_est and the current rho.  out: [group][knot][rows][32].
+// (enum KnotView: launchers.h)
+template <class Model, int CON>
+__global__ void __launch_bounds__(128) k_knot_view(const __grid_constant__ DeviceProblem P, int what, int rows,
+                                                   double* out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (b >= P.B) return;
+  using TS = TrajSolver<Model, CON>;
+  constexpr int n = Model::n, m = Model::m;
+  TS s(P, b);
+  s.rho = CON ? P.rho[b] : 1.0;
+  const bool terminal = (k == P.N);
+  double* o = out + ((long)(b >> 5) * (P.N + 1) + k) * rows * 32 + (b & 31);
+  if (what == KV_RHO) {
+    o[0] = s.rho;
+  } else if (what == KV_LXX || what == KV_LUU || what == KV_LUX) {
+    double lxx[n * n], luu[m * m], lux[m * n];
+    for (int i = 0; i < m * m; ++i) luu[i] = 0.0;
+    for (int i = 0; i < m * n; ++i) lux[i] = 0.0;
+    s.cost_hessian(k, terminal, lxx, luu, lux);
+    s.al_hessian(k, terminal, lxx, luu, lux);
+    if (what == KV_LXX)
+      for (int i = 0; i < n * n; ++i) o[i * 32] = lxx[i];
+    if (what == KV_LUU)
+      for (int i = 0; i < m * m; ++i) o[i * 32] = luu[i];
+    if (what == KV_LUX)
+      for (int i = 0; i < m * n; ++i) o[i * 32] = lux[i];
+  } else if constexpr (CON != 0) {
+    double x[n], u[m];
+    load_block<n>(s.F(P.x), s.S, k, x);
+    if (!terminal) {
+      load_block<m>(s.F(P.u), s.S, k, u);
+    } else {
+      for (int i = 0; i < m; ++i) u[i] = 0.0;
+    }
+    const ConTable& T = P.contab;
+    for (int j = 0; j < T.ncon; ++j) {
+      const ConSlot& c = T.slot[j];
+      if (k < c.k_start || k >= c.k_stop) continue;
+      double val[kMaxConDim];
+      if (what == KV_CONSTRAINT_VAL) {
+        if constexpr (CON == 2) {
+          s.con_eval(c, x, u, val, nullptr);
+        } else {
+          for (int i = 0; i < c.dim; ++i) val[i] = s.row_value(c, i, x, u);
+        }
+      } else {  // KV_Z_PROJ: projection of the stored z_est onto the dual cone
+        double zt[kMaxConDim];
+        const long zrow = s.zoff(k, c.row0);
+        for (int i = 0; i < c.dim; ++i) zt[i] = P.zest[zrow + i * 32];
+        if (CON == 2 && c.cone == CONE_SOC) {
+          soc_projection(c.dim, zt, val);
+        } else {
+          for (int i = 0; i < c.dim; ++i) {
+            double v = 0.0;
+            if (c.cone == CONE_EQUALITY) v = zt[i];
+            if (c.cone == CONE_INEQUALITY) v = fmin(0.0, zt[i]);
+            val[i] = v;
+          }
+        }
+      }
+      for (int i = 0; i < c.dim; ++i) o[(c.row0 + i) * 32] = val[i];
+    }
+  }
+}
+
 // ALTROSolver::CalcCost (solver.cpp:163-174): sum_k cost(k) incl. the AL terms at the working
 // trajectory; refreshes the projected duals like the reference does.
 template <class Model, int CON>
@@ -798,3 +903,5 @@ __global__ void __launch_bounds__(32) k_calc_cost(const __grid_constant__ Device
 }
 
 }  // namespace altro_b200
+
+#include "solver_team.cuh"

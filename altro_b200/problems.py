@@ -21,7 +21,7 @@ MODEL_LINEAR, MODEL_DOUBLE_INTEGRATOR, MODEL_PENDULUM, MODEL_BICYCLE4, MODEL_BIC
 # how the LQR reference of each problem is given
 REF_SHARED, REF_FULL, REF_GOAL, REF_WINDOW = 0, 1, 2, 3
 
-_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
 
 @dataclass
@@ -186,8 +186,9 @@ def bicycle(B=16384, N=100, tf=3.0, seed=1, n=5, iterations_max=30):
 
 
 def load_scotty():
-    """tests/golden/scotty_ref.json (from test/scotty.json): xref [501,4], uref [501,2], h."""
-    d = json.load(open(os.path.join(_GOLDEN, "scotty_ref.json")))
+    """altro_b200/data/scotty_ref.json (the numbers of test/scotty.json; input data of the tracking
+    configs, written by tests/golden/make_golden.py): xref [501,4], uref [501,2], h."""
+    d = json.load(open(os.path.join(_DATA, "scotty_ref.json")))
     xref = np.array(d["state_trajectory"], dtype=float)
     uref = np.array(d["input_trajectory"], dtype=float)
     Nref = int(d["N"]) - 1                    # test_utils.cpp:287

@@ -80,6 +80,9 @@ def load_library():
         L.altro_b200_set_lqr_cost_window.argtypes = [vp, dptr, dptr, dptr, dptr, C.c_int, iptr]
         L.altro_b200_set_diagonal_cost.argtypes = [vp, dptr, dptr, dptr, dptr, dptr, C.c_int, C.c_int, C.c_int]
         L.altro_b200_update_linear_costs.argtypes = [vp, dptr, dptr, dptr, C.c_int, C.c_int, C.c_int]
+        L.altro_b200_set_quadratic_cost.argtypes = [vp, dptr, dptr, dptr, dptr, dptr, dptr, C.c_int, C.c_int, C.c_int]
+        L.altro_b200_set_constraint_affine.argtypes = [vp, C.c_int, C.c_int, dptr, dptr, dptr, C.c_int, C.c_int]
+        L.altro_b200_set_constraint_disc.argtypes = [vp, C.c_int, C.c_int, dptr, dptr, C.c_int, C.c_int]
         L.altro_b200_advance_window.argtypes = [vp, C.c_int]
         L.altro_b200_advance_window_linear.argtypes = [vp, C.c_int, C.c_double]
         L.altro_b200_set_mpc_cost_update.argtypes = [vp, C.c_int, C.c_double]
@@ -90,8 +93,9 @@ def load_library():
         L.altro_b200_set_state.argtypes = [vp, dptr, C.c_int, C.c_int, C.c_int]
         L.altro_b200_set_options.argtypes = [vp, C.POINTER(Options)]
         L.altro_b200_calc_cost.argtypes = [vp, dptr]
+        L.altro_b200_set_penalty.argtypes = [vp, C.c_double]
         for f in ("reset_duals", "reset_trajectory", "shift_trajectory", "solve", "solve_async", "synchronize",
-                  "open_loop_rollout", "mpc_step"):
+                  "open_loop_rollout", "mpc_step", "knot_eval"):
             getattr(L, "altro_b200_" + f).argtypes = [vp]
         for f in ("get_states", "get_inputs", "get_dual_dynamics", "get_feedback_gains",
                   "get_feedforward_gains", "get_final_objective", "get_stationarity",
@@ -101,7 +105,11 @@ def load_library():
             getattr(L, "altro_b200_" + f).argtypes = [vp, iptr]
         L.altro_b200_get_linesearch_histogram.argtypes = [vp, C.POINTER(C.c_long), C.c_int]
         L.altro_b200_get_field.argtypes = [vp, C.c_char_p, dptr, C.POINTER(C.c_int)]
+        L.altro_b200_get_dual_general.argtypes = [vp, C.c_int, C.c_int, dptr]
+        L.altro_b200_set_dual_general.argtypes = [vp, C.c_int, C.c_int, dptr, C.c_int]
+        L.altro_b200_get_num_constraints.argtypes = [vp]
         L.altro_b200_set_solve_mode.argtypes = [vp, C.c_int]
+        L.altro_b200_set_backward_mode.argtypes = [vp, C.c_int]
         L.altro_b200_set_profiling.argtypes = [vp, C.c_int]
         L.altro_b200_set_speculation.argtypes = [vp, C.c_int]
         L.altro_b200_set_candidate_store.argtypes = [vp, C.c_int]
@@ -212,6 +220,19 @@ class BatchSolver:
         self._ck(self.L.altro_b200_set_diagonal_cost(self.h, ap, bp, qp, rp, cp, per, k_start, k_stop),
                  "SetDiagonalCost")
 
+    def SetQuadraticCost(self, Q, R, H, q, r, c, k_start=AllIndices, k_stop=0):
+        """Dense Q (n x n), R (m x m), H (m x n) as 2-D arrays (stored column-major for the ABI)."""
+        qq = np.asarray(q, dtype=float)
+        per = 1 if qq.ndim >= 2 else 0
+        Qa, Qp = _d(np.asarray(Q, dtype=float).T)
+        Ra, Rp = _d(None if R is None else np.asarray(R, dtype=float).T)
+        Ha, Hp = _d(None if H is None else np.asarray(H, dtype=float).T)
+        qa, qp = _d(qq)
+        ra, rp = _d(r)
+        ca, cp = _d(np.atleast_1d(np.asarray(c, dtype=float)))
+        self._ck(self.L.altro_b200_set_quadratic_cost(self.h, Qp, Rp, Hp, qp, rp, cp, per, k_start, k_stop),
+                 "SetQuadraticCost")
+
     def UpdateLinearCosts(self, q, r, c, k_start=AllIndices, k_stop=0):
         qa, qp = _d(q)
         ra, rp = _d(r)
@@ -238,6 +259,22 @@ class BatchSolver:
         ob, obp = _d(off_b)
         self._ck(self.L.altro_b200_set_constraint(self.h, cone, dim, ia, sp, op, obp, k_start, k_stop),
                  "SetConstraint")
+
+    def SetConstraintAffine(self, cone, J, e, k_start, k_stop=0, e_b=None):
+        """General affine rows c = J [x;u] + e, J a 2-D array (dim x (n+m))."""
+        Jm = np.asarray(J, dtype=float)
+        Ja, Jp = _d(Jm.T)  # column-major
+        ea, ep = _d(e)
+        eb, ebp = _d(e_b)
+        self._ck(self.L.altro_b200_set_constraint_affine(self.h, cone, Jm.shape[0], Jp, ep, ebp, k_start, k_stop),
+                 "SetConstraintAffine")
+
+    def SetConstraintDisc(self, idx_a, idx_b, disc, k_start, k_stop=0, disc_b=None):
+        """Keep-out disc r^2 - (v_a-cx)^2 - (v_b-cy)^2 <= 0; disc = (cx, cy, r)."""
+        da, dp = _d(disc)
+        db, dbp = _d(disc_b)
+        self._ck(self.L.altro_b200_set_constraint_disc(self.h, idx_a, idx_b, dp, dbp, k_start, k_stop),
+                 "SetConstraintDisc")
 
     def SetInitialState(self, x0):
         x = np.asarray(x0, dtype=float)
@@ -268,6 +305,10 @@ class BatchSolver:
     def SetSolveMode(self, mode):
         """0: two-kernel-per-iteration pipeline (default); 1: single persistent kernel (test twin)."""
         self._ck(self.L.altro_b200_set_solve_mode(self.h, mode), "SetSolveMode")
+
+    def SetBackwardMode(self, team):
+        """0: Riccati sweep by one warp per group; 1: by the warps of a CTA (column teams)."""
+        self._ck(self.L.altro_b200_set_backward_mode(self.h, int(team)), "SetBackwardMode")
 
     def SetSpeculation(self, nslots):
         self._ck(self.L.altro_b200_set_speculation(self.h, nslots), "SetSpeculation")
@@ -312,6 +353,13 @@ class BatchSolver:
 
     def ShiftTrajectory(self):
         self._ck(self.L.altro_b200_shift_trajectory(self.h), "ShiftTrajectory")
+
+    def KnotEval(self):
+        """Per-knot expansions (A, B, constraint values, projected duals, lx, lu) at x_, u_."""
+        self._ck(self.L.altro_b200_knot_eval(self.h), "KnotEval")
+
+    def SetPenalty(self, rho):
+        self._ck(self.L.altro_b200_set_penalty(self.h, C.c_double(rho)), "SetPenalty")
 
     def OpenLoopRollout(self):
         self._ck(self.L.altro_b200_open_loop_rollout(self.h), "OpenLoopRollout")
@@ -368,6 +416,16 @@ class BatchSolver:
         out = np.empty((self.B, self.N + 1, rows.value))
         self._ck(self.L.altro_b200_get_field(self.h, name.encode(), out.ctypes.data_as(dptr), None), "GetField")
         return out
+
+    def GetDualGeneral(self, constraint, k, dim):
+        out = np.empty((self.B, dim))
+        self._ck(self.L.altro_b200_get_dual_general(self.h, constraint, k, out.ctypes.data_as(dptr)), "GetDualGeneral")
+        return out
+
+    def SetDualGeneric(self, constraint, k, z):
+        za = np.asarray(z, dtype=float)
+        a, p = _d(za)
+        self._ck(self.L.altro_b200_set_dual_general(self.h, constraint, k, p, 1 if za.ndim == 2 else 0), "SetDualGeneric")
 
     def GetStatus(self, out=None):
         return self._get("get_status", (self.B,), np.int32, out=out)

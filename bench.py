@@ -45,9 +45,13 @@ def workload(name, per_gpu_batch, rank, world):
         "bicycle": lambda total: PR.bicycle(B=total, N=100, n=5),
         "pendulum": lambda total: PR.pendulum(B=total, N=100),
         "scotty": lambda total: PR.scotty(B=total, N=50, n=5),
+        "scotty_mpc": lambda total: PR.scotty(B=total, N=50, n=5),
         "chain12": lambda total: PR.chain(B=total, n=12, m=4, N=200),
         "chain6": lambda total: PR.chain(B=total, n=6, m=2, N=200),
-    }[name]
+    }.get(name)
+    if gen is None and name.startswith("chain-"):   # chain-n-m-N: any shape of the BASELINE sweep
+        cn, cm, cN = [int(v) for v in name.split("-")[1:4]]
+        gen = lambda total: PR.chain(B=total, n=cn, m=cm, N=cN)
     P = gen(B * world)
     return P.subset(rank * B, (rank + 1) * B)
 
@@ -267,10 +271,13 @@ def main():
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--split", type=int, default=0, help="pipelined sub-batches (0 = automatic)")
     ap.add_argument("--slots", type=int, default=None, help="candidate steps per line-search round")
+    ap.add_argument("--store", type=int, default=None, help="speculative candidates that keep their trajectory")
+    ap.add_argument("--mpc-steps", type=int, default=10,
+                    help="scotty_mpc: receding-horizon solves per bench step (all on the device)")
     args = ap.parse_args()
     if args.batch is None:
-        args.batch = {"bicycle": 16384, "pendulum": 4096, "scotty": 8192, "chain12": 4096,
-                      "chain6": 32768}[args.workload]
+        args.batch = {"bicycle": 16384, "pendulum": 4096, "scotty": 8192, "scotty_mpc": 8192, "chain12": 4096,
+                      "chain6": 32768}.get(args.workload, 32768)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -299,17 +306,34 @@ def main():
     solver = altro_b200.make_solver(P, device=local_rank, nslots=args.slots)
     solver.SetStream(torch.cuda.current_stream().cuda_stream)
     solver.SetPipelineSplit(args.split)
+    if args.store is not None:
+        solver.SetCandidateStore(args.store)
     B, N, n, m = P.B, P.N, P.n, P.m
+    # scotty_mpc: a bench step is `mpc_steps` consecutive receding-horizon solves of every problem,
+    # the MPC step between two solves (x0 <- x_[1], ShiftTrajectory, window + 1 with the reference's
+    # cost update) done by altro_b200_mpc_step on the device: no host round trip inside the step
+    mpc_steps = args.mpc_steps if args.workload == "scotty_mpc" else 1
+    if mpc_steps > 1:
+        u0 = P.U0[0, 0]
+        solver.SetMpcCostUpdate(1, float(0.5 * u0 @ (P.Rd[0] * u0)))
+    solves_per_step = mpc_steps
 
     # ------------------------------------------------------------ (1) resident-in-HBM steps
     def resident_step(ev=None):
         solver.ResetTrajectory()
         solver.ResetDuals()
+        if mpc_steps > 1:
+            solver.SetInitialState(P.x0)
         if ev:
             ev[0].record()
         solver.SolveAsync()
+        for _ in range(mpc_steps - 1):
+            solver.MpcStep()
+            solver.SolveAsync()
         if ev:
             ev[1].record()
+        if mpc_steps > 1:                # window back to where it started (q, r, c of offset 0)
+            solver.AdvanceWindow(-(mpc_steps - 1))
 
     for _ in range(args.warmup):
         resident_step()
@@ -352,6 +376,12 @@ def main():
         solver.SetInput(U0_h)
         solver.ResetDuals()
         solver.Solve()
+        for _ in range(mpc_steps - 1):
+            solver.GetInputs(out=U_h)        # the control an MPC loop applies comes back every step
+            solver.MpcStep()
+            solver.Solve()
+        if mpc_steps > 1:
+            solver.AdvanceWindow(-(mpc_steps - 1))
         solver.GetStates(out=X_h)
         solver.GetInputs(out=U_h)
         solver.GetStatus(out=st_h)
@@ -362,7 +392,7 @@ def main():
         h2d += 2 * (xref_h.nbytes + uref_h.nbytes)
     elif P.ref_mode == PR.REF_WINDOW:
         h2d += P.xref.nbytes + P.uref.nbytes + P.offsets.nbytes
-    d2h = X_h.nbytes + U_h.nbytes + st_h.nbytes + phi_h.nbytes
+    d2h = X_h.nbytes + U_h.nbytes * mpc_steps + st_h.nbytes + phi_h.nbytes
     for _ in range(args.warmup):
         e2e_step()
     barrier()
@@ -403,10 +433,12 @@ def main():
 
     out = None
     if rank == 0:
-        value = total_solves * args.steps / (elapsed_ms * 1e-3)
-        e2e_value = total_solves * args.steps / (e2e_ms * 1e-3)
+        value = total_solves * solves_per_step * args.steps / (elapsed_ms * 1e-3)
+        e2e_value = total_solves * solves_per_step * args.steps / (e2e_ms * 1e-3)
         peak, peak_src = peak_hbm()
-        alg_bytes = algorithmic_bytes(P, iters, evals)
+        # scotty_mpc: the statistics are those of the step's LAST solve; the warm-started solves of
+        # one step do similar work, so the step's bytes are taken as mpc_steps times that
+        alg_bytes = algorithmic_bytes(P, iters, evals) * solves_per_step
         models = kernel_models(P, iters, evals)
         whole = ("init_rollout", "expand", "backward", "forward")   # launches; fwd_* are shares of forward
         tot_ms = sum(phase_stats[k]["ms"] for k in whole)

@@ -166,11 +166,17 @@ struct DeviceDynamics {
   ExplicitDynamicsJacobian Jacobian() const;
 };
 
-// Constraint rows c_i = scale_i * [x;u][idx_i] + off_i (idx_i = -1: c_i = off_i).
+// Device constraint families replacing the c(x,u) / Jacobian callbacks (typedefs.hpp:48-52):
+//   Selector  rows c_i = scale_i * [x;u][idx_i] + off_i (idx_i = -1: c_i = off_i)
+//   Affine    c = J [x;u] + e with a dense dim x (n+m) column-major J
+//   Disc      c = r^2 - ([x;u][idx_0] - cx)^2 - ([x;u][idx_1] - cy)^2 (nonlinear, dim 1, INEQUALITY)
 struct DeviceConstraint {
+  enum Kind { Selector = 0, AffineRows = 1, Disc = 2 };
+  int kind = Selector;
   std::vector<int> idx;
-  std::vector<double> scale, off;
-  std::vector<double> off_batch;  // optional per-problem offsets [B][dim]
+  std::vector<double> scale, off;  // Affine: off = e;  Disc: off = {cx, cy, r}
+  std::vector<double> jac;         // Affine: J, column-major dim x (n+m)
+  std::vector<double> off_batch;   // optional per-problem offsets / e / discs [B][dim or 3]
   bool is_jacobian = false;
   DeviceConstraint(std::vector<int> idx, std::vector<double> scale, std::vector<double> off);
   void operator()(a_float* out, const a_float* x, const a_float* u) const;
@@ -181,6 +187,8 @@ struct DeviceConstraint {
   static DeviceConstraint InputBox(int n, const std::vector<double>& u_max);
   static DeviceConstraint InputNormBound(int n, int m, double u_max);  // SOC rows [u; u_max]
   static DeviceConstraint StateBound(int index, double lo, double hi);
+  static DeviceConstraint Affine(int dim, std::vector<double> J_colmajor, std::vector<double> e);
+  static DeviceConstraint KeepOutDisc(int idx_a, int idx_b, double cx, double cy, double r);
 };
 
 }  // namespace b200
@@ -285,9 +293,15 @@ class ALTROSolver {
   ErrorCodes GetDualDynamics(a_float* y, int k) const;
   ErrorCodes GetFeedbackGain(a_float* K, int k) const;
   ErrorCodes GetFeedforwardGain(a_float* d, int k) const;
+  // duals of a general constraint (declared, never defined in the reference: altro_solver.hpp:359,
+  // :416); constraint_index comes from SetConstraint's con_inds
+  ErrorCodes SetDualGeneric(const a_float* z, const ConstraintIndex& constraint_index);
+  ErrorCodes GetDualGeneral(a_float* z, const ConstraintIndex& constraint_index) const;
   // KnotPointData member `name` of knot k of the first problem (the views the reference's tests
-  // reach through solver_->data_[k]): "x" "u" "y" "xbar" "ubar" "A" "B" "lx" "lu" "K" "d" "P" "p"
-  // "q" "r" "c"; `out` holds the column-major block.
+  // reach through solver_->data_[k]): "x" "u" "y" (x_, u_, y_) "xbar" "ubar" (x, u) "A" "B" "lx" "lu"
+  // "K" "d" "P" "p" "q" "r" "c" "z" "z_est" "z_proj" "constraint_val" "lxx" "luu" "lux" "rho" -- the
+  // reference's spelling with a trailing underscore ("K_", "lxx_", "z_est_" ...) is accepted too;
+  // `out` holds the column-major block.
   ErrorCodes GetKnotPointField(const char* name, a_float* out, int k) const;
 
   void PrintStateTrajectory() const;

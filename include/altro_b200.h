@@ -179,6 +179,12 @@ int altro_b200_set_lqr_cost_window(altro_b200_solver *s, const double *Qd, const
 int altro_b200_set_diagonal_cost(altro_b200_solver *s, const double *Qd, const double *Rd,
                                  const double *q, const double *r, const double *c,
                                  int per_problem, int k_start, int k_stop);
+/* SetQuadraticCost (altro_solver.cpp:118-136, knotpoint_data.cpp:64-85): dense Q [n*n], R [m*m],
+ * H [m*n] (column-major, shared by the batch; H may be NULL = 0; R, r ignored on the terminal
+ * knot); q, r, c as in altro_b200_set_diagonal_cost. */
+int altro_b200_set_quadratic_cost(altro_b200_solver *s, const double *Q, const double *R,
+                                  const double *H, const double *q, const double *r,
+                                  const double *c, int per_problem, int k_start, int k_stop);
 /* UpdateLinearCosts (altro_solver.cpp:266-281): q and/or r may be NULL */
 int altro_b200_update_linear_costs(altro_b200_solver *s, const double *q, const double *r,
                                    const double *c, int per_problem, int k_start, int k_stop);
@@ -201,6 +207,17 @@ int altro_b200_set_constraint(altro_b200_solver *s, int cone, int dim, const int
                               const double *scale, const double *off, const double *off_b,
                               int k_start, int k_stop);
 
+/* SetConstraint, general affine rows: c = J [x;u] + e with a dense J [dim x (n+m)] (column-major,
+ * the layout of the reference's constraint Jacobian, altro_solver.hpp:69-70) shared by the batch;
+ * e [dim] shared, or e_b [B][dim] per problem (then e is ignored but must be non-NULL). */
+int altro_b200_set_constraint_affine(altro_b200_solver *s, int cone, int dim, const double *J,
+                                     const double *e, const double *e_b, int k_start, int k_stop);
+/* SetConstraint, nonlinear family "keep-out disc" (INEQUALITY, dim 1):
+ *   c = r^2 - ([x;u][idx_a] - cx)^2 - ([x;u][idx_b] - cy)^2 <= 0,  disc = {cx, cy, r},
+ * disc_b: optional per-problem discs [B][3]. */
+int altro_b200_set_constraint_disc(altro_b200_solver *s, int idx_a, int idx_b, const double *disc,
+                                   const double *disc_b, int k_start, int k_stop);
+
 int altro_b200_set_initial_state(altro_b200_solver *s, const double *x0, int per_problem);
 int altro_b200_initialize(altro_b200_solver *s);
 /* SetInput: layout 0: u[m] for every knot in range and every problem; 1: [k_stop-k_start][m]
@@ -222,6 +239,14 @@ int altro_b200_mpc_step(altro_b200_solver *s);
  * batch be re-solved from the same starting point without a host round trip) */
 int altro_b200_reset_trajectory(altro_b200_solver *s);
 
+/* KnotPointData expansions at the working trajectory x_, u_ for every knot of every problem:
+ * CalcDynamicsExpansion, CalcConstraints, CalcConstraintJacobians, CalcProjectedDuals,
+ * CalcCostGradient (knotpoint_data.cpp:406-437, :473-487, :523-595) with the current duals and
+ * penalty; read the results with altro_b200_get_field.  This is the entry point the reference's
+ * knotpoint_data_test.cpp bodies map onto. */
+int altro_b200_knot_eval(altro_b200_solver *s);
+/* KnotPointData::SetPenalty for every constraint of every problem (rho > 0) */
+int altro_b200_set_penalty(altro_b200_solver *s, double rho);
 /* OpenLoopRollout (altro_solver.cpp:253): x_[k+1] = f(x_[k], u_[k]) from the initial state */
 int altro_b200_open_loop_rollout(altro_b200_solver *s);
 /* CalcCost (altro_solver.cpp:313): total cost incl. AL terms of the working trajectory, [B] */
@@ -238,6 +263,10 @@ int altro_b200_synchronize(altro_b200_solver *s);
  * 1: one persistent kernel for the whole solve (thread per trajectory; the bit-exact twin the
  * tests compare mode 0 against) */
 int altro_b200_set_solve_mode(altro_b200_solver *s, int mode);
+/* Riccati sweep of the default mode: 0 one warp per group of 32 problems (thread = trajectory),
+ * 1 the blocks of a problem spread by columns over the warps of a CTA (exchange through shared
+ * memory; what lets n = 12 stay on chip).  Bit-identical results. */
+int altro_b200_set_backward_mode(altro_b200_solver *s, int team);
 /* pipelined sub-batches: the batch is cut into `nsplit` contiguous ranges (1..8; 0 = automatic),
  * each on its own stream (one host thread enqueues all) so the sweeps of one range overlap the
  * rollouts of another.  Results do not depend on nsplit. */
@@ -271,10 +300,21 @@ int altro_b200_get_inputs(altro_b200_solver *s, double *U);  /* [B][N][m]    Get
 int altro_b200_get_dual_dynamics(altro_b200_solver *s, double *Y); /* [B][N+1][n]             */
 int altro_b200_get_feedback_gains(altro_b200_solver *s, double *K); /* [B][N][m*n]            */
 int altro_b200_get_feedforward_gains(altro_b200_solver *s, double *d); /* [B][N][m]           */
-/* any KnotPointData member by name (knotpoint_data.hpp:160-233): "x" "u" "y" "xbar" "ubar" "A" "B"
- * "lx" "lu" "K" "d" "P" "p" "q" "r" "c".  out: [B][N+1][rows] (column-major blocks); rows_out
- * receives the rows per knot; out may be NULL to query rows only. */
+/* any KnotPointData member by name (knotpoint_data.hpp:160-233).  Stored: "x" "u" "y" (x_, u_, y_)
+ * "xbar" "ubar" (x, u) "A" "B" "lx" "lu" "K" "d" "P" "p" "q" "r" "c" "z" "z_est"; re-created on
+ * demand at the working trajectory: "constraint_val" "z_proj" "lxx" "luu" "lux" "rho".  Constraint
+ * members hold all slots of the knot one after the other (rows of slots that do not apply at a
+ * knot are zero).  out: [B][N+1][rows] (column-major blocks); rows_out receives the rows per knot;
+ * out may be NULL to query rows only. */
 int altro_b200_get_field(altro_b200_solver *s, const char *name, double *out, int *rows_out);
+/* GetDualGeneral / SetDualGeneric (altro_solver.hpp:359, :416): dual z of constraint `constraint`
+ * (the order of the SetConstraint calls) at knot k, [B][dim]; set: z [dim] shared (per_problem 0)
+ * or [B][dim]. */
+int altro_b200_get_dual_general(altro_b200_solver *s, int constraint, int k, double *z);
+int altro_b200_set_dual_general(altro_b200_solver *s, int constraint, int k, const double *z,
+                                int per_problem);
+int altro_b200_get_num_constraints(const altro_b200_solver *s);
+int altro_b200_get_constraint_dim(const altro_b200_solver *s, int constraint); /* 0 if out of range */
 int altro_b200_get_status(altro_b200_solver *s, int *status);       /* [B] SolveStatus        */
 int altro_b200_get_iterations(altro_b200_solver *s, int *iters);    /* [B] GetIterations      */
 int altro_b200_get_merit_evals(altro_b200_solver *s, int *evals);   /* [B]                    */
@@ -288,6 +328,31 @@ int altro_b200_get_state_dim(const altro_b200_solver *s);
 int altro_b200_get_input_dim(const altro_b200_solver *s);
 /* bytes of HBM held by the handle */
 long altro_b200_device_bytes(const altro_b200_solver *s);
+
+/* ================================================================================ section D
+ * Trajectory files with the reference's keys (host only, no device needed).  test/scotty.json
+ * (read by ReadScottyTrajectory, test/test_utils.cpp:240-289): "N", "tf", "state_trajectory"
+ * [knots][n], "input_trajectory" [knots][m]; test/scotty_mpc.json (written by
+ * test/bicycle_test.cpp:344-359) adds "solve_iters" [steps] and "tracking_error" [steps].  A BATCH
+ * file carries "batch": B and one more leading dimension on every array; a file without "batch" is
+ * one problem, so the reference's own files load unchanged.                                     */
+typedef struct altro_b200_traj_file altro_b200_traj_file;
+/* parse `path`; NULL on failure with *err = ALTRO_B200_FILE_ERROR / DIMENSION_MISMATCH */
+altro_b200_traj_file *altro_b200_traj_open(const char *path, int *err);
+/* any output may be NULL.  batch = 1 for a single-problem file; steps = length of solve_iters /
+ * tracking_error (0 when absent) */
+int altro_b200_traj_dims(const altro_b200_traj_file *f, int *batch, int *N, float *tf, int *knots_x,
+                         int *n, int *knots_u, int *m, int *steps);
+/* X [batch][knots_x][n], U [batch][knots_u][m], solve_iters [batch][steps],
+ * tracking_error [batch][steps]; any may be NULL */
+int altro_b200_traj_read(const altro_b200_traj_file *f, double *X, double *U, int *solve_iters,
+                         double *tracking_error);
+void altro_b200_traj_close(altro_b200_traj_file *f);
+/* batch = 0 writes the reference's single-problem layout (no "batch" key, 2-D arrays);
+ * solve_iters / tracking_error may be NULL */
+int altro_b200_traj_write(const char *path, int batch, int N, float tf, int knots_x, int n,
+                          const double *X, int knots_u, int m, const double *U, int steps,
+                          const int *solve_iters, const double *tracking_error);
 
 #ifdef __cplusplus
 }

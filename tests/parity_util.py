@@ -83,8 +83,11 @@ def compare_all(gpu, ref):
         ex, eu, ec = errors(sub, rsub)
     else:
         ex = eu = ec = np.zeros(0)
+    worst = np.maximum(np.maximum(ex, eu), ec) if ex.size else np.zeros(0)
     return dict(n=int(nb), same_status_and_iterations=int(same.sum()),
                 finite_both=int(both.sum()), finite_mismatch=int((fin != gfin).sum()),
                 max_state_err=float(ex.max(initial=0)), max_input_err=float(eu.max(initial=0)),
                 max_cost_rel=float(ec.max(initial=0)),
-                p99_state_err=float(np.quantile(ex, 0.99)) if ex.size else 0.0)
+                p99_state_err=float(np.quantile(ex, 0.99)) if ex.size else 0.0,
+                median_err=float(np.median(worst)) if worst.size else 0.0,
+                n_above_1e9=int((worst > 1e-9).sum()), n_above_1e6=int((worst > 1e-6).sum()))

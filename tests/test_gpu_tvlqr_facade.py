@@ -217,6 +217,62 @@ int double_integrator(bool control_bounds) {
   return 0;
 }
 
+// The declared-but-undefined bound setters of the reference (altro_solver.hpp:257-290) as
+// INEQUALITY rows: same control-box problem as double_integrator(true), same pinned answers
+// (double_integrator_test.cpp:367-374), plus the dual getters / setters (:359, :416).
+int double_integrator_bound_api() {
+  const int N = 10, n = 4, m = 2;
+  const float h = 5.0f / N;
+  std::vector<double> Q(n, 1.0), R(m, 1e-2), x0 = {2.0, 2.0, 0.0, 0.0}, xf(n, 0.0), uf(m, 0.0);
+  ALTROSolver solver(N);
+  CHECK(solver.SetDimension(n, m, 0, LastIndex) == ErrorCodes::NoError);
+  CHECK(solver.SetTimeStep(h, 0, LastIndex) == ErrorCodes::NoError);
+  b200::DeviceDynamics model(b200::DeviceDynamics::DoubleIntegrator, {2});
+  CHECK(solver.SetExplicitDynamics(model.Function(), model.Jacobian(), 0, LastIndex) == ErrorCodes::NoError);
+  CHECK(solver.SetLQRCost(n, m, Q.data(), R.data(), xf.data(), uf.data(), 0, LastIndex) == ErrorCodes::NoError);
+  CHECK(solver.SetInitialState(x0.data(), n) == ErrorCodes::NoError);
+  auto goal = b200::DeviceConstraint::Goal(xf);
+  std::vector<ConstraintIndex> goal_idx;
+  CHECK(solver.SetConstraint(goal.Function(), goal.Jacobian(), n, ConstraintType::EQUALITY, "Goal constraint", N, 0, &goal_idx) == ErrorCodes::NoError);
+  CHECK(goal_idx.size() == 1 && goal_idx[0].KnotPointIndex() == N);
+  std::vector<double> umax = {1.0, 1.0}, umin = {-1.0, -1.0};
+  CHECK(solver.SetInputUpperBound(umax.data(), 0, N) == ErrorCodes::NoError);
+  CHECK(solver.SetInputLowerBound(umin.data(), 0, N) == ErrorCodes::NoError);
+  CHECK(solver.SetInputUpperBound(umax.data(), N) == ErrorCodes::InvalidOptAtTerminalKnotPoint);
+  CHECK(solver.Initialize() == ErrorCodes::NoError);
+  std::vector<double> uinit(m, 0.0);
+  CHECK(solver.SetInput(uinit.data(), m, 0, LastIndex) == ErrorCodes::NoError);
+  AltroOptions opts;
+  opts.penalty_scaling = 100;
+  opts.penalty_initial = 100;
+  solver.SetOptions(opts);
+  CHECK(solver.Solve() == SolveStatus::Success);
+  CHECK(solver.GetIterations() == 5);
+  std::vector<double> u0(m), xN(n);
+  solver.GetInput(u0.data(), 0);
+  CHECK(std::fabs(u0[0] + 1.0) < 1e-4 && std::fabs(u0[1] + 1.0) < 1e-4);
+  solver.GetState(xN.data(), N);
+  double dist = 0; for (double v : xN) dist += v * v;
+  CHECK(std::sqrt(dist) < 1e-4);
+  // goal dual: readable, writable, and what the KnotPointData view shows
+  std::vector<double> z(n), zview(n + 0), z2(n);
+  CHECK(solver.GetDualGeneral(z.data(), goal_idx[0]) == ErrorCodes::NoError);
+  double zn = 0; for (double v : z) zn += v * v;
+  CHECK(zn > 0);
+  std::vector<double> zall(n + 2 * m);   // all constraint rows of the handle: goal + two bound slots
+  CHECK(solver.GetKnotPointField("z_", zall.data(), N) == ErrorCodes::NoError);
+  for (int i = 0; i < n; ++i) CHECK(zall[i] == z[i]);
+  for (int i = 0; i < n; ++i) z2[i] = 0.5 * z[i];
+  CHECK(solver.SetDualGeneric(z2.data(), goal_idx[0]) == ErrorCodes::NoError);
+  CHECK(solver.GetDualGeneral(z.data(), goal_idx[0]) == ErrorCodes::NoError);
+  for (int i = 0; i < n; ++i) CHECK(z[i] == z2[i]);
+  // the lower input bound is active at knot 0: its dual is negative (negative orthant)
+  std::vector<double> zk(n + 2 * m);
+  CHECK(solver.GetKnotPointField("z", zk.data(), 0) == ErrorCodes::NoError);
+  CHECK(zk[n + m] < 0 && zk[n + m + 1] < 0 && zk[n] == 0 && zk[n + 1] == 0);
+  return 0;
+}
+
 int pendulum() {
   const int n = 2, m = 1, N = 50;
   const float h = 3.0f / N;
@@ -251,6 +307,7 @@ int main() {
   if (double_integrator(false)) return 1;
   if (double_integrator(true)) return 2;
   if (pendulum()) return 3;
+  if (double_integrator_bound_api()) return 4;
   std::printf("FACADE OK\n");
   return 0;
 }
