@@ -257,7 +257,7 @@ struct BulkRing {
           : "=r"(ok)
           : "r"(a), "r"(parity)
           : "memory");
-      if (!ok && ++spins > (1ull << 24)) {  // a protocol bug must fail the launch, not hang the device
+      if (!ok && ++spins > (1ull << 21)) {  // a protocol bug must fail the launch, not hang the device
         printf("altro_b200: ring wait stuck (block %d thread %d stage %d parity %u)\n", (int)blockIdx.x,
                (int)threadIdx.x, s, parity);
         __trap();
@@ -276,50 +276,55 @@ struct BulkRing {
   }
 };
 
-// ---- The same staging for SEVERAL consumer warps that are NOT kept in lockstep (k_phase_forward):
-// a classic full/empty mbarrier pipeline.  `full[s]` completes when the bulk copies of a stage have
-// landed (1 arrival + transaction bytes); `empty[s]` completes when every participating warp has
-// released the stage (one elected arrival per warp, issued after the warp consumed what it read).
-// The producer thread refills a stage only after its `empty` phase completed, so fast warps run up
-// to depth - 1 knots ahead of slow ones instead of meeting at a CTA barrier every knot (ncu r01:
-// 9 barrier stalls per issue in the late line-search rounds).  A pass = one sweep over the knots;
-// the barriers are re-armed per pass for the warps that take part in it (begin_pass), so stage and
-// parity are functions of the pass-local knot counter.
+// ---- The same staging for SEVERAL consumer warps that are NOT kept in lockstep (k_phase_forward,
+// k_phase_backward_team): a classic full/empty mbarrier pipeline.  `full[s]` completes when the
+// bulk copies of a stage have landed (1 arrival + transaction bytes); `empty[s]` completes when
+// every consumer warp has released the stage (one elected arrival per warp, issued after the warp
+// consumed what it read).  The producer thread refills a stage only after its `empty` phase
+// completed, so fast warps run up to depth - 1 knots ahead of slow ones instead of meeting at a
+// CTA barrier every knot (ncu r01: 9 barrier stalls per issue in the late line-search rounds).
+// A pass = one sweep over the knots.  The barriers are initialised ONCE per kernel with a fixed
+// consumer count and never invalidated: stage and parity of pass-local knot k follow from the
+// running count c0 of knots the pipe has carried in earlier passes.  (Re-arming the barriers per
+// pass with mbarrier.inval + init lost arrivals as soon as two CTAs shared an SM -- found on the
+// B200 with the watchdog below; every warp of the CTA is therefore a consumer of every pass, a warp
+// with nothing to compute just waits and releases.)
 struct BulkPipe {
   unsigned long long* full;   // [depth]
   unsigned long long* empty;  // [depth]
   double* data;               // [depth][stage_doubles], 128-byte aligned
   int depth, stage_doubles;
+  int c0;                     // knots carried by earlier passes
 
+  static constexpr int kBarBytes = 128;  // barrier block of one pipe: full[<=8] | empty[<=8]
   __host__ __device__ static size_t bytes(int depth, int stage_doubles) {
     return 256 + (size_t)depth * stage_doubles * 8;
   }
-  // pointer carving only; all threads
-  ALTRO_DEV void setup(unsigned char* smem, int depth_, int stage_doubles_) {
-    full = reinterpret_cast<unsigned long long*>(smem);
-    empty = full + 16;
-    data = reinterpret_cast<double*>(smem + 256);
+  // pointer carving only; all threads.  bars: kBarBytes of shared memory, data: the stages
+  ALTRO_DEV void setup(unsigned char* bars, double* data_, int depth_, int stage_doubles_) {
+    full = reinterpret_cast<unsigned long long*>(bars);
+    empty = full + 8;
+    data = data_;
     depth = depth_;
     stage_doubles = stage_doubles_;
+    c0 = 0;
   }
-  // ONE thread, with a CTA barrier before (nobody still uses the previous pass) and after.
-  // `used`: the barriers hold valid objects from an earlier pass and must be invalidated first.
-  ALTRO_DEV void begin_pass(int consumer_warps, bool used) const {
+  // ONE thread, once per kernel, followed by a CTA barrier
+  ALTRO_DEV void init(int consumer_warps) const {
     for (int j = 0; j < depth; ++j) {
       const unsigned f = (unsigned)__cvta_generic_to_shared(full + j);
       const unsigned e = (unsigned)__cvta_generic_to_shared(empty + j);
-      if (used) {
-        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(f) : "memory");
-        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(e) : "memory");
-      }
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(f) : "memory");
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(e), "r"(consumer_warps) : "memory");
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // every thread that tracks the pipe, after a pass of `knots` knots
+  ALTRO_DEV void end_pass(int knots) { c0 += knots; }
+
   // A wait that cannot complete is a protocol bug; it must surface as a kernel error (trap -> the
   // launch fails, the C ABI returns an error), never as a hung device.
-  ALTRO_DEV static void spin(unsigned addr, unsigned parity) {
+  ALTRO_DEV static void spin(unsigned addr, unsigned parity, int what = 0, int k = -1) {
     unsigned ok = 0;
     unsigned long long spins = 0;
     while (!ok) {
@@ -328,9 +333,11 @@ struct BulkPipe {
           : "=r"(ok)
           : "r"(addr), "r"(parity)
           : "memory");
-      if (!ok && ++spins > (1ull << 24)) {
-        printf("altro_b200: mbarrier wait stuck (block %d thread %d addr %u parity %u)\n", (int)blockIdx.x,
-               (int)threadIdx.x, addr, parity);
+      if (!ok && ++spins > (1ull << 22)) {
+        if ((threadIdx.x & 31) == 0 || what == 2)
+          printf("altro_b200: mbarrier wait stuck: %s knot %d (block %d of %d, thread %d of %d, addr %u parity %u)\n",
+                 what == 0 ? "full" : (what == 1 ? "empty/warp" : "empty/producer"), k, (int)blockIdx.x,
+                 (int)gridDim.x, (int)threadIdx.x, (int)blockDim.x, addr, parity);
         __trap();
       }
     }
@@ -340,14 +347,16 @@ struct BulkPipe {
   // producer thread converged with its warp (a lone spinning lane would make the warp execute the
   // next knot twice: once without it, once for it).
   ALTRO_DEV void wait_writable(int k) const {
-    const int use = k / depth;
-    if (use > 0) spin((unsigned)__cvta_generic_to_shared(empty + k % depth), (unsigned)((use - 1) & 1));
+    const int g = c0 + k;
+    const int use = g / depth;
+    if (use > 0) spin((unsigned)__cvta_generic_to_shared(empty + g % depth), (unsigned)((use - 1) & 1), 1, k);
   }
-  // producer thread: make stage k % depth writable for pass-local knot k, announce `bytes`
+  // producer thread: make the stage of pass-local knot k writable, announce `bytes`; returns the stage
   ALTRO_DEV int acquire(int k, unsigned bytes) const {
-    const int st = k % depth;
-    const int use = k / depth;
-    if (use > 0) spin((unsigned)__cvta_generic_to_shared(empty + st), (unsigned)((use - 1) & 1));
+    const int g = c0 + k;
+    const int st = g % depth;
+    const int use = g / depth;
+    if (use > 0) spin((unsigned)__cvta_generic_to_shared(empty + st), (unsigned)((use - 1) & 1), 2, k);
     const unsigned a = (unsigned)__cvta_generic_to_shared(full + st);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
     return st;
@@ -362,15 +371,16 @@ struct BulkPipe {
   }
   // consumer, all lanes: wait for pass-local knot k; returns the stage's first row
   ALTRO_DEV const double* wait(int k) const {
-    const int st = k % depth;
-    spin((unsigned)__cvta_generic_to_shared(full + st), (unsigned)((k / depth) & 1));
+    const int g = c0 + k;
+    const int st = g % depth;
+    spin((unsigned)__cvta_generic_to_shared(full + st), (unsigned)((g / depth) & 1), 0, k);
     return data + (long)st * stage_doubles;
   }
   // consumer, all lanes of the warp, AFTER the arithmetic that consumed the stage's values
   ALTRO_DEV void release(int k, int lane) const {
     __syncwarp();
     if (lane == 0) {
-      const unsigned a = (unsigned)__cvta_generic_to_shared(empty + (k % depth));
+      const unsigned a = (unsigned)__cvta_generic_to_shared(empty + ((c0 + k) % depth));
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
     }
   }

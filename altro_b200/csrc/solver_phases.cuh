@@ -358,8 +358,15 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
   const unsigned act_mask = __ballot_sync(kAll, (fl & TF_ACTIVE) != 0);
   if (!act_mask) return;
 
-  BulkPipe pipe;
-  pipe.setup(altro_smem, depth, stage_rows * 32);
+  // two pipes over the same stages: `pipe` for the rollout passes (every warp of the CTA consumes),
+  // `scan` for the d(phi) scans (warp 0 alone); barriers armed once, never invalidated
+  BulkPipe pipe, scan;
+  pipe.setup(altro_smem, reinterpret_cast<double*>(altro_smem + 256), depth, stage_rows * 32);
+  scan.setup(altro_smem + BulkPipe::kBarBytes, reinterpret_cast<double*>(altro_smem + 256), depth, stage_rows * 32);
+  if (TS::kStaged && tid == 0) {
+    pipe.init((int)(blockDim.x >> 5));
+    scan.init(1);
+  }
   double* wsm = reinterpret_cast<double*>(altro_smem + BulkPipe::bytes(depth, stage_rows * 32));
   const int nq = (P.N + 1) * n, nr = P.N * m;
   if (wcount > 0) {
@@ -387,7 +394,6 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
   const double* rec = P.xbar + (long)g * P.GS;  // row 0 of the group's knot-0 record
   const double* zrec = CON ? P.z + (long)g * P.GSz : nullptr;
   const LsOptions lo = ls_options(P.opts);
-  bool pipe_used = false;
   __syncthreads();
 
   // ================================================================= line-search rounds
@@ -418,13 +424,9 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
         slot = p / nneedy + 1;
       }
     }
-    const int np = 1 + (nneedy * nspec + 31) / 32;  // warps that take part in the pass
-    const bool warp_in = wid < np;
-    if (TS::kStaged) {
-      if (tid == 0) pipe.begin_pass(np, pipe_used);
-      pipe_used = true;
-      __syncthreads();
-    }
+    // every warp consumes the pass (fixed arrival count of the empty barriers); a warp without a
+    // candidate only waits and releases.  Without staging the idle warps skip the pass.
+    const bool warp_in = TS::kStaged || wid == 0 || (wid - 1) * 32 < nneedy * nspec;
     if (warp_in) {
       const int b = g * 32 + lane;
       TS s(P, need ? b : g * 32);
@@ -484,6 +486,7 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
             if (lid == 0) fetch(k - 1 + depth);
           }
         }
+        pipe.end_pass(P.N);
         if (need) s.rollout_terminal(x, xo, so, phi);
       } else {
         if (need) phi = s.phase_rollout(alpha, xo, uo, so);
@@ -527,13 +530,11 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
           // stage contents: [K d] [J] [lx lu]
           constexpr int kV = TS::kV;
           constexpr int kRows1 = m * n + m;
-          if (lid == 0) pipe.begin_pass(1, true);
-          __syncwarp();
           auto fetch = [&](int k) {
-            const int st = pipe.acquire(k, (unsigned)TS::kRowsDphi * 256u);
-            pipe.copy(st, 0, rec + (long)k * P.R + TS::rK * 32, kRows1 * 256);
-            pipe.copy(st, kRows1, rec + (long)k * P.R + TS::rA * 32, kV * 256);
-            pipe.copy(st, kRows1 + kV, rec + (long)k * P.R + TS::rLx * 32, (n + m) * 256);
+            const int st = scan.acquire(k, (unsigned)TS::kRowsDphi * 256u);
+            scan.copy(st, 0, rec + (long)k * P.R + TS::rK * 32, kRows1 * 256);
+            scan.copy(st, kRows1, rec + (long)k * P.R + TS::rA * 32, kV * 256);
+            scan.copy(st, kRows1 + kV, rec + (long)k * P.R + TS::rLx * 32, (n + m) * 256);
           };
           if (lid == 0)
             for (int j = 0; j < depth && j < P.N; ++j) fetch(j);
@@ -541,7 +542,7 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
 #pragma unroll
           for (int i = 0; i < n; ++i) dxda[i] = 0.0;
           for (int k = 0; k < P.N; ++k) {
-            const double* st = pipe.wait(k);
+            const double* st = scan.wait(k);
             double K[m * n], d[m], A[n * n], Bm[n * m], lx[n], lu[m];
             if (had_deriv) {
               unstage_block<m * n>(st, 0, lid, K);
@@ -551,12 +552,13 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
               unstage_block<m>(st, kRows1 + kV + n, lid, lu);
               s.dphi_step(K, d, A, Bm, lx, lu, dxda, dphi);
             }
-            pipe.release(k, lid);
+            scan.release(k, lid);
             if (k >= 1 && k - 1 + depth < P.N) {
-              pipe.wait_writable(k - 1 + depth);
+              scan.wait_writable(k - 1 + depth);
               if (lid == 0) fetch(k - 1 + depth);
             }
           }
+          scan.end_pass(P.N);
           if (had_deriv) dphi = s.dphi_terminal(dxda, dphi);
         } else {
           if (had_deriv) dphi = s.phase_dphi_scan();

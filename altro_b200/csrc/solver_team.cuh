@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(32 * TeamShape<Model::n, Model::m>::W)
   const int scan_rows = TS::kRowsBackwardKernel + zr;
   // shared memory: [pipe barriers 256 B][stages: max(sweep, scan ring)][exchange rows][weights]
   BulkPipe pipe;
-  pipe.setup(altro_smem, depth, sweep_rows * 32);
+  pipe.setup(altro_smem, reinterpret_cast<double*>(altro_smem + 256), depth, sweep_rows * 32);
   const size_t stage_bytes =
       TS::kStaged ? max(BulkPipe::bytes(depth, sweep_rows * 32), 256 + BulkRing::bytes(ring_depth, scan_rows * 32))
                   : BulkPipe::bytes(depth, sweep_rows * 32);
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(32 * TeamShape<Model::n, Model::m>::W)
   double* xQux = xQK + m * n * 32;
   double* xpv = xQux + m * n * 32;
   stage_weights(s, P, xch + Shape::kXchRows * 32, wcount);
-  if (tid == 0) pipe.begin_pass(W, false);
+  if (tid == 0) pipe.init(W);
   __syncthreads();
 
   const double* rec = P.xbar + (long)g * P.GS;  // row 0 of the group's knot-0 record
