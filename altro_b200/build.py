@@ -22,7 +22,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
 N_INST = 8
-UNITS = [("capi", "capi.cu", []), ("tvlqr", "tvlqr.cu", []), ("facade", "altro_solver.cpp", []),
+UNITS = [("capi", "capi.cu", []), ("tvlqr", "tvlqr.cu", []), ("tvlqr_batch", "tvlqr_batch.cu", []),
+         ("facade", "altro_solver.cpp", []),
          ("json_io", "json_io.cpp", [])] + \
         [(f"solve_inst_{g}", "solve_inst.cu", [f"-DALTRO_INST={g}"]) for g in range(N_INST)]
 
@@ -58,7 +59,7 @@ def build(verbose=False, jobs=None):
     only = os.environ.get("ALTRO_ONLY")
     skip = set()
     if only:
-        keep = {f"solve_inst_{g}" for g in only.split(",")} | {"capi", "tvlqr", "facade", "json_io"}
+        keep = {f"solve_inst_{g}" for g in only.split(",")} | {"capi", "tvlqr", "tvlqr_batch", "facade", "json_io"}
         # stale objects of the other groups are linked as they are (their mtime is left alone, so
         # the next full build recompiles them)
         skip = {name for name, _, _ in UNITS

@@ -236,11 +236,13 @@ struct altro_b200_solver {
   unsigned long long* ls_hist = nullptr;
   PhaseHost ph;        // accumulated statistics + device limits
   int solve_mode = 0;  // 0: phase pipeline (default), 1: single persistent kernel
-  int backward_team = 0;  // Riccati sweep: 0 one warp per group, 1 the warps of a CTA (solver_team.cuh)
+  // Riccati sweep: 0 one warp per group, 1 the warps of a CTA (solver_team.cuh), -1 by block size:
+  // the team form where the blocks do not fit the registers of one thread (n > 6)
+  int backward_team = -1;
   // pipelined sub-batches: the groups are cut into `nsplit` contiguous ranges, each on its own
   // stream, so that the sweeps of one range (one busy warp per group) overlap the rollouts and
   // knot-parallel phases of another.  One host thread enqueues all of them.
-  static constexpr int kMaxSplit = 8;
+  static constexpr int kMaxSplit = 32;
   int nsplit = 0;  // 0: choose from the batch size
   cudaStream_t sub_stream[kMaxSplit] = {nullptr};
   PhaseHost sub_ph[kMaxSplit];
@@ -1353,7 +1355,7 @@ int altro_b200_solve_async(altro_b200_solver* s) {  // altro_solver.cpp:257-260
     H.d_done = s->d_done + i;
     H.d_prof = s->d_prof + 8 * i;
     H.fwd_warps = std::max(4, s->nslots);
-    H.backward_team = s->backward_team;
+    H.backward_team = s->backward_team >= 0 ? s->backward_team : (s->n > kUnrollDim ? 1 : 0);
     for (int j = 0; j < PH_COUNT; ++j) {
       H.ms[j] = 0.0;
       H.launches[j] = 0;
@@ -1472,7 +1474,7 @@ int altro_b200_set_solve_mode(altro_b200_solver* s, int mode) {
 
 int altro_b200_set_backward_mode(altro_b200_solver* s, int team) {
   if (!s) return ALTRO_B200_INVALID_POINTER;
-  if (team != 0 && team != 1) return ALTRO_B200_BAD_INDEX;
+  if (team < -1 || team > 1) return ALTRO_B200_BAD_INDEX;
   s->backward_team = team;
   return ALTRO_B200_NO_ERROR;
 }

@@ -364,6 +364,15 @@ bool have_device() {
 
 extern "C" {
 
+// fixed-size, TMA-staged workspace path for the compiled-in shapes (tvlqr_batch.cu); -1 = not compiled in
+int altro_b200_tvlqr_cached_backward(int batch, int n, int m, int N, const double* A, const double* B,
+                                     const double* f, const double* Q, const double* R, const double* H,
+                                     const double* q, const double* r, double reg, bool is_diag, double* K,
+                                     double* d, double* P, double* p, double* delta_V, int* status);
+int altro_b200_tvlqr_cached_forward(int batch, int n, int m, int N, const double* A, const double* B,
+                                    const double* f, const double* K, const double* d, const double* P,
+                                    const double* p, const double* x0, double* x, double* u, double* y);
+
 int altro_b200_tvlqr_backward_batch(int batch, int n, int m, int N, const double* A,
                                     const double* B, const double* f, const double* Q,
                                     const double* R, const double* H, const double* q,
@@ -375,6 +384,11 @@ int altro_b200_tvlqr_backward_batch(int batch, int n, int m, int N, const double
   if (n <= 0 || m <= 0 || batch <= 0 || N <= 0) return ALTRO_B200_DIMENSION_UNKNOWN;
   if (n > 16 || m > 8) return ALTRO_B200_ERR_UNSUPPORTED;
   if (!have_device()) return ALTRO_B200_ERR_NO_DEVICE;
+  {
+    const int e = altro_b200_tvlqr_cached_backward(batch, n, m, N, A, B, f, Q, R, H, q, r, reg, is_diag, K, d,
+                                                   P, p, delta_V, status);
+    if (e != -1) return e;
+  }
   const long S = ((long)batch + 31) / 32 * 32;
   Scratch sc;
   TvArgs a;
@@ -441,6 +455,10 @@ int altro_b200_tvlqr_forward_batch(int batch, int n, int m, int N, const double*
   if (n <= 0 || m <= 0 || batch <= 0 || N <= 0) return ALTRO_B200_DIMENSION_UNKNOWN;
   if (n > 16 || m > 8) return ALTRO_B200_ERR_UNSUPPORTED;
   if (!have_device()) return ALTRO_B200_ERR_NO_DEVICE;
+  {
+    const int e = altro_b200_tvlqr_cached_forward(batch, n, m, N, A, B, f, K, d, P, p, x0, x, u, y);
+    if (e != -1) return e;
+  }
   const long S = ((long)batch + 31) / 32 * 32;
   Scratch sc;
   TvArgs a;

@@ -128,6 +128,31 @@ int altro_b200_tvlqr_forward_batch(int batch, int n, int m, int num_horizon, con
                                    const double *d, const double *P, const double *p,
                                    const double *x0, double *x, double *u, double *y);
 
+/* Device-resident workspace behind the two calls above, for callers that run the sweep more than
+ * once: upload the LQ data once, run backward()/forward() many times -- no allocation and no
+ * synchronisation inside backward().  Compiled-in shapes (n, m): (2,1) (4,2) (4,4) (5,2) (6,2) (6,3)
+ * (6,4); create returns NULL for any other shape (use the stateless calls, which fall back to a
+ * run-time-dimension kernel) or without a CUDA device.  Arrays as in section B. */
+typedef struct altro_b200_tvlqr_ws altro_b200_tvlqr_ws;
+altro_b200_tvlqr_ws *altro_b200_tvlqr_ws_create(int batch, int n, int m, int num_horizon, bool is_diag,
+                                                int device);
+void altro_b200_tvlqr_ws_destroy(altro_b200_tvlqr_ws *w);
+/* any array may be NULL (left as it is) */
+int altro_b200_tvlqr_ws_upload(altro_b200_tvlqr_ws *w, const double *A, const double *B, const double *f,
+                               const double *Q, const double *R, const double *H, const double *q,
+                               const double *r);
+int altro_b200_tvlqr_ws_backward(altro_b200_tvlqr_ws *w, double reg); /* asynchronous */
+int altro_b200_tvlqr_ws_download(altro_b200_tvlqr_ws *w, double *K, double *d, double *P, double *p,
+                                 double *delta_V, int *status);
+/* gains / cost-to-go from the host instead of a previous backward() */
+int altro_b200_tvlqr_ws_set_gains(altro_b200_tvlqr_ws *w, const double *K, const double *d, const double *P,
+                                  const double *p);
+int altro_b200_tvlqr_ws_forward(altro_b200_tvlqr_ws *w, const double *x0, double *x, double *u, double *y);
+/* CUDA-event time of `reps` back-to-back backward() launches (after one warm-up), per launch */
+int altro_b200_tvlqr_ws_time_backward(altro_b200_tvlqr_ws *w, double reg, int reps, float *ms_per_launch);
+/* compulsory HBM bytes of one backward step of one problem (all input rows read, K d P p written) */
+long altro_b200_tvlqr_ws_bytes_per_knot(const altro_b200_tvlqr_ws *w);
+
 /* ================================================================================ section C */
 typedef struct altro_b200_solver altro_b200_solver;
 
@@ -265,9 +290,10 @@ int altro_b200_synchronize(altro_b200_solver *s);
 int altro_b200_set_solve_mode(altro_b200_solver *s, int mode);
 /* Riccati sweep of the default mode: 0 one warp per group of 32 problems (thread = trajectory),
  * 1 the blocks of a problem spread by columns over the warps of a CTA (exchange through shared
- * memory; what lets n = 12 stay on chip).  Bit-identical results. */
+ * memory; what lets n = 12 stay on chip), -1 (default) by block size: 1 for n > 6.  Bit-identical
+ * results. */
 int altro_b200_set_backward_mode(altro_b200_solver *s, int team);
-/* pipelined sub-batches: the batch is cut into `nsplit` contiguous ranges (1..8; 0 = automatic),
+/* pipelined sub-batches: the batch is cut into `nsplit` contiguous ranges (1..32; 0 = automatic),
  * each on its own stream (one host thread enqueues all) so the sweeps of one range overlap the
  * rollouts of another.  Results do not depend on nsplit. */
 int altro_b200_set_pipeline_split(altro_b200_solver *s, int nsplit);

@@ -157,6 +157,78 @@ def test_tvlqr_batched_random_dims(oracle):
             assert np.allclose(f[b, k] + A[b, k] @ X[b, k] + Bm[b, k] @ u, X[b, k + 1], rtol=1e-10, atol=1e-10)
 
 
+def test_tvlqr_workspace_diag_status_and_timing(oracle):
+    """The device-resident TVLQR workspace (section B): diagonal-cost mode against the oracle, the
+    per-problem Cholesky status (tvlqr.cpp:162-164), repeated launches without re-upload, and the
+    CUDA-event timing entry point behind the kernel's roofline line."""
+    L = altro_b200.load_library()
+    L.altro_b200_tvlqr_ws_create.restype = C.c_void_p
+    L.altro_b200_tvlqr_ws_create.argtypes = [C.c_int] * 4 + [C.c_bool, C.c_int]
+    vp = C.c_void_p
+    L.altro_b200_tvlqr_ws_upload.argtypes = [vp] + [dp] * 8
+    L.altro_b200_tvlqr_ws_backward.argtypes = [vp, C.c_double]
+    L.altro_b200_tvlqr_ws_download.argtypes = [vp, dp, dp, dp, dp, dp, C.POINTER(C.c_int)]
+    L.altro_b200_tvlqr_ws_time_backward.argtypes = [vp, C.c_double, C.c_int, C.POINTER(C.c_float)]
+    L.altro_b200_tvlqr_ws_bytes_per_knot.restype = C.c_long
+    L.altro_b200_tvlqr_ws_bytes_per_knot.argtypes = [vp]
+    L.altro_b200_tvlqr_ws_destroy.argtypes = [vp]
+    assert not L.altro_b200_tvlqr_ws_create(8, 7, 3, 10, True, 0)        # shape not compiled in
+    rng = np.random.default_rng(9)
+    n, m, N, B = 6, 2, 40, 100
+    A = np.eye(n) + 0.05 * rng.normal(size=(B, N, n, n))
+    Bm = rng.normal(size=(B, N, n, m))
+    f = 0.1 * rng.normal(size=(B, N, n))
+    Qd = 0.5 + rng.uniform(size=(B, N + 1, n))
+    Rd = 0.1 + rng.uniform(size=(B, N, m))
+    Rd[7, 11] = -1e6                                                      # problem 7 fails at knot 11
+    q, r = rng.normal(size=(B, N + 1, n)), rng.normal(size=(B, N, m))
+    cm = lambda M: np.ascontiguousarray(np.swapaxes(M, -1, -2))
+    Ac, Bc = cm(A), cm(Bm)
+    ptr = lambda a: a.ctypes.data_as(dp)
+    w = vp(L.altro_b200_tvlqr_ws_create(B, n, m, N, True, 0))
+    assert w.value
+    assert L.altro_b200_tvlqr_ws_bytes_per_knot(w) == 8 * (n * n + n * m + n + n + m + n + m + m * n + m + n * n + n)
+    assert L.altro_b200_tvlqr_ws_upload(w, ptr(Ac), ptr(Bc), ptr(f), ptr(Qd), ptr(Rd), None, ptr(q), ptr(r)) == 0
+    K = np.zeros((B, N, n, m)); d = np.zeros((B, N, m)); P = np.zeros((B, N + 1, n, n))
+    p = np.zeros((B, N + 1, n)); dV = np.zeros((B, 2)); st = np.zeros(B, dtype=np.int32)
+    for rep in range(2):                                                  # second launch: no upload
+        assert L.altro_b200_tvlqr_ws_backward(w, 0.0) == 0
+        assert L.altro_b200_tvlqr_ws_download(w, ptr(K), ptr(d), ptr(P), ptr(p), ptr(dV),
+                                              st.ctypes.data_as(C.POINTER(C.c_int))) == 0
+        assert st[7] == 11 and np.all(np.delete(st, 7) == -1)
+    ms = C.c_float()
+    assert L.altro_b200_tvlqr_ws_time_backward(w, 0.0, 5, C.byref(ms)) == 0 and ms.value > 0
+    L.altro_b200_tvlqr_ws_destroy(w)
+    OL = oracle.lib()
+    for b in (0, 50, 99):
+        def tab(arrs):
+            keep = [np.ascontiguousarray(a, dtype=float).reshape(-1) for a in arrs]
+            return (dp * len(keep))(*[a.ctypes.data_as(dp) for a in keep]), keep
+        tA, k1 = tab(list(Ac[b])); tB, k2 = tab(list(Bc[b])); tf, k3 = tab(list(f[b]))
+        tQ, k4 = tab(list(Qd[b])); tR, k5 = tab(list(Rd[b])); tH, k6 = tab([np.zeros(m * n)] * N)
+        tq, k7 = tab(list(q[b])); tr, k8 = tab(list(r[b]))
+        o = {}
+        for name, size, cnt in [("K", m * n, N), ("d", m, N), ("P", n * n, N + 1), ("p", n, N + 1),
+                                ("Qxx", n * n, N), ("Quu", m * m, N), ("Qux", m * n, N), ("Qx", n, N),
+                                ("Qu", m, N), ("Qxx_tmp", n * n, N), ("Quu_tmp", m * m, N),
+                                ("Qux_tmp", m * n, N), ("Qx_tmp", n, N), ("Qu_tmp", m, N)]:
+            o[name] = tab([np.zeros(size) for _ in range(cnt)])
+        nx = (C.c_int * (N + 1))(*([n] * (N + 1))); nu = (C.c_int * N)(*([m] * N))
+        odV = np.zeros(2)
+        T = lambda k: o[k][0]
+        res = OL.oracle_tvlqr_backward_pass(nx, nu, N, tA, tB, tf, tQ, tR, tH, tq, tr, C.c_double(0.0),
+                                            T("K"), T("d"), T("P"), T("p"), odV.ctypes.data_as(dp),
+                                            T("Qxx"), T("Quu"), T("Qux"), T("Qx"), T("Qu"), T("Qxx_tmp"),
+                                            T("Quu_tmp"), T("Qux_tmp"), T("Qx_tmp"), T("Qu_tmp"), 0, 1)
+        assert res == -1
+        for k in range(N):
+            assert np.allclose(K[b, k].reshape(-1), o["K"][1][k], rtol=1e-9, atol=1e-10)
+            assert np.allclose(d[b, k], o["d"][1][k], rtol=1e-9, atol=1e-10)
+        assert np.allclose(P[b, 0].reshape(-1), o["P"][1][0], rtol=1e-9, atol=1e-9)
+        assert np.allclose(p[b, 0], o["p"][1][0], rtol=1e-9, atol=1e-9)
+        assert np.allclose(dV[b], odV, rtol=1e-9)
+
+
 CONSUMER = r'''
 // The reference's own end-to-end tests re-expressed against the facade
 // (test/double_integrator_test.cpp:169-256, :258-375; test/pendulum_test.cpp:45-115).

@@ -10,8 +10,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv \
     --log-file gpurun_out/${TAG}_launches_${WL}.csv \
     python bench.py --workload ${WL} --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_launches_${WL}.log 2>&1
 # (2) full captures of the phase kernels (3 launches each, mid-solve, sub-batch pipelining off)
-for K in k_phase_backward k_phase_rollout k_phase_lsupdate k_phase_expand k_phase_residual k_phase_costate; do
-  ncu --set full --clock-control none --import-source on -k regex:${K} -s 12 -c 3 -f \
+for K in k_phase_backward k_phase_forward; do
+  ncu --set full --clock-control none --import-source on -k regex:${K} -s 8 -c 2 -f \
       -o gpurun_out/${TAG}_${WL}_${K} python tools/phase_profile.py ${WL} 16384 0 1 > gpurun_out/${TAG}_${WL}_${K}.log 2>&1
 done
 ls -la gpurun_out | tail -20

@@ -7,8 +7,7 @@ import re
 import sys
 
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-PHASE = {"k_phase_backward": "backward", "k_phase_rollout": "rollout", "k_phase_lsupdate": "lsupdate",
-         "k_phase_expand": "expand", "k_phase_residual": "criteria", "k_phase_costate": "criteria"}
+PHASE = {"k_phase_backward": "backward", "k_phase_forward": "forward", "k_phase_expand": "expand"}
 
 
 def val(s):
