@@ -239,6 +239,7 @@ struct altro_b200_solver {
   // Riccati sweep: 0 one warp per group, 1 the warps of a CTA (solver_team.cuh), -1 by block size:
   // the team form where the blocks do not fit the registers of one thread (n > 6)
   int backward_team = -1;
+  int fwd_depth = 8;  // staging depth cap of k_phase_forward (BulkPipe holds up to 8 stages)
   // pipelined sub-batches: the groups are cut into `nsplit` contiguous ranges, each on its own
   // stream, so that the sweeps of one range (one busy warp per group) overlap the rollouts and
   // knot-parallel phases of another.  One host thread enqueues all of them.
@@ -479,6 +480,7 @@ altro_b200_solver* altro_b200_create(int horizon_length, int batch, int device) 
   memset(&s->con_h, 0, sizeof(s->con_h));
   // test hook: run a whole test suite with the other Riccati schedule (results are bit-identical)
   if (const char* env = getenv("ALTRO_B200_BACKWARD_TEAM")) s->backward_team = atoi(env) != 0;
+  if (const char* env = getenv("ALTRO_B200_FWD_DEPTH")) s->fwd_depth = std::max(2, std::min(8, atoi(env)));
   return s;
 }
 
@@ -1355,6 +1357,7 @@ int altro_b200_solve_async(altro_b200_solver* s) {  // altro_solver.cpp:257-260
     H.d_done = s->d_done + i;
     H.d_prof = s->d_prof + 8 * i;
     H.fwd_warps = std::max(4, s->nslots);
+    H.fwd_depth = s->fwd_depth;
     H.backward_team = s->backward_team >= 0 ? s->backward_team : (s->n > kUnrollDim ? 1 : 0);
     for (int j = 0; j < PH_COUNT; ++j) {
       H.ms[j] = 0.0;

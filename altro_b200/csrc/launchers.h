@@ -46,6 +46,7 @@ struct PhaseHost {
   double units[PH_COUNT];      // trajectories (or trajectory-knots for PH_EXPAND) processed
   long syncs;                  // host waits on the device (lagged stop-counter checks)
   int fwd_warps;               // warps per CTA of k_phase_forward (1 + speculative candidates)
+  int fwd_depth;               // cap of the forward kernel's staging depth (knots in flight, <= 8)
   int backward_team;           // 1: Riccati sweep by the warps of a CTA (solver_team.cuh), 0: one warp
   cudaEvent_t ev0, ev1;
   static constexpr int kDoneRing = 4;

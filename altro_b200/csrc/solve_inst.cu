@@ -58,10 +58,10 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
   const int wdoubles = (N + 1) * n + N * m;
   const int wcount = (TS::kStaged && wdoubles * 8 <= 16 * 1024) ? wdoubles : 0;
   const size_t wbytes = (size_t)wcount * 8;
-  auto ring_depth = [&](int per_sm, size_t stage_bytes, size_t fixed) -> int {
+  auto ring_depth = [&](int per_sm, size_t stage_bytes, size_t fixed, int max_depth = kMaxStageDepth) -> int {
     const size_t budget =
         std::min<size_t>(H->smem_per_sm / std::max(per_sm, 1) - 1024, H->smem_per_cta) - fixed - wbytes;
-    return (int)std::max<size_t>(2, std::min<size_t>(kMaxStageDepth, budget / stage_bytes));
+    return (int)std::max<size_t>(2, std::min<size_t>((size_t)max_depth, budget / stage_bytes));
   };
   const int zr = CON ? 2 * P.zrows : 0;  // dual record rows staged with the main rows
   if (H->backward_team) {
@@ -105,8 +105,12 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
     size_t sm = 0;
     if (TS::kStaged) {
       rows = std::max(TS::kRowsRoll + zr, TS::kRowsDphi);
-      depth = ring_depth((P.Gtot + H->num_sms - 1) / H->num_sms, (size_t)rows * 256, 256);
-      sm = BulkPipe::bytes(depth, rows * 32) + wbytes;
+      // The forward CTAs are register-limited to two per SM, so the ring may use up to half an SM's
+      // shared memory minus what a co-resident backward CTA needs: up to kFwdStageDepth knots in
+      // flight (ncu r02e: a third of the kernel's stall samples waited for a stage to land at depth 4)
+      const int per_sm = std::min(2, (P.Gtot + H->num_sms - 1) / H->num_sms);
+      depth = ring_depth(per_sm, (size_t)rows * 256, 256 + (size_t)(N + 1) * 4 + 16 + 24 * 1024, H->fwd_depth);
+      sm = BulkPipe::bytes(depth, rows * 32) + wbytes + (size_t)((N + 1) * 4 + 15) / 16 * 16;
     }
     const int warps = std::max(1, std::min(H->fwd_warps, 8));
     DeviceProblem Pf = P;

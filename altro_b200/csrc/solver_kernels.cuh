@@ -1081,6 +1081,17 @@ struct TrajSolver {
     }
   }
 
+  // L2 prefetch of what phase_expand_knot(k, ., slot, .) will load (the knot-parallel phases are
+  // bound by the latency of these first loads: ncu r02e, long scoreboard)
+  ALTRO_DEV void phase_expand_prefetch(int k, int slot) const {
+    prefetch_block<n>(xw(slot), sw(slot), k);
+    prefetch_block<n>(F(P.q), S, k);
+    if (k < N) {
+      prefetch_block<m>(uw(slot), sw(slot), k);
+      prefetch_block<m>(F(P.r), S, k);
+    }
+  }
+
   // Expansion of ONE knot: [A B] (if with_dyn), projected duals, cost gradient with AL terms
   // (CalcDynamicsExpansion, CalcConstraintJacobians, CalcProjectedDuals, CalcCostGradient;
   // knotpoint_data.cpp:406-437).  The trajectory is read from candidate `slot`; when that is not

@@ -394,6 +394,8 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
   const double* rec = P.xbar + (long)g * P.GS;  // row 0 of the group's knot-0 record
   const double* zrec = CON ? P.z + (long)g * P.GSz : nullptr;
   const LsOptions lo = ls_options(P.opts);
+  // ready[k]: flagged lanes whose expansion of knot k is published (this round)
+  int* ready = reinterpret_cast<int*>(wsm + wcount);
   __syncthreads();
 
   // ================================================================= line-search rounds
@@ -405,6 +407,8 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
     fl = valid ? P.flags[bl] : 0;
     const unsigned pend = __ballot_sync(kAll, (fl & (TF_NEED_EVAL | TF_REROLL)) != 0);
     if (!pend) break;
+    if (TS::kStaged)  // cleared for this round; the barrier behind the rollout pass orders it
+      for (int i = tid; i <= P.N; i += blockDim.x) ready[i] = 0;
     const unsigned needy = __ballot_sync(kAll, (fl & TF_NEED_EVAL) && (fl & TF_SPECULATE));
     const unsigned dmask = __ballot_sync(kAll, (fl & TF_WANT_DERIV) != 0);
     const int nneedy = nspec > 0 ? __popc(needy) : 0;
@@ -501,21 +505,56 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
     __syncthreads();
     tick(FS_ROLLOUT);
 
-    // ---- expansion of the trial point of the lanes that asked for the derivative
+    // ---- expansion of the trial point of the lanes that asked for the derivative.  Staged models:
+    // warps >= 1 expand in knot-major order and publish every finished knot (ready[k] counts the
+    // flagged lanes done), so warp 0 can run the sequential d(phi) scan BEHIND them instead of
+    // after them -- the scan's bulk copy of knot k is issued once ready[k] is complete.
+    const int nl = __popc(dmask);
     if (dmask) {
-      for_knot_items(dmask, g, P.N + 1, [&](int b, int k) {
-        TS s(P, b);
-        weights(s);
-        s.rho = CON ? P.rho[b] : 1.0;
-        s.phase_expand_knot(k, true, -1, false);
-      });
-      // [J] [lx lu] were written through the generic proxy; the d(phi) scan reads them with bulk
-      // copies (async proxy)
-      __threadfence();
-      asm volatile("fence.proxy.async;" ::: "memory");
-      __syncthreads();
+      if constexpr (TS::kStaged) {
+        if (wid > 0) {
+          const int items = nl * (P.N + 1), step = (int)blockDim.x - 32;
+          for (int i = tid - 32; i < items; i += step) {
+            const int k = i / nl;
+            const int b = g * 32 + __fns(dmask, 0, i % nl + 1);
+            TS s(P, b);
+            weights(s);
+            s.rho = CON ? P.rho[b] : 1.0;
+            if (i + step < items) {  // the next item's rows on their way into L2 meanwhile
+              TS sn(P, g * 32 + __fns(dmask, 0, (i + step) % nl + 1));
+              sn.phase_expand_prefetch((i + step) / nl, -1);
+            }
+            s.phase_expand_knot(k, true, -1, false);
+            // [J] [lx lu] went through the generic proxy; the scan reads them with bulk copies
+            // (async proxy): fence, then publish
+            __threadfence();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            atomicAdd(ready + k, 1);
+          }
+        }
+      } else {
+        for_knot_items(dmask, g, P.N + 1, [&](int b, int k) {
+          TS s(P, b);
+          weights(s);
+          s.rho = CON ? P.rho[b] : 1.0;
+          s.phase_expand_knot(k, true, -1, false);
+        });
+        __syncthreads();
+      }
     }
     tick(FS_EXPAND);
+    // all lanes of warp 0: wait until every flagged lane's expansion of knot k has been published
+    auto wait_ready = [&](int k) {
+      volatile int* r = ready;
+      unsigned long long spins = 0;
+      while (r[k] < nl) {
+        if (++spins > (1ull << 26)) {
+          if (lid == 0) printf("altro_b200: expansion of knot %d never published (group %d)\n", k, g);
+          __trap();
+        }
+      }
+      __threadfence_block();
+    };
 
     // ---- d(phi) scan + line-search machines: warp 0, lane = problem
     if (wid == 0) {
@@ -536,8 +575,10 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
             scan.copy(st, kRows1, rec + (long)k * P.R + TS::rA * 32, kV * 256);
             scan.copy(st, kRows1 + kV, rec + (long)k * P.R + TS::rLx * 32, (n + m) * 256);
           };
-          if (lid == 0)
-            for (int j = 0; j < depth && j < P.N; ++j) fetch(j);
+          for (int j = 0; j < depth && j < P.N; ++j) {
+            wait_ready(j);
+            if (lid == 0) fetch(j);
+          }
           double dxda[n];
 #pragma unroll
           for (int i = 0; i < n; ++i) dxda[i] = 0.0;
@@ -555,10 +596,12 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
             scan.release(k, lid);
             if (k >= 1 && k - 1 + depth < P.N) {
               scan.wait_writable(k - 1 + depth);
+              wait_ready(k - 1 + depth);
               if (lid == 0) fetch(k - 1 + depth);
             }
           }
           scan.end_pass(P.N);
+          wait_ready(P.N);  // lx of the terminal knot (read below with plain loads)
           if (had_deriv) dphi = s.dphi_terminal(dxda, dphi);
         } else {
           if (had_deriv) dphi = s.phase_dphi_scan();
