@@ -29,6 +29,17 @@ struct TeamShape {
   static constexpr int kXchRows = N_ * N_ + 4 * M_ * N_ + N_;
 };
 
+// element (r, j) of a register-resident R x C block for a column index j that is only known at run
+// time (the warp's own column): a chain of selects over static indices keeps the block in
+// registers, where M[r + R * j] would force it into local memory
+template <int R, int C>
+__device__ __forceinline__ double col_pick(const double* M, int r, int j) {
+  double v = 0.0;
+#pragma unroll
+  for (int c = 0; c < C; ++c) v = (c == j) ? M[r + R * c] : v;
+  return v;
+}
+
 // diagonal of the cost Hessian + Gauss-Newton AL terms when every contribution is diagonal
 // (diagonal cost, selector rows with linear cones: CON <= 1); same additions in the same order as
 // cost_hessian + al_hessian, so the diagonal entries carry the same bits
@@ -139,7 +150,7 @@ __global__ void __launch_bounds__(32 * TeamShape<Model::n, Model::m>::W)
         const int j = w + jj * W;
         if (j < n) {
 #pragma unroll
-          for (int i = 0; i < n; ++i) Pc[jj][i] = Hxx[i + n * j];
+          for (int i = 0; i < n; ++i) Pc[jj][i] = col_pick<n, n>(Hxx, i, j);
         }
       }
     } else {
@@ -150,7 +161,7 @@ __global__ void __launch_bounds__(32 * TeamShape<Model::n, Model::m>::W)
         const int j = w + jj * W;
         if (j < n) {
 #pragma unroll
-          for (int i = 0; i < n; ++i) Pc[jj][i] = (i == j) ? dxx[j] : 0.0;
+          for (int i = 0; i < n; ++i) Pc[jj][i] = col_pick<1, n>(dxx, 0, i == j ? j : -1);
         }
       }
     }
@@ -161,8 +172,9 @@ __global__ void __launch_bounds__(32 * TeamShape<Model::n, Model::m>::W)
         double* Pg = s.F(P.P) + (long)P.N * s.S + (long)n * j * 32;
 #pragma unroll
         for (int i = 0; i < n; ++i) Pg[i * 32] = Pc[jj][i];
-        s.F(P.p)[(long)P.N * s.S + j * 32] = pN[j];
-        xpv[j * 32] = pN[j];
+        const double pNj = col_pick<1, n>(pN, 0, j);
+        s.F(P.p)[(long)P.N * s.S + j * 32] = pNj;
+        xpv[j * 32] = pNj;
       }
     }
   }
@@ -177,34 +189,41 @@ __global__ void __launch_bounds__(32 * TeamShape<Model::n, Model::m>::W)
     if constexpr (kRegJ) {
       if (alive) s.unstage_jac(st, 0, lane, A, Bm);
     }
-    auto Aat = [&](int l, int i) -> double {
-      if constexpr (kRegJ) return A[l + n * i];
-      else return sl[(l + n * i) * 32];
-    };
-    auto Bat = [&](int l, int i) -> double {
-      if constexpr (kRegJ) return Bm[l + n * i];
-      else return sl[(n * n + l + n * i) * 32];
-    };
+    // element (l, i) of A / B: registers for the small blocks, in place from the stage otherwise
+    // (macros, not lambdas: a by-reference capture would pin the arrays in local memory)
+#define ALTRO_AAT(l, i) (kRegJ ? A[kRegJ ? (l) + n * (i) : 0] : sl[((l) + n * (i)) * 32])
+#define ALTRO_BAT(l, i) (kRegJ ? Bm[kRegJ ? (l) + n * (i) : 0] : sl[(n * n + (l) + n * (i)) * 32])
+    // (one shared-memory operand feeds the NC own columns: the jj loop is innermost everywhere)
     if (alive) {
 #pragma unroll
-      for (int jj = 0; jj < NC; ++jj) {
-        const int j = w + jj * W;
-        if (j < n) {
+      for (int i = 0; i < n; ++i) {
+        double acc[NC];
 #pragma unroll
-          for (int i = 0; i < n; ++i) {
-            double acc = 0.0;
+        for (int jj = 0; jj < NC; ++jj) acc[jj] = 0.0;
 #pragma unroll
-            for (int l = 0; l < n; ++l) acc = fma(Aat(l, i), Pc[jj][l], acc);
-            xT1[(i + n * j) * 32] = acc;
-          }
+        for (int l = 0; l < n; ++l) {
+          const double a = ALTRO_AAT(l, i);
 #pragma unroll
-          for (int i = 0; i < m; ++i) {
-            double acc = 0.0;
-#pragma unroll
-            for (int l = 0; l < n; ++l) acc = fma(Bat(l, i), Pc[jj][l], acc);
-            xT2[(i + m * j) * 32] = acc;
-          }
+          for (int jj = 0; jj < NC; ++jj) acc[jj] = fma(a, Pc[jj][l], acc[jj]);
         }
+#pragma unroll
+        for (int jj = 0; jj < NC; ++jj)
+          if (w + jj * W < n) xT1[(i + n * (w + jj * W)) * 32] = acc[jj];
+      }
+#pragma unroll
+      for (int i = 0; i < m; ++i) {
+        double acc[NC];
+#pragma unroll
+        for (int jj = 0; jj < NC; ++jj) acc[jj] = 0.0;
+#pragma unroll
+        for (int l = 0; l < n; ++l) {
+          const double a = ALTRO_BAT(l, i);
+#pragma unroll
+          for (int jj = 0; jj < NC; ++jj) acc[jj] = fma(a, Pc[jj][l], acc[jj]);
+        }
+#pragma unroll
+        for (int jj = 0; jj < NC; ++jj)
+          if (w + jj * W < n) xT2[(i + m * (w + jj * W)) * 32] = acc[jj];
       }
     }
     __syncthreads();  // T1, T2 and p+ complete
@@ -236,7 +255,7 @@ __global__ void __launch_bounds__(32 * TeamShape<Model::n, Model::m>::W)
         for (int i = 0; i < m; ++i) {
           double acc = 0.0;
 #pragma unroll
-          for (int l = 0; l < n; ++l) acc = fma(xT2[(i + m * l) * 32], Bat(l, j), acc);
+          for (int l = 0; l < n; ++l) acc = fma(xT2[(i + m * l) * 32], ALTRO_BAT(l, j), acc);
           Quu[i + m * j] += acc;
         }
       // Qu = r + B' p+                                                  :151-152 (f = 0)
@@ -244,40 +263,69 @@ __global__ void __launch_bounds__(32 * TeamShape<Model::n, Model::m>::W)
       for (int i = 0; i < m; ++i) {
         double acc = 0.0;
 #pragma unroll
-        for (int l = 0; l < n; ++l) acc = fma(Bat(l, i), pfull[l], acc);
+        for (int l = 0; l < n; ++l) acc = fma(ALTRO_BAT(l, i), pfull[l], acc);
         Qu[i] = sl[(kV + n + i) * 32] + acc;
       }
+      // own columns of A in registers: the products below then take ONE shared-memory operand
+      // (T1 / T2 element) per NC multiply-adds
+      double Acol[NC][n];
+#pragma unroll
+      for (int jj = 0; jj < NC; ++jj) {
+        const int j = (w + jj * W < n) ? w + jj * W : 0;
+#pragma unroll
+        for (int l = 0; l < n; ++l) {
+          if constexpr (kRegJ) Acol[jj][l] = col_pick<n, n>(A, l, j);
+          else Acol[jj][l] = sl[(l + n * j) * 32];
+        }
+      }
+      // Qxx[:, j] = Q[:, j] + T1 A[:, j]                                :136
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        double acc[NC];
+#pragma unroll
+        for (int jj = 0; jj < NC; ++jj) acc[jj] = 0.0;
+#pragma unroll
+        for (int l = 0; l < n; ++l) {
+          const double t = xT1[(i + n * l) * 32];
+#pragma unroll
+          for (int jj = 0; jj < NC; ++jj) acc[jj] = fma(t, Acol[jj][l], acc[jj]);
+        }
+#pragma unroll
+        for (int jj = 0; jj < NC; ++jj) {
+          const int j = w + jj * W;
+          double h0;
+          if constexpr (kFullH) h0 = col_pick<n, n>(Hxx, i, j);
+          else h0 = col_pick<1, n>(dxx, 0, i == j ? j : -1);
+          Qxxc[jj][i] = h0 + acc[jj];
+        }
+      }
+      // Qux[:, j] = H[:, j] + T2 A[:, j]                                :143
+#pragma unroll
+      for (int i = 0; i < m; ++i) {
+        double acc[NC];
+#pragma unroll
+        for (int jj = 0; jj < NC; ++jj) acc[jj] = 0.0;
+#pragma unroll
+        for (int l = 0; l < n; ++l) {
+          const double t = xT2[(i + m * l) * 32];
+#pragma unroll
+          for (int jj = 0; jj < NC; ++jj) acc[jj] = fma(t, Acol[jj][l], acc[jj]);
+        }
+#pragma unroll
+        for (int jj = 0; jj < NC; ++jj) {
+          double h0 = 0.0;
+          if constexpr (kFullH) h0 = col_pick<m, n>(Hux, i, w + jj * W);
+          Quxc[jj][i] = h0 + acc[jj];
+        }
+      }
+      // Qx[j] = q[j] + A[:, j]' p+                                      :147-150
 #pragma unroll
       for (int jj = 0; jj < NC; ++jj) {
         const int j = w + jj * W;
-        if (j < n) {
-          // Qxx[:, j] = Q[:, j] + T1 A[:, j]                            :136
+        double acc = 0.0;
 #pragma unroll
-          for (int i = 0; i < n; ++i) {
-            double acc = 0.0;
-#pragma unroll
-            for (int l = 0; l < n; ++l) acc = fma(xT1[(i + n * l) * 32], Aat(l, j), acc);
-            double h0;
-            if constexpr (kFullH) h0 = Hxx[i + n * j];
-            else h0 = (i == j) ? dxx[j] : 0.0;
-            Qxxc[jj][i] = h0 + acc;
-          }
-          // Qux[:, j] = H[:, j] + T2 A[:, j]                            :143
-#pragma unroll
-          for (int i = 0; i < m; ++i) {
-            double acc = 0.0;
-#pragma unroll
-            for (int l = 0; l < n; ++l) acc = fma(xT2[(i + m * l) * 32], Aat(l, j), acc);
-            double h0 = 0.0;
-            if constexpr (kFullH) h0 = Hux[i + m * j];
-            Quxc[jj][i] = h0 + acc;
-          }
-          // Qx[j] = q[j] + A[:, j]' p+                                  :147-150
-          double acc = 0.0;
-#pragma unroll
-          for (int l = 0; l < n; ++l) acc = fma(Aat(l, j), pfull[l], acc);
-          Qxj[jj] = sl[(kV + j) * 32] + acc;
-        }
+        for (int l = 0; l < n; ++l) acc = fma(Acol[jj][l], pfull[l], acc);
+        Qxj[jj] = sl[(kV + (j < n ? j : 0)) * 32] + acc;
       }
       // K = Qux, d = -Qu, L = chol(Quu)                                  :157-164
       double L[m * m];
@@ -335,50 +383,52 @@ __global__ void __launch_bounds__(32 * TeamShape<Model::n, Model::m>::W)
     __syncthreads();  // K, Quu K, Qux complete
     // ---- (d) cost-to-go: own columns                                   tvlqr.cpp:173-186
     if (alive) {
+      double Pj[NC][n];
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        double a1[NC], a2[NC], a3[NC];
+#pragma unroll
+        for (int jj = 0; jj < NC; ++jj) a1[jj] = a2[jj] = a3[jj] = 0.0;
+#pragma unroll
+        for (int l = 0; l < m; ++l) {
+          const double qk = xQK[(l + m * i) * 32], kk = xK[(l + m * i) * 32], qq = xQux[(l + m * i) * 32];
+#pragma unroll
+          for (int jj = 0; jj < NC; ++jj) {
+            a1[jj] = fma(qk, Kc[jj][l], a1[jj]);    // ((Quu K)' K)[i, j]
+            a2[jj] = fma(kk, Quxc[jj][l], a2[jj]);  // (K' Qux)[i, j]
+            a3[jj] = fma(Kc[jj][l], qq, a3[jj]);    // (K' Qux)[j, i]
+          }
+        }
+#pragma unroll
+        for (int jj = 0; jj < NC; ++jj) {
+          double v = Qxxc[jj][i] + a1[jj];
+          v -= a2[jj];
+          v -= a3[jj];
+          Pj[jj][i] = v;
+        }
+      }
 #pragma unroll
       for (int jj = 0; jj < NC; ++jj) {
         const int j = w + jj * W;
         if (j < n) {
-          double Pj[n];
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            double acc = 0.0;  // ((Quu K)' K)[i, j]
-#pragma unroll
-            for (int l = 0; l < m; ++l) acc = fma(xQK[(l + m * i) * 32], Kc[jj][l], acc);
-            Pj[i] = Qxxc[jj][i] + acc;
-          }
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            double acc = 0.0;  // (K' Qux)[i, j]
-#pragma unroll
-            for (int l = 0; l < m; ++l) acc = fma(xK[(l + m * i) * 32], Quxc[jj][l], acc);
-            Pj[i] -= acc;
-          }
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            double acc = 0.0;  // (K' Qux)[j, i]
-#pragma unroll
-            for (int l = 0; l < m; ++l) acc = fma(Kc[jj][l], xQux[(l + m * i) * 32], acc);
-            Pj[i] -= acc;
-          }
           double pj = Qxj[jj];
           {
-            double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            double b1 = 0.0, b2 = 0.0, b3 = 0.0;
 #pragma unroll
-            for (int l = 0; l < m; ++l) a1 = fma(QKc[jj][l], dd[l], a1);
+            for (int l = 0; l < m; ++l) b1 = fma(QKc[jj][l], dd[l], b1);
 #pragma unroll
-            for (int l = 0; l < m; ++l) a2 = fma(Kc[jj][l], Qu[l], a2);
+            for (int l = 0; l < m; ++l) b2 = fma(Kc[jj][l], Qu[l], b2);
 #pragma unroll
-            for (int l = 0; l < m; ++l) a3 = fma(Quxc[jj][l], dd[l], a3);
-            pj -= a1;
-            pj -= a2;
-            pj += a3;
+            for (int l = 0; l < m; ++l) b3 = fma(Quxc[jj][l], dd[l], b3);
+            pj -= b1;
+            pj -= b2;
+            pj += b3;
           }
           double* Pg = s.F(P.P) + (long)k * s.S + (long)n * j * 32;
 #pragma unroll
           for (int i = 0; i < n; ++i) {
-            Pg[i * 32] = Pj[i];
-            Pc[jj][i] = Pj[i];
+            Pg[i * 32] = Pj[jj][i];
+            Pc[jj][i] = Pj[jj][i];
           }
           s.F(P.p)[(long)k * s.S + j * 32] = pj;
           xpv[j * 32] = pj;
@@ -404,5 +454,8 @@ __global__ void __launch_bounds__(32 * TeamShape<Model::n, Model::m>::W)
   }
   backward_finish(P, b, active, phi0, dphi0);
 }
+
+#undef ALTRO_AAT
+#undef ALTRO_BAT
 
 }  // namespace altro_b200

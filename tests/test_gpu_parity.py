@@ -92,6 +92,16 @@ def test_chain_sweep(oracle, n, m, N, box):
     compare(*run_both(oracle, P))
 
 
+@pytest.mark.parametrize("n,m,N", [(12, 2, 200), (12, 4, 500), (6, 2, 500), (4, 4, 500), (6, 4, 200)])
+def test_chain_sweep_long_horizons_and_large_blocks(oracle, n, m, N):
+    """The sweep shapes the round-1 tests never compared with the oracle (N = 500, n = 12 at
+    N >= 200), on the hard instances (5-20 iterations) the sweep table is measured on."""
+    P = PR.chain(B=33, n=n, m=m, N=N, hard=True)
+    gpu, ref = run_both(oracle, P)
+    rep = compare(gpu, ref, tail_frac=0.07)
+    assert rep["converged"] >= 0.9 * P.B and rep["mean_iters"] > 4
+
+
 def test_mpc_warm_start_sequence(oracle):
     """The reference's 200-step receding-horizon run (bicycle_test.cpp:247-337) on one handle:
     Solve -> GetInput -> simulate -> UpdateLinearCosts(q, nullptr, c) per knot -> SetInitialState

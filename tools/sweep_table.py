@@ -3,7 +3,8 @@
 pendulum-chain model, one GPU.  For every shape: solves/s with the batch resident in
 HBM, ms per solve of the batch, mean iterations, and the dominant kernel with its achieved fraction
 of the HBM copy peak (algorithmic bytes of bench.kernel_models / CUDA-event time of the kernel).
-Writes profiles/r01_sweep_table.json and prints a markdown table."""
+Hard instances (problems.chain(hard=True): 5-20 iterations).  Writes gpurun_out/r02_sweep_table.json
+and prints a markdown table."""
 import json
 import os
 import sys
@@ -24,7 +25,7 @@ def main():
     for n in (4, 6, 12):
         for m in (2, 4):
             for N in (50, 200, 500):
-                P = PR.chain(B=B, n=n, m=m, N=N)
+                P = PR.chain(B=B, n=n, m=m, N=N, hard=True)
                 s = altro_b200.make_solver(P)
                 s.Solve()                                   # warm-up
                 ts = []
@@ -37,7 +38,7 @@ def main():
                 st, _ = s.GetPhaseStats()
                 models = bench.kernel_models(P, iters, evals)
                 ker = {}
-                for ph in ("backward", "rollout", "expand", "lsupdate", "criteria"):
+                for ph in ("backward", "forward"):
                     if st[ph]["launches"]:
                         by = 8.0 * models[ph]["doubles"] * models[ph]["units"] + models[ph].get("extra_bytes", 0.0)
                         ker[ph] = dict(ms=st[ph]["ms"], gbs=by / (st[ph]["ms"] * 1e-3) / 1e9)
@@ -45,13 +46,15 @@ def main():
                 t = min(ts)
                 rows.append(dict(n=n, m=m, N=N, B=B, solves_per_s=B / t, ms=1e3 * t, mean_iters=float(iters.mean()),
                                  success=float((status == 0).mean()), dominant=dom,
+                                 backward_ms_per_launch=st["backward"]["ms"] / max(st["backward"]["launches"], 1),
+                                 backward_gbs=ker["backward"]["gbs"], backward_frac=ker["backward"]["gbs"] / peak,
                                  dominant_share=ker[dom]["ms"] / sum(v["ms"] for v in ker.values()),
                                  dominant_gbs=ker[dom]["gbs"], dominant_frac=ker[dom]["gbs"] / peak,
                                  hbm_gb=s.DeviceBytes() / 1e9))
                 s.close()
                 print(json.dumps(rows[-1]), flush=True)
     out = dict(peak_gbs=peak, peak_source=src, rows=rows)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "r01_sweep_table.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "r02_sweep_table.json"), "w"), indent=1)
     print("| n | m | N | solves/s | ms/batch | iters | dominant kernel | share | GB/s | frac of peak | HBM GB |")
     print("|---|---|---|---|---|---|---|---|---|---|---|")
     for r in rows:
