@@ -197,6 +197,24 @@ def ncu_traffic(workload_name, phase):
     return None
 
 
+def step_traffic(workload_name, kernels, ms_per_step, peak):
+    """DRAM bytes the step actually moves: ncu dram read+write per full-batch launch of each kernel
+    (profiles/traffic.json, captured with the sub-batch split off) x its launches per step, against
+    the step time -- how close the step is to the memory system's limit on the traffic it generates
+    (as opposed to `step_roofline`, which counts only the bytes the algorithm needs)."""
+    tot, used = 0.0, []
+    for ph in ("backward", "forward", "expand"):
+        t = ncu_traffic(workload_name, ph)
+        if t and ph in kernels:
+            tot += t * kernels[ph]["launches"]
+            used.append(ph)
+    if not used:
+        return None
+    gbs = tot / (ms_per_step * 1e-3) / 1e9
+    return {"dram_bytes_per_step": tot, "achieved": gbs, "unit": "GB/s", "frac_of_peak": gbs / peak,
+            "kernels": used, "source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"}
+
+
 def host_threads():
     """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which is not what
     the CPU arm is meant to measure, so the count is taken from the affinity mask)."""
@@ -483,6 +501,7 @@ def main():
                                  "achieved": alg_bytes / (elapsed_ms / args.steps * 1e-3) / 1e9,
                                  "frac": alg_bytes / (elapsed_ms / args.steps * 1e-3) / 1e9 / peak,
                                  "note": "SURVEY 8(d) bytes of the whole solve / step time"},
+               "step_traffic": step_traffic(args.workload, kernels, elapsed_ms / args.steps, peak),
                "solve_stats": {"mean_iterations": float(iters.mean()),
                                "mean_merit_evals": float(evals.mean()),
                                "success_frac": float((status == 0).mean()),
