@@ -239,6 +239,7 @@ struct altro_b200_solver {
   // Riccati sweep: 0 one warp per group, 1 the warps of a CTA (solver_team.cuh), -1 by block size:
   // the team form where the blocks do not fit the registers of one thread (n > 6)
   int backward_team = -1;
+  int inline_deriv = 1;  // forward kernel: derivative half of a merit evaluation in line with its rollout
   int fwd_depth = 8;  // staging depth cap of k_phase_forward (BulkPipe holds up to 8 stages)
   // pipelined sub-batches: the groups are cut into `nsplit` contiguous ranges, each on its own
   // stream, so that the sweeps of one range (one busy warp per group) overlap the rollouts and
@@ -480,6 +481,7 @@ altro_b200_solver* altro_b200_create(int horizon_length, int batch, int device) 
   memset(&s->con_h, 0, sizeof(s->con_h));
   // test hook: run a whole test suite with the other Riccati schedule (results are bit-identical)
   if (const char* env = getenv("ALTRO_B200_BACKWARD_TEAM")) s->backward_team = atoi(env) != 0;
+  if (const char* env = getenv("ALTRO_B200_INLINE_DERIV")) s->inline_deriv = atoi(env) != 0;
   if (const char* env = getenv("ALTRO_B200_FWD_DEPTH")) s->fwd_depth = std::max(2, std::min(8, atoi(env)));
   return s;
 }
@@ -1261,6 +1263,7 @@ static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   P.alpha_bt = s->alpha_bt;
   P.nslots = s->nslots;
   P.nstore = s->nslots > 1 ? s->nstore : 0;
+  P.inline_deriv = s->inline_deriv;
   P.xs = s->xs;
   P.us = s->us;
   P.phi_s = s->phi_s;

@@ -139,6 +139,9 @@ struct DeviceProblem {
   // concurrently, each into its own copy of the working trajectory
   int nslots;           // candidates per speculative round (>= 1): slot 0 = the requested step
   int nstore;           // speculative slots 1..nstore also keep their trajectory (slot buffers)
+  // 1: the rollout of a request that wants phi' does the trial point's expansion and the phi'
+  // recurrence in line (no separate expansion / d(phi) scan, no re-read of x, u, [J], lx, lu)
+  int inline_deriv;
   double *xs, *us;      // slot record stream; us = xs + n * 32
   double* phi_s;        // [kMaxHalvings + 1][Bp] merit value of halving j (alpha0 * 2^-j), j >= 1
   int* spec_base;       // [Bp] halving index rolled out by slot 1 of the pending / last round

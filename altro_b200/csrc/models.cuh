@@ -266,6 +266,16 @@ struct has_xdot_jac<CM, decltype(CM::xdot_jac(nullptr, nullptr, nullptr, nullptr
   static constexpr bool value = true;
 };
 
+// detects an optional fused Model::dynamics_jacobian
+template <class M, class = void>
+struct has_dynamics_jacobian {
+  static constexpr bool value = false;
+};
+template <class M>
+struct has_dynamics_jacobian<M, decltype(M::dynamics_jacobian(nullptr, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr), void())> {
+  static constexpr bool value = true;
+};
+
 // ------------------------------------------------------------------ explicit midpoint
 template <class CM>
 struct Midpoint {
@@ -284,6 +294,47 @@ struct Midpoint {
     CM::xdot(prm, xm, u, f);
 #pragma unroll
     for (int i = 0; i < n; ++i) xn[i] = fma(hd, f[i], x[i]);
+  }
+  // dynamics() and jacobian() of the same point in one go: the two share the evaluation of the
+  // continuous model at x and at the midpoint (for the bicycle: the trigonometry, by far the most
+  // expensive part).  Same functions on the same inputs in the same order as the separate calls,
+  // so xn, Ad, Bd carry the same bits.
+  ALTRO_DEV static void dynamics_jacobian(const double* prm, const double* x, const double* u, float h,
+                                          double* xn, double* Ad, double* Bd) {
+    const double hh = h / 2;
+    const double hd = h;
+    double xm[n], f[n];
+    double T[n * n], Bc[n * m], Am[n * n], Bm[n * m];
+    if constexpr (has_xdot_jac<CM>::value) {
+      CM::xdot_jac(prm, x, u, xm, T, Bc);
+    } else {
+      CM::xdot(prm, x, u, xm);
+      CM::jac(prm, x, u, T, Bc);
+    }
+#pragma unroll
+    for (int i = 0; i < n; ++i) xm[i] = fma(xm[i], hh, x[i]);
+    if constexpr (has_xdot_jac<CM>::value) {
+      CM::xdot_jac(prm, xm, u, f, Am, Bm);
+    } else {
+      CM::xdot(prm, xm, u, f);
+      CM::jac(prm, xm, u, Am, Bm);
+    }
+#pragma unroll
+    for (int i = 0; i < n; ++i) xn[i] = fma(hd, f[i], x[i]);
+#pragma unroll
+    for (int j = 0; j < n; ++j)
+#pragma unroll
+      for (int i = 0; i < n; ++i) T[i + n * j] = (i == j ? 1.0 : 0.0) + hh * T[i + n * j];
+#pragma unroll
+    for (int i = 0; i < n * m; ++i) Bc[i] *= hh;
+    mm<n, n, n, false, false, 0>(Am, T, Ad);
+#pragma unroll
+    for (int j = 0; j < n; ++j)
+#pragma unroll
+      for (int i = 0; i < n; ++i) Ad[i + n * j] = (i == j ? 1.0 : 0.0) + hd * Ad[i + n * j];
+    mm<n, m, n, false, false, 0>(Am, Bc, Bd);
+#pragma unroll
+    for (int i = 0; i < n * m; ++i) Bd[i] = hd * (Bd[i] + Bm[i]);
   }
   // test_utils.cpp:99-132:  A_d = I + h Am (I + h/2 A),  B_d = h (Am h/2 B + Bm)
   ALTRO_DEV static void jacobian(const double* prm, const double* x, const double* u, float h,

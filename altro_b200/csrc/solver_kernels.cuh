@@ -262,6 +262,18 @@ struct TrajSolver {
     }
   }
 
+  // x+ = f(x,u) and [A B] = df/d[x;u] of the same point, sharing what the two have in common when
+  // the model offers it (same values as dynamics() + jacobian())
+  ALTRO_DEV void dynamics_jacobian(int k, const double* x, const double* u, double* xn, double* A,
+                                   double* B) const {
+    if constexpr (!kLinear && has_dynamics_jacobian<Model>::value) {
+      Model::dynamics_jacobian(P.model_params, x, u, P.h, xn, A, B);
+    } else {
+      dynamics(k, x, u, xn);
+      jacobian(k, x, u, A, B);
+    }
+  }
+
   // ---- original (diagonal LQR) cost, knotpoint_data.cpp:636-645, :670-678
   ALTRO_DEV double stage_cost(int k, const double* x, const double* u, const double* q,
                               const double* r, bool terminal) const {
@@ -1219,6 +1231,49 @@ struct TrajSolver {
            al_terms(k, x, u, false, false, nullptr, nullptr, false);
 #pragma unroll
     for (int i = 0; i < n; ++i) x[i] = xn[i];
+  }
+  // The same step WITH the derivative half of MeritFunction (solver.cpp:303-315) done in line,
+  // the way the reference does it: [A B] of (x_k, u_k) (stored), cost gradient with AL terms
+  // (stored, z_est stored), and the phi' recurrence -- so the trial point's expansion and the
+  // d(phi) scan never have to re-read x, u, [J], lx, lu from HBM.
+  ALTRO_DEV void rollout_step_deriv(int k, double alpha, const double* xb, const double* ub,
+                                    const double* K, const double* d, const double* q, const double* r,
+                                    double cval, double* x, double* xo, double* uo, long so, double& phi,
+                                    double* dxda, double& dphi) {
+    double dx[n], u[m], xn[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) dx[i] = x[i] - xb[i];
+    {
+      double Kdx[m];
+      mm<m, 1, n, false, false, 0>(K, dx, Kdx);
+#pragma unroll
+      for (int i = 0; i < m; ++i) u[i] = ub[i] + (-Kdx[i] + alpha * d[i]);
+    }
+    store_block<n>(xo, so, k, x);
+    store_block<m>(uo, so, k, u);
+    double A[n * n], Bm[n * m], lx[n], lu[m];
+    dynamics_jacobian(k, x, u, xn, A, Bm);
+    store_jac(k, A, Bm);
+    stage_gradient(k, x, u, q, r, false, lx, lu);
+    phi += stage_cost(k, x, u, q, r, false, cval) + al_terms(k, x, u, false, true, lx, lu);
+    store_block<n>(F(P.lx), S, k, lx);
+    store_block<m>(F(P.lu), S, k, lu);
+    dphi_step(K, d, A, Bm, lx, lu, dxda, dphi);
+#pragma unroll
+    for (int i = 0; i < n; ++i) x[i] = xn[i];
+  }
+  // terminal knot of the same (solver.cpp:319-332)
+  ALTRO_DEV void rollout_terminal_deriv(const double* x, double* xo, long so, double& phi,
+                                        const double* dxda, double& dphi) {
+    double q[n], u0[m], lx[n];
+    load_block<n>(F(P.q), S, N, q);
+#pragma unroll
+    for (int i = 0; i < m; ++i) u0[i] = 0.0;
+    stage_gradient(N, x, u0, q, nullptr, true, lx, nullptr);
+    phi += stage_cost(N, x, u0, q, nullptr, true) + al_terms(N, x, u0, true, true, lx, nullptr);
+    store_block<n>(xo, so, N, x);
+    store_block<n>(F(P.lx), S, N, lx);
+    dphi += dot<n>(lx, dxda);
   }
   ALTRO_DEV void rollout_terminal(const double* x, double* xo, long so, double& phi) {
     double q[n], u0[m];

@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
   const double* rec = P.xbar + (long)g * P.GS;  // row 0 of the group's knot-0 record
   const double* zrec = CON ? P.z + (long)g * P.GSz : nullptr;
   const LsOptions lo = ls_options(P.opts);
+  const bool inline_deriv = TS::kStaged && P.inline_deriv != 0;
   // ready[k]: flagged lanes whose expansion of knot k is published (this round)
   int* ready = reinterpret_cast<int*>(wsm + wcount);
   __syncthreads();
@@ -428,6 +429,7 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
         slot = p / nneedy + 1;
       }
     }
+    double dphi_inline = 0.0;
     // every warp consumes the pass (fixed arrival count of the empty barriers); a warp without a
     // candidate only waits and releases.  Without staging the idle warps skip the pass.
     const bool warp_in = TS::kStaged || wid == 0 || (wid - 1) * 32 < nneedy * nspec;
@@ -455,6 +457,12 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
         }
       }
       double phi = 0.0;
+      // warp 0, in-line derivative mode: the lanes whose request wants phi' do the expansion and the
+      // phi' recurrence of every knot right where x_k, u_k are produced (rollout_step_deriv)
+      const bool wderiv = inline_deriv && wid == 0 && need && (fl & TF_WANT_DERIV) && !(fl & TF_REROLL);
+      double dxda[n];
+#pragma unroll
+      for (int i = 0; i < n; ++i) dxda[i] = 0.0;
       if constexpr (TS::kStaged) {
         constexpr int kRows = TS::kRowsRoll;  // [xbar ubar q r c K d] (+ the dual record)
         auto fetch = [&](int k) {
@@ -479,7 +487,10 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
             unstage_block<m>(st, TS::rD, lane, d);
           }
           if (zr) s.zstage = st + kRows * 32 + lane;
-          if (need) s.rollout_step(k, alpha, xb, ub, K, d, q, r, cval, x, xo, uo, so, phi);
+          if (wderiv)
+            s.rollout_step_deriv(k, alpha, xb, ub, K, d, q, r, cval, x, xo, uo, so, phi, dxda, dphi_inline);
+          else if (need)
+            s.rollout_step(k, alpha, xb, ub, K, d, q, r, cval, x, xo, uo, so, phi);
           s.zstage = nullptr;
           // release only after the step consumed what was read from the stage (see BulkRing)
           pipe.release(k, lid);
@@ -491,7 +502,10 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
           }
         }
         pipe.end_pass(P.N);
-        if (need) s.rollout_terminal(x, xo, so, phi);
+        if (wderiv)
+          s.rollout_terminal_deriv(x, xo, so, phi, dxda, dphi_inline);
+        else if (need)
+          s.rollout_terminal(x, xo, so, phi);
       } else {
         if (need) phi = s.phase_rollout(alpha, xo, uo, so);
       }
@@ -509,19 +523,21 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
     // warps >= 1 expand in knot-major order and publish every finished knot (ready[k] counts the
     // flagged lanes done), so warp 0 can run the sequential d(phi) scan BEHIND them instead of
     // after them -- the scan's bulk copy of knot k is issued once ready[k] is complete.
-    const int nl = __popc(dmask);
-    if (dmask) {
+    // in-line derivative mode: nothing left to expand or scan, warp 0 already holds phi'
+    const unsigned dmask_sep = inline_deriv ? 0u : dmask;
+    const int nl = __popc(dmask_sep);
+    if (dmask_sep) {
       if constexpr (TS::kStaged) {
         if (wid > 0) {
           const int items = nl * (P.N + 1), step = (int)blockDim.x - 32;
           for (int i = tid - 32; i < items; i += step) {
             const int k = i / nl;
-            const int b = g * 32 + __fns(dmask, 0, i % nl + 1);
+            const int b = g * 32 + __fns(dmask_sep, 0, i % nl + 1);
             TS s(P, b);
             weights(s);
             s.rho = CON ? P.rho[b] : 1.0;
             if (i + step < items) {  // the next item's rows on their way into L2 meanwhile
-              TS sn(P, g * 32 + __fns(dmask, 0, (i + step) % nl + 1));
+              TS sn(P, g * 32 + __fns(dmask_sep, 0, (i + step) % nl + 1));
               sn.phase_expand_prefetch((i + step) / nl, -1);
             }
             s.phase_expand_knot(k, true, -1, false);
@@ -533,7 +549,7 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
           }
         }
       } else {
-        for_knot_items(dmask, g, P.N + 1, [&](int b, int k) {
+        for_knot_items(dmask_sep, g, P.N + 1, [&](int b, int k) {
           TS s(P, b);
           weights(s);
           s.rho = CON ? P.rho[b] : 1.0;
@@ -562,8 +578,8 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
       int f = fl;
       const bool pending = (f & (TF_NEED_EVAL | TF_REROLL)) != 0;
       const bool had_deriv = (f & TF_NEED_EVAL) && (f & TF_WANT_DERIV) && !(f & TF_REROLL);
-      double dphi = 0.0;
-      if (dmask) {
+      double dphi = dphi_inline;
+      if (dmask_sep) {
         TS s(P, had_deriv ? b : g * 32);
         if constexpr (TS::kStaged) {
           // stage contents: [K d] [J] [lx lu]

@@ -197,9 +197,11 @@ def load_scotty():
     return xref, uref, h
 
 
-def scotty(B=65536, N=50, n=5, seed=2, iterations_max=80):
+def scotty(B=65536, N=50, n=5, seed=2, iterations_max=80, margin=0):
     """BASELINE C3: one tracking-MPC horizon per problem, windows along the scotty trajectory,
-    steering-angle bound +-60deg at every knot (test/bicycle_test.cpp:144-224)."""
+    steering-angle bound +-60deg at every knot (test/bicycle_test.cpp:144-224).
+    margin: rows of the reference table left free behind every window, i.e. how many
+    receding-horizon steps each problem can take."""
     m = 2
     xr4, ur4, h = load_scotty()
     T = xr4.shape[0]
@@ -212,7 +214,7 @@ def scotty(B=65536, N=50, n=5, seed=2, iterations_max=80):
         xtab, utab = xr4, ur4
         sigma = np.array([0.05, 0.05, 0.02, 0.01])
         model = MODEL_BICYCLE4
-    offsets = (np.arange(B) % (T - 1 - N)).astype(np.int32)
+    offsets = (np.arange(B) % (T - 1 - N - margin)).astype(np.int32)
     rng = np.random.default_rng(seed)
     x0 = xtab[offsets] + rng.normal(size=(B, n)) * sigma
     U0 = np.zeros((B, N, m))

@@ -45,7 +45,7 @@ def workload(name, per_gpu_batch, rank, world):
         "bicycle": lambda total: PR.bicycle(B=total, N=100, n=5),
         "pendulum": lambda total: PR.pendulum(B=total, N=100),
         "scotty": lambda total: PR.scotty(B=total, N=50, n=5),
-        "scotty_mpc": lambda total: PR.scotty(B=total, N=50, n=5),
+        "scotty_mpc": lambda total: PR.scotty(B=total, N=50, n=5, margin=64),
         "chain12": lambda total: PR.chain(B=total, n=12, m=4, N=200),
         "chain6": lambda total: PR.chain(B=total, n=6, m=2, N=200),
     }.get(name)
@@ -290,7 +290,7 @@ def main():
     ap.add_argument("--split", type=int, default=0, help="pipelined sub-batches (0 = automatic)")
     ap.add_argument("--slots", type=int, default=None, help="candidate steps per line-search round")
     ap.add_argument("--store", type=int, default=None, help="speculative candidates that keep their trajectory")
-    ap.add_argument("--mpc-steps", type=int, default=10,
+    ap.add_argument("--mpc-steps", type=int, default=10, choices=range(1, 65),
                     help="scotty_mpc: receding-horizon solves per bench step (all on the device)")
     args = ap.parse_args()
     if args.batch is None:
