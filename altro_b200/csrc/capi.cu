@@ -239,7 +239,9 @@ struct altro_b200_solver {
   // Riccati sweep: 0 one warp per group, 1 the warps of a CTA (solver_team.cuh), -1 by block size:
   // the team form where the blocks do not fit the registers of one thread (n > 6)
   int backward_team = -1;
-  int inline_deriv = 1;  // forward kernel: derivative half of a merit evaluation in line with its rollout
+  // forward kernel variant with the derivative half of a merit evaluation in line with its rollout:
+  // 1 / 0, -1 = by line search (in line for strong Wolfe, separate for backtracking)
+  int inline_deriv = -1;
   int fwd_depth = 8;  // staging depth cap of k_phase_forward (BulkPipe holds up to 8 stages)
   // pipelined sub-batches: the groups are cut into `nsplit` contiguous ranges, each on its own
   // stream, so that the sweeps of one range (one busy warp per group) overlap the rollouts and
@@ -1263,7 +1265,8 @@ static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   P.alpha_bt = s->alpha_bt;
   P.nslots = s->nslots;
   P.nstore = s->nslots > 1 ? s->nstore : 0;
-  P.inline_deriv = s->inline_deriv;
+  // in-line derivative variant of the forward kernel: by default for the strong-Wolfe search
+  P.inline_deriv = s->inline_deriv >= 0 ? s->inline_deriv : (s->opts.use_backtracking_linesearch ? 0 : 1);
   P.xs = s->xs;
   P.us = s->us;
   P.phi_s = s->phi_s;

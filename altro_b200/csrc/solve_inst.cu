@@ -37,7 +37,8 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
       const int mx = (int)H->smem_per_cta;
       if (TS::kStaged) {
         cudaFuncSetAttribute(k_phase_backward<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(k_phase_forward<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k_phase_forward<Model, CON, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k_phase_forward<Model, CON, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
       }
       cudaFuncSetAttribute(k_phase_backward_team<Model, CON>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     }
@@ -112,13 +113,17 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
       depth = ring_depth(per_sm, (size_t)rows * 256, 256 + (size_t)(N + 1) * 4 + 16 + 24 * 1024, H->fwd_depth);
       sm = BulkPipe::bytes(depth, rows * 32) + wbytes + (size_t)((N + 1) * 4 + 15) / 16 * 16;
     }
-    const int warps = std::max(1, std::min(H->fwd_warps, 8));
+    const bool inl = TS::kStaged && P.inline_deriv != 0;
+    const int warps = std::max(1, std::min(H->fwd_warps, inl ? 4 : 8));
     DeviceProblem Pf = P;
     Pf.prof = H->profile ? H->d_prof : nullptr;
     if (H->profile) cudaMemsetAsync(H->d_prof, 0, 8 * sizeof(unsigned long long), st);
     const double ms_before = H->ms[PH_FORWARD];
     timed(PH_FORWARD, (double)G * 32, [&] {
-      k_phase_forward<Model, CON><<<G, 32 * warps, sm, st>>>(Pf, depth, rows, wcount, H->d_done);
+      if (inl)
+        k_phase_forward<Model, CON, true><<<G, 32 * warps, sm, st>>>(Pf, depth, rows, wcount, H->d_done);
+      else
+        k_phase_forward<Model, CON, false><<<G, 32 * warps, sm, st>>>(Pf, depth, rows, wcount, H->d_done);
     });
     if (H->profile) {  // split the kernel's time by the in-kernel sub-phase clocks
       unsigned long long ns[8];

@@ -340,9 +340,16 @@ __device__ __forceinline__ void for_knot_items(unsigned lanemask, int g, int kno
 // then, still in the same launch: the post-search expansion of an accepted backtracking step
 // (:256-262), costates, residuals, the decision, and the expansion after a dual update (:483-486).
 // active_out: incremented by the number of problems of the group that stopped in this iteration.
-template <class Model, int CON>
-__global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_forward(const __grid_constant__ DeviceProblem P, int depth,
-                                                          int stage_rows, int wcount, int* done_out) {
+// INLINE: the rollout of a request that wants phi' does the derivative half of the merit
+// evaluation in line (TrajSolver::rollout_step_deriv) instead of the separate expansion + scan.
+// It is a template parameter because the fused step needs ~200 registers: as a run-time branch it
+// made the lean variant spill (bicycle step 45 -> 55 ms).  The in-line variant runs with at most
+// four warps per CTA (255 registers, two CTAs per SM) and is the default for the strong-Wolfe
+// search, which has no speculative candidates to feed more warps anyway; the lean variant (128
+// registers, up to eight warps) serves the backtracking search.
+template <class Model, int CON, bool INLINE>
+__global__ void __launch_bounds__(INLINE ? 128 : 256, (Model::n > kUnrollDim) ? 1 : 2)
+    k_phase_forward(const __grid_constant__ DeviceProblem P, int depth, int stage_rows, int wcount, int* done_out) {
   using TS = TrajSolver<Model, CON>;
   constexpr int n = Model::n, m = Model::m;
   constexpr unsigned kAll = 0xffffffffu;
@@ -394,7 +401,7 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
   const double* rec = P.xbar + (long)g * P.GS;  // row 0 of the group's knot-0 record
   const double* zrec = CON ? P.z + (long)g * P.GSz : nullptr;
   const LsOptions lo = ls_options(P.opts);
-  const bool inline_deriv = TS::kStaged && P.inline_deriv != 0;
+  constexpr bool inline_deriv = TS::kStaged && INLINE;
   // ready[k]: flagged lanes whose expansion of knot k is published (this round)
   int* ready = reinterpret_cast<int*>(wsm + wcount);
   __syncthreads();
@@ -460,9 +467,11 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
       // warp 0, in-line derivative mode: the lanes whose request wants phi' do the expansion and the
       // phi' recurrence of every knot right where x_k, u_k are produced (rollout_step_deriv)
       const bool wderiv = inline_deriv && wid == 0 && need && (fl & TF_WANT_DERIV) && !(fl & TF_REROLL);
-      double dxda[n];
+      double dxda[inline_deriv ? n : 1];
+      if constexpr (inline_deriv) {
 #pragma unroll
-      for (int i = 0; i < n; ++i) dxda[i] = 0.0;
+        for (int i = 0; i < n; ++i) dxda[i] = 0.0;
+      }
       if constexpr (TS::kStaged) {
         constexpr int kRows = TS::kRowsRoll;  // [xbar ubar q r c K d] (+ the dual record)
         auto fetch = [&](int k) {
@@ -487,10 +496,14 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
             unstage_block<m>(st, TS::rD, lane, d);
           }
           if (zr) s.zstage = st + kRows * 32 + lane;
-          if (wderiv)
-            s.rollout_step_deriv(k, alpha, xb, ub, K, d, q, r, cval, x, xo, uo, so, phi, dxda, dphi_inline);
-          else if (need)
-            s.rollout_step(k, alpha, xb, ub, K, d, q, r, cval, x, xo, uo, so, phi);
+          if constexpr (inline_deriv) {
+            if (wderiv)
+              s.rollout_step_deriv(k, alpha, xb, ub, K, d, q, r, cval, x, xo, uo, so, phi, dxda, dphi_inline);
+            else if (need)
+              s.rollout_step(k, alpha, xb, ub, K, d, q, r, cval, x, xo, uo, so, phi);
+          } else {
+            if (need) s.rollout_step(k, alpha, xb, ub, K, d, q, r, cval, x, xo, uo, so, phi);
+          }
           s.zstage = nullptr;
           // release only after the step consumed what was read from the stage (see BulkRing)
           pipe.release(k, lid);
@@ -502,10 +515,14 @@ __global__ void __launch_bounds__(256, (Model::n > kUnrollDim) ? 1 : 2) k_phase_
           }
         }
         pipe.end_pass(P.N);
-        if (wderiv)
-          s.rollout_terminal_deriv(x, xo, so, phi, dxda, dphi_inline);
-        else if (need)
-          s.rollout_terminal(x, xo, so, phi);
+        if constexpr (inline_deriv) {
+          if (wderiv)
+            s.rollout_terminal_deriv(x, xo, so, phi, dxda, dphi_inline);
+          else if (need)
+            s.rollout_terminal(x, xo, so, phi);
+        } else {
+          if (need) s.rollout_terminal(x, xo, so, phi);
+        }
       } else {
         if (need) phi = s.phase_rollout(alpha, xo, uo, so);
       }
