@@ -239,9 +239,11 @@ struct altro_b200_solver {
   // Riccati sweep: 0 one warp per group, 1 the warps of a CTA (solver_team.cuh), -1 by block size:
   // the team form where the blocks do not fit the registers of one thread (n > 6)
   int backward_team = -1;
-  // forward kernel variant with the derivative half of a merit evaluation in line with its rollout:
-  // 1 / 0, -1 = by line search (in line for strong Wolfe, separate for backtracking)
-  int inline_deriv = -1;
+  // forward kernel variant: 1 the derivative half of a merit evaluation is done by a follower warp
+  // behind the rollout warp (default), 0 separate knot-parallel expansion + d(phi) scan
+  int inline_deriv = 1;
+  int qrc_uniform_enable = 1;  // ALTRO_B200_QRC_UNIFORM=0 streams [q r c] with every knot regardless
+  int fused_post = 1;  // forward kernel: everything between the search and the decision as one pass over the knots
   int fwd_depth = 8;  // staging depth cap of k_phase_forward (BulkPipe holds up to 8 stages)
   // pipelined sub-batches: the groups are cut into `nsplit` contiguous ranges, each on its own
   // stream, so that the sweeps of one range (one busy warp per group) overlap the rollouts and
@@ -265,6 +267,10 @@ struct altro_b200_solver {
   std::vector<double*> off_b;
   // host mirrors of the shared weights
   std::vector<double> Qd_h, Rd_h, lin_h;
+  // which setter call wrote the linear cost terms q_k, r_k, c_k of knot k: knots written by ONE call
+  // with k-independent values share an id (> 0), anything else is -1 (DeviceProblem::qrc_uniform)
+  std::vector<int> qrc_id;
+  int qrc_next = 0;
   // dense quadratic cost (SetQuadraticCost): host mirrors of every knot's Q, R, H (diagonal-cost
   // knots hold diag(Qd), diag(Rd), 0) and their device copies, uploaded once a dense knot exists
   std::vector<double> Qf_h, Rf_h, Hf_h;
@@ -484,6 +490,8 @@ altro_b200_solver* altro_b200_create(int horizon_length, int batch, int device) 
   // test hook: run a whole test suite with the other Riccati schedule (results are bit-identical)
   if (const char* env = getenv("ALTRO_B200_BACKWARD_TEAM")) s->backward_team = atoi(env) != 0;
   if (const char* env = getenv("ALTRO_B200_INLINE_DERIV")) s->inline_deriv = atoi(env) != 0;
+  if (const char* env = getenv("ALTRO_B200_QRC_UNIFORM")) s->qrc_uniform_enable = atoi(env) != 0;
+  if (const char* env = getenv("ALTRO_B200_FUSED_POST")) s->fused_post = atoi(env) != 0;
   if (const char* env = getenv("ALTRO_B200_FWD_DEPTH")) s->fwd_depth = std::max(2, std::min(8, atoi(env)));
   return s;
 }
@@ -525,6 +533,7 @@ int altro_b200_set_dimension(altro_b200_solver* s, int n, int m) {  // altro_sol
   s->m = m;
   const long N = s->N, S = s->Bp;
   s->Qd_h.assign((size_t)(N + 1) * n, 0.0);
+  s->qrc_id.assign((size_t)N + 1, -1);
   s->Rd_h.assign((size_t)N * m, 0.0);
   s->Qf_h.assign((size_t)(N + 1) * n * n, 0.0);
   s->Rf_h.assign((size_t)N * m * m, 0.0);
@@ -653,6 +662,19 @@ static int upload_dense_cost(altro_b200_solver* s) {
   return 0;
 }
 
+// bookkeeping for DeviceProblem::qrc_uniform; same_for_all_knots: the call wrote identical q, r, c
+// to every knot of [k0, k1) (per problem)
+static void mark_qrc(altro_b200_solver* s, int k0, int k1, bool same_for_all_knots) {
+  const int id = same_for_all_knots ? ++s->qrc_next : -1;
+  for (int k = std::max(k0, 0); k < k1 && k < (int)s->qrc_id.size(); ++k) s->qrc_id[k] = id;
+}
+static int qrc_uniform(const altro_b200_solver* s) {
+  if (s->qrc_id.empty() || s->qrc_id[0] <= 0) return 0;
+  for (int k = 1; k < s->N; ++k)
+    if (s->qrc_id[k] != s->qrc_id[0]) return 0;
+  return 1;
+}
+
 static int store_weights(altro_b200_solver* s, const double* Qd, const double* Rd, int k0, int k1) {
   const int n = s->n, m = s->m;
   for (int k = k0; k < k1; ++k) {
@@ -703,11 +725,15 @@ int altro_b200_set_lqr_cost(altro_b200_solver* s, const double* Qd, const double
   s->launches++;
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(s->stream));
+  // one weight set and a knot-independent reference: q, r, c do not depend on k inside the range
+  // (c differs between a stage knot and the terminal knot, which is never part of the flag)
+  mark_qrc(s, k_start, k_stop, true);
   s->cost_set = true;
   return ALTRO_B200_NO_ERROR;
 }
 
 static int apply_window(altro_b200_solver* s) {
+  mark_qrc(s, 0, s->N + 1, false);
   dim3 grid((s->B + 127) / 128, (unsigned)(s->N + 1));
   k_lqr_cost<<<grid, 128, 0, s->stream>>>(s->n, s->m, s->N, s->B, 0, s->N + 1, s->Qd, s->Rd, s->xtab,
                                           s->utab, 2, s->offsets, fview(s, s->q, s->n),
@@ -782,6 +808,7 @@ int altro_b200_advance_window_linear(altro_b200_solver* s, int steps, double c_u
   if (!s->initialized) return ALTRO_B200_SOLVER_NOT_INITIALIZED;  // UpdateLinearCosts, altro_solver.cpp:268
   int e = move_window(s, steps);
   if (e) return e;
+  mark_qrc(s, 0, s->N + 1, false);
   dim3 grid((s->B + 127) / 128, (unsigned)(s->N + 1));
   k_window_linear_update<<<grid, 128, 0, s->stream>>>(s->n, s->N, s->B, s->Qd, s->xtab, s->offsets,
                                                       fview(s, s->q, s->n), fview(s, s->c, 1), c_u);
@@ -804,6 +831,7 @@ static int set_linear_terms(altro_b200_solver* s, const double* q, const double*
   const int nk = k1 - k0;
   const int nku = (k1 > s->N ? s->N : k1) - k0;  // knots that carry an input
   int e = 0;
+  mark_qrc(s, k0, k1, !per_problem && q && c && (r || nku <= 0));
   if (per_problem) {
     if (q) e = upload_pm(s, q, (long)nk * n, fview(s, s->q, n, k0));
     if (!e && r && nku > 0) {
@@ -1265,8 +1293,7 @@ static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   P.alpha_bt = s->alpha_bt;
   P.nslots = s->nslots;
   P.nstore = s->nslots > 1 ? s->nstore : 0;
-  // in-line derivative variant of the forward kernel: by default for the strong-Wolfe search
-  P.inline_deriv = s->inline_deriv >= 0 ? s->inline_deriv : (s->opts.use_backtracking_linesearch ? 0 : 1);
+  P.inline_deriv = s->inline_deriv;
   P.xs = s->xs;
   P.us = s->us;
   P.phi_s = s->phi_s;

@@ -142,6 +142,11 @@ struct DeviceProblem {
   // 1: the rollout of a request that wants phi' does the trial point's expansion and the phi'
   // recurrence in line (no separate expansion / d(phi) scan, no re-read of x, u, [J], lx, lu)
   int inline_deriv;
+  // 1: the linear cost terms q_k, r_k, c_k are the same for every k < N (one SetLQRCost call over the
+  // stage knots with a goal-type reference): the sweeps read them once from knot 0 instead of
+  // streaming [q r c] with every knot
+  int qrc_uniform;
+  int fused_post;  // k_phase_forward: post-search expansion + costates + residuals + copy as one pass
   double *xs, *us;      // slot record stream; us = xs + n * 32
   double* phi_s;        // [kMaxHalvings + 1][Bp] merit value of halving j (alpha0 * 2^-j), j >= 1
   int* spec_base;       // [Bp] halving index rolled out by slot 1 of the pending / last round

@@ -104,23 +104,30 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
   {
     int depth = 0, rows = 0;
     size_t sm = 0;
+    // follower variant: the derivative half of a merit evaluation by a warp behind the rollout warp
+    const bool follow = TS::kStaged && P.inline_deriv != 0;
     if (TS::kStaged) {
-      rows = std::max(TS::kRowsRoll + zr, TS::kRowsDphi);
+      // stage rows: the rollout's [xbar ubar q r c K d] (+ duals) plus, in follower mode, x_k, u_k of
+      // the rollout warp; otherwise the d(phi) scan's [K d] [J] [lx lu] must fit as well
+      rows = follow ? TS::kRowsRoll + zr + n + m : std::max(TS::kRowsRoll + zr, TS::kRowsDphi);
+      // behind the ring: cost weights, ready[] counters, the resident [q r c] rows of knot 0, x_N and phi'
+      const size_t tail = (size_t)((N + 1) * 4 + 15) / 16 * 16 + (size_t)(TS::rK - TS::rQ + n + 1) * 256;
       // The forward CTAs are register-limited to two per SM, so the ring may use up to half an SM's
       // shared memory minus what a co-resident backward CTA needs: up to kFwdStageDepth knots in
       // flight (ncu r02e: a third of the kernel's stall samples waited for a stage to land at depth 4)
       const int per_sm = std::min(2, (P.Gtot + H->num_sms - 1) / H->num_sms);
-      depth = ring_depth(per_sm, (size_t)rows * 256, 256 + (size_t)(N + 1) * 4 + 16 + 24 * 1024, H->fwd_depth);
-      sm = BulkPipe::bytes(depth, rows * 32) + wbytes + (size_t)((N + 1) * 4 + 15) / 16 * 16;
+      depth = ring_depth(per_sm, (size_t)rows * 256, 256 + tail + 24 * 1024, H->fwd_depth);
+      sm = BulkPipe::bytes(depth, rows * 32) + wbytes + tail;
     }
-    const bool inl = TS::kStaged && P.inline_deriv != 0;
-    const int warps = std::max(1, std::min(H->fwd_warps, inl ? 4 : 8));
+    // 192 threads at most (256 for the large-block models); the follower variant needs the rollout
+    // warp, the follower and the speculating warps
+    const int warps = std::max(follow ? 2 : 1, std::min(H->fwd_warps + (follow ? 1 : 0), TS::kStaged ? 6 : 8));
     DeviceProblem Pf = P;
     Pf.prof = H->profile ? H->d_prof : nullptr;
     if (H->profile) cudaMemsetAsync(H->d_prof, 0, 8 * sizeof(unsigned long long), st);
     const double ms_before = H->ms[PH_FORWARD];
     timed(PH_FORWARD, (double)G * 32, [&] {
-      if (inl)
+      if (follow)
         k_phase_forward<Model, CON, true><<<G, 32 * warps, sm, st>>>(Pf, depth, rows, wcount, H->d_done);
       else
         k_phase_forward<Model, CON, false><<<G, 32 * warps, sm, st>>>(Pf, depth, rows, wcount, H->d_done);

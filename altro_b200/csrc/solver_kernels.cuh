@@ -1038,6 +1038,9 @@ struct TrajSolver {
   // (trajectory, knot), and (ii) the sequential sweeps carry as little as possible and prefetch
   // the next knot while they work on the current one.  Used by solver_phases.cuh.
 
+  // knot whose [q r c] rows hold knot k's linear cost terms (DeviceProblem::qrc_uniform)
+  ALTRO_DEV int kq(int k) const { return (P.qrc_uniform && k < N) ? 0 : k; }
+
   // working trajectory of candidate `slot` (-1: the main x_, u_ arrays)
   ALTRO_DEV double* xw(int slot) const {
     return slot < 0 ? F(P.x) : P.xs + slot_off(slot);
@@ -1097,10 +1100,10 @@ struct TrajSolver {
   // bound by the latency of these first loads: ncu r02e, long scoreboard)
   ALTRO_DEV void phase_expand_prefetch(int k, int slot) const {
     prefetch_block<n>(xw(slot), sw(slot), k);
-    prefetch_block<n>(F(P.q), S, k);
+    if (!P.qrc_uniform) prefetch_block<n>(F(P.q), S, k);
     if (k < N) {
       prefetch_block<m>(uw(slot), sw(slot), k);
-      prefetch_block<m>(F(P.r), S, k);
+      if (!P.qrc_uniform) prefetch_block<m>(F(P.r), S, k);
     }
   }
 
@@ -1112,11 +1115,11 @@ struct TrajSolver {
     const bool terminal = (k == N);
     double x[n], u[m], q[n], r[m], lx[n], lu[m];
     load_block<n>(xw(slot), sw(slot), k, x);
-    load_block<n>(F(P.q), S, k, q);
+    load_block<n>(F(P.q), S, kq(k), q);
     if (slot >= 0) store_block<n>(F(P.x), S, k, x);
     if (!terminal) {
       load_block<m>(uw(slot), sw(slot), k, u);
-      load_block<m>(F(P.r), S, k, r);
+      load_block<m>(F(P.r), S, kq(k), r);
       if (slot >= 0) store_block<m>(F(P.u), S, k, u);
       if (with_dyn) {
         double A[n * n], Bm[n * m];
@@ -1210,18 +1213,21 @@ struct TrajSolver {
   // (phase_costate_knot).  z_est is not stored here: every candidate that can be accepted is
   // expanded afterwards, which stores it.  rollout_step advances x from knot k to k + 1; xo/uo
   // (may be null: merit value only) receive the trial trajectory with knot stride `so`.
-  ALTRO_DEV void rollout_step(int k, double alpha, const double* xb, const double* ub,
-                              const double* K, const double* d, const double* q, const double* r,
-                              double cval, double* x, double* xo, double* uo, long so, double& phi) {
-    double dx[n], u[m], xn[n];
+  // the control of knot k on the closed-loop rollout at step alpha (solver.cpp:287-291)
+  ALTRO_DEV void rollout_control(double alpha, const double* xb, const double* ub, const double* K,
+                                 const double* d, const double* x, double* u) const {
+    double dx[n];
 #pragma unroll
     for (int i = 0; i < n; ++i) dx[i] = x[i] - xb[i];
-    {
-      double Kdx[m];
-      mm<m, 1, n, false, false, 0>(K, dx, Kdx);
+    double Kdx[m];
+    mm<m, 1, n, false, false, 0>(K, dx, Kdx);
 #pragma unroll
-      for (int i = 0; i < m; ++i) u[i] = ub[i] + (-Kdx[i] + alpha * d[i]);
-    }
+    for (int i = 0; i < m; ++i) u[i] = ub[i] + (-Kdx[i] + alpha * d[i]);
+  }
+  // ... and the rest of the step: stores, x_{k+1}, the knot's share of the merit value
+  ALTRO_DEV void rollout_advance(int k, const double* u, const double* q, const double* r, double cval,
+                                 double* x, double* xo, double* uo, long so, double& phi) {
+    double xn[n];
     if (xo) {
       store_block<n>(xo, so, k, x);
       store_block<m>(uo, so, k, u);
@@ -1232,46 +1238,42 @@ struct TrajSolver {
 #pragma unroll
     for (int i = 0; i < n; ++i) x[i] = xn[i];
   }
-  // The same step WITH the derivative half of MeritFunction (solver.cpp:303-315) done in line,
-  // the way the reference does it: [A B] of (x_k, u_k) (stored), cost gradient with AL terms
-  // (stored, z_est stored), and the phi' recurrence -- so the trial point's expansion and the
-  // d(phi) scan never have to re-read x, u, [J], lx, lu from HBM.
-  ALTRO_DEV void rollout_step_deriv(int k, double alpha, const double* xb, const double* ub,
-                                    const double* K, const double* d, const double* q, const double* r,
-                                    double cval, double* x, double* xo, double* uo, long so, double& phi,
-                                    double* dxda, double& dphi) {
-    double dx[n], u[m], xn[n];
-#pragma unroll
-    for (int i = 0; i < n; ++i) dx[i] = x[i] - xb[i];
-    {
-      double Kdx[m];
-      mm<m, 1, n, false, false, 0>(K, dx, Kdx);
-#pragma unroll
-      for (int i = 0; i < m; ++i) u[i] = ub[i] + (-Kdx[i] + alpha * d[i]);
-    }
-    store_block<n>(xo, so, k, x);
-    store_block<m>(uo, so, k, u);
+  ALTRO_DEV void rollout_step(int k, double alpha, const double* xb, const double* ub,
+                              const double* K, const double* d, const double* q, const double* r,
+                              double cval, double* x, double* xo, double* uo, long so, double& phi) {
+    double u[m];
+    rollout_control(alpha, xb, ub, K, d, x, u);
+    rollout_advance(k, u, q, r, cval, x, xo, uo, so, phi);
+  }
+  // The derivative half of MeritFunction (solver.cpp:303-315) for knot k of a trial trajectory, by
+  // the FOLLOWER warp of k_phase_forward right behind the rollout warp, which hands it x_k, u_k
+  // through shared memory: [A B] (stored), cost gradient with AL terms (stored, z_est stored) and
+  // the phi' recurrence -- the trial point's expansion and d(phi) scan without re-reading x, u, [J],
+  // lx, lu from HBM and off the critical path of the state recursion.
+  ALTRO_DEV void follow_step(int k, const double* x, const double* u, const double* q, const double* r,
+                             const double* K, const double* d, double* dxda, double& dphi) {
     double A[n * n], Bm[n * m], lx[n], lu[m];
-    dynamics_jacobian(k, x, u, xn, A, Bm);
-    store_jac(k, A, Bm);
+    jacobian(k, x, u, A, Bm);
+    {
+      double J[kV];  // through the packed form, like every other reader of [A B]
+      JP::pack(A, Bm, J);
+      store_block<kV>(P.A + go, S, k, J);
+      JP::unpack(J, P.h, A, Bm);
+    }
     stage_gradient(k, x, u, q, r, false, lx, lu);
-    phi += stage_cost(k, x, u, q, r, false, cval) + al_terms(k, x, u, false, true, lx, lu);
+    al_terms(k, x, u, false, true, lx, lu);
     store_block<n>(F(P.lx), S, k, lx);
     store_block<m>(F(P.lu), S, k, lu);
     dphi_step(K, d, A, Bm, lx, lu, dxda, dphi);
-#pragma unroll
-    for (int i = 0; i < n; ++i) x[i] = xn[i];
   }
-  // terminal knot of the same (solver.cpp:319-332)
-  ALTRO_DEV void rollout_terminal_deriv(const double* x, double* xo, long so, double& phi,
-                                        const double* dxda, double& dphi) {
+  // terminal knot of the same (solver.cpp:327-331)
+  ALTRO_DEV void follow_terminal(const double* x, const double* dxda, double& dphi) {
     double q[n], u0[m], lx[n];
     load_block<n>(F(P.q), S, N, q);
 #pragma unroll
     for (int i = 0; i < m; ++i) u0[i] = 0.0;
     stage_gradient(N, x, u0, q, nullptr, true, lx, nullptr);
-    phi += stage_cost(N, x, u0, q, nullptr, true) + al_terms(N, x, u0, true, true, lx, nullptr);
-    store_block<n>(xo, so, N, x);
+    al_terms(N, x, u0, true, true, lx, nullptr);
     store_block<n>(F(P.lx), S, N, lx);
     dphi += dot<n>(lx, dxda);
   }
@@ -1291,12 +1293,12 @@ struct TrajSolver {
       {
         const int kn = k + 1;
         prefetch_block<n>(F(P.xbar), S, kn);
-        prefetch_block<n>(F(P.q), S, kn);
+        if (!P.qrc_uniform || kn == N) prefetch_block<n>(F(P.q), S, kn);
         if (kn < N) {
           prefetch_block<m>(F(P.ubar), S, kn);
           prefetch_block<m * n>(F(P.K), S, kn);
           prefetch_block<m>(F(P.d), S, kn);
-          prefetch_block<m>(F(P.r), S, kn);
+          if (!P.qrc_uniform) prefetch_block<m>(F(P.r), S, kn);
         }
       }
       double xb[n], ub[m], K[m * n], d[m], q[n], r[m];
@@ -1304,9 +1306,9 @@ struct TrajSolver {
       load_block<m>(F(P.ubar), S, k, ub);
       load_block<m * n>(F(P.K), S, k, K);
       load_block<m>(F(P.d), S, k, d);
-      load_block<n>(F(P.q), S, k, q);
-      load_block<m>(F(P.r), S, k, r);
-      rollout_step(k, alpha, xb, ub, K, d, q, r, F(P.c)[(long)k * S], x, xo, uo, so, phi);
+      load_block<n>(F(P.q), S, kq(k), q);
+      load_block<m>(F(P.r), S, kq(k), r);
+      rollout_step(k, alpha, xb, ub, K, d, q, r, F(P.c)[(long)kq(k) * S], x, xo, uo, so, phi);
     }
     rollout_terminal(x, xo, so, phi);
     return phi;
@@ -1374,6 +1376,101 @@ struct TrajSolver {
     load_block<n>(F(P.p), S, k, y);
     mm<n, 1, n, false, false, 1>(Pk, dx, y);
     store_block<n>(F(P.y), S, k, y);
+  }
+
+  // ---- everything between the line search and the convergence decision, ONE pass over the knots:
+  // the post-search expansion of an accepted backtracking step (solver.cpp:256-262, `refresh`; the
+  // accepted candidate may still sit in candidate slot `slot`), the costates y_k (:293, :324),
+  // Stationarity (:207-222), Feasibility (:224-231) and CopyTrajectory (:148-157).  A thread walks
+  // its chunk of knots [k0, k1) DOWNWARDS carrying y_{k+1} in registers, so every block of the
+  // record is read once and y, [A B], lx, lu never make the round trip through HBM that the
+  // separate expand / costate / residual passes paid for.  post_boundary computes y_{k1} (from the
+  // old xbar_{k1}, which the neighbouring chunk overwrites at its very end: the caller puts a CTA
+  // barrier between post_boundary and post_chunk).
+  ALTRO_DEV void costate_of(int k, const double* x, double* y) const {
+    double xb[n], dx[n], Pk[n * n];
+    load_block<n>(F(P.xbar), S, k, xb);
+#pragma unroll
+    for (int i = 0; i < n; ++i) dx[i] = x[i] - xb[i];
+    load_block<n * n>(F(P.P), S, k, Pk);
+    load_block<n>(F(P.p), S, k, y);
+    mm<n, 1, n, false, false, 1>(Pk, dx, y);
+  }
+  ALTRO_DEV void post_boundary(int k, int slot, double* y) const {
+    double x[n];
+    load_block<n>(xw(slot), sw(slot), k, x);
+    costate_of(k, x, y);
+  }
+  // L2 prefetch of what post_chunk reads at knot k, spread over the lanes of the warp (128-byte
+  // lines of the group's record: [xbar ubar q r c], [x u J], [lx lu], [P p])
+  ALTRO_DEV void post_prefetch(int k) const {
+    const char* rec = reinterpret_cast<const char*>(P.xbar + (long)(b >> 5) * P.GS + (long)k * S);
+    const int lane = b & 31;
+    auto range = [&](int row0, int rows) {
+      for (int i = lane; i < rows * 2; i += 32)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + (long)row0 * 256 + i * 128));
+    };
+    range(rXbar, (P.qrc_uniform ? rQ : rK) - rXbar);
+    range(rX, rA + kV - rX);
+    range(rLx, rY - rLx);
+    range(rP, rUinit - rP);
+  }
+  ALTRO_DEV void post_chunk(int k0, int k1, bool refresh, int slot, double* yn) {
+    double res = 0.0, viol = 0.0;
+    for (int k = k1 - 1; k >= k0; --k) {
+      if (k > k0) post_prefetch(k - 1);
+      const bool terminal = (k == N);
+      double x[n], u[m], lx[n], lu[m], y[n], A[n * n], Bm[n * m];
+      load_block<n>(xw(slot), sw(slot), k, x);
+      if (!terminal) {
+        load_block<m>(uw(slot), sw(slot), k, u);
+      } else {
+#pragma unroll
+        for (int i = 0; i < m; ++i) u[i] = 0.0;
+      }
+      if (refresh) {
+        double q[n], r[m];
+        load_block<n>(F(P.q), S, kq(k), q);
+        if (slot >= 0) store_block<n>(F(P.x), S, k, x);
+        if (!terminal) {
+          load_block<m>(F(P.r), S, kq(k), r);
+          if (slot >= 0) store_block<m>(F(P.u), S, k, u);
+          jacobian(k, x, u, A, Bm);
+          // through the packed form, like every other reader of [A B]
+          double J[kV];
+          JP::pack(A, Bm, J);
+          store_block<kV>(P.A + go, S, k, J);
+          JP::unpack(J, P.h, A, Bm);
+        }
+        stage_gradient(k, x, u, q, r, terminal, lx, lu);
+        al_terms(k, x, u, terminal, true, lx, lu);
+        store_block<n>(F(P.lx), S, k, lx);
+        if (!terminal) store_block<m>(F(P.lu), S, k, lu);
+      } else {
+        load_block<n>(F(P.lx), S, k, lx);
+        if (!terminal) {
+          load_block<m>(F(P.lu), S, k, lu);
+          load_jac(k, A, Bm);
+        }
+      }
+      costate_of(k, x, y);
+      store_block<n>(F(P.y), S, k, y);
+      if (!terminal) {
+        mm<n, 1, n, true, false, 1>(A, yn, lx);  // lx + A' y+
+        mm<m, 1, n, true, false, 1>(Bm, yn, lu);
+#pragma unroll
+        for (int i = 0; i < m; ++i) res = fmax(res, fabs(lu[i]));
+        store_block<m>(F(P.ubar), S, k, u);
+      }
+#pragma unroll
+      for (int i = 0; i < n; ++i) res = fmax(res, fabs(lx[i] - y[i]));
+      viol = fmax(viol, al_violation(k, x, u));
+      store_block<n>(F(P.xbar), S, k, x);
+#pragma unroll
+      for (int i = 0; i < n; ++i) yn[i] = y[i];
+    }
+    if (res > 0.0) atomicMax(P.stat_acc + b, (unsigned long long)__double_as_longlong(res));
+    if (CON && viol > 0.0) atomicMax(P.feas_acc + b, (unsigned long long)__double_as_longlong(viol));
   }
 
   // knot k's contribution to Stationarity (solver.cpp:207-222) and Feasibility (:224-231), and its

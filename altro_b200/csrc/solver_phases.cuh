@@ -340,15 +340,15 @@ __device__ __forceinline__ void for_knot_items(unsigned lanemask, int g, int kno
 // then, still in the same launch: the post-search expansion of an accepted backtracking step
 // (:256-262), costates, residuals, the decision, and the expansion after a dual update (:483-486).
 // active_out: incremented by the number of problems of the group that stopped in this iteration.
-// INLINE: the rollout of a request that wants phi' does the derivative half of the merit
-// evaluation in line (TrajSolver::rollout_step_deriv) instead of the separate expansion + scan.
-// It is a template parameter because the fused step needs ~200 registers: as a run-time branch it
-// made the lean variant spill (bicycle step 45 -> 55 ms).  The in-line variant runs with at most
-// four warps per CTA (255 registers, two CTAs per SM) and is the default for the strong-Wolfe
-// search, which has no speculative candidates to feed more warps anyway; the lean variant (128
-// registers, up to eight warps) serves the backtracking search.
-template <class Model, int CON, bool INLINE>
-__global__ void __launch_bounds__(INLINE ? 128 : 256, (Model::n > kUnrollDim) ? 1 : 2)
+// FOLLOW: the derivative half of a merit evaluation (solver.cpp:303-315: [A B], gradients, the phi'
+// recurrence) is done by a FOLLOWER warp (warp 1) right behind the rollout warp, which hands it
+// x_k, u_k through extra rows of the knot's stage (TrajSolver::follow_step) -- no separate
+// expansion / d(phi) scan and no re-read of x, u, [J], lx, lu from HBM, while the state recursion
+// of warp 0, the critical path of a pass, stays as short as a plain rollout.  Speculative
+// candidates use warps >= 2.  It is a template parameter so that the variant with the separate
+// knot-parallel expansion + scan (warps >= 1 speculate) stays available for comparison.
+template <class Model, int CON, bool FOLLOW>
+__global__ void __launch_bounds__((Model::n > kUnrollDim) ? 256 : 192, (Model::n > kUnrollDim) ? 1 : 2)
     k_phase_forward(const __grid_constant__ DeviceProblem P, int depth, int stage_rows, int wcount, int* done_out) {
   using TS = TrajSolver<Model, CON>;
   constexpr int n = Model::n, m = Model::m;
@@ -357,7 +357,9 @@ __global__ void __launch_bounds__(INLINE ? 128 : 256, (Model::n > kUnrollDim) ? 
   const int tid = threadIdx.x, lid = tid & 31, wid = tid >> 5;
   // speculative candidates per round: one warp each, at most what SetSpeculation asked for (extra
   // warps only serve the knot-parallel sub-phases)
-  const int nspec = min((int)(blockDim.x >> 5) - 1, P.nslots - 1);
+  constexpr bool follow = TrajSolver<Model, CON>::kStaged && FOLLOW;
+  constexpr int kSpecWarp0 = follow ? 2 : 1;  // first warp that rolls out speculative candidates
+  const int nspec = max(0, min((int)(blockDim.x >> 5) - kSpecWarp0, P.nslots - 1));
   const int bl = g * 32 + lid;                   // the problem this thread's lane index names
   const bool valid = bl < P.B;
   int fl = valid ? P.flags[bl] : 0;
@@ -370,6 +372,7 @@ __global__ void __launch_bounds__(INLINE ? 128 : 256, (Model::n > kUnrollDim) ? 
   BulkPipe pipe, scan;
   pipe.setup(altro_smem, reinterpret_cast<double*>(altro_smem + 256), depth, stage_rows * 32);
   scan.setup(altro_smem + BulkPipe::kBarBytes, reinterpret_cast<double*>(altro_smem + 256), depth, stage_rows * 32);
+  // follower mode: scan.full[] are the "x_k, u_k of the rollout warp are in the stage" barriers
   if (TS::kStaged && tid == 0) {
     pipe.init((int)(blockDim.x >> 5));
     scan.init(1);
@@ -401,9 +404,18 @@ __global__ void __launch_bounds__(INLINE ? 128 : 256, (Model::n > kUnrollDim) ? 
   const double* rec = P.xbar + (long)g * P.GS;  // row 0 of the group's knot-0 record
   const double* zrec = CON ? P.z + (long)g * P.GSz : nullptr;
   const LsOptions lo = ls_options(P.opts);
-  constexpr bool inline_deriv = TS::kStaged && INLINE;
   // ready[k]: flagged lanes whose expansion of knot k is published (this round)
   int* ready = reinterpret_cast<int*>(wsm + wcount);
+  // uniform linear cost terms: [q r c] of knot 0 for the group's 32 problems, kept in shared memory
+  // for the whole kernel and laid out like the rows rQ.. of a stage
+  constexpr int kQrcRows = TS::rK - TS::rQ;
+  double* qrc0 = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ready) + ((P.N + 1) * 4 + 15) / 16 * 16);
+  const bool quni = TS::kStaged && P.qrc_uniform != 0;
+  if (quni)
+    for (int i = tid; i < kQrcRows * 32; i += blockDim.x) qrc0[i] = rec[TS::rQ * 32 + i];
+  // follower mode: x_N of the rollout warp [n][32] and the follower's phi' [32]
+  double* xN_sm = qrc0 + kQrcRows * 32;
+  double* dphi_sm = xN_sm + n * 32;
   __syncthreads();
 
   // ================================================================= line-search rounds
@@ -421,22 +433,25 @@ __global__ void __launch_bounds__(INLINE ? 128 : 256, (Model::n > kUnrollDim) ? 
     const unsigned dmask = __ballot_sync(kAll, (fl & TF_WANT_DERIV) != 0);
     const int nneedy = nspec > 0 ? __popc(needy) : 0;
 
-    // ---- rollout pass.  Warp 0: thread = problem lane, candidate 0 (the requested step).  Warps
-    // >= 1: pair p -> lane rank p % nneedy (consecutive threads = different lanes: conflict-free
-    // shared-memory columns, neighbouring global stores), halving p / nneedy + 1.
+    // ---- rollout pass.  Warp 0: thread = problem lane, candidate 0 (the requested step).  Follower
+    // (warp 1 in follower mode): lane = problem, the derivative half of the requests that want it.
+    // Speculating warps: pair p -> lane rank p % nneedy (consecutive threads = different lanes:
+    // conflict-free shared-memory columns, neighbouring global stores), halving p / nneedy + 1.
+    const bool is_follow = follow && wid == 1;
     int lane = lid, slot = 0;
     bool need;
     if (wid == 0) {
       need = (fl & (TF_NEED_EVAL | TF_REROLL)) != 0;
+    } else if (is_follow) {
+      need = (fl & TF_NEED_EVAL) && (fl & TF_WANT_DERIV) && !(fl & TF_REROLL);
     } else {
-      const int p = (wid - 1) * 32 + lid;
+      const int p = (wid - kSpecWarp0) * 32 + lid;
       need = p < nneedy * nspec;
       if (need) {
         lane = __fns(needy, 0, p % nneedy + 1);
         slot = p / nneedy + 1;
       }
     }
-    double dphi_inline = 0.0;
     // every warp consumes the pass (fixed arrival count of the empty barriers); a warp without a
     // candidate only waits and releases.  Without staging the idle warps skip the pass.
     const bool warp_in = TS::kStaged || wid == 0 || (wid - 1) * 32 < nneedy * nspec;
@@ -448,7 +463,7 @@ __global__ void __launch_bounds__(INLINE ? 128 : 256, (Model::n > kUnrollDim) ? 
       double alpha = 0.0;
       double *xo = nullptr, *uo = nullptr;
       long so = 0;
-      if (need) {
+      if (need && !is_follow) {
         if (slot == 0) {
           alpha = P.alpha_eval[b];
           xo = s.xw(-1);
@@ -464,17 +479,17 @@ __global__ void __launch_bounds__(INLINE ? 128 : 256, (Model::n > kUnrollDim) ? 
         }
       }
       double phi = 0.0;
-      // warp 0, in-line derivative mode: the lanes whose request wants phi' do the expansion and the
-      // phi' recurrence of every knot right where x_k, u_k are produced (rollout_step_deriv)
-      const bool wderiv = inline_deriv && wid == 0 && need && (fl & TF_WANT_DERIV) && !(fl & TF_REROLL);
-      double dxda[inline_deriv ? n : 1];
-      if constexpr (inline_deriv) {
-#pragma unroll
-        for (int i = 0; i < n; ++i) dxda[i] = 0.0;
-      }
       if constexpr (TS::kStaged) {
         constexpr int kRows = TS::kRowsRoll;  // [xbar ubar q r c K d] (+ the dual record)
+        const int xu_row = kRows + zr;        // follower mode: x_k, u_k of the rollout warp
         auto fetch = [&](int k) {
+          if (quni) {  // [xbar ubar] and [K d] only
+            const int st = pipe.acquire(k, (unsigned)(kRows - kQrcRows + zr) * 256u);
+            pipe.copy(st, 0, rec + (long)k * P.R, TS::rQ * 256);
+            pipe.copy(st, TS::rK, rec + (long)k * P.R + TS::rK * 32, (kRows - TS::rK) * 256);
+            if (zr) pipe.copy(st, kRows, zrec + (long)k * P.Rz, zr * 256);
+            return;
+          }
           const int st = pipe.acquire(k, (unsigned)(kRows + zr) * 256u);
           pipe.copy(st, 0, rec + (long)k * P.R, kRows * 256);
           if (zr) pipe.copy(st, kRows, zrec + (long)k * P.Rz, zr * 256);
@@ -482,27 +497,54 @@ __global__ void __launch_bounds__(INLINE ? 128 : 256, (Model::n > kUnrollDim) ? 
         if (tid == 0)
           for (int j = 0; j < depth && j < P.N; ++j) fetch(j);
         double x[n];
-        if (need) load_block<n>(s.G(P.x0, n), 0, 0, x);
+        if (need && !is_follow) load_block<n>(s.G(P.x0, n), 0, 0, x);
+        double dxda[follow ? n : 1], dphi = 0.0;
+        if constexpr (follow) {
+#pragma unroll
+          for (int i = 0; i < n; ++i) dxda[i] = 0.0;
+        }
         for (int k = 0; k < P.N; ++k) {
           const double* st = pipe.wait(k);
-          double xb[n], ub[m], q[n], r[m], K[m * n], d[m], cval = 0.0;
+          const double* qst = quni ? qrc0 - TS::rQ * 32 : st;
+          double u[m], q[n], r[m], K[m * n], d[m], cval = 0.0;
           if (need) {
-            unstage_block<n>(st, TS::rXbar, lane, xb);
-            unstage_block<m>(st, TS::rUbar, lane, ub);
-            unstage_block<n>(st, TS::rQ, lane, q);
-            unstage_block<m>(st, TS::rR, lane, r);
-            cval = st[TS::rC * 32 + lane];
+            unstage_block<n>(qst, TS::rQ, lane, q);
+            unstage_block<m>(qst, TS::rR, lane, r);
             unstage_block<m * n>(st, TS::rK, lane, K);
             unstage_block<m>(st, TS::rD, lane, d);
           }
           if (zr) s.zstage = st + kRows * 32 + lane;
-          if constexpr (inline_deriv) {
-            if (wderiv)
-              s.rollout_step_deriv(k, alpha, xb, ub, K, d, q, r, cval, x, xo, uo, so, phi, dxda, dphi_inline);
-            else if (need)
-              s.rollout_step(k, alpha, xb, ub, K, d, q, r, cval, x, xo, uo, so, phi);
+          if (follow && is_follow) {
+            // x_k, u_k arrive from the rollout warp through the stage
+            scan.wait(k);
+            if (need) {
+              unstage_block<n>(st, xu_row, lane, x);
+              unstage_block<m>(st, xu_row + n, lane, u);
+              s.follow_step(k, x, u, q, r, K, d, dxda, dphi);
+            }
           } else {
-            if (need) s.rollout_step(k, alpha, xb, ub, K, d, q, r, cval, x, xo, uo, so, phi);
+            if (need) {
+              double xb[n], ub[m];
+              unstage_block<n>(st, TS::rXbar, lane, xb);
+              unstage_block<m>(st, TS::rUbar, lane, ub);
+              cval = qst[TS::rC * 32 + lane];
+              s.rollout_control(alpha, xb, ub, K, d, x, u);
+            }
+            if (follow && wid == 0) {
+              if (need) {
+                double* xu = const_cast<double*>(st) + xu_row * 32 + lane;
+#pragma unroll
+                for (int i = 0; i < n; ++i) xu[i * 32] = x[i];
+#pragma unroll
+                for (int i = 0; i < m; ++i) xu[(n + i) * 32] = u[i];
+              }
+              __syncwarp();
+              if (lid == 0) {
+                const unsigned a = (unsigned)__cvta_generic_to_shared(scan.full + ((scan.c0 + k) % depth));
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+              }
+            }
+            if (need) s.rollout_advance(k, u, q, r, cval, x, xo, uo, so, phi);
           }
           s.zstage = nullptr;
           // release only after the step consumed what was read from the stage (see BulkRing)
@@ -515,18 +557,27 @@ __global__ void __launch_bounds__(INLINE ? 128 : 256, (Model::n > kUnrollDim) ? 
           }
         }
         pipe.end_pass(P.N);
-        if constexpr (inline_deriv) {
-          if (wderiv)
-            s.rollout_terminal_deriv(x, xo, so, phi, dxda, dphi_inline);
-          else if (need)
-            s.rollout_terminal(x, xo, so, phi);
-        } else {
-          if (need) s.rollout_terminal(x, xo, so, phi);
+        if constexpr (follow) scan.end_pass(P.N);
+        if (need && !is_follow) s.rollout_terminal(x, xo, so, phi);
+        if constexpr (follow) {
+          // hand x_N to the follower, which finishes phi' behind the CTA barrier below
+          if (wid == 0 && need) {
+#pragma unroll
+            for (int i = 0; i < n; ++i) xN_sm[i * 32 + lane] = x[i];
+          }
+          __syncthreads();
+          if (is_follow) {
+            if (need) {
+              unstage_block<n>(xN_sm, 0, lane, x);
+              s.follow_terminal(x, dxda, dphi);
+            }
+            dphi_sm[lid] = dphi;
+          }
         }
       } else {
         if (need) phi = s.phase_rollout(alpha, xo, uo, so);
       }
-      if (need) {
+      if (need && !is_follow) {
         if (slot == 0)
           P.phi_eval[b] = phi;
         else
@@ -540,8 +591,8 @@ __global__ void __launch_bounds__(INLINE ? 128 : 256, (Model::n > kUnrollDim) ? 
     // warps >= 1 expand in knot-major order and publish every finished knot (ready[k] counts the
     // flagged lanes done), so warp 0 can run the sequential d(phi) scan BEHIND them instead of
     // after them -- the scan's bulk copy of knot k is issued once ready[k] is complete.
-    // in-line derivative mode: nothing left to expand or scan, warp 0 already holds phi'
-    const unsigned dmask_sep = inline_deriv ? 0u : dmask;
+    // follower mode: nothing left to expand or scan, the follower warp left phi' in shared memory
+    const unsigned dmask_sep = follow ? 0u : dmask;
     const int nl = __popc(dmask_sep);
     if (dmask_sep) {
       if constexpr (TS::kStaged) {
@@ -595,7 +646,7 @@ __global__ void __launch_bounds__(INLINE ? 128 : 256, (Model::n > kUnrollDim) ? 
       int f = fl;
       const bool pending = (f & (TF_NEED_EVAL | TF_REROLL)) != 0;
       const bool had_deriv = (f & TF_NEED_EVAL) && (f & TF_WANT_DERIV) && !(f & TF_REROLL);
-      double dphi = dphi_inline;
+      double dphi = (follow && had_deriv) ? dphi_sm[lid] : 0.0;
       if (dmask_sep) {
         TS s(P, had_deriv ? b : g * 32);
         if constexpr (TS::kStaged) {
@@ -755,7 +806,25 @@ __global__ void __launch_bounds__(INLINE ? 128 : 256, (Model::n > kUnrollDim) ? 
   // ================================================================= after the search
   // accepted backtracking step: A, B, lx, lu at the accepted point, read from the candidate slot
   // that holds it (solver.cpp:256-262)
-  {
+  // -- fused with the costates of the accepted point, the stationarity / feasibility residuals and
+  // CopyTrajectory into one pass: warp w walks the w-th chunk of the knots downwards, lane =
+  // problem (TrajSolver::post_chunk)
+  if (P.fused_post) {
+    const int W = (int)(blockDim.x >> 5);
+    const int C = (P.N + 1 + W - 1) / W;
+    const int k0 = wid * C, k1 = min(k0 + C, P.N + 1);
+    const bool act = valid && (fl & TF_ACTIVE) && k0 < k1;
+    TS s(P, act ? bl : g * 32);
+    weights(s);
+    s.rho = (CON && act) ? P.rho[bl] : 1.0;
+    const bool refresh = (fl & TF_REFRESH_DYN) != 0;
+    const int slot = (act && refresh) ? P.sel[bl] : -1;
+    double yn[n];
+    if (act && k1 <= P.N) s.post_boundary(k1, slot, yn);
+    __syncthreads();
+    if (act) s.post_chunk(k0, k1, refresh, slot, yn);
+    __syncthreads();
+  } else {
     const unsigned rmask = __ballot_sync(kAll, (fl & TF_REFRESH_DYN) != 0);
     if (rmask) {
       for_knot_items(rmask, g, P.N + 1, [&](int b, int k) {
@@ -766,19 +835,19 @@ __global__ void __launch_bounds__(INLINE ? 128 : 256, (Model::n > kUnrollDim) ? 
       });
       __syncthreads();
     }
+    tick(FS_EXPAND);
+    // costates of the accepted point, then stationarity / feasibility residuals + CopyTrajectory
+    for_knot_items(act_mask, g, P.N + 1, [&](int b, int k) {
+      TS s(P, b);
+      s.phase_costate_knot(k);
+    });
+    __syncthreads();
+    for_knot_items(act_mask, g, P.N + 1, [&](int b, int k) {
+      TS s(P, b);
+      s.phase_residual_knot(k);
+    });
+    __syncthreads();
   }
-  tick(FS_EXPAND);
-  // costates of the accepted point, then stationarity / feasibility residuals + CopyTrajectory
-  for_knot_items(act_mask, g, P.N + 1, [&](int b, int k) {
-    TS s(P, b);
-    s.phase_costate_knot(k);
-  });
-  __syncthreads();
-  for_knot_items(act_mask, g, P.N + 1, [&](int b, int k) {
-    TS s(P, b);
-    s.phase_residual_knot(k);
-  });
-  __syncthreads();
   // convergence test, dual / penalty update decision (solver.cpp:459-489, :503-506)
   if (wid == 0) {
     const int b = bl;
