@@ -21,6 +21,10 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # explicit fma().
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
+# experiment knobs: CTA shape of the forward kernel (solver_phases.cuh)
+for _k in ("ALTRO_FWD_THREADS", "ALTRO_FWD_CTAS"):
+    if os.environ.get(_k):
+        FLAGS += [f"-D{_k}={os.environ[_k]}"]
 N_INST = 8
 UNITS = [("capi", "capi.cu", []), ("tvlqr", "tvlqr.cu", []), ("tvlqr_batch", "tvlqr_batch.cu", []),
          ("facade", "altro_solver.cpp", []),

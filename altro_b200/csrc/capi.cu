@@ -232,7 +232,7 @@ struct altro_b200_solver {
   int nstore_alloc = 0;  // slot buffers allocated by Initialize
   int *flags = nullptr, *iter_count = nullptr;
   int* d_done = nullptr;                 // [kMaxSplit] stopped problems per sub-batch
-  unsigned long long* d_prof = nullptr;  // [kMaxSplit][8] sub-phase clocks of k_phase_forward
+  unsigned long long* d_prof = nullptr;  // [kMaxSplit][16] sub-phase clocks of k_phase_forward
   unsigned long long* ls_hist = nullptr;
   PhaseHost ph;        // accumulated statistics + device limits
   int solve_mode = 0;  // 0: phase pipeline (default), 1: single persistent kernel
@@ -243,6 +243,7 @@ struct altro_b200_solver {
   // behind the rollout warp (default), 0 separate knot-parallel expansion + d(phi) scan
   int inline_deriv = 1;
   int qrc_uniform_enable = 1;  // ALTRO_B200_QRC_UNIFORM=0 streams [q r c] with every knot regardless
+  int spec_round1 = 1;
   int fused_post = 1;  // forward kernel: everything between the search and the decision as one pass over the knots
   int fwd_depth = 8;  // staging depth cap of k_phase_forward (BulkPipe holds up to 8 stages)
   // pipelined sub-batches: the groups are cut into `nsplit` contiguous ranges, each on its own
@@ -491,6 +492,7 @@ altro_b200_solver* altro_b200_create(int horizon_length, int batch, int device) 
   if (const char* env = getenv("ALTRO_B200_BACKWARD_TEAM")) s->backward_team = atoi(env) != 0;
   if (const char* env = getenv("ALTRO_B200_INLINE_DERIV")) s->inline_deriv = atoi(env) != 0;
   if (const char* env = getenv("ALTRO_B200_QRC_UNIFORM")) s->qrc_uniform_enable = atoi(env) != 0;
+  if (const char* env = getenv("ALTRO_B200_SPEC_ROUND1")) s->spec_round1 = atoi(env) != 0;
   if (const char* env = getenv("ALTRO_B200_FUSED_POST")) s->fused_post = atoi(env) != 0;
   if (const char* env = getenv("ALTRO_B200_FWD_DEPTH")) s->fwd_depth = std::max(2, std::min(8, atoi(env)));
   return s;
@@ -594,7 +596,7 @@ int altro_b200_set_dimension(altro_b200_solver* s, int n, int m) {  // altro_sol
   DALLOC(s, s->flags, S);
   DALLOC(s, s->iter_count, S);
   DALLOC(s, s->d_done, altro_b200_solver::kMaxSplit);
-  DALLOC(s, s->d_prof, 8 * altro_b200_solver::kMaxSplit);
+  DALLOC(s, s->d_prof, 16 * altro_b200_solver::kMaxSplit);
   DALLOC(s, s->ls_hist, 32);
   memset(&s->ph, 0, sizeof(s->ph));
   {  // device limits that size the staging rings of the sequential sweeps (solve_inst.cu)
@@ -1294,6 +1296,11 @@ static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   P.nslots = s->nslots;
   P.nstore = s->nslots > 1 ? s->nstore : 0;
   P.inline_deriv = s->inline_deriv;
+  P.fused_post = s->fused_post;
+  P.spec_round1 = s->spec_round1;
+  P.role_shift = getenv("ALTRO_B200_ROLE_SHIFT") ? atoi(getenv("ALTRO_B200_ROLE_SHIFT")) : 0;
+  P.prof_tid = getenv("ALTRO_B200_PROF_TID") ? atoi(getenv("ALTRO_B200_PROF_TID")) : 0;
+  P.qrc_uniform = s->qrc_uniform_enable ? qrc_uniform(s) : 0;
   P.xs = s->xs;
   P.us = s->us;
   P.phi_s = s->phi_s;
@@ -1389,7 +1396,7 @@ int altro_b200_solve_async(altro_b200_solver* s) {  // altro_solver.cpp:257-260
     H.smem_per_sm = s->ph.smem_per_sm;
     H.smem_per_cta = s->ph.smem_per_cta;
     H.d_done = s->d_done + i;
-    H.d_prof = s->d_prof + 8 * i;
+    H.d_prof = s->d_prof + 16 * i;
     H.fwd_warps = std::max(4, s->nslots);
     H.fwd_depth = s->fwd_depth;
     H.backward_team = s->backward_team >= 0 ? s->backward_team : (s->n > kUnrollDim ? 1 : 0);

@@ -146,6 +146,12 @@ struct DeviceProblem {
   // stage knots with a goal-type reference): the sweeps read them once from knot 0 instead of
   // streaming [q r c] with every knot
   int qrc_uniform;
+  // 1: the halvings of a backtracking search are rolled out speculatively from the first round on
+  // (next to alpha0); 0: from the second round on, next to the cubic-first probe -- the same number
+  // of rounds, but no speculative work for the searches that accept alpha0
+  int role_shift;  // k_phase_forward: hardware warp that plays the rollout warp
+  int prof_tid;  // profile mode: the thread whose clocks are recorded (0: rollout warp, 32: follower, 64..: speculating)
+  int spec_round1;
   int fused_post;  // k_phase_forward: post-search expansion + costates + residuals + copy as one pass
   double *xs, *us;      // slot record stream; us = xs + n * 32
   double* phi_s;        // [kMaxHalvings + 1][Bp] merit value of halving j (alpha0 * 2^-j), j >= 1

@@ -39,7 +39,7 @@ struct PhaseHost {
                        // [group][knot][n*n + n*m][32]
   int* d_done;         // device: problems of the sub-batch that have stopped (zeroed by the prologue)
   int* h_done;         // pinned [kDoneRing]: copies of *d_done taken after each iteration
-  unsigned long long* d_prof;  // device [8]: sub-phase nanoseconds of k_phase_forward (profile mode)
+  unsigned long long* d_prof;  // device [16]: sub-phase clocks of k_phase_forward (profile mode)
   bool profile;        // record CUDA events around every launch
   double ms[PH_COUNT];         // accumulated kernel time per phase (profile mode)
   long launches[PH_COUNT];     // launches per phase

@@ -376,12 +376,147 @@ struct BulkPipe {
     spin((unsigned)__cvta_generic_to_shared(full + st), (unsigned)((g / depth) & 1), 0, k);
     return data + (long)st * stage_doubles;
   }
+  // ---- counted release (k_phase_forward's rollout passes): instead of an `empty` mbarrier that a
+  // producer thread has to wait on, every consumer warp counts itself out of the stage and the warp
+  // that counts LAST refills it -- nobody ever blocks on a slower warp (with the producer duty inside
+  // the rollout warp's loop that warp, the critical path of a pass, spent a quarter of its time
+  // waiting for the slowest warp to release the stage it wanted to refill: r02o).  The counters
+  // live in the `empty` slots, which this mode does not use as barriers.
+  ALTRO_DEV void init_counted() const {  // ONE thread, once per kernel, followed by a CTA barrier
+    for (int j = 0; j < depth; ++j) {
+      const unsigned f = (unsigned)__cvta_generic_to_shared(full + j);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(f) : "memory");
+      empty[j] = 0ull;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // producer side without the wait: announce `bytes` for the stage of pass-local knot k
+  ALTRO_DEV int acquire_nowait(int k, unsigned bytes) const {
+    const int st = (c0 + k) % depth;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(full + st);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+    return st;
+  }
+  // consumer, all lanes of the warp, AFTER the arithmetic that consumed the stage's values; returns
+  // true (warp-uniform) in the warp that released the stage last: its lane 0 refills the stage
+  ALTRO_DEV bool release_counted(int k, int lane, int consumer_warps) const {
+    __syncwarp();
+    unsigned last = 0;
+    if (lane == 0) {
+      unsigned* cnt = reinterpret_cast<unsigned*>(empty + ((c0 + k) % depth));
+      __threadfence_block();
+      const unsigned old = atomicAdd(cnt, 1u);
+      if (old == (unsigned)consumer_warps - 1u) {
+        *reinterpret_cast<volatile unsigned*>(cnt) = 0u;
+        __threadfence_block();
+        last = 1u;
+      }
+    }
+    return __shfl_sync(0xffffffffu, last, 0) != 0u;
+  }
   // consumer, all lanes of the warp, AFTER the arithmetic that consumed the stage's values
   ALTRO_DEV void release(int k, int lane) const {
     __syncwarp();
     if (lane == 0) {
       const unsigned a = (unsigned)__cvta_generic_to_shared(empty + ((c0 + k) % depth));
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+    }
+  }
+};
+
+// ---- The staging pipeline of k_phase_forward's rollout passes.  Like BulkPipe, but built for a
+// critical-path consumer (the rollout warp), measured with per-warp clocks on the B200 (r02o-r02r:
+// the rollout warp spent a third of every knot in pipeline bookkeeping):
+//   * no `empty` barrier and no producer that waits: every consumer warp counts itself out of a
+//     stage (lane 0, one shared-memory atomic whose result is looked at one knot LATER, so its
+//     latency is never exposed) and the warp that counted last refills the stage;
+//   * the number of consumers is a per-pass argument: warps without work sit the pass out instead
+//     of waiting and releasing every knot (their spin loops took a third of the kernel's issued
+//     instructions);
+//   * stage index and phase parity are kept incrementally (pass-local stage = k mod depth advanced
+//     by the caller, one parity bit per stage) -- no integer division by the run-time depth.
+struct RollPipe {
+  unsigned long long* full;  // [<= 8] "stage landed" mbarriers: one arrival + the copies' bytes
+  unsigned* cnt;             // [<= 8] consumer warps that released the stage's current use
+  double* data;              // [depth][stage_doubles], 128-byte aligned
+  int depth, stage_doubles;
+  unsigned parbits;          // bit s: the parity the next wait on stage s expects
+  unsigned passmask;         // stages that are used an odd number of times by a pass of N knots
+
+  // pointer carving only; all threads.  bars: 128 bytes (full[8] | cnt[8] + padding)
+  ALTRO_DEV void setup(unsigned char* bars, double* data_, int depth_, int stage_doubles_, int N) {
+    full = reinterpret_cast<unsigned long long*>(bars);
+    cnt = reinterpret_cast<unsigned*>(full + 8);
+    data = data_;
+    depth = depth_;
+    stage_doubles = stage_doubles_;
+    parbits = 0u;
+    passmask = 0u;
+    for (int s = 0; s < depth && s < N; ++s)
+      if (((N - s + depth - 1) / depth) & 1) passmask |= 1u << s;
+  }
+  ALTRO_DEV void init() const {  // ONE thread, once per kernel, followed by a CTA barrier
+    for (int j = 0; j < depth; ++j) {
+      const unsigned f = (unsigned)__cvta_generic_to_shared(full + j);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(f) : "memory");
+      cnt[j] = 0u;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // whoever refills stage st: announce `bytes`, then issue the copies that add up to it
+  ALTRO_DEV void arm(int st, unsigned bytes) const {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(full + st);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+  }
+  ALTRO_DEV void copy(int st, int row, const double* src, unsigned bytes) const {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(full + st);
+    const unsigned d = (unsigned)__cvta_generic_to_shared(data + (long)st * stage_doubles + row * 32);
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+        "l"(src), "r"(bytes), "r"(a)
+        : "memory");
+  }
+  // consumer, all lanes: wait for the next use of stage st; returns the stage's first row
+  ALTRO_DEV double* wait(int st) {
+    mbar_wait((unsigned)__cvta_generic_to_shared(full + st), (parbits >> st) & 1u);
+    parbits ^= 1u << st;
+    return data + (long)st * stage_doubles;
+  }
+  // a warp that sits a pass out keeps its parities in step
+  ALTRO_DEV void skip_pass() { parbits ^= passmask; }
+  // lane 0 of a consumer warp, after the warp consumed the stage (behind a __syncwarp): count out;
+  // the returned value says, when it equals consumers - 1, that this warp was the last one
+  ALTRO_DEV unsigned count_out(int st) const {
+    __threadfence_block();
+    return atomicAdd(cnt + st, 1u);
+  }
+  ALTRO_DEV void reset(int st) const {
+    *reinterpret_cast<volatile unsigned*>(cnt + st) = 0u;
+    __threadfence_block();
+  }
+  // A wait that cannot complete is a protocol bug; it must surface as a kernel error (trap), never
+  // as a hung device.  try_wait suspends the thread in hardware for up to the hinted time, so the
+  // loop around it turns over rarely.
+  ALTRO_DEV static void mbar_wait(unsigned addr, unsigned parity) {
+    unsigned ok = 0;
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    unsigned spins = 0;
+    while (!ok) {
+      asm volatile(
+          "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+          : "=r"(ok)
+          : "r"(addr), "r"(parity), "r"(20000u)
+          : "memory");
+      if (!ok && ++spins > (1u << 20)) {
+        if ((threadIdx.x & 31) == 0)
+          printf("altro_b200: stage wait stuck (block %d of %d, thread %d of %d, addr %u parity %u)\n",
+                 (int)blockIdx.x, (int)gridDim.x, (int)threadIdx.x, (int)blockDim.x, addr, parity);
+        __trap();
+      }
     }
   }
 };

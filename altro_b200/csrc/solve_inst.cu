@@ -115,16 +115,16 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
       // The forward CTAs are register-limited to two per SM, so the ring may use up to half an SM's
       // shared memory minus what a co-resident backward CTA needs: up to kFwdStageDepth knots in
       // flight (ncu r02e: a third of the kernel's stall samples waited for a stage to land at depth 4)
-      const int per_sm = std::min(2, (P.Gtot + H->num_sms - 1) / H->num_sms);
-      depth = ring_depth(per_sm, (size_t)rows * 256, 256 + tail + 24 * 1024, H->fwd_depth);
+      const int per_sm = std::min(kFwdCtasPerSm, (P.Gtot + H->num_sms - 1) / H->num_sms);
+      depth = ring_depth(per_sm, (size_t)rows * 256, 256 + tail + (size_t)(48 * 1024) / std::max(per_sm, 1), H->fwd_depth);
       sm = BulkPipe::bytes(depth, rows * 32) + wbytes + tail;
     }
     // 192 threads at most (256 for the large-block models); the follower variant needs the rollout
     // warp, the follower and the speculating warps
-    const int warps = std::max(follow ? 2 : 1, std::min(H->fwd_warps + (follow ? 1 : 0), TS::kStaged ? 6 : 8));
+    const int warps = std::max(follow ? 2 : 1, std::min(H->fwd_warps + (follow ? 1 : 0), TS::kStaged ? kFwdThreads / 32 : 8));
     DeviceProblem Pf = P;
     Pf.prof = H->profile ? H->d_prof : nullptr;
-    if (H->profile) cudaMemsetAsync(H->d_prof, 0, 8 * sizeof(unsigned long long), st);
+    if (H->profile) cudaMemsetAsync(H->d_prof, 0, 16 * sizeof(unsigned long long), st);
     const double ms_before = H->ms[PH_FORWARD];
     timed(PH_FORWARD, (double)G * 32, [&] {
       if (follow)
@@ -133,8 +133,14 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
         k_phase_forward<Model, CON, false><<<G, 32 * warps, sm, st>>>(Pf, depth, rows, wcount, H->d_done);
     });
     if (H->profile) {  // split the kernel's time by the in-kernel sub-phase clocks
-      unsigned long long ns[8];
+      unsigned long long ns[16];
       cudaMemcpy(ns, H->d_prof, sizeof(ns), cudaMemcpyDeviceToHost);
+      if (getenv("ALTRO_B200_PROF_DUMP"))
+        fprintf(stderr,
+                "fwd prof iter %d: ctas %llu  ns rollout %llu expand %llu dphi_ls %llu criteria %llu | rollout warp cycles: "
+                "wait-full %llu release %llu pass %llu | pass cycles by round %llu %llu %llu %llu passes %llu %llu %llu %llu\n",
+                H->iter, ns[4], ns[0], ns[1], ns[2], ns[3], ns[5], ns[6], ns[7], ns[8], ns[9], ns[10], ns[11], ns[12],
+                ns[13], ns[14], ns[15]);
       const double tot = (double)(ns[0] + ns[1] + ns[2] + ns[3]);
       const double ms = H->ms[PH_FORWARD] - ms_before;
       for (int i = 0; i < 4; ++i) {

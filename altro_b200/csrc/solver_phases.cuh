@@ -207,7 +207,7 @@ __device__ __forceinline__ void backward_finish(const DeviceProblem& P, int b, b
       f |= TF_NEED_EVAL | TF_WANT_DERIV;
       P.alpha_eval[b] = ls.alpha;
       P.spec_known[b] = 0;
-      if (lo.use_backtracking && P.nslots > 1) {
+      if (lo.use_backtracking && P.nslots > 1 && P.spec_round1) {
         // the halvings SimpleBacktracking(alpha0 * beta_decrease) will try if alpha0 and the
         // cubic-first probe are rejected (linesearch.cpp:130-132, :385-412)
         f |= TF_SPECULATE;
@@ -340,6 +340,16 @@ __device__ __forceinline__ void for_knot_items(unsigned lanemask, int g, int kno
 // then, still in the same launch: the post-search expansion of an accepted backtracking step
 // (:256-262), costates, residuals, the decision, and the expansion after a dual update (:483-486).
 // active_out: incremented by the number of problems of the group that stopped in this iteration.
+// CTA shape of the staged variants (register budget = 65536 / (threads * CTAs per SM))
+#ifndef ALTRO_FWD_THREADS
+#define ALTRO_FWD_THREADS 192
+#endif
+#ifndef ALTRO_FWD_CTAS
+#define ALTRO_FWD_CTAS 2
+#endif
+constexpr int kFwdThreads = ALTRO_FWD_THREADS;
+constexpr int kFwdCtasPerSm = ALTRO_FWD_CTAS;
+
 // FOLLOW: the derivative half of a merit evaluation (solver.cpp:303-315: [A B], gradients, the phi'
 // recurrence) is done by a FOLLOWER warp (warp 1) right behind the rollout warp, which hands it
 // x_k, u_k through extra rows of the knot's stage (TrajSolver::follow_step) -- no separate
@@ -348,13 +358,16 @@ __device__ __forceinline__ void for_knot_items(unsigned lanemask, int g, int kno
 // candidates use warps >= 2.  It is a template parameter so that the variant with the separate
 // knot-parallel expansion + scan (warps >= 1 speculate) stays available for comparison.
 template <class Model, int CON, bool FOLLOW>
-__global__ void __launch_bounds__((Model::n > kUnrollDim) ? 256 : 192, (Model::n > kUnrollDim) ? 1 : 2)
+__global__ void __launch_bounds__((Model::n > kUnrollDim) ? 256 : kFwdThreads, (Model::n > kUnrollDim) ? 1 : kFwdCtasPerSm)
     k_phase_forward(const __grid_constant__ DeviceProblem P, int depth, int stage_rows, int wcount, int* done_out) {
   using TS = TrajSolver<Model, CON>;
   constexpr int n = Model::n, m = Model::m;
   constexpr unsigned kAll = 0xffffffffu;
   const int g = P.g0 + blockIdx.x;
-  const int tid = threadIdx.x, lid = tid & 31, wid = tid >> 5;
+  const int tid = threadIdx.x, lid = tid & 31;
+  // role of this warp (0 rollout warp, then follower / speculating warps): hardware warp w of a CTA
+  // sits on scheduler w mod 4, so rotating the roles changes which roles share a scheduler
+  const int wid = ((tid >> 5) + (int)(blockDim.x >> 5) - P.role_shift) % (int)(blockDim.x >> 5);
   // speculative candidates per round: one warp each, at most what SetSpeculation asked for (extra
   // warps only serve the knot-parallel sub-phases)
   constexpr bool follow = TrajSolver<Model, CON>::kStaged && FOLLOW;
@@ -367,16 +380,19 @@ __global__ void __launch_bounds__((Model::n > kUnrollDim) ? 256 : 192, (Model::n
   const unsigned act_mask = __ballot_sync(kAll, (fl & TF_ACTIVE) != 0);
   if (!act_mask) return;
 
-  // two pipes over the same stages: `pipe` for the rollout passes (every warp of the CTA consumes),
-  // `scan` for the d(phi) scans (warp 0 alone); barriers armed once, never invalidated
-  BulkPipe pipe, scan;
-  pipe.setup(altro_smem, reinterpret_cast<double*>(altro_smem + 256), depth, stage_rows * 32);
+  // two pipes over the same stages: `pipe` for the rollout passes (the warps with work consume),
+  // `scan` for the d(phi) scans (warp 0 alone); barriers armed once, never invalidated.  Follower
+  // mode has no scan: scan.full[] serve as the "x_k, u_k of the rollout warp are in the stage"
+  // barriers, with the follower's own parity bits.
+  RollPipe pipe;
+  BulkPipe scan;
+  pipe.setup(altro_smem, reinterpret_cast<double*>(altro_smem + 256), depth, stage_rows * 32, P.N);
   scan.setup(altro_smem + BulkPipe::kBarBytes, reinterpret_cast<double*>(altro_smem + 256), depth, stage_rows * 32);
-  // follower mode: scan.full[] are the "x_k, u_k of the rollout warp are in the stage" barriers
   if (TS::kStaged && tid == 0) {
-    pipe.init((int)(blockDim.x >> 5));
+    pipe.init();
     scan.init(1);
   }
+  unsigned xubits = 0u;
   double* wsm = reinterpret_cast<double*>(altro_smem + BulkPipe::bytes(depth, stage_rows * 32));
   const int nq = (P.N + 1) * n, nr = P.N * m;
   if (wcount > 0) {
@@ -391,7 +407,7 @@ __global__ void __launch_bounds__((Model::n > kUnrollDim) ? 256 : 192, (Model::n
     }
   };
   unsigned long long t_prev = 0;
-  const bool prof = P.prof != nullptr && tid == 0;
+  const bool prof = P.prof != nullptr && tid == P.prof_tid;
   if (prof) t_prev = global_ns();
   auto tick = [&](int sub) {
     if (prof) {
@@ -437,29 +453,35 @@ __global__ void __launch_bounds__((Model::n > kUnrollDim) ? 256 : 192, (Model::n
     // (warp 1 in follower mode): lane = problem, the derivative half of the requests that want it.
     // Speculating warps: pair p -> lane rank p % nneedy (consecutive threads = different lanes:
     // conflict-free shared-memory columns, neighbouring global stores), halving p / nneedy + 1.
+    // Warps without work sit the pass out.
     const bool is_follow = follow && wid == 1;
+    const unsigned fmask =
+        follow ? __ballot_sync(kAll, (fl & TF_NEED_EVAL) && (fl & TF_WANT_DERIV) && !(fl & TF_REROLL)) : 0u;
+    const int spec_warps = (nneedy * nspec + 31) >> 5;
+    const int nact = 1 + (fmask ? 1 : 0) + spec_warps;  // consumer warps of this pass
     int lane = lid, slot = 0;
-    bool need;
+    bool need, warp_in;
     if (wid == 0) {
       need = (fl & (TF_NEED_EVAL | TF_REROLL)) != 0;
+      warp_in = true;
     } else if (is_follow) {
-      need = (fl & TF_NEED_EVAL) && (fl & TF_WANT_DERIV) && !(fl & TF_REROLL);
+      need = (fmask >> lid) & 1u;
+      warp_in = fmask != 0u;
     } else {
       const int p = (wid - kSpecWarp0) * 32 + lid;
       need = p < nneedy * nspec;
+      warp_in = wid - kSpecWarp0 < spec_warps;
       if (need) {
         lane = __fns(needy, 0, p % nneedy + 1);
         slot = p / nneedy + 1;
       }
     }
-    // every warp consumes the pass (fixed arrival count of the empty barriers); a warp without a
-    // candidate only waits and releases.  Without staging the idle warps skip the pass.
-    const bool warp_in = TS::kStaged || wid == 0 || (wid - 1) * 32 < nneedy * nspec;
+    const int b = g * 32 + lane;
+    TS s(P, need ? b : g * 32);
+    weights(s);
+    s.rho = (CON && need) ? P.rho[b] : 1.0;
+    double fdxda[follow ? n : 1], fdphi = 0.0;  // the follower's phi' recurrence
     if (warp_in) {
-      const int b = g * 32 + lane;
-      TS s(P, need ? b : g * 32);
-      weights(s);
-      s.rho = (CON && need) ? P.rho[b] : 1.0;
       double alpha = 0.0;
       double *xo = nullptr, *uo = nullptr;
       long so = 0;
@@ -482,57 +504,62 @@ __global__ void __launch_bounds__((Model::n > kUnrollDim) ? 256 : 192, (Model::n
       if constexpr (TS::kStaged) {
         constexpr int kRows = TS::kRowsRoll;  // [xbar ubar q r c K d] (+ the dual record)
         const int xu_row = kRows + zr;        // follower mode: x_k, u_k of the rollout warp
-        auto fetch = [&](int k) {
+        auto fetch = [&](int k, int st) {
           if (quni) {  // [xbar ubar] and [K d] only
-            const int st = pipe.acquire(k, (unsigned)(kRows - kQrcRows + zr) * 256u);
+            pipe.arm(st, (unsigned)(kRows - kQrcRows + zr) * 256u);
             pipe.copy(st, 0, rec + (long)k * P.R, TS::rQ * 256);
             pipe.copy(st, TS::rK, rec + (long)k * P.R + TS::rK * 32, (kRows - TS::rK) * 256);
-            if (zr) pipe.copy(st, kRows, zrec + (long)k * P.Rz, zr * 256);
-            return;
+          } else {
+            pipe.arm(st, (unsigned)(kRows + zr) * 256u);
+            pipe.copy(st, 0, rec + (long)k * P.R, kRows * 256);
           }
-          const int st = pipe.acquire(k, (unsigned)(kRows + zr) * 256u);
-          pipe.copy(st, 0, rec + (long)k * P.R, kRows * 256);
           if (zr) pipe.copy(st, kRows, zrec + (long)k * P.Rz, zr * 256);
         };
-        if (tid == 0)
-          for (int j = 0; j < depth && j < P.N; ++j) fetch(j);
+        if (wid == 0 && lid == 0)
+          for (int j = 0; j < depth && j < P.N; ++j) fetch(j, j);
         double x[n];
         if (need && !is_follow) load_block<n>(s.G(P.x0, n), 0, 0, x);
-        double dxda[follow ? n : 1], dphi = 0.0;
         if constexpr (follow) {
 #pragma unroll
-          for (int i = 0; i < n; ++i) dxda[i] = 0.0;
+          for (int i = 0; i < n; ++i) fdxda[i] = 0.0;
         }
+        long long c_full = 0, c_wr = 0, c_t0 = 0, c_pass = 0;  // profile mode: clocks of thread 0
+        if (prof) c_pass = clock64();
+        int st = 0, st_prev = 0;     // stage of knot k = k mod depth, kept incrementally
+        unsigned out_prev = ~0u;     // lane 0: what the count-out of knot k - 1 returned
         for (int k = 0; k < P.N; ++k) {
-          const double* st = pipe.wait(k);
-          const double* qst = quni ? qrc0 - TS::rQ * 32 : st;
+          if (prof) c_t0 = clock64();
+          double* stg = pipe.wait(st);
+          if (prof) c_full += clock64() - c_t0;
+          const double* qst = quni ? qrc0 - TS::rQ * 32 : stg;
           double u[m], q[n], r[m], K[m * n], d[m], cval = 0.0;
           if (need) {
             unstage_block<n>(qst, TS::rQ, lane, q);
             unstage_block<m>(qst, TS::rR, lane, r);
-            unstage_block<m * n>(st, TS::rK, lane, K);
-            unstage_block<m>(st, TS::rD, lane, d);
+            unstage_block<m * n>(stg, TS::rK, lane, K);
+            unstage_block<m>(stg, TS::rD, lane, d);
           }
-          if (zr) s.zstage = st + kRows * 32 + lane;
+          if (zr) s.zstage = stg + kRows * 32 + lane;
           if (follow && is_follow) {
             // x_k, u_k arrive from the rollout warp through the stage
-            scan.wait(k);
+            RollPipe::mbar_wait((unsigned)__cvta_generic_to_shared(scan.full + st), (xubits >> st) & 1u);
+            xubits ^= 1u << st;
             if (need) {
-              unstage_block<n>(st, xu_row, lane, x);
-              unstage_block<m>(st, xu_row + n, lane, u);
-              s.follow_step(k, x, u, q, r, K, d, dxda, dphi);
+              unstage_block<n>(stg, xu_row, lane, x);
+              unstage_block<m>(stg, xu_row + n, lane, u);
+              s.follow_step(k, x, u, q, r, K, d, fdxda, fdphi);
             }
           } else {
             if (need) {
               double xb[n], ub[m];
-              unstage_block<n>(st, TS::rXbar, lane, xb);
-              unstage_block<m>(st, TS::rUbar, lane, ub);
+              unstage_block<n>(stg, TS::rXbar, lane, xb);
+              unstage_block<m>(stg, TS::rUbar, lane, ub);
               cval = qst[TS::rC * 32 + lane];
               s.rollout_control(alpha, xb, ub, K, d, x, u);
             }
-            if (follow && wid == 0) {
+            if (follow && wid == 0 && fmask) {
               if (need) {
-                double* xu = const_cast<double*>(st) + xu_row * 32 + lane;
+                double* xu = stg + xu_row * 32 + lane;
 #pragma unroll
                 for (int i = 0; i < n; ++i) xu[i * 32] = x[i];
 #pragma unroll
@@ -540,38 +567,44 @@ __global__ void __launch_bounds__((Model::n > kUnrollDim) ? 256 : 192, (Model::n
               }
               __syncwarp();
               if (lid == 0) {
-                const unsigned a = (unsigned)__cvta_generic_to_shared(scan.full + ((scan.c0 + k) % depth));
+                const unsigned a = (unsigned)__cvta_generic_to_shared(scan.full + st);
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
               }
             }
             if (need) s.rollout_advance(k, u, q, r, cval, x, xo, uo, so, phi);
           }
           s.zstage = nullptr;
-          // release only after the step consumed what was read from the stage (see BulkRing)
-          pipe.release(k, lid);
-          // the refill runs one knot behind warp 0, so warp 0 never waits for the knot it just
-          // released to be released by the slower warps
-          if (wid == 0 && k >= 1 && k - 1 + depth < P.N) {
-            pipe.wait_writable(k - 1 + depth);
-            if (lid == 0) fetch(k - 1 + depth);
+          // count out of the stage only after the step consumed what was read from it (see
+          // BulkRing).  Lane 0 looks at the count it got for the PREVIOUS knot -- that atomic's
+          // latency is long over -- and refills that stage if this warp was the last one out.
+          if (prof) c_t0 = clock64();
+          __syncwarp();
+          if (lid == 0) {
+            if (out_prev == (unsigned)nact - 1u) {
+              pipe.reset(st_prev);
+              if (k - 1 + depth < P.N) fetch(k - 1 + depth, st_prev);
+            }
+            out_prev = pipe.count_out(st);
           }
+          st_prev = st;
+          st = (st + 1 == depth) ? 0 : st + 1;
+          if (prof) c_wr += clock64() - c_t0;
         }
-        pipe.end_pass(P.N);
-        if constexpr (follow) scan.end_pass(P.N);
+        if (lid == 0 && out_prev == (unsigned)nact - 1u) pipe.reset(st_prev);
+        if (prof) {  // rollout warp: cycles waiting for a stage to land / counting out, per pass
+          const unsigned long long c_all = (unsigned long long)(clock64() - c_pass);
+          atomicAdd(P.prof + 5, (unsigned long long)c_full);
+          atomicAdd(P.prof + 6, (unsigned long long)c_wr);
+          atomicAdd(P.prof + 7, c_all);
+          atomicAdd(P.prof + 8 + min(round, 3), c_all);
+          atomicAdd(P.prof + 12 + min(round, 3), 1ull);
+        }
         if (need && !is_follow) s.rollout_terminal(x, xo, so, phi);
         if constexpr (follow) {
           // hand x_N to the follower, which finishes phi' behind the CTA barrier below
-          if (wid == 0 && need) {
+          if (wid == 0 && need && fmask) {
 #pragma unroll
             for (int i = 0; i < n; ++i) xN_sm[i * 32 + lane] = x[i];
-          }
-          __syncthreads();
-          if (is_follow) {
-            if (need) {
-              unstage_block<n>(xN_sm, 0, lane, x);
-              s.follow_terminal(x, dxda, dphi);
-            }
-            dphi_sm[lid] = dphi;
           }
         }
       } else {
@@ -582,6 +615,21 @@ __global__ void __launch_bounds__((Model::n > kUnrollDim) ? 256 : 192, (Model::n
           P.phi_eval[b] = phi;
         else
           P.phi_s[(long)min(P.spec_base[b] + slot - 1, kMaxHalvings) * P.Bp + b] = phi;
+      }
+    } else if (TS::kStaged) {
+      pipe.skip_pass();
+    }
+    if constexpr (follow) {
+      if (fmask) {  // CTA-uniform
+        __syncthreads();
+        if (is_follow) {
+          if (need) {
+            double x[n];
+            unstage_block<n>(xN_sm, 0, lane, x);
+            s.follow_terminal(x, fdxda, fdphi);
+          }
+          dphi_sm[lid] = fdphi;
+        }
       }
     }
     __syncthreads();
@@ -598,7 +646,7 @@ __global__ void __launch_bounds__((Model::n > kUnrollDim) ? 256 : 192, (Model::n
       if constexpr (TS::kStaged) {
         if (wid > 0) {
           const int items = nl * (P.N + 1), step = (int)blockDim.x - 32;
-          for (int i = tid - 32; i < items; i += step) {
+          for (int i = (wid - 1) * 32 + lid; i < items; i += step) {
             const int k = i / nl;
             const int b = g * 32 + __fns(dmask_sep, 0, i % nl + 1);
             TS s(P, b);
