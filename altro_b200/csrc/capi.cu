@@ -1298,7 +1298,6 @@ static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   P.inline_deriv = s->inline_deriv;
   P.fused_post = s->fused_post;
   P.spec_round1 = s->spec_round1;
-  P.role_shift = getenv("ALTRO_B200_ROLE_SHIFT") ? atoi(getenv("ALTRO_B200_ROLE_SHIFT")) : 0;
   P.prof_tid = getenv("ALTRO_B200_PROF_TID") ? atoi(getenv("ALTRO_B200_PROF_TID")) : 0;
   P.qrc_uniform = s->qrc_uniform_enable ? qrc_uniform(s) : 0;
   P.xs = s->xs;

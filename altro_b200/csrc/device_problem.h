@@ -149,7 +149,6 @@ struct DeviceProblem {
   // 1: the halvings of a backtracking search are rolled out speculatively from the first round on
   // (next to alpha0); 0: from the second round on, next to the cubic-first probe -- the same number
   // of rounds, but no speculative work for the searches that accept alpha0
-  int role_shift;  // k_phase_forward: hardware warp that plays the rollout warp
   int prof_tid;  // profile mode: the thread whose clocks are recorded (0: rollout warp, 32: follower, 64..: speculating)
   int spec_round1;
   int fused_post;  // k_phase_forward: post-search expansion + costates + residuals + copy as one pass

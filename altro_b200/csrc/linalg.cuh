@@ -376,44 +376,6 @@ struct BulkPipe {
     spin((unsigned)__cvta_generic_to_shared(full + st), (unsigned)((g / depth) & 1), 0, k);
     return data + (long)st * stage_doubles;
   }
-  // ---- counted release (k_phase_forward's rollout passes): instead of an `empty` mbarrier that a
-  // producer thread has to wait on, every consumer warp counts itself out of the stage and the warp
-  // that counts LAST refills it -- nobody ever blocks on a slower warp (with the producer duty inside
-  // the rollout warp's loop that warp, the critical path of a pass, spent a quarter of its time
-  // waiting for the slowest warp to release the stage it wanted to refill: r02o).  The counters
-  // live in the `empty` slots, which this mode does not use as barriers.
-  ALTRO_DEV void init_counted() const {  // ONE thread, once per kernel, followed by a CTA barrier
-    for (int j = 0; j < depth; ++j) {
-      const unsigned f = (unsigned)__cvta_generic_to_shared(full + j);
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(f) : "memory");
-      empty[j] = 0ull;
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  // producer side without the wait: announce `bytes` for the stage of pass-local knot k
-  ALTRO_DEV int acquire_nowait(int k, unsigned bytes) const {
-    const int st = (c0 + k) % depth;
-    const unsigned a = (unsigned)__cvta_generic_to_shared(full + st);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
-    return st;
-  }
-  // consumer, all lanes of the warp, AFTER the arithmetic that consumed the stage's values; returns
-  // true (warp-uniform) in the warp that released the stage last: its lane 0 refills the stage
-  ALTRO_DEV bool release_counted(int k, int lane, int consumer_warps) const {
-    __syncwarp();
-    unsigned last = 0;
-    if (lane == 0) {
-      unsigned* cnt = reinterpret_cast<unsigned*>(empty + ((c0 + k) % depth));
-      __threadfence_block();
-      const unsigned old = atomicAdd(cnt, 1u);
-      if (old == (unsigned)consumer_warps - 1u) {
-        *reinterpret_cast<volatile unsigned*>(cnt) = 0u;
-        __threadfence_block();
-        last = 1u;
-      }
-    }
-    return __shfl_sync(0xffffffffu, last, 0) != 0u;
-  }
   // consumer, all lanes of the warp, AFTER the arithmetic that consumed the stage's values
   ALTRO_DEV void release(int k, int lane) const {
     __syncwarp();

@@ -14,6 +14,7 @@
 // Model ids must match altro_b200/problems.py and include/altro_b200.h.
 #pragma once
 #include "linalg.cuh"
+#include "fastmath.cuh"
 
 namespace altro_b200 {
 
@@ -151,14 +152,27 @@ struct Bicycle5C {  // state [x,y,theta,delta,v], input [a, delta_dot]
   };
   ALTRO_DEV static Trig trig(const double* prm, const double* x) {
     const double L = prm[0], lr = prm[1];
+    // sincos and 1/x through fastmath.cuh: the library's bits, but one range test per pair of calls
+    // instead of a convergence region around each, so the four chains interleave
     double sd, cd, st, ct;
-    sincos(x[3], &sd, &cd);
-    sincos(x[2], &st, &ct);
+    if (sincos_in_range(x[3]) && sincos_in_range(x[2])) {
+      sincos_inrange(x[3], &sd, &cd);
+      sincos_inrange(x[2], &st, &ct);
+    } else {
+      sincos(x[3], &sd, &cd);
+      sincos(x[2], &st, &ct);
+    }
     const double by = lr * x[3];
     const double h2 = L * L + by * by;
     const double hyp = sqrt(h2);
-    const double inv = 1.0 / hyp;
-    const double icd = 1.0 / cd;
+    double inv, icd;
+    if (rcp_in_range(hyp) && rcp_in_range(cd)) {
+      inv = rcp_inrange(hyp);
+      icd = rcp_inrange(cd);
+    } else {
+      inv = 1.0 / hyp;
+      icd = 1.0 / cd;
+    }
     Trig t;
     t.cb = L * inv;
     t.sb = by * inv;

@@ -364,10 +364,7 @@ __global__ void __launch_bounds__((Model::n > kUnrollDim) ? 256 : kFwdThreads, (
   constexpr int n = Model::n, m = Model::m;
   constexpr unsigned kAll = 0xffffffffu;
   const int g = P.g0 + blockIdx.x;
-  const int tid = threadIdx.x, lid = tid & 31;
-  // role of this warp (0 rollout warp, then follower / speculating warps): hardware warp w of a CTA
-  // sits on scheduler w mod 4, so rotating the roles changes which roles share a scheduler
-  const int wid = ((tid >> 5) + (int)(blockDim.x >> 5) - P.role_shift) % (int)(blockDim.x >> 5);
+  const int tid = threadIdx.x, lid = tid & 31, wid = tid >> 5;
   // speculative candidates per round: one warp each, at most what SetSpeculation asked for (extra
   // warps only serve the knot-parallel sub-phases)
   constexpr bool follow = TrajSolver<Model, CON>::kStaged && FOLLOW;

@@ -93,19 +93,21 @@ def kernel_models(P, iters, evals):
     roll = float(np.maximum(evals.astype(np.float64) - iters, 0).sum())  # rollouts the search consumed
     # Jacobian entries kept in HBM: dense n^2 + nm unless the model packs them (models.cuh, JacPack)
     jac = {PR.MODEL_BICYCLE5: 15, PR.MODEL_BICYCLE4: 12}.get(P.model_id, n * n + n * m)
-    # sub-phases of k_phase_forward
+    # sub-phases of k_phase_forward.  The derivative half of a merit evaluation
+    # is done by the follower warp INSIDE the rollout pass (x_k, u_k handed over in shared memory),
+    # so it only adds the writes of [J], lx, lu (+ z_est): once per iteration for the backtracking
+    # search (the alpha0 evaluation), with every evaluation for the strong-Wolfe search
+    deriv = it if P.options.get("use_backtracking_linesearch") else roll
+    roll_d = 2 * (n + m) + 1 + m * n + m + (n + m) + rows       # r [xbar ubar q r c K d] (+ z)  w x,u
+    deriv_d = jac + n + m + 2 * rows                              # w J,lx,lu (+ z_est)
     sub = {
-        # r [xbar ubar q r c K d] (+ z rows)   w x,u
-        "fwd_rollout": dict(doubles=(2 * (n + m) + 1 + m * n + m) + (n + m) + rows, units=roll * N),
-        # one expansion per iteration (the point the search accepts): r x,u,q,r  w J,lx,lu (+ z, z_est)
-        "fwd_expand": dict(doubles=2 * (n + m) + (jac + n + m) + 2 * rows, units=it * (N + 1)),
-        # d(phi) scan: r K,d,J,lx,lu
-        "fwd_dphi_ls": dict(doubles=m * n + m + jac + n + m, units=it * N),
-        # costates r x,xbar,P,p  w y;  residuals r x,u,y,y+,J,lx,lu  w xbar,ubar
-        "fwd_criteria": dict(doubles=(2 * n + n * n + n) + n + (2 * n + jac + 2 * (n + m)) + (n + m) + rows,
+        "fwd_rollout": dict(doubles=roll_d, units=roll * N, extra_bytes=8.0 * deriv_d * deriv * N),
+        # post-search pass: r x,u, xbar, P,p, J,lx,lu (or q,r where the accepted point still needs its
+        # expansion)  w y, xbar, ubar
+        "fwd_criteria": dict(doubles=(n + m) + n + (n * n + n) + (jac + n + m) + n + (n + m) + rows,
                              units=it * (N + 1)),
     }
-    fwd_bytes = sum(8.0 * v["doubles"] * v["units"] for v in sub.values())
+    fwd_bytes = sum(8.0 * v["doubles"] * v["units"] + v.get("extra_bytes", 0.0) for v in sub.values())
     models = {
         # sweep: r J,lx,lu  w K,d,P,p (+ z_est rows).  scan: r q,r,c,K,d,x,u,J  w lx,lu (+ duals);
         # unconstrained problems after their first iteration scan only K,d,J,lx,lu and write nothing
@@ -115,8 +117,8 @@ def kernel_models(P, iters, evals):
                             else (m * n + m + jac + n + m)),
                          units=it * N,
                          extra_bytes=0.0 if rows else 8.0 * (n + m + 1 + n + m) * P.B * N),
-        "forward": dict(kernel="k_phase_forward (line search: rollouts + expansion + d(phi) scan + "
-                               "state machines; costates, residuals, AL update)",
+        "forward": dict(kernel="k_phase_forward (line search: rollout + follower + speculating warps, "
+                               "state machines; fused expansion / costate / residual / copy pass, AL update)",
                         doubles=0.0, units=0.0, extra_bytes=fwd_bytes),
         "expand": dict(kernel="k_phase_expand (prologue: Jacobians, projected duals, gradients)",
                        doubles=2 * (n + m) + (jac + n + m) + 2 * rows, units=P.B * (N + 1)),
