@@ -10,9 +10,10 @@
 //                     accepted trajectory, ~40 % of the reference's merit evaluations; the scan
 //                     provably reproduces it, TrajSolver::phi0_step), streaming the knot records
 //                     through a shared-memory ring of TMA bulk copies (linalg.cuh, BulkRing).
-//   k_phase_forward   one CTA per group: the whole line search (rounds of speculative rollouts,
-//                     knot-parallel expansion, d(phi) scan, state machines), then costates,
-//                     residuals, the convergence / AL decision and the post-update expansion.
+//   k_phase_forward   one CTA per group: the whole line search (rounds of one pass each: rollout
+//                     warp, follower warp for the derivative half, speculating warps; state
+//                     machines), then one fused expansion / costate / residual / copy pass, the
+//                     convergence / AL decision and the post-update expansion.
 // The host enqueues iterations back to back on the sub-batch's stream and looks at a stop counter
 // two iterations late (an asynchronous 4-byte copy), so the GPU never waits for the host.
 // Decisions (line search, dual/penalty update, convergence) are identical to the reference.
@@ -321,24 +322,28 @@ __device__ __forceinline__ void for_knot_items(unsigned lanemask, int g, int kno
 // (:207-231, :148-157), the convergence test and the dual / penalty update (:459-489) -- for ONE
 // group of 32 problems per CTA, with no host in the loop.  The CTA iterates line-search ROUNDS
 // until every lane's state machine is done:
-//   rollout pass    warp 0 rolls out the step each lane's machine asked for (alpha_eval) into the
-//                   working trajectory x_, u_; warps >= 1 roll out, for the lanes whose search is
-//                   (or is about to be) backtracking, the halvings SimpleBacktracking would try
-//                   next (linesearch.cpp:385-412) -- the (lane, halving) pairs are packed densely
-//                   over their threads; halvings <= nstore keep their trajectory in a candidate
-//                   slot, deeper ones return the merit value only (an accepted one is rolled out
-//                   again, TF_REROLL).  All warps consume ONE staged copy of the knot rows
-//                   [xbar ubar q r c K d] through a full/empty mbarrier pipeline (BulkPipe): no
-//                   CTA barrier per knot, warps drift up to depth - 1 knots apart.
-//   expansion       knot-parallel over the whole CTA: [A B], projected duals, lx, lu of the trial
-//                   point of the lanes that asked for the derivative (solver.cpp:303-312).
-//   d(phi) + update warp 0: the phi' recurrence (solver.cpp:306-315) as a staged scan, then every
-//                   lane's LsMachine is fed the value of its request and, while it keeps
-//                   backtracking, the precomputed halvings in the order the reference would have
-//                   evaluated them; feeding stops at the first accept, so decisions and evaluation
-//                   counts are those of the sequential search.
-// then, still in the same launch: the post-search expansion of an accepted backtracking step
-// (:256-262), costates, residuals, the decision, and the expansion after a dual update (:483-486).
+//   rollout pass    the ROLLOUT warp (warp 0, lane = problem) rolls out the step each lane's machine
+//                   asked for (alpha_eval) into the working trajectory x_, u_; the speculating
+//                   warps roll out, for the lanes whose search is (or is about to be)
+//                   backtracking, the halvings SimpleBacktracking would try next
+//                   (linesearch.cpp:385-412) -- the (lane, halving) pairs are packed densely over
+//                   their threads; halvings <= nstore keep their trajectory in a candidate slot,
+//                   deeper ones return the merit value only (an accepted one is rolled out again,
+//                   TF_REROLL).  The warps with work consume ONE staged copy of the knot rows
+//                   [xbar ubar q r c K d] through RollPipe (linalg.cuh): no CTA barrier per knot,
+//                   nobody waits on a slower warp, the last warp out of a stage refills it.
+//   derivatives     FOLLOW variant (default): the FOLLOWER warp (warp 1) does [A B], projected duals,
+//                   lx, lu and the phi' recurrence of the requested step (solver.cpp:303-315) one
+//                   knot behind the rollout warp, from x_k, u_k handed over in the stage.
+//                   Otherwise: knot-parallel expansion by warps >= 1 and a staged phi' scan by warp 0
+//                   behind them.
+//   update          warp 0: every lane's LsMachine is fed the value of its request and, while it
+//                   keeps backtracking, the precomputed halvings in the order the reference would
+//                   have evaluated them; feeding stops at the first accept, so decisions and
+//                   evaluation counts are those of the sequential search.
+// then, still in the same launch: ONE pass that does the post-search expansion of an accepted
+// backtracking step (:256-262), the costates, the residuals and CopyTrajectory
+// (TrajSolver::post_chunk), the decision, and the expansion after a dual update (:483-486).
 // active_out: incremented by the number of problems of the group that stopped in this iteration.
 // CTA shape of the staged variants (register budget = 65536 / (threads * CTAs per SM))
 #ifndef ALTRO_FWD_THREADS
