@@ -221,13 +221,7 @@ ErrorCodes ALTROSolver::SetTimeStep(float h, int k_start, int k_stop) {
   if (err != ErrorCodes::NoError) return err;
   if (h <= 0.0f) return ErrorCodes::TimestepNotPositive;
   for (int k = k_start; k < k_stop; ++k) solver_->h_[k] = h;
-  for (int k = 0; k < GetHorizonLength(); ++k) {
-    if (solver_->h_[k] > 0.0f && solver_->h_[k] != h) {
-      return ALTRO_THROW("The device path needs one time step for the whole horizon.",
-                         ErrorCodes::Unsupported);
-    }
-  }
-  return EC(altro_b200_set_time_step(solver_->handle, h));
+  return EC(altro_b200_set_time_step_range(solver_->handle, h, k_start, k_stop));
 }
 
 // altro_solver.cpp:68-81

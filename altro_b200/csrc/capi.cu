@@ -268,6 +268,9 @@ struct altro_b200_solver {
   std::vector<double*> off_b;
   // host mirrors of the shared weights
   std::vector<double> Qd_h, Rd_h, lin_h;
+  std::vector<float> h_h;   // per-knot time steps (empty until SetTimeStep is used with a range)
+  bool h_uniform = true;
+  float* hk = nullptr;      // device copy of h_h while the steps differ
   // which setter call wrote the linear cost terms q_k, r_k, c_k of knot k: knots written by ONE call
   // with k-independent values share an id (> 0), anything else is -1 (DeviceProblem::qrc_uniform)
   std::vector<int> qrc_id;
@@ -616,6 +619,30 @@ int altro_b200_set_time_step(altro_b200_solver* s, float h) {  // altro_solver.c
   if (!s) return ALTRO_B200_INVALID_POINTER;
   if (h <= 0.0f) return ALTRO_B200_TIMESTEP_NOT_POSITIVE;
   s->h = h;
+  if (!s->h_h.empty()) std::fill(s->h_h.begin(), s->h_h.end(), h);
+  s->h_uniform = true;
+  return ALTRO_B200_NO_ERROR;
+}
+
+// SetTimeStep(h, k_start, k_stop) (altro_solver.cpp:49-63): knots [k_start, k_stop) of the horizon.
+// While all N steps are equal the kernels use the scalar; otherwise a per-knot table on the device.
+int altro_b200_set_time_step_range(altro_b200_solver* s, float h, int k_start, int k_stop) {
+  if (!s) return ALTRO_B200_INVALID_POINTER;
+  int e = resolve_range(s, k_start, k_stop, false);
+  if (e) return e;
+  if (h <= 0.0f) return ALTRO_B200_TIMESTEP_NOT_POSITIVE;
+  if (empty_range(k_start, k_stop)) return ALTRO_B200_NO_ERROR;
+  if (s->h_h.empty()) s->h_h.assign((size_t)s->N, s->h);  // s->h is 0 until a step has been set
+  for (int k = k_start; k < k_stop && k < s->N; ++k) s->h_h[k] = h;
+  s->h_uniform = true;
+  for (int k = 1; k < s->N; ++k) s->h_uniform = s->h_uniform && s->h_h[k] == s->h_h[0];
+  s->h = s->h_uniform ? s->h_h[0] : 0.0f;
+  if (!s->h_uniform) {
+    CUDA_OK(cudaSetDevice(s->device));
+    if (!s->hk) DALLOC(s, s->hk, (long)s->N);
+    CUDA_OK(cudaMemcpyAsync(s->hk, s->h_h.data(), sizeof(float) * s->N, cudaMemcpyHostToDevice, s->stream));
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+  }
   return ALTRO_B200_NO_ERROR;
 }
 
@@ -1076,7 +1103,12 @@ int altro_b200_initialize(altro_b200_solver* s) {  // altro_solver.cpp:225-229
   if (!s) return ALTRO_B200_INVALID_POINTER;
   if (s->initialized) return ALTRO_B200_SOLVER_ALREADY_INITIALIZED;
   if (!s->dims_set) return ALTRO_B200_STATE_DIM_UNKNOWN;          // knotpoint_data.cpp:242-246
-  if (!(s->h > 0.0f)) return ALTRO_B200_TIMESTEP_NOT_POSITIVE;    // :259-263
+  if (s->h_uniform) {
+    if (!(s->h > 0.0f)) return ALTRO_B200_TIMESTEP_NOT_POSITIVE;    // :259-263
+  } else {
+    for (int k = 0; k < s->N; ++k)
+      if (!(s->h_h[k] > 0.0f)) return ALTRO_B200_TIMESTEP_NOT_POSITIVE;
+  }
   if (s->model < 0) return ALTRO_B200_DYNAMICS_FUN_NOT_SET;       // :264-269
   if (!s->cost_set) return ALTRO_B200_COST_FUN_NOT_SET;           // :271-275
   if (!find_launcher(s->model, s->n, s->m, s->params)) return ALTRO_B200_ERR_UNSUPPORTED;
@@ -1255,6 +1287,7 @@ static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   P.Rs = s->Rs;
   P.zrows = s->con_h.rows;
   P.h = s->h;
+  P.hk = s->h_uniform ? nullptr : s->hk;
   memcpy(P.model_params, s->params, sizeof(P.model_params));
   P.lin = s->lin;
   P.Qd = s->Qd;

@@ -90,6 +90,7 @@ struct DeviceProblem {
   int zrows;     // constraint rows per knot (0 when unconstrained)
   long Rs;       // candidate-slot record stream [slot][group][knot][x rows | u rows][32]
   float h;
+  const float* hk;  // [N] per-knot time steps, or null when every knot uses h
   double model_params[8];
   const double* lin;  // MODEL_LINEAR: per knot [A (n*n) | B (n*m) | f (n)], shared by the batch
 

@@ -168,16 +168,19 @@ struct TrajSolver {
     JP::pack(A, Bm, J);
     store_block<kV>(P.A + go, S, k, J);
   }
+  // time step of knot k (SetTimeStep(h, k_start, k_stop), altro_solver.cpp:49-63): one value for
+  // the horizon unless the host installed a per-knot table
+  ALTRO_DEV float hof(int k) const { return P.hk ? P.hk[k] : P.h; }
   ALTRO_DEV void load_jac(int k, double* A, double* Bm) const {
     double J[kV];
     load_block<kV>(P.A + go, S, k, J);
-    JP::unpack(J, P.h, A, Bm);
+    JP::unpack(J, hof(k), A, Bm);
   }
-  // the same from a landed stage of the TMA ring (J rows start at `row`)
-  ALTRO_DEV void unstage_jac(const double* stage, int row, int lane, double* A, double* Bm) const {
+  // the same from a landed stage of the TMA ring (J rows of knot k start at `row`)
+  ALTRO_DEV void unstage_jac(const double* stage, int row, int lane, int k, double* A, double* Bm) const {
     double J[kV];
     unstage_block<kV>(stage, row, lane, J);
-    JP::unpack(J, P.h, A, Bm);
+    JP::unpack(J, hof(k), A, Bm);
   }
 
   // rows per knot each sequential sweep stages through the TMA ring (solver_phases.cuh)
@@ -247,7 +250,7 @@ struct TrajSolver {
 #pragma unroll
       for (int i = 0; i < n; ++i) xn[i] = t[i] + T[n * n + n * m + i];
     } else {
-      Model::dynamics(P.model_params, x, u, P.h, xn);
+      Model::dynamics(P.model_params, x, u, hof(k), xn);
     }
   }
   ALTRO_DEV void jacobian(int k, const double* x, const double* u, double* A, double* B) const {
@@ -258,7 +261,7 @@ struct TrajSolver {
 #pragma unroll
       for (int i = 0; i < n * m; ++i) B[i] = T[n * n + i];
     } else {
-      Model::jacobian(P.model_params, x, u, P.h, A, B);
+      Model::jacobian(P.model_params, x, u, hof(k), A, B);
     }
   }
 
@@ -267,7 +270,7 @@ struct TrajSolver {
   ALTRO_DEV void dynamics_jacobian(int k, const double* x, const double* u, double* xn, double* A,
                                    double* B) const {
     if constexpr (!kLinear && has_dynamics_jacobian<Model>::value) {
-      Model::dynamics_jacobian(P.model_params, x, u, P.h, xn, A, B);
+      Model::dynamics_jacobian(P.model_params, x, u, hof(k), xn, A, B);
     } else {
       dynamics(k, x, u, xn);
       jacobian(k, x, u, A, B);
@@ -1258,7 +1261,7 @@ struct TrajSolver {
       double J[kV];  // through the packed form, like every other reader of [A B]
       JP::pack(A, Bm, J);
       store_block<kV>(P.A + go, S, k, J);
-      JP::unpack(J, P.h, A, Bm);
+      JP::unpack(J, hof(k), A, Bm);
     }
     stage_gradient(k, x, u, q, r, false, lx, lu);
     al_terms(k, x, u, false, true, lx, lu);
@@ -1440,7 +1443,7 @@ struct TrajSolver {
           double J[kV];
           JP::pack(A, Bm, J);
           store_block<kV>(P.A + go, S, k, J);
-          JP::unpack(J, P.h, A, Bm);
+          JP::unpack(J, hof(k), A, Bm);
         }
         stage_gradient(k, x, u, q, r, terminal, lx, lu);
         al_terms(k, x, u, terminal, true, lx, lu);

@@ -132,7 +132,7 @@ __device__ __forceinline__ void backward_scans(const DeviceProblem& P, TrajSolve
         if (active) {
           unstage_block<m * n>(st, 0, lane, K);
           unstage_block<m>(st, m * n, lane, d);
-          s.unstage_jac(st, kRows1, lane, A, Bm);
+          s.unstage_jac(st, kRows1, lane, k, A, Bm);
           unstage_block<n>(st, kRows1 + kV, lane, lx);
           unstage_block<m>(st, kRows1 + kV + n, lane, lu);
           s.dphi_step(K, d, A, Bm, lx, lu, dxda, dphi0);
@@ -171,7 +171,7 @@ __device__ __forceinline__ void backward_scans(const DeviceProblem& P, TrajSolve
         unstage_block<m>(st, oD, lane, d);
         unstage_block<n>(st, oX, lane, x);
         unstage_block<m>(st, oU, lane, u);
-        s.unstage_jac(st, oJ, lane, A, Bm);
+        s.unstage_jac(st, oJ, lane, k, A, Bm);
       }
       if (zr) s.zstage = st + kRowsPhi * 32 + lane;
       if (active) s.phi0_step(k, x, u, q, r, cval, K, d, A, Bm, dxda, phi0, dphi0);
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(32) k_phase_backward(const __grid_constant__ D
       const double* st = ring.wait();
       double A[n * n], Bm[n * m], Qx[n], Qu[m];
       if (alive) {
-        s.unstage_jac(st, 0, lane, A, Bm);
+        s.unstage_jac(st, 0, lane, k, A, Bm);
         unstage_block<n>(st, kV, lane, Qx);
         unstage_block<m>(st, kV + n, lane, Qu);
       }
@@ -722,7 +722,7 @@ __global__ void __launch_bounds__((Model::n > kUnrollDim) ? 256 : kFwdThreads, (
             if (had_deriv) {
               unstage_block<m * n>(st, 0, lid, K);
               unstage_block<m>(st, m * n, lid, d);
-              s.unstage_jac(st, kRows1, lid, A, Bm);
+              s.unstage_jac(st, kRows1, lid, k, A, Bm);
               unstage_block<n>(st, kRows1 + kV, lid, lx);
               unstage_block<m>(st, kRows1 + kV + n, lid, lu);
               s.dphi_step(K, d, A, Bm, lx, lu, dxda, dphi);

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(32 * TeamShape<Model::n, Model::m>::W)
     // ---- (b) T1 = A' P+, T2 = B' P+ : own columns                      tvlqr.cpp:135, :139
     double A[kRegJ ? n * n : 1], Bm[kRegJ ? n * m : 1];
     if constexpr (kRegJ) {
-      if (alive) s.unstage_jac(st, 0, lane, A, Bm);
+      if (alive) s.unstage_jac(st, 0, lane, k, A, Bm);
     }
     // element (l, i) of A / B: registers for the small blocks, in place from the stage otherwise
     // (macros, not lambdas: a by-reference capture would pin the arrays in local memory)

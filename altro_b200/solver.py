@@ -71,6 +71,7 @@ def load_library():
         L.altro_b200_device_bytes.restype = C.c_long
         L.altro_b200_device_bytes.argtypes = [C.c_void_p]
         L.altro_b200_set_time_step.argtypes = [C.c_void_p, C.c_float]
+        L.altro_b200_set_time_step_range.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int]
         L.altro_b200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         vp = C.c_void_p
         L.altro_b200_set_dimension.argtypes = [vp, C.c_int, C.c_int]
@@ -177,8 +178,12 @@ class BatchSolver:
         self._ck(self.L.altro_b200_set_dimension(self.h, num_states, num_inputs), "SetDimension")
         self.n, self.m = num_states, num_inputs
 
-    def SetTimeStep(self, h):
-        self._ck(self.L.altro_b200_set_time_step(self.h, C.c_float(h)), "SetTimeStep")
+    def SetTimeStep(self, h, k_start=None, k_stop=0):
+        """SetTimeStep(h) for the whole horizon, or (h, k_start, k_stop) for knots [k_start, k_stop)."""
+        if k_start is None:
+            self._ck(self.L.altro_b200_set_time_step(self.h, C.c_float(h)), "SetTimeStep")
+        else:
+            self._ck(self.L.altro_b200_set_time_step_range(self.h, C.c_float(h), k_start, k_stop), "SetTimeStep")
 
     def SetExplicitDynamics(self, model_id, params=()):
         prm, pp = _d(list(params) + [0.0] * (8 - len(params)))

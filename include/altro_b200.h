@@ -181,6 +181,9 @@ int altro_b200_set_stream(altro_b200_solver *s, void *cuda_stream);
 
 int altro_b200_set_dimension(altro_b200_solver *s, int num_states, int num_inputs); /* SetDimension */
 int altro_b200_set_time_step(altro_b200_solver *s, float h);                        /* SetTimeStep  */
+/* SetTimeStep(h, k_start, k_stop) (src/altro/altro_solver.cpp:49-63) for knots [k_start, k_stop) of
+ * the horizon; index conventions of the reference (ALL_INDICES / LAST_INDEX, k_stop = 0: one knot) */
+int altro_b200_set_time_step_range(altro_b200_solver *s, float h, int k_start, int k_stop);
 /* SetExplicitDynamics with a device model id instead of callbacks */
 int altro_b200_set_model(altro_b200_solver *s, int model_id, const double *params, int nparams);
 /* KnotPointData::SetLinearDynamics for knots [k_start,k_stop): A n*n, B n*m, f n (f may be NULL);

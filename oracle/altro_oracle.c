@@ -494,6 +494,11 @@ void oracle_set_options(oracle_solver *s, const oracle_options *o) { s->opts = *
 void oracle_set_time_step(oracle_solver *s, float h) {
   for (int k = 0; k < s->N; ++k) s->data_[k].h = h;
 }
+/* SetTimeStep(h, k_start, k_stop), altro_solver.cpp:49-63 */
+void oracle_set_time_step_range(oracle_solver *s, float h, int k_start, int k_stop) {
+  for (int k = k_start; k < k_stop && k < s->N; ++k)
+    if (k >= 0) s->data_[k].h = h;
+}
 
 void oracle_set_model(oracle_solver *s, int model_id, const double *params, int nparams) {
   s->model_id = model_id;

@@ -134,6 +134,7 @@ oracle_solver *oracle_create(int N, int n, int m);
 void oracle_destroy(oracle_solver *s);
 void oracle_set_options(oracle_solver *s, const oracle_options *o);
 void oracle_set_time_step(oracle_solver *s, float h);
+void oracle_set_time_step_range(oracle_solver *s, float h, int k_start, int k_stop);
 void oracle_set_model(oracle_solver *s, int model_id, const double *params, int nparams);
 void oracle_set_dynamics_callback(oracle_solver *s, oracle_dyn_fn dyn, oracle_dyn_fn jac,
                                   void *ud);

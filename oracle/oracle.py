@@ -123,6 +123,7 @@ def lib():
             getattr(L, f).restype = C.c_double
         L.oracle_get_merit_evals.restype = C.c_long
         L.oracle_set_time_step.argtypes = [C.c_void_p, C.c_float]
+        L.oracle_set_time_step_range.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int]
         L.oracle_set_penalty.argtypes = [C.c_void_p, C.c_double]
         L.oracle_merit_function.argtypes = [C.c_void_p, C.c_double, dptr, dptr]
         L.oracle_ls_run.argtypes = [C.POINTER(LineSearch), MERIT_CB, C.c_void_p, C.c_double,
@@ -308,8 +309,11 @@ class OracleSolver:
     def SetOptions(self, opts):
         self.L.oracle_set_options(self.h, C.byref(opts))
 
-    def SetTimeStep(self, h):
-        self.L.oracle_set_time_step(self.h, C.c_float(h))
+    def SetTimeStep(self, h, k_start=None, k_stop=None):
+        if k_start is None:
+            self.L.oracle_set_time_step(self.h, C.c_float(h))
+        else:
+            self.L.oracle_set_time_step_range(self.h, C.c_float(h), k_start, k_stop)
 
     def SetModel(self, model_id, params=()):
         prm, pp = _d(list(params) + [0.0] * (8 - len(params)))

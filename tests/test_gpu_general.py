@@ -317,3 +317,63 @@ def test_bound_setters_reproduce_control_box(oracle):
     assert np.abs(u0 + 1.0).max() < 1e-4
     assert np.linalg.norm(s.GetStates()[0, -1]) < 1e-4
     s.close()
+
+
+def test_per_knot_time_steps_match_oracle(oracle):
+    """SetTimeStep(h, k_start, k_stop) (altro_solver.cpp:49-63) with two different steps over the
+    horizon on the nonlinear pendulum (Jacobians, rollouts, packed [A B] all depend on h_k): the
+    pipeline against the oracle, and bit for bit against the persistent twin."""
+    rng = np.random.default_rng(21)
+    n, m, N, B = 2, 1, 40, 40
+    h1, h2, ksw = np.float32(0.05), np.float32(0.075), 17   # (0.1 makes this search fail on CPU and GPU alike)
+    Qd, Rd, Qf = np.full(n, 1e-2), np.full(m, 1e-3), np.full(n, 1.0)
+    xf = np.array([np.pi, 0.0])
+    x0 = rng.uniform(-0.5, 0.5, size=(B, n))
+
+    def build(mode):
+        s = BatchSolver(N, B)
+        s.SetDimension(n, m)
+        s.SetTimeStep(float(h1), 0, ksw)
+        s.SetTimeStep(float(h2), ksw, N)
+        s.SetExplicitDynamics(PR.MODEL_PENDULUM, [])
+        s.SetInitialState(x0)
+        s.SetLQRCost(Qd, Rd, xf, np.zeros(m), 0, N)
+        s.SetLQRCost(Qf, Rd, xf, np.zeros(m), N, N + 1)
+        s.Initialize()
+        s.SetInput(np.array([0.1]))
+        s.SetOptions(default_options(iterations_max=60))
+        s.SetSolveMode(mode)
+        s.Solve()
+        return s
+
+    s = build(0)
+    twin = build(1)
+    assert np.array_equal(s.GetStates(), twin.GetStates()) and np.array_equal(s.GetInputs(), twin.GetInputs())
+    assert np.array_equal(s.GetIterations(), twin.GetIterations())
+    twin.close()
+    for b in range(0, B, 5):
+        o = oracle.OracleSolver(N, n, m)
+        o.SetTimeStep(float(h1), 0, ksw)
+        o.SetTimeStep(float(h2), ksw, N)
+        o.SetModel(oracle.MODEL_PENDULUM, [])
+        o.SetInitialState(x0[b])
+        for k in range(N):
+            o.SetLQRCost(k, Qd, Rd, xf, np.zeros(m))
+        o.SetLQRCost(N, Qf, Rd, xf, np.zeros(m))
+        o.Initialize()
+        o.SetInput(np.array([0.1]))
+        o.SetOptions(oracle.default_options(iterations_max=60))
+        st = o.Solve()
+        assert st == 0 and o.GetIterations() > 4
+        assert_same_solve(s, o, b, st)
+    # a horizon with a knot that never got a step is refused like the reference refuses it
+    s2 = BatchSolver(N, 2)
+    s2.SetDimension(n, m)
+    s2.SetTimeStep(0.05, 0, N - 1)
+    s2.SetExplicitDynamics(PR.MODEL_PENDULUM, [])
+    s2.SetInitialState(x0[:2])
+    s2.SetLQRCost(Qd, Rd, xf, np.zeros(m), 0, N + 1)
+    with pytest.raises(altro_b200.AltroB200Error):
+        s2.Initialize()
+    s2.close()
+    s.close()
