@@ -179,9 +179,10 @@ def test_results_do_not_depend_on_batch_neighbours(oracle):
     lambda: PR.chain(B=64, n=6, m=2, N=50, control_box=True),
 ])
 def test_phase_pipeline_equals_persistent_kernel(make):
-    """The production path (two kernels per iteration: staged sweeps, speculative line-search rounds,
-    knot-parallel expansion, alpha=0 scan instead of a re-rollout) and the single persistent kernel
-    are two schedules of the same arithmetic: results must be bit-identical."""
+    """The production path (two kernels per iteration: staged sweeps, line-search rounds with the
+    rollout / follower / speculating warps, fused post-search pass, alpha=0 scan instead of a
+    re-rollout) and the single persistent kernel are two schedules of the same arithmetic: results
+    must be bit-identical."""
     P = make()
     a = altro_b200.solve_problem(P, mode=0)
     b = altro_b200.solve_problem(P, mode=1)
