@@ -1395,9 +1395,12 @@ int altro_b200_solve_async(altro_b200_solver* s) {  // altro_solver.cpp:257-260
   for (int i = 0; i <= PH_FORWARD; ++i) before += s->ph.launches[i];
   int nsplit = s->nsplit;
   // DESIGN.md "pipelined sub-batches": the Riccati sweep keeps one warp per group busy, the
-  // forward kernel up to eight; sub-batches on separate streams let the two overlap
-  // (bicycle 16384, one B200: 57.6 ms with 1, 47.2 with 4, 45.0 with 8, the same with 16 and 32)
-  if (nsplit <= 0) nsplit = s->G >= 512 ? 8 : (s->G >= 256 ? 4 : (s->G >= 128 ? 2 : 1));
+  // forward kernel up to six; sub-batches on separate streams let the kernels of different
+  // iterations overlap (bicycle 16384, one B200: 45.3 ms with 1, 37.8 with 4, 37.3 with 8, 38.0 with
+  // 16).  It only pays when the batch does not fit the machine at once -- two line-search CTAs per
+  // SM; below that every split just adds launches to a latency-bound chain (scotty 8192 = 256
+  // groups: 57.2 ms with 1, 62.0 with 4)
+  if (nsplit <= 0) nsplit = s->G > 2 * s->ph.num_sms ? 8 : 1;
   nsplit = std::min(std::min(nsplit, (int)altro_b200_solver::kMaxSplit), s->G);
   const int per = (s->G + nsplit - 1) / nsplit;
   nsplit = (s->G + per - 1) / per;  // no empty sub-batch
