@@ -241,7 +241,7 @@ struct altro_b200_solver {
   int backward_team = -1;
   // forward kernel variant: 1 the derivative half of a merit evaluation is done by a follower warp
   // behind the rollout warp (default), 0 separate knot-parallel expansion + d(phi) scan
-  int inline_deriv = 1;
+  int follow_deriv = 1;
   int qrc_uniform_enable = 1;  // ALTRO_B200_QRC_UNIFORM=0 streams [q r c] with every knot regardless
   int spec_round1 = 1;
   int fused_post = 1;  // forward kernel: everything between the search and the decision as one pass over the knots
@@ -493,7 +493,7 @@ altro_b200_solver* altro_b200_create(int horizon_length, int batch, int device) 
   memset(&s->con_h, 0, sizeof(s->con_h));
   // test hook: run a whole test suite with the other Riccati schedule (results are bit-identical)
   if (const char* env = getenv("ALTRO_B200_BACKWARD_TEAM")) s->backward_team = atoi(env) != 0;
-  if (const char* env = getenv("ALTRO_B200_INLINE_DERIV")) s->inline_deriv = atoi(env) != 0;
+  if (const char* env = getenv("ALTRO_B200_FOLLOWER")) s->follow_deriv = atoi(env) != 0;
   if (const char* env = getenv("ALTRO_B200_QRC_UNIFORM")) s->qrc_uniform_enable = atoi(env) != 0;
   if (const char* env = getenv("ALTRO_B200_SPEC_ROUND1")) s->spec_round1 = atoi(env) != 0;
   if (const char* env = getenv("ALTRO_B200_FUSED_POST")) s->fused_post = atoi(env) != 0;
@@ -1328,7 +1328,7 @@ static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   P.alpha_bt = s->alpha_bt;
   P.nslots = s->nslots;
   P.nstore = s->nslots > 1 ? s->nstore : 0;
-  P.inline_deriv = s->inline_deriv;
+  P.follow_deriv = s->follow_deriv;
   P.fused_post = s->fused_post;
   P.spec_round1 = s->spec_round1;
   P.prof_tid = getenv("ALTRO_B200_PROF_TID") ? atoi(getenv("ALTRO_B200_PROF_TID")) : 0;

@@ -140,9 +140,10 @@ struct DeviceProblem {
   // concurrently, each into its own copy of the working trajectory
   int nslots;           // candidates per speculative round (>= 1): slot 0 = the requested step
   int nstore;           // speculative slots 1..nstore also keep their trajectory (slot buffers)
-  // 1: the rollout of a request that wants phi' does the trial point's expansion and the phi'
-  // recurrence in line (no separate expansion / d(phi) scan, no re-read of x, u, [J], lx, lu)
-  int inline_deriv;
+  // 1: a follower warp of k_phase_forward does the derivative half of a merit evaluation behind the
+  // rollout warp (no separate expansion / d(phi) scan, no re-read of x, u, [J], lx, lu); 0: separate
+  // knot-parallel expansion + staged scan
+  int follow_deriv;
   // 1: the linear cost terms q_k, r_k, c_k are the same for every k < N (one SetLQRCost call over the
   // stage knots with a goal-type reference): the sweeps read them once from knot 0 instead of
   // streaming [q r c] with every knot

@@ -105,7 +105,7 @@ static int run_phased(const DeviceProblem& P, cudaStream_t st, PhaseHost* H) {
     int depth = 0, rows = 0;
     size_t sm = 0;
     // follower variant: the derivative half of a merit evaluation by a warp behind the rollout warp
-    const bool follow = TS::kStaged && P.inline_deriv != 0;
+    const bool follow = TS::kStaged && P.follow_deriv != 0;
     if (TS::kStaged) {
       // stage rows: the rollout's [xbar ubar q r c K d] (+ duals) plus, in follower mode, x_k, u_k of
       // the rollout warp; otherwise the d(phi) scan's [K d] [J] [lx lu] must fit as well

@@ -1,5 +1,5 @@
 #!/bin/bash
-T=${1:-r02r}
+T=${1:-r02}
 mkdir -p gpurun_out
 run() {  # name, env...
   name=$1; shift
@@ -20,8 +20,8 @@ if tot[8]:
         if tot[13+r]: print("   round %d: passes %d, cycles/knot %.0f" % (r, tot[13+r], tot[9+r]/tot[13+r]/100))
 PY
 }
-run follow ALTRO_B200_INLINE_DERIV=1
-run lean ALTRO_B200_INLINE_DERIV=0
-SLOTS=1 run follow_nospec ALTRO_B200_INLINE_DERIV=1
-SLOTS=1 run lean_nospec ALTRO_B200_INLINE_DERIV=0
-SLOTS=3 run follow_2spec ALTRO_B200_INLINE_DERIV=1
+run w0 ALTRO_B200_PROF_TID=0
+run follower ALTRO_B200_PROF_TID=32
+run spec1 ALTRO_B200_PROF_TID=64
+run spec4 ALTRO_B200_PROF_TID=160
+python tools/diag_hang.py 16384 8 6
