@@ -33,6 +33,8 @@ struct TvArgs {
   double reg;
   int is_diag;
   double *K, *d, *P, *p, *dV;
+  // optional: the action-value expansion of every knot (outputs of the reference, tvlqr.cpp:123-152)
+  double *oQxx, *oQuu, *oQux, *oQx, *oQu;
   int* status;
   // forward
   const double* x0;
@@ -132,6 +134,13 @@ __global__ void k_tvlqr_backward(TvArgs a) {
       double s = ld(a.r + b, S, k, m, i);
       for (int l = 0; l < n; ++l) s = fma(Bm[l + n * i], t[l], s);
       Qu[i] = s;
+    }
+    if (a.oQxx) {
+      for (int i = 0; i < n * n; ++i) a.oQxx[((long)k * n * n + i) * S + b] = Qxx[i];
+      for (int i = 0; i < m * m; ++i) a.oQuu[((long)k * m * m + i) * S + b] = Quu[i];
+      for (int i = 0; i < m * n; ++i) a.oQux[((long)k * m * n + i) * S + b] = Qux[i];
+      for (int i = 0; i < n; ++i) a.oQx[((long)k * n + i) * S + b] = Qx[i];
+      for (int i = 0; i < m; ++i) a.oQu[((long)k * m + i) * S + b] = Qu[i];
     }
     // gains, :155-166
     for (int i = 0; i < m * n; ++i) K[i] = Qux[i];
@@ -360,35 +369,13 @@ bool have_device() {
   return cudaGetDeviceCount(&cnt) == cudaSuccess && cnt > 0;
 }
 
-}  // namespace
-
-extern "C" {
-
-// fixed-size, TMA-staged workspace path for the compiled-in shapes (tvlqr_batch.cu); -1 = not compiled in
-int altro_b200_tvlqr_cached_backward(int batch, int n, int m, int N, const double* A, const double* B,
-                                     const double* f, const double* Q, const double* R, const double* H,
-                                     const double* q, const double* r, double reg, bool is_diag, double* K,
-                                     double* d, double* P, double* p, double* delta_V, int* status);
-int altro_b200_tvlqr_cached_forward(int batch, int n, int m, int N, const double* A, const double* B,
-                                    const double* f, const double* K, const double* d, const double* P,
-                                    const double* p, const double* x0, double* x, double* u, double* y);
-
-int altro_b200_tvlqr_backward_batch(int batch, int n, int m, int N, const double* A,
-                                    const double* B, const double* f, const double* Q,
-                                    const double* R, const double* H, const double* q,
-                                    const double* r, double reg, bool is_diag, double* K,
-                                    double* d, double* P, double* p, double* delta_V,
-                                    int* status) {
-  if (!A || !B || !f || !Q || !R || !q || !r) return ALTRO_B200_INVALID_POINTER;
-  if (!is_diag && !H) return ALTRO_B200_INVALID_POINTER;
-  if (n <= 0 || m <= 0 || batch <= 0 || N <= 0) return ALTRO_B200_DIMENSION_UNKNOWN;
-  if (n > 16 || m > 8) return ALTRO_B200_ERR_UNSUPPORTED;
-  if (!have_device()) return ALTRO_B200_ERR_NO_DEVICE;
-  {
-    const int e = altro_b200_tvlqr_cached_backward(batch, n, m, N, A, B, f, Q, R, H, q, r, reg, is_diag, K, d,
-                                                   P, p, delta_V, status);
-    if (e != -1) return e;
-  }
+// The generic (problem-fastest SoA, one thread per problem) backward pass; Qxx..Qu (host, problem-
+// major like the other outputs, may be NULL) receive the action-value expansion of every knot.
+static int backward_generic(int batch, int n, int m, int N, const double* A, const double* B,
+                            const double* f, const double* Q, const double* R, const double* H,
+                            const double* q, const double* r, double reg, bool is_diag, double* K,
+                            double* d, double* P, double* p, double* delta_V, int* status,
+                            double* Qxx, double* Quu, double* Qux, double* Qx, double* Qu) {
   const long S = ((long)batch + 31) / 32 * 32;
   Scratch sc;
   TvArgs a;
@@ -427,6 +414,14 @@ int altro_b200_tvlqr_backward_batch(int batch, int n, int m, int N, const double
   int* dstatus = (int*)sc.alloc((size_t)S);
   a.status = dstatus;
   if (!a.K || !a.d || !a.P || !a.p || !a.dV || !dstatus) return ALTRO_B200_ERR_NO_DEVICE;
+  if (Qxx && Quu && Qux && Qx && Qu) {
+    a.oQxx = sc.alloc((size_t)N * n * n * S);
+    a.oQuu = sc.alloc((size_t)N * m * m * S);
+    a.oQux = sc.alloc((size_t)N * m * n * S);
+    a.oQx = sc.alloc((size_t)N * n * S);
+    a.oQu = sc.alloc((size_t)N * m * S);
+    if (!a.oQxx || !a.oQuu || !a.oQux || !a.oQx || !a.oQu) return ALTRO_B200_ERR_NO_DEVICE;
+  }
   if (n <= 4 && m <= 2)
     launch_backward<4, 2>(a);
   else if (n <= 6 && m <= 4)
@@ -441,9 +436,50 @@ int altro_b200_tvlqr_backward_batch(int batch, int n, int m, int N, const double
   if ((e = to_host(sc, a.P, batch, (long)(N + 1) * n * n, S, P))) return e;
   if ((e = to_host(sc, a.p, batch, (long)(N + 1) * n, S, p))) return e;
   if ((e = to_host(sc, a.dV, batch, 2, S, delta_V))) return e;
+  if (a.oQxx) {
+    if ((e = to_host(sc, a.oQxx, batch, (long)N * n * n, S, Qxx))) return e;
+    if ((e = to_host(sc, a.oQuu, batch, (long)N * m * m, S, Quu))) return e;
+    if ((e = to_host(sc, a.oQux, batch, (long)N * m * n, S, Qux))) return e;
+    if ((e = to_host(sc, a.oQx, batch, (long)N * n, S, Qx))) return e;
+    if ((e = to_host(sc, a.oQu, batch, (long)N * m, S, Qu))) return e;
+  }
   if (status) TV_CUDA_OK(cudaMemcpy(status, dstatus, sizeof(int) * batch, cudaMemcpyDeviceToHost));
   TV_CUDA_OK(cudaDeviceSynchronize());
   return ALTRO_B200_NO_ERROR;
+}
+
+
+}  // namespace
+
+extern "C" {
+
+// fixed-size, TMA-staged workspace path for the compiled-in shapes (tvlqr_batch.cu); -1 = not compiled in
+int altro_b200_tvlqr_cached_backward(int batch, int n, int m, int N, const double* A, const double* B,
+                                     const double* f, const double* Q, const double* R, const double* H,
+                                     const double* q, const double* r, double reg, bool is_diag, double* K,
+                                     double* d, double* P, double* p, double* delta_V, int* status);
+int altro_b200_tvlqr_cached_forward(int batch, int n, int m, int N, const double* A, const double* B,
+                                    const double* f, const double* K, const double* d, const double* P,
+                                    const double* p, const double* x0, double* x, double* u, double* y);
+
+int altro_b200_tvlqr_backward_batch(int batch, int n, int m, int N, const double* A,
+                                    const double* B, const double* f, const double* Q,
+                                    const double* R, const double* H, const double* q,
+                                    const double* r, double reg, bool is_diag, double* K,
+                                    double* d, double* P, double* p, double* delta_V,
+                                    int* status) {
+  if (!A || !B || !f || !Q || !R || !q || !r) return ALTRO_B200_INVALID_POINTER;
+  if (!is_diag && !H) return ALTRO_B200_INVALID_POINTER;
+  if (n <= 0 || m <= 0 || batch <= 0 || N <= 0) return ALTRO_B200_DIMENSION_UNKNOWN;
+  if (n > 16 || m > 8) return ALTRO_B200_ERR_UNSUPPORTED;
+  if (!have_device()) return ALTRO_B200_ERR_NO_DEVICE;
+  {
+    const int e = altro_b200_tvlqr_cached_backward(batch, n, m, N, A, B, f, Q, R, H, q, r, reg, is_diag, K, d,
+                                                   P, p, delta_V, status);
+    if (e != -1) return e;
+  }
+  return backward_generic(batch, n, m, N, A, B, f, Q, R, H, q, r, reg, is_diag, K, d, P, p, delta_V, status,
+                          nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
 int altro_b200_tvlqr_forward_batch(int batch, int n, int m, int N, const double* A,
@@ -565,8 +601,11 @@ int tvlqr_BackwardPass(const int* nx, const int* nu, int N, const lqr_float* con
                        lqr_float** Qx_tmp, lqr_float** Qu_tmp, bool linear_only_update,
                        bool is_diag) {
   (void)linear_only_update;  // accepted and ignored, tvlqr.cpp:78
-  (void)Qxx; (void)Quu; (void)Qux; (void)Qx; (void)Qu;  // scratch lives in registers on the GPU
+  // the *_tmp tables are the reference's scratch (the GPU keeps scratch in registers); Qxx..Qu are
+  // OUTPUTS of the reference (the action-value expansion of every knot, tvlqr.cpp:123-152) and are
+  // written when the caller passes all five tables
   (void)Qxx_tmp; (void)Quu_tmp; (void)Qux_tmp; (void)Qx_tmp; (void)Qu_tmp;
+  const bool want_q = Qxx && Quu && Qux && Qx && Qu;
   int n, m;
   if (!uniform_dims(nx, nu, N, &n, &m)) return -2;
   std::vector<double> hA, hB, hf, hQ, hR, hH, hq, hr;
@@ -587,12 +626,36 @@ int tvlqr_BackwardPass(const int* nx, const int* nu, int N, const lqr_float* con
   }
   double dV[2] = {0, 0};
   int status = -1;
-  int e = altro_b200_tvlqr_backward_batch(1, n, m, N, hA.data(), hB.data(), hf.data(), hQ.data(),
-                                          hR.data(), is_diag ? nullptr : hH.data(), hq.data(),
-                                          hr.data(), reg, is_diag, hK.data(), hd.data(), hP.data(),
-                                          hp.data(), dV, &status);
+  std::vector<double> hQxx, hQuu, hQux, hQx, hQu;
+  int e;
+  if (want_q) {
+    if (n > 16 || m > 8 || !have_device()) return -2;
+    hQxx.resize((size_t)N * n * n);
+    hQuu.resize((size_t)N * m * m);
+    hQux.resize((size_t)N * m * n);
+    hQx.resize((size_t)N * n);
+    hQu.resize((size_t)N * m);
+    e = backward_generic(1, n, m, N, hA.data(), hB.data(), hf.data(), hQ.data(), hR.data(),
+                         is_diag ? nullptr : hH.data(), hq.data(), hr.data(), reg, is_diag, hK.data(),
+                         hd.data(), hP.data(), hp.data(), dV, &status, hQxx.data(), hQuu.data(),
+                         hQux.data(), hQx.data(), hQu.data());
+  } else {
+    e = altro_b200_tvlqr_backward_batch(1, n, m, N, hA.data(), hB.data(), hf.data(), hQ.data(),
+                                        hR.data(), is_diag ? nullptr : hH.data(), hq.data(),
+                                        hr.data(), reg, is_diag, hK.data(), hd.data(), hP.data(),
+                                        hp.data(), dV, &status);
+  }
   if (e != ALTRO_B200_NO_ERROR) return -2;
   const int k_first = (status == -1) ? 0 : status;  // knots below a failed factorisation are untouched
+  if (want_q) {  // the reference has written the expansion of the failing knot as well
+    for (int k = N - 1; k >= k_first; --k) {
+      if (Qxx[k]) memcpy(Qxx[k], &hQxx[(size_t)k * n * n], sizeof(double) * n * n);
+      if (Quu[k]) memcpy(Quu[k], &hQuu[(size_t)k * m * m], sizeof(double) * m * m);
+      if (Qux[k]) memcpy(Qux[k], &hQux[(size_t)k * m * n], sizeof(double) * m * n);
+      if (Qx[k]) memcpy(Qx[k], &hQx[(size_t)k * n], sizeof(double) * n);
+      if (Qu[k]) memcpy(Qu[k], &hQu[(size_t)k * m], sizeof(double) * m);
+    }
+  }
   for (int k = N; k >= k_first; --k) {
     if (k < N) {
       if (K && K[k]) memcpy(K[k], &hK[(size_t)k * m * n], sizeof(double) * m * n);

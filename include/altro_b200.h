@@ -84,7 +84,9 @@ enum {
  * same return convention: TVLQR_SUCCESS = -1, or the knot index whose Cholesky failed,
  * tvlqr.cpp:162-164).  Host pointer tables, one pointer per knot; the caller owns all memory.
  * Dimensions must be uniform over the horizon (every reference call site is); otherwise -2.
- * The Q*_tmp scratch tables may be NULL (the GPU path keeps scratch in registers).          */
+ * The Q*_tmp scratch tables may be NULL (the GPU path keeps scratch in registers).  Qxx, Quu,
+ * Qux, Qx, Qu -- outputs of the reference: the action-value expansion of every knot
+ * (tvlqr.cpp:123-152) -- are written when all five tables are passed, and skipped when NULL. */
 #ifndef TVLQR_SUCCESS
 #define TVLQR_SUCCESS -1
 #endif

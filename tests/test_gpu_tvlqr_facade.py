@@ -19,7 +19,7 @@ def _cm(M):
     return np.asarray(M, dtype=float).T.reshape(-1).copy()
 
 
-def gpu_tvlqr_single(pr, is_diag=True, reg=0.0):
+def gpu_tvlqr_single(pr, is_diag=True, reg=0.0, with_q=False):
     """tvlqr_BackwardPass / tvlqr_ForwardPass through the reference's own pointer-table signature."""
     L = altro_b200.load_library()
     n, m, N = pr["n"], pr["m"], pr["N"]
@@ -42,7 +42,8 @@ def gpu_tvlqr_single(pr, is_diag=True, reg=0.0):
     r, kr = table([pr["r"]] * N)
     outs = {}
     for name, size, cnt in [("K", m * n, N), ("d", m, N), ("P", n * n, N + 1), ("p", n, N + 1),
-                            ("x", n, N + 1), ("u", m, N), ("y", n, N + 1)]:
+                            ("x", n, N + 1), ("u", m, N), ("y", n, N + 1), ("Qxx", n * n, N), ("Quu", m * m, N),
+                            ("Qux", m * n, N), ("Qx", n, N), ("Qu", m, N)]:
         outs[name] = table([np.zeros(size) for _ in range(cnt)])
     nx = (C.c_int * (N + 1))(*([n] * (N + 1)))
     nu = (C.c_int * N)(*([m] * N))
@@ -51,7 +52,10 @@ def gpu_tvlqr_single(pr, is_diag=True, reg=0.0):
     NULL = None
     L.tvlqr_BackwardPass.restype = C.c_int
     res = L.tvlqr_BackwardPass(nx, nu, N, A, Bt, f, Q, R, H, q, r, C.c_double(reg), T("K"), T("d"),
-                               T("P"), T("p"), dV.ctypes.data_as(dp), NULL, NULL, NULL, NULL, NULL,
+                               T("P"), T("p"), dV.ctypes.data_as(dp),
+                               T("Qxx") if with_q else NULL, T("Quu") if with_q else NULL,
+                               T("Qux") if with_q else NULL, T("Qx") if with_q else NULL,
+                               T("Qu") if with_q else NULL,
                                NULL, NULL, NULL, NULL, NULL, C.c_bool(False), C.c_bool(is_diag))
     x0 = np.ascontiguousarray(pr["x0"])
     res2 = L.tvlqr_ForwardPass(nx, nu, N, A, Bt, f, T("K"), T("d"), T("P"), T("p"),
@@ -72,15 +76,19 @@ def test_tvlqr_dropin_goldens():
 
 
 def test_tvlqr_dropin_matches_oracle_all_outputs(oracle):
+    """Every output of the reference's signature, incl. the action-value expansion tables Qxx, Quu,
+    Qux, Qx, Qu (tvlqr.cpp:123-152), with and without the caller passing those tables."""
     for is_diag in (True, False):
-        pr = tvlqr_problem(np.float32(0.01))
-        res, res2, outs, dV = gpu_tvlqr_single(pr, is_diag)
-        ores, _, oK0, od0, oxN, oyN, odV, oouts = run_tvlqr(oracle, pr, is_diag)
-        assert res == ores
-        for name in ("K", "d", "P", "p", "x", "u", "y"):
-            for k in range(len(outs[name][1])):
-                assert np.allclose(outs[name][1][k], oouts[name][1][k], rtol=1e-12, atol=1e-12), (name, k)
-        assert np.allclose(dV, odV, rtol=1e-12)
+        for with_q in (False, True):
+            pr = tvlqr_problem(np.float32(0.01))
+            res, res2, outs, dV = gpu_tvlqr_single(pr, is_diag, with_q=with_q)
+            ores, _, oK0, od0, oxN, oyN, odV, oouts = run_tvlqr(oracle, pr, is_diag)
+            assert res == ores
+            names = ("K", "d", "P", "p", "x", "u", "y") + (("Qxx", "Quu", "Qux", "Qx", "Qu") if with_q else ())
+            for name in names:
+                for k in range(len(outs[name][1])):
+                    assert np.allclose(outs[name][1][k], oouts[name][1][k], rtol=1e-12, atol=1e-12), (name, k)
+            assert np.allclose(dV, odV, rtol=1e-12)
 
 
 def test_tvlqr_cholesky_failure_convention(oracle):
