@@ -214,20 +214,56 @@ struct TrajSolver {
   }
 
   // ---- selector helpers (static indices only, so x/u stay in registers)
+  // The selected variable is the same for every lane of the warp (the constraint table is shared by
+  // the batch), so a switch is a uniform jump instead of a select chain over all n + m variables
+  // (2 x 21 and 2 x 28 instructions per row in the rollout / follower paths of the constrained
+  // kernels); the values are the same: x - 0.0 == x for the entries the chain left alone.
+  template <int E>
+  ALTRO_DEV static double pick_from(int e, const double* v) {
+    if constexpr (E == 1) {
+      return v[0];
+    } else {
+      switch (e) {
+#define ALTRO_PICK_CASE(c) \
+  case c:                  \
+    if constexpr (c < E) return v[c]; else return 0.0;
+        ALTRO_PICK_CASE(0) ALTRO_PICK_CASE(1) ALTRO_PICK_CASE(2) ALTRO_PICK_CASE(3)
+        ALTRO_PICK_CASE(4) ALTRO_PICK_CASE(5) ALTRO_PICK_CASE(6) ALTRO_PICK_CASE(7)
+        ALTRO_PICK_CASE(8) ALTRO_PICK_CASE(9) ALTRO_PICK_CASE(10) ALTRO_PICK_CASE(11)
+        ALTRO_PICK_CASE(12) ALTRO_PICK_CASE(13) ALTRO_PICK_CASE(14) ALTRO_PICK_CASE(15)
+#undef ALTRO_PICK_CASE
+        default:
+          return 0.0;
+      }
+    }
+  }
+  template <int E>
+  ALTRO_DEV static void sub_at(int e, double val, double* v) {
+    switch (e) {
+#define ALTRO_SUB_CASE(c)            \
+  case c:                            \
+    if constexpr (c < E) v[c] -= val; \
+    break;
+      ALTRO_SUB_CASE(0) ALTRO_SUB_CASE(1) ALTRO_SUB_CASE(2) ALTRO_SUB_CASE(3)
+      ALTRO_SUB_CASE(4) ALTRO_SUB_CASE(5) ALTRO_SUB_CASE(6) ALTRO_SUB_CASE(7)
+      ALTRO_SUB_CASE(8) ALTRO_SUB_CASE(9) ALTRO_SUB_CASE(10) ALTRO_SUB_CASE(11)
+      ALTRO_SUB_CASE(12) ALTRO_SUB_CASE(13) ALTRO_SUB_CASE(14) ALTRO_SUB_CASE(15)
+#undef ALTRO_SUB_CASE
+      default:
+        break;
+    }
+  }
+  static_assert(NS_ <= 16 && NI_ <= 16, "selector switch covers 16 variables per block");
   ALTRO_DEV static double pick(int id, const double* x, const double* u) {
-    double v = 0.0;
-#pragma unroll
-    for (int e = 0; e < n; ++e) v = (id == e) ? x[e] : v;
-#pragma unroll
-    for (int e = 0; e < m; ++e) v = (id == n + e) ? u[e] : v;
-    return v;
+    if (id < 0) return 0.0;
+    return id < n ? pick_from<n>(id, x) : pick_from<m>(id - n, u);
   }
   ALTRO_DEV static void scatter_sub(int id, double val, double* lx, double* lu, bool terminal) {
-#pragma unroll
-    for (int e = 0; e < n; ++e) lx[e] -= (id == e) ? val : 0.0;
-    if (!terminal) {
-#pragma unroll
-      for (int e = 0; e < m; ++e) lu[e] -= (id == n + e) ? val : 0.0;
+    if (id < 0) return;
+    if (id < n) {
+      sub_at<n>(id, val, lx);
+    } else if (!terminal) {
+      sub_at<m>(id - n, val, lu);
     }
   }
   ALTRO_DEV double row_offset(const ConSlot& s, int i) const {
