@@ -244,7 +244,6 @@ struct altro_b200_solver {
   int follow_deriv = 1;
   int qrc_uniform_enable = 1;  // ALTRO_B200_QRC_UNIFORM=0 streams [q r c] with every knot regardless
   int spec_round1 = 1;
-  int fused_post = 1;  // forward kernel: everything between the search and the decision as one pass over the knots
   int fwd_depth = 8;  // staging depth cap of k_phase_forward (BulkPipe holds up to 8 stages)
   // pipelined sub-batches: the groups are cut into `nsplit` contiguous ranges, each on its own
   // stream, so that the sweeps of one range (one busy warp per group) overlap the rollouts and
@@ -496,7 +495,6 @@ altro_b200_solver* altro_b200_create(int horizon_length, int batch, int device) 
   if (const char* env = getenv("ALTRO_B200_FOLLOWER")) s->follow_deriv = atoi(env) != 0;
   if (const char* env = getenv("ALTRO_B200_QRC_UNIFORM")) s->qrc_uniform_enable = atoi(env) != 0;
   if (const char* env = getenv("ALTRO_B200_SPEC_ROUND1")) s->spec_round1 = atoi(env) != 0;
-  if (const char* env = getenv("ALTRO_B200_FUSED_POST")) s->fused_post = atoi(env) != 0;
   if (const char* env = getenv("ALTRO_B200_FWD_DEPTH")) s->fwd_depth = std::max(2, std::min(8, atoi(env)));
   return s;
 }
@@ -1329,7 +1327,6 @@ static void fill_device_problem(const altro_b200_solver* s, DeviceProblem& P) {
   P.nslots = s->nslots;
   P.nstore = s->nslots > 1 ? s->nstore : 0;
   P.follow_deriv = s->follow_deriv;
-  P.fused_post = s->fused_post;
   P.spec_round1 = s->spec_round1;
   P.prof_tid = getenv("ALTRO_B200_PROF_TID") ? atoi(getenv("ALTRO_B200_PROF_TID")) : 0;
   P.qrc_uniform = s->qrc_uniform_enable ? qrc_uniform(s) : 0;

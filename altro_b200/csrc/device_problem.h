@@ -153,7 +153,6 @@ struct DeviceProblem {
   // of rounds, but no speculative work for the searches that accept alpha0
   int prof_tid;  // profile mode: the thread whose clocks are recorded (0: rollout warp, 32: follower, 64..: speculating)
   int spec_round1;
-  int fused_post;  // k_phase_forward: post-search expansion + costates + residuals + copy as one pass
   double *xs, *us;      // slot record stream; us = xs + n * 32
   double* phi_s;        // [kMaxHalvings + 1][Bp] merit value of halving j (alpha0 * 2^-j), j >= 1
   int* spec_base;       // [Bp] halving index rolled out by slot 1 of the pending / last round

@@ -1249,7 +1249,7 @@ struct TrajSolver {
   // The simulation half of MeritFunction (solver.cpp:285-301, :319-322): closed-loop rollout at
   // step alpha, returning the merit value.  Derivative work is left to phase_expand_knot
   // (parallel over knots) + the d(phi) scan; y_ is produced for the accepted point only
-  // (phase_costate_knot).  z_est is not stored here: every candidate that can be accepted is
+  // (post_chunk).  z_est is not stored here: every candidate that can be accepted is
   // expanded afterwards, which stores it.  rollout_step advances x from knot k to k + 1; xo/uo
   // (may be null: merit value only) receive the trial trajectory with knot stride `so`.
   // the control of knot k on the closed-loop rollout at step alpha (solver.cpp:287-291)
@@ -1404,19 +1404,6 @@ struct TrajSolver {
     return dphi_terminal(dxda, dphi);
   }
 
-  // y_k = P_k (x_k - xbar_k) + p_k for the accepted point (solver.cpp:293, :324)
-  ALTRO_DEV void phase_costate_knot(int k) {
-    double x[n], xb[n], dx[n], Pk[n * n], y[n];
-    load_block<n>(F(P.x), S, k, x);
-    load_block<n>(F(P.xbar), S, k, xb);
-#pragma unroll
-    for (int i = 0; i < n; ++i) dx[i] = x[i] - xb[i];
-    load_block<n * n>(F(P.P), S, k, Pk);
-    load_block<n>(F(P.p), S, k, y);
-    mm<n, 1, n, false, false, 1>(Pk, dx, y);
-    store_block<n>(F(P.y), S, k, y);
-  }
-
   // ---- everything between the line search and the convergence decision, ONE pass over the knots:
   // the post-search expansion of an accepted backtracking step (solver.cpp:256-262, `refresh`; the
   // accepted candidate may still sit in candidate slot `slot`), the costates y_k (:293, :324),
@@ -1508,44 +1495,6 @@ struct TrajSolver {
 #pragma unroll
       for (int i = 0; i < n; ++i) yn[i] = y[i];
     }
-    if (res > 0.0) atomicMax(P.stat_acc + b, (unsigned long long)__double_as_longlong(res));
-    if (CON && viol > 0.0) atomicMax(P.feas_acc + b, (unsigned long long)__double_as_longlong(viol));
-  }
-
-  // knot k's contribution to Stationarity (solver.cpp:207-222) and Feasibility (:224-231), and its
-  // share of CopyTrajectory (:148-157).  Max-reduced over knots with atomics on the bit patterns
-  // (all values are >= 0; NaNs are skipped exactly as std::max skips them).
-  ALTRO_DEV void phase_residual_knot(int k) {
-    double res = 0.0, viol = 0.0;
-    double x[n], u[m];
-    load_block<n>(F(P.x), S, k, x);
-    if (k < N) {
-      double y[n], yn[n], A[n * n], Bm[n * m], lx[n], lu[m];
-      load_block<n>(F(P.y), S, k, y);
-      load_block<n>(F(P.y), S, k + 1, yn);
-      load_jac(k, A, Bm);
-      load_block<n>(F(P.lx), S, k, lx);
-      load_block<m>(F(P.lu), S, k, lu);
-      load_block<m>(F(P.u), S, k, u);
-      mm<n, 1, n, true, false, 1>(A, yn, lx);
-      mm<m, 1, n, true, false, 1>(Bm, yn, lu);
-#pragma unroll
-      for (int i = 0; i < n; ++i) res = fmax(res, fabs(lx[i] - y[i]));
-#pragma unroll
-      for (int i = 0; i < m; ++i) res = fmax(res, fabs(lu[i]));
-      viol = al_violation(k, x, u);
-      store_block<m>(F(P.ubar), S, k, u);
-    } else {
-      double y[n], lx[n];
-      load_block<n>(F(P.y), S, N, y);
-      load_block<n>(F(P.lx), S, N, lx);
-#pragma unroll
-      for (int i = 0; i < n; ++i) res = fmax(res, fabs(lx[i] - y[i]));
-#pragma unroll
-      for (int i = 0; i < m; ++i) u[i] = 0.0;
-      viol = al_violation(N, x, u);
-    }
-    store_block<n>(F(P.xbar), S, k, x);
     if (res > 0.0) atomicMax(P.stat_acc + b, (unsigned long long)__double_as_longlong(res));
     if (CON && viol > 0.0) atomicMax(P.feas_acc + b, (unsigned long long)__double_as_longlong(viol));
   }

@@ -859,7 +859,7 @@ __global__ void __launch_bounds__((Model::n > kUnrollDim) ? 256 : kFwdThreads, (
   // -- fused with the costates of the accepted point, the stationarity / feasibility residuals and
   // CopyTrajectory into one pass: warp w walks the w-th chunk of the knots downwards, lane =
   // problem (TrajSolver::post_chunk)
-  if (P.fused_post) {
+  {
     const int W = (int)(blockDim.x >> 5);
     const int C = (P.N + 1 + W - 1) / W;
     const int k0 = wid * C, k1 = min(k0 + C, P.N + 1);
@@ -873,29 +873,6 @@ __global__ void __launch_bounds__((Model::n > kUnrollDim) ? 256 : kFwdThreads, (
     if (act && k1 <= P.N) s.post_boundary(k1, slot, yn);
     __syncthreads();
     if (act) s.post_chunk(k0, k1, refresh, slot, yn);
-    __syncthreads();
-  } else {
-    const unsigned rmask = __ballot_sync(kAll, (fl & TF_REFRESH_DYN) != 0);
-    if (rmask) {
-      for_knot_items(rmask, g, P.N + 1, [&](int b, int k) {
-        TS s(P, b);
-        weights(s);
-        s.rho = CON ? P.rho[b] : 1.0;
-        s.phase_expand_knot(k, true, P.sel[b], false);
-      });
-      __syncthreads();
-    }
-    tick(FS_EXPAND);
-    // costates of the accepted point, then stationarity / feasibility residuals + CopyTrajectory
-    for_knot_items(act_mask, g, P.N + 1, [&](int b, int k) {
-      TS s(P, b);
-      s.phase_costate_knot(k);
-    });
-    __syncthreads();
-    for_knot_items(act_mask, g, P.N + 1, [&](int b, int k) {
-      TS s(P, b);
-      s.phase_residual_knot(k);
-    });
     __syncthreads();
   }
   // convergence test, dual / penalty update decision (solver.cpp:459-489, :503-506)
