@@ -98,7 +98,10 @@ def kernel_models(P, iters, evals):
     # so it only adds the writes of [J], lx, lu (+ z_est): once per iteration for the backtracking
     # search (the alpha0 evaluation), with every evaluation for the strong-Wolfe search
     deriv = it if P.options.get("use_backtracking_linesearch") else roll
-    roll_d = 2 * (n + m) + 1 + m * n + m + (n + m) + rows       # r [xbar ubar q r c K d] (+ z)  w x,u
+    # goal-type costs (one SetLQRCost call, knot-independent reference): q, r, c of the stage knots are
+    # read once per kernel, not streamed with every knot (DeviceProblem::qrc_uniform)
+    qrc = 0 if P.ref_mode in (PR.REF_GOAL, PR.REF_SHARED) else n + m + 1
+    roll_d = (n + m) + qrc + m * n + m + (n + m) + rows          # r [xbar ubar (q r c) K d] (+ z)  w x,u
     deriv_d = jac + n + m + 2 * rows                              # w J,lx,lu (+ z_est)
     sub = {
         "fwd_rollout": dict(doubles=roll_d, units=roll * N, extra_bytes=8.0 * deriv_d * deriv * N),
@@ -121,7 +124,7 @@ def kernel_models(P, iters, evals):
                                "state machines; fused expansion / costate / residual / copy pass, AL update)",
                         doubles=0.0, units=0.0, extra_bytes=fwd_bytes),
         "expand": dict(kernel="k_phase_expand (prologue: Jacobians, projected duals, gradients)",
-                       doubles=2 * (n + m) + (jac + n + m) + 2 * rows, units=P.B * (N + 1)),
+                       doubles=(n + m) + max(qrc - 1, 0) + (jac + n + m) + 2 * rows, units=P.B * (N + 1)),
     }
     for k, v in sub.items():
         models[k] = dict(kernel=f"k_phase_forward / {k[4:]}", **v)
