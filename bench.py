@@ -93,21 +93,21 @@ def kernel_models(P, iters, evals):
     roll = float(np.maximum(evals.astype(np.float64) - iters, 0).sum())  # rollouts the search consumed
     # Jacobian entries kept in HBM: dense n^2 + nm unless the model packs them (models.cuh, JacPack)
     jac = {PR.MODEL_BICYCLE5: 15, PR.MODEL_BICYCLE4: 12}.get(P.model_id, n * n + n * m)
-    # sub-phases of k_phase_forward.  The derivative half of a merit evaluation
-    # is done by the follower warp INSIDE the rollout pass (x_k, u_k handed over in shared memory),
-    # so it only adds the writes of [J], lx, lu (+ z_est): once per iteration for the backtracking
-    # search (the alpha0 evaluation), with every evaluation for the strong-Wolfe search
-    deriv = it if P.options.get("use_backtracking_linesearch") else roll
-    # goal-type costs (one SetLQRCost call, knot-independent reference): q, r, c of the stage knots are
-    # read once per kernel, not streamed with every knot (DeviceProblem::qrc_uniform)
-    qrc = 0 if P.ref_mode in (PR.REF_GOAL, PR.REF_SHARED) else n + m + 1
-    roll_d = (n + m) + qrc + m * n + m + (n + m) + rows          # r [xbar ubar (q r c) K d] (+ z)  w x,u
-    deriv_d = jac + n + m + 2 * rows                              # w J,lx,lu (+ z_est)
+    # sub-phases of k_phase_forward.  ALGORITHMIC bytes = the SURVEY 8(d) split of the reference
+    # formulation, unchanged since round 1 so that the fractions stay comparable: per consumed
+    # rollout r [xbar ubar q r c K d] (+ z) w x,u; per iteration one expansion (r x,u,q,r  w J,lx,lu
+    # (+ z, z_est)) and one d(phi) scan (r K,d,J,lx,lu); costates + residuals + copy
+    # (r x,xbar,P,p  w y;  r x,u,y,y+,J,lx,lu  w xbar,ubar).  The round-2 kernel moves less than that
+    # (the follower warp needs no re-reads, goal-type costs do not stream
+    # [q r c], the post-search pass reads every block once); the time of the expansion and of the
+    # scan is inside the rollout passes now, so their bytes are booked there.
+    roll_d = 2 * (n + m) + 1 + m * n + m + (n + m) + rows
+    expand_d = 2 * (n + m) + (jac + n + m) + 2 * rows
+    dphi_d = m * n + m + jac + n + m
     sub = {
-        "fwd_rollout": dict(doubles=roll_d, units=roll * N, extra_bytes=8.0 * deriv_d * deriv * N),
-        # post-search pass: r x,u, xbar, P,p, J,lx,lu (or q,r where the accepted point still needs its
-        # expansion)  w y, xbar, ubar
-        "fwd_criteria": dict(doubles=(n + m) + n + (n * n + n) + (jac + n + m) + n + (n + m) + rows,
+        "fwd_rollout": dict(doubles=roll_d, units=roll * N,
+                            extra_bytes=8.0 * (expand_d * it * (N + 1) + dphi_d * it * N)),
+        "fwd_criteria": dict(doubles=(2 * n + n * n + n) + n + (2 * n + jac + 2 * (n + m)) + (n + m) + rows,
                              units=it * (N + 1)),
     }
     fwd_bytes = sum(8.0 * v["doubles"] * v["units"] + v.get("extra_bytes", 0.0) for v in sub.values())
@@ -124,7 +124,7 @@ def kernel_models(P, iters, evals):
                                "state machines; fused expansion / costate / residual / copy pass, AL update)",
                         doubles=0.0, units=0.0, extra_bytes=fwd_bytes),
         "expand": dict(kernel="k_phase_expand (prologue: Jacobians, projected duals, gradients)",
-                       doubles=(n + m) + max(qrc - 1, 0) + (jac + n + m) + 2 * rows, units=P.B * (N + 1)),
+                       doubles=2 * (n + m) + (jac + n + m) + 2 * rows, units=P.B * (N + 1)),
     }
     for k, v in sub.items():
         models[k] = dict(kernel=f"k_phase_forward / {k[4:]}", **v)

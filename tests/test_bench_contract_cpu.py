@@ -38,12 +38,12 @@ def test_kernel_byte_model_matches_design_table():
     # DESIGN.md section 4, (5,2) with the packed Jacobian (V = 15), bytes per trajectory-knot
     assert 8 * m["backward"]["doubles"] == 784        # 904 in a problem's first iteration
     assert m["backward"]["extra_bytes"] == (904 - 784) * P.B * 100
-    assert 8 * m["fwd_rollout"]["doubles"] == 272 - 64   # goal-type cost: [q r c] (8 rows) not streamed
-    # the follower's share of a merit evaluation with derivative: w J, lx, lu, once per iteration
-    # for the backtracking search
-    assert m["fwd_rollout"]["extra_bytes"] == 176 * P.B * 10 * 100
-    assert 8 * m["expand"]["doubles"] == 288 - 56
-    assert 8 * m["fwd_criteria"]["doubles"] == 608
+    assert 8 * m["fwd_rollout"]["doubles"] == 272
+    # expansion (288 B per knot, N + 1 knots) and d(phi) scan (272 B per knot) of every iteration: done
+    # inside the rollout passes by the follower warp, booked there
+    assert m["fwd_rollout"]["extra_bytes"] == (288 * 101 + 272 * 100) * P.B * 10
+    assert 8 * m["expand"]["doubles"] == 288
+    assert 8 * m["fwd_criteria"]["doubles"] == 360 + 368
     assert m["backward"]["units"] == P.B * 10 * 100 and m["fwd_rollout"]["units"] == P.B * 20 * 100
     # k_phase_forward carries the sum of its sub-phases
     assert m["forward"]["extra_bytes"] == sum(8.0 * m[k]["doubles"] * m[k]["units"] + m[k].get("extra_bytes", 0.0)
